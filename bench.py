@@ -1,0 +1,300 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark of the batched TinyMPC ADMM hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+Workload (BASELINE.json metric "MPC QP solves/sec (batched quadrotor, N=10) ...", configs[2]):
+quadrotor hover nx=12 nu=4 N=10, 2^20 independent problems PER GPU with per-problem x0 and
+per-problem full Xref/Uref arrays, box constraints, tol 1e-3, max_iter 100.
+One "step" = one pass of the hot path over the whole batch.  Multi-GPU = the batch sharded by
+problem index, one process per GPU, no collective on the data path ("weak" scaling: 2^20 per GPU).
+
+Printed JSON line (rank 0):
+  value      solves/s, whole job, inputs/outputs resident in HBM, CUDA-event timed, max over ranks
+  e2e        the same through the host-buffer C-ABI call (pinned host memory, H2D + D2H inside)
+  roofline   FP32 CUDA-core roofline of the solve kernel (the bounding one) + HBM fraction
+  cpu_baseline  the reference C++ solver (oracle/_ref) looped over a bounded prefix of the same batch
+--impl reference times that CPU reference as the main line instead.
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+# algorithmic work per ADMM iteration / bytes per solve, SURVEY.md section 8d (box constraints)
+def flops_per_iter(n, m, N):
+    return (N - 1) * (4 * n * n + 8 * n * m + 2 * m * m + 5 * n + 3 * m) + 15 * (n * N + m * (N - 1)) + (2 * n * n + 3 * n)
+
+
+def bytes_per_solve(n, m, N):
+    return 4 * (n + n * N + m * (N - 1)) + 4 * (n * N + m * (N - 1)) + 8
+
+
+def fp32_peak_tflops():
+    """FP32 CUDA-core peak: measured by profiles/microbench/ffma_bench.cu on this pool (see
+    profiles/microbench/RESULTS.md); MEASURED_PEAKS.json carries no FP32 figure."""
+    f = ROOT / "profiles" / "microbench" / "fp32_peak.json"
+    if f.exists():
+        d = json.loads(f.read_text())
+        return float(d["fp32_tflops"]), d.get("how", "measured FFMA micro-benchmark")
+    return 148 * 128 * 2 * 1.965e9 / 1e12, "nominal 148 SM x 128 lanes x 2 x 1.965 GHz (no measurement file)"
+
+
+def hbm_peak_gbs():
+    f = ROOT / "MEASURED_PEAKS.json"
+    if f.exists():
+        return float(json.loads(f.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.samples, self.stop_flag, self.t = index, [], threading.Event(), None
+
+    def _run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([t.strip() for t in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.1)
+
+    def __enter__(self):
+        self.t = threading.Thread(target=self._run, daemon=True)
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop_flag.set()
+        self.t.join(timeout=6)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no_samples"]}
+        sm = sorted(float(s[0]) for s in self.samples)
+        reasons = []
+        for k, name in enumerate(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]):
+            if any(s[2 + k].lower().startswith("active") for s in self.samples):
+                reasons.append(name)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons, "samples": len(sm)}
+
+
+def reference_arm(args, P, spec, batch_np):
+    """The reference's own CPU implementation (oracle/_ref = unmodified reference C++ built by
+    oracle/Makefile; falls back to the C port) on all host threads, bounded sample per step."""
+    sys.path.insert(0, str(ROOT / "oracle"))
+    import oracle as O
+    kind = "reference" if O.available("ref") else "port"
+    impl = "ref" if kind == "reference" else "port"
+    if kind == "port" and not O.available("port"):
+        subprocess.check_call(["make", "-C", str(ROOT / "oracle"), "liboracle_port.so"])
+    cores = os.cpu_count() or 1
+    # probe to size the sample at ~ args.cpu_seconds per step
+    probe = batch_np.slice(0, min(batch_np.size, 64 * cores))
+    t0 = time.perf_counter(); O.solve_batch(spec, probe, impl, cores); dt = time.perf_counter() - t0
+    rate = probe.size / max(dt, 1e-6)
+    n = int(min(batch_np.size, max(probe.size, rate * args.cpu_seconds)))
+    sample = batch_np.slice(0, n)
+    for _ in range(min(args.warmup, 1)):
+        O.solve_batch(spec, sample, impl, cores)
+    t0 = time.perf_counter()
+    iters = 0
+    for _ in range(args.steps_cpu):
+        r = O.solve_batch(spec, sample, impl, cores)
+        iters += int(r["iter"].sum())
+    dt = time.perf_counter() - t0
+    sps = n * args.steps_cpu / dt
+    return dict(value=sps, unit="solves/s", cores=cores, kind=kind,
+                sample=f"first {n} problems of the same batch x {args.steps_cpu} passes, {cores} threads, cold start per problem",
+                ns_per_admm_iter=dt * 1e9 / max(iters, 1), ms_per_step=dt * 1e3 / args.steps_cpu, mean_iters=iters / (n * args.steps_cpu))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=1 << 20, help="problems per GPU")
+    ap.add_argument("--scale", type=float, default=1.0, help="difficulty of the synthetic batch (SURVEY 8d: 0.3 easy, 1.0 hard)")
+    ap.add_argument("--config", default="quadrotor", choices=["quadrotor", "cartpole", "rocket", "quadrotor_adaptive"])
+    ap.add_argument("--precision", type=int, default=32)
+    ap.add_argument("--cpu-seconds", dest="cpu_seconds", type=float, default=8.0)
+    ap.add_argument("--steps-cpu", dest="steps_cpu", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = 3   # timing rule: at least 3 warm-up steps
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    P = importlib.import_module("tinympc-matlab_b200.problems")
+    spec = dict(quadrotor=P.quadrotor, cartpole=P.cartpole, rocket=P.rocket,
+                quadrotor_adaptive=lambda: P.quadrotor(adaptive=True))[args.config]()
+    n, m, N = spec.nx, spec.nu, spec.N
+    workload = f"{args.config} nx={n} nu={m} N={N}, {args.batch} problems/GPU, per-problem x0+Xref+Uref, box constraints, " \
+               f"tol {spec.abs_pri_tol:g}, max_iter {spec.max_iter}, difficulty scale {args.scale}"
+    config = {"workload": workload, "batch_per_gpu": args.batch, "scale": args.scale,
+              "l2_policy": "inputs+outputs per step (%.0f MB) exceed the 126 MB L2" % (bytes_per_solve(n, m, N) * args.batch / 1e6),
+              "parallelism": f"problem-index shards x{world}, no collective"}
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        batch_np = P.make_batch(spec, min(args.batch, 1 << 18), args.scale, seed=1234 + 3)
+        args.steps_cpu = max(1, args.steps)
+        cb = reference_arm(args, P, spec, batch_np)
+        line = {"impl": "reference", "metric": "solves_per_sec", "value": cb["value"], "unit": "solves/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+                "ns_per_admm_iter": cb["ns_per_admm_iter"], "mean_iters": cb["mean_iters"],
+                "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": cb["value"], "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    # ------------------------------------------------------------------ B200 arm
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    tm = importlib.import_module("tinympc-matlab_b200")
+    B = args.batch
+    batch_np = P.make_batch(spec, B, args.scale, seed=1234 + 3 + 1000 * rank)   # each rank owns its shard
+    solver = tm.TinyMPC()
+    solver.setup_from_spec(spec, devices=[local])
+    solver.cuda.set_option("precision", args.precision)
+
+    tdev = lambda a: None if a is None else torch.from_numpy(a).to(dev)
+    x0, Xref, Uref = tdev(batch_np.x0), tdev(batch_np.Xref), tdev(batch_np.Uref)
+    x = torch.empty((B, N, n), device=dev); u = torch.empty((B, N - 1, m), device=dev)
+    it = torch.empty(B, dtype=torch.int32, device=dev); st = torch.empty(B, dtype=torch.int32, device=dev)
+    ptr = lambda a: None if a is None else a.data_ptr()
+    stream = torch.cuda.current_stream()
+
+    def step():
+        solver.cuda.solve_batch_device(B, ptr(x0), ptr(Xref), ptr(Uref), ptr(x), ptr(u), ptr(it), ptr(st), stream=stream.cuda_stream)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    launches0 = solver.cuda.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        e0.record(stream)
+        for _ in range(args.steps):
+            step()
+        e1.record(stream)
+        barrier()
+    ms = e0.elapsed_time(e1)
+    launches = solver.cuda.launch_count - launches0
+    iters_one = int(it.sum().item())                 # identical every step (same inputs)
+    unsolved = float((st == 11).float().mean().item())
+    tmax = torch.tensor([ms], device=dev)
+    tot = torch.tensor([float(iters_one), float(launches)], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    ms_all = float(tmax.item())
+    iters_all, launches_all = float(tot[0].item()), int(tot[1].item())
+    value = world * B * args.steps / (ms_all * 1e-3)
+    ns_iter = ms_all * 1e6 / (iters_all * args.steps)
+
+    # ---- end to end through the host-buffer C-ABI call (pinned host memory, copies inside the timed region)
+    e2e = None
+    if not args.no_e2e:
+        pin = lambda a: None if a is None else torch.from_numpy(a).pin_memory()
+        hx0, hXr, hUr = pin(batch_np.x0), pin(batch_np.Xref), pin(batch_np.Uref)
+        hout = dict(x=torch.empty((B, N, n)).pin_memory().numpy(), u=torch.empty((B, N - 1, m)).pin_memory().numpy(),
+                    iter=torch.empty(B, dtype=torch.int32).pin_memory().numpy(), status=torch.empty(B, dtype=torch.int32).pin_memory().numpy())
+        npv = lambda t: None if t is None else t.numpy()
+        solver.cuda.solve_batch(npv(hx0), npv(hXr), npv(hUr), out=hout)     # warm-up (allocations)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(max(1, args.steps // 2)):
+            solver.cuda.solve_batch(npv(hx0), npv(hXr), npv(hUr), out=hout)
+        barrier()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], device=dev)
+        if dist is not None:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        k = max(1, args.steps // 2)
+        h2d = 4 * (B * n + (B * N * n if hXr is not None else 0) + (B * (N - 1) * m if hUr is not None else 0))
+        d2h = 4 * (B * N * n + B * (N - 1) * m) + 8 * B
+        e2e = {"value": world * B * k / float(tt.item()), "unit": "solves/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "ms_per_step": float(tt.item()) * 1e3 / k, "pipeline": solver.cuda.last_timing()}
+        assert np.array_equal(hout["iter"], it.cpu().numpy()), "host-buffer path and device path disagree"
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    F = flops_per_iter(n, m, N)
+    peak_tf, peak_how = fp32_peak_tflops()
+    hbm_pk, hbm_how = hbm_peak_gbs()
+    t_launch = ms / args.steps * 1e-3                              # rank-0 kernel launch duration (1 kernel / step)
+    ach_tf = F * iters_one / t_launch / 1e12
+    ach_gbs = bytes_per_solve(n, m, N) * B / t_launch / 1e9
+    roof = {"bound": "fp32_cuda_core", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf,
+            "traffic": None, "peak_source": peak_how, "flops_per_admm_iter": F, "kernel": solver.cuda.last_kernel,
+            "hbm": {"achieved": ach_gbs, "peak": hbm_pk, "unit": "GB/s", "frac": ach_gbs / hbm_pk, "peak_source": hbm_how,
+                    "bytes_per_solve": bytes_per_solve(n, m, N)}}
+    prof = ROOT / "profiles" / "r01_traffic.json"
+    if prof.exists():
+        roof["traffic"] = json.loads(prof.read_text()).get("dram_bytes_per_launch")
+
+    line = {"metric": "solves_per_sec", "value": value, "unit": "solves/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_all / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" if args.precision == 32 else "f64", "data": "synthetic", "config": config,
+            "ns_per_admm_iter": ns_iter, "mean_iters": iters_all / (world * B), "unsolved_frac": unsolved,
+            "clocks": clk.summary(), "e2e": e2e, "gpu_launches": launches_all, "roofline": roof}
+    if not args.no_cpu_baseline:
+        try:
+            cb = reference_arm(args, P, spec, batch_np.slice(0, min(B, 1 << 18)))
+            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "ns_per_admm_iter")}
+        except Exception as ex:  # the checker is optional for the GPU number, never the other way round
+            line["cpu_baseline"] = {"value": None, "unit": "solves/s", "cores": os.cpu_count(), "kind": "unavailable", "sample": repr(ex)}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,138 @@
+/*
+ * tinympc_b200.h -- thin C ABI of the B200-native batched TinyMPC ADMM solver.
+ *
+ * This is the drop-in boundary for the reference's hot path: everything between tiny_solve()
+ * being entered (tinympc/TinyMPC/src/tinympc/tiny_api.cpp:321-323) and solve() returning
+ * (tinympc/TinyMPC/src/tinympc/admm.cpp:274-389).  The reference's own "extern C" API passes Eigen
+ * objects by value (tiny_api.hpp:10-50) and is therefore not a C ABI; the host C++ mirror of that
+ * API (tinympc-matlab_b200/csrc/host/tiny_api.hpp) and the MEX layer call THIS interface, which
+ * uses only plain pointers, ints and doubles.  INTEGRATION.md shows the binding a maintainer of the
+ * reference would add.
+ *
+ * Conventions
+ *   - "family" data (dynamics, cache, settings, shared constraints) is what one TinySolver holds
+ *     (types.hpp:43-187): column-major double arrays on the HOST, copied at set_family time.
+ *   - batch data is float32, one contiguous chunk per problem: x0[b][nx], Xref[b][N][nx]
+ *     (= column-major nx x N per problem, as TinyWorkspace::Xref), Uref[b][N-1][nu], etc.
+ *   - every entry point returns 0 on success, a TINYMPC_CUDA_E* code otherwise;
+ *     tinympc_cuda_last_error() gives the text.  There is NO CPU fallback: without a usable CUDA
+ *     device every solve call fails with TINYMPC_CUDA_ENODEVICE.
+ *   - cold-start semantics per problem: workspace as tiny_setup leaves it (tiny_api.cpp:68-105) and
+ *     the pristine cache, i.e. exactly what a fresh tiny_setup + tiny_set_x0/x_ref/u_ref +
+ *     tiny_solve produces.  solution = (vnew, znew) (admm.cpp:370-371, 386-387), status 1 solved /
+ *     11 unsolved (admm.cpp:279, 365), iter = work->iter.
+ */
+#ifndef TINYMPC_B200_H
+#define TINYMPC_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TINYMPC_CUDA_OK          0
+#define TINYMPC_CUDA_EINVAL      1   /* bad argument / dimension mismatch (cf. check_dimension, tiny_api.cpp:13-19) */
+#define TINYMPC_CUDA_ENODEVICE   2   /* no CUDA device / driver: the product never falls back to the CPU */
+#define TINYMPC_CUDA_ECUDA       3   /* a CUDA runtime call failed */
+#define TINYMPC_CUDA_EUNSUPPORTED 4  /* problem shape has no compiled kernel */
+#define TINYMPC_CUDA_ENOTREADY   5   /* solve before set_family */
+
+#define TINYMPC_MAX_CONES 4
+
+typedef struct tinympc_cuda_solver tinympc_cuda_solver;   /* opaque */
+
+/* What one TinySolver holds after tiny_setup + the constraint setters (replaces reading
+ * solver->work / solver->cache / solver->settings directly, types.hpp:43-197). */
+typedef struct {
+    int nx, nu, N;
+    /* TinyWorkspace dynamics and cost diagonals (types.hpp:165-169); Q, R are work->Q, work->R,
+       i.e. diag(Q)+rho, diag(R)+rho as tiny_setup stores them (tiny_api.cpp:107-108) */
+    const double *Adyn, *Bdyn, *fdyn, *Q, *R;
+    /* TinyCache (types.hpp:43-59) */
+    double rho;
+    const double *Kinf, *Pinf, *Quu_inv, *AmBKt, *APf, *BPf;
+    const double *dKinf_drho, *dPinf_drho;   /* read only when adaptive_rho != 0; C1/C2 are dead on the
+                                                iteration path (admm.cpp:17-18) and are not needed */
+    /* TinySettings (types.hpp:63-80) */
+    double abs_pri_tol, abs_dua_tol;
+    int max_iter, check_termination;
+    int en_state_bound, en_input_bound, en_state_soc, en_input_soc, en_state_linear, en_input_linear;
+    int adaptive_rho;
+    double adaptive_rho_min, adaptive_rho_max;
+    int adaptive_rho_enable_clipping;
+    /* shared bounds (types.hpp:115-118), nx*N and nu*(N-1) column-major; may be NULL when the
+       matching en_* flag is 0 or when every batch supplies per-problem bounds */
+    const double *x_min, *x_max, *u_min, *u_max;
+    /* cones as they sit in the workspace (types.hpp:122-129) */
+    int numStateCones, numInputCones;
+    const int *Acx, *qcx; const double *cx;
+    const int *Acu, *qcu; const double *cu;
+    /* linear inequality rows (types.hpp:143-150), Alin_x is numStateLinear x nx column-major */
+    int numStateLinear, numInputLinear;
+    const double *Alin_x, *blin_x, *Alin_u, *blin_u;
+} tinympc_cuda_family;
+
+/* One batch of independent problems of the family.  Pointers are HOST pointers for
+ * tinympc_cuda_solve_batch and DEVICE pointers (16-byte aligned) for tinympc_cuda_solve_batch_device. */
+typedef struct {
+    int batch;
+    const float *x0;      /* batch*nx                        replaces tiny_set_x0   (tiny_api.cpp:375-385) */
+    const float *Xref;    /* batch*nx*N      or NULL = zeros replaces tiny_set_x_ref (tiny_api.cpp:387-397) */
+    const float *Uref;    /* batch*nu*(N-1)  or NULL = zeros replaces tiny_set_u_ref (tiny_api.cpp:399-409) */
+    const float *x_min, *x_max;   /* optional per-problem bounds, batch*nx*N     (all four or none) */
+    const float *u_min, *u_max;   /*                              batch*nu*(N-1)                    */
+} tinympc_cuda_batch_in;
+
+typedef struct {
+    float *x;           /* batch*nx*N      solution->x */
+    float *u;           /* batch*nu*(N-1)  solution->u */
+    int   *iter;        /* batch           solution->iter */
+    int   *status;      /* batch           work->status (1 / 11) */
+    float *residuals;   /* batch*4 or NULL: primal_residual_state, dual_residual_state,
+                           primal_residual_input, dual_residual_input (types.hpp:181-184) */
+    float *rho;         /* batch or NULL: cache->rho at exit (adaptive rho) */
+} tinympc_cuda_batch_out;
+
+/* ---- life cycle ---------------------------------------------------------------------------- */
+/* devices: list of CUDA ordinals to shard batches over (contiguous split by problem index, no
+   collective); n_devices <= 0 means "the current device only". */
+int  tinympc_cuda_create(tinympc_cuda_solver **out, const int *devices, int n_devices);
+int  tinympc_cuda_destroy(tinympc_cuda_solver *s);
+/* replaces tiny_setup's workspace/cache hand-over + tiny_set_bound/cone/linear_constraints +
+   tiny_update_settings for the batched path (tiny_api.cpp:21-242, 325-345) */
+int  tinympc_cuda_set_family(tinympc_cuda_solver *s, const tinympc_cuda_family *fam);
+
+/* ---- the hot path -------------------------------------------------------------------------- */
+/* replaces a loop of { tiny_set_x0; tiny_set_x_ref; tiny_set_u_ref; tiny_solve } over `batch` fresh
+   solvers (tiny_api.cpp:321-323 -> admm.cpp:274-389).  Host buffers; H2D, kernel and D2H inside. */
+int  tinympc_cuda_solve_batch(tinympc_cuda_solver *s, const tinympc_cuda_batch_in *in, const tinympc_cuda_batch_out *out);
+/* same, data already resident on device `dev_index` (index into the create() list); enqueued on
+   `stream` (a cudaStream_t, NULL = default stream) and asynchronous with respect to the host. */
+int  tinympc_cuda_solve_batch_device(tinympc_cuda_solver *s, int dev_index, const tinympc_cuda_batch_in *in,
+                                     const tinympc_cuda_batch_out *out, void *stream);
+
+/* ---- knobs and introspection ----------------------------------------------------------------- */
+/* option names: "precision" (32 = fp32 arithmetic [default], 64 = fp64 parity mode),
+   "ctas_per_sm" (0 = occupancy API), "chunks" (host pipeline depth, 0 = auto),
+   "variant" (kernel tuning variant, 0 = default) */
+int  tinympc_cuda_set_option(tinympc_cuda_solver *s, const char *name, double value);
+int  tinympc_cuda_device_count(void);
+int  tinympc_cuda_num_devices(const tinympc_cuda_solver *s);
+/* name of the kernel the last solve launched, and the number of kernel launches so far */
+const char *tinympc_cuda_last_kernel(const tinympc_cuda_solver *s);
+long long tinympc_cuda_launch_count(const tinympc_cuda_solver *s);
+/* last tinympc_cuda_solve_batch(): ms[0] host wall time of the call, ms[1] summed device time of its kernels
+   (CUDA events, max over devices), ms[2] number of pipeline chunks */
+int  tinympc_cuda_last_timing(const tinympc_cuda_solver *s, double ms[3]);
+const char *tinympc_cuda_last_error(const tinympc_cuda_solver *s);
+const char *tinympc_cuda_version(void);
+
+/* pinned host memory helpers for callers that want full-rate H2D/D2H */
+void *tinympc_cuda_host_alloc(size_t bytes);
+void  tinympc_cuda_host_free(void *p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TINYMPC_B200_H */

@@ -31,3 +31,19 @@ def load(name):
     g = dict(np.load(GOLDEN / f"{name}.npz"))
     b = P.Batch(g["x0"], g.get("Xref"), g.get("Uref"), g.get("x_min"), g.get("x_max"), g.get("u_min"), g.get("u_max"))
     return CASES[name](), b, g
+
+
+def family_from_spec(p, cache):
+    """ProblemSpec + cache dict (Kinf, Pinf, Quu_inv, AmBKt, APf, BPf, dKinf, dPinf) -> the dict
+    tinympc-matlab_b200/capi.py:family_struct expects (= contents of a TinySolver)."""
+    fam = dict(nx=p.nx, nu=p.nu, N=p.N, Adyn=p.A, Bdyn=p.B, fdyn=p.f, Q=p.Qdiag + p.rho, R=p.Rdiag + p.rho, rho=p.rho,
+               Kinf=cache["Kinf"], Pinf=cache["Pinf"], Quu_inv=cache["Quu_inv"], AmBKt=cache["AmBKt"],
+               APf=cache["APf"], BPf=cache["BPf"])
+    for k in ("abs_pri_tol", "abs_dua_tol", "max_iter", "check_termination", "en_state_bound", "en_input_bound",
+              "en_state_soc", "en_input_soc", "en_state_linear", "en_input_linear", "adaptive_rho", "adaptive_rho_min",
+              "adaptive_rho_max", "adaptive_rho_enable_clipping", "x_min", "x_max", "u_min", "u_max",
+              "Acx", "qcx", "cx", "Acu", "qcu", "cu", "Alin_x", "blin_x", "Alin_u", "blin_u"):
+        fam[k] = getattr(p, k)
+    if p.adaptive_rho:
+        fam["dKinf_drho"], fam["dPinf_drho"] = cache["dKinf"], cache["dPinf"]
+    return fam

@@ -1,0 +1,247 @@
+"""ctypes binding of the C ABI in include/tinympc_b200.h (libtinympc_b200.so, built in-tree).
+
+This is plumbing only: it marshals numpy / torch buffers into the plain-pointer structs of the C ABI.
+All solver arithmetic happens in the CUDA library; if the library is missing or no CUDA device is
+usable the calls raise -- there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+
+HERE = Path(__file__).resolve().parent
+LIB_PATH = HERE / "libtinympc_b200.so"
+
+c_dp = C.POINTER(C.c_double)
+c_fp = C.POINTER(C.c_float)
+c_ip = C.POINTER(C.c_int)
+
+ERRORS = {1: "EINVAL", 2: "ENODEVICE", 3: "ECUDA", 4: "EUNSUPPORTED", 5: "ENOTREADY"}
+
+EXPORTS = [
+    "tinympc_cuda_create", "tinympc_cuda_destroy", "tinympc_cuda_set_family", "tinympc_cuda_solve_batch",
+    "tinympc_cuda_solve_batch_device", "tinympc_cuda_set_option", "tinympc_cuda_device_count", "tinympc_cuda_num_devices",
+    "tinympc_cuda_last_kernel", "tinympc_cuda_launch_count", "tinympc_cuda_last_timing", "tinympc_cuda_last_error",
+    "tinympc_cuda_version", "tinympc_cuda_host_alloc", "tinympc_cuda_host_free",
+]
+
+
+class TinympcCudaError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"tinympc_cuda error {ERRORS.get(code, code)}: {msg}")
+        self.code = code
+
+
+class CFamily(C.Structure):
+    _fields_ = [
+        ("nx", C.c_int), ("nu", C.c_int), ("N", C.c_int),
+        ("Adyn", c_dp), ("Bdyn", c_dp), ("fdyn", c_dp), ("Q", c_dp), ("R", c_dp),
+        ("rho", C.c_double),
+        ("Kinf", c_dp), ("Pinf", c_dp), ("Quu_inv", c_dp), ("AmBKt", c_dp), ("APf", c_dp), ("BPf", c_dp),
+        ("dKinf_drho", c_dp), ("dPinf_drho", c_dp),
+        ("abs_pri_tol", C.c_double), ("abs_dua_tol", C.c_double),
+        ("max_iter", C.c_int), ("check_termination", C.c_int),
+        ("en_state_bound", C.c_int), ("en_input_bound", C.c_int), ("en_state_soc", C.c_int), ("en_input_soc", C.c_int),
+        ("en_state_linear", C.c_int), ("en_input_linear", C.c_int),
+        ("adaptive_rho", C.c_int), ("adaptive_rho_min", C.c_double), ("adaptive_rho_max", C.c_double),
+        ("adaptive_rho_enable_clipping", C.c_int),
+        ("x_min", c_dp), ("x_max", c_dp), ("u_min", c_dp), ("u_max", c_dp),
+        ("numStateCones", C.c_int), ("numInputCones", C.c_int),
+        ("Acx", c_ip), ("qcx", c_ip), ("cx", c_dp), ("Acu", c_ip), ("qcu", c_ip), ("cu", c_dp),
+        ("numStateLinear", C.c_int), ("numInputLinear", C.c_int),
+        ("Alin_x", c_dp), ("blin_x", c_dp), ("Alin_u", c_dp), ("blin_u", c_dp),
+    ]
+
+
+class CBatchIn(C.Structure):
+    _fields_ = [("batch", C.c_int), ("x0", C.c_void_p), ("Xref", C.c_void_p), ("Uref", C.c_void_p),
+                ("x_min", C.c_void_p), ("x_max", C.c_void_p), ("u_min", C.c_void_p), ("u_max", C.c_void_p)]
+
+
+class CBatchOut(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("u", C.c_void_p), ("iter", C.c_void_p), ("status", C.c_void_p),
+                ("residuals", C.c_void_p), ("rho", C.c_void_p)]
+
+
+_lib = None
+
+
+def load():
+    """Load the in-tree CUDA library; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise FileNotFoundError(f"{LIB_PATH} not built: run `python tinympc-matlab_b200/build.py` (or __graft_entry__.build())")
+        L = C.CDLL(str(LIB_PATH))
+        L.tinympc_cuda_create.argtypes = [C.POINTER(C.c_void_p), c_ip, C.c_int]
+        L.tinympc_cuda_destroy.argtypes = [C.c_void_p]
+        L.tinympc_cuda_set_family.argtypes = [C.c_void_p, C.POINTER(CFamily)]
+        L.tinympc_cuda_solve_batch.argtypes = [C.c_void_p, C.POINTER(CBatchIn), C.POINTER(CBatchOut)]
+        L.tinympc_cuda_solve_batch_device.argtypes = [C.c_void_p, C.c_int, C.POINTER(CBatchIn), C.POINTER(CBatchOut), C.c_void_p]
+        L.tinympc_cuda_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_double]
+        L.tinympc_cuda_num_devices.argtypes = [C.c_void_p]
+        L.tinympc_cuda_last_kernel.argtypes = [C.c_void_p]
+        L.tinympc_cuda_last_kernel.restype = C.c_char_p
+        L.tinympc_cuda_launch_count.argtypes = [C.c_void_p]
+        L.tinympc_cuda_launch_count.restype = C.c_longlong
+        L.tinympc_cuda_last_timing.argtypes = [C.c_void_p, c_dp]
+        L.tinympc_cuda_last_error.argtypes = [C.c_void_p]
+        L.tinympc_cuda_last_error.restype = C.c_char_p
+        L.tinympc_cuda_version.restype = C.c_char_p
+        L.tinympc_cuda_host_alloc.argtypes = [C.c_size_t]
+        L.tinympc_cuda_host_alloc.restype = C.c_void_p
+        L.tinympc_cuda_host_free.argtypes = [C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def _colmajor(a):
+    return np.ascontiguousarray(np.asarray(a, np.float64).T).ravel()
+
+
+class _Hold:
+    def __init__(self):
+        self.refs = []
+
+    def d(self, a, matrix=False):
+        if a is None:
+            return None
+        a = _colmajor(a) if matrix else np.ascontiguousarray(np.asarray(a, np.float64)).ravel()
+        self.refs.append(a)
+        return a.ctypes.data_as(c_dp)
+
+    def i(self, a):
+        a = np.ascontiguousarray(np.asarray(a, np.int32)).ravel()
+        self.refs.append(a)
+        return a.ctypes.data_as(c_ip)
+
+
+def family_struct(fam: dict, hold: _Hold) -> CFamily:
+    """fam: dict with the TinySolver contents (math-shaped numpy arrays; trajectories (steps, dim))."""
+    f = CFamily()
+    nx, nu, N = int(fam["nx"]), int(fam["nu"]), int(fam["N"])
+    f.nx, f.nu, f.N = nx, nu, N
+    f.Adyn, f.Bdyn = hold.d(fam["Adyn"], True), hold.d(np.asarray(fam["Bdyn"]).reshape(nx, nu), True)
+    f.fdyn, f.Q, f.R = hold.d(fam.get("fdyn", np.zeros(nx))), hold.d(fam["Q"]), hold.d(fam["R"])
+    f.rho = float(fam["rho"])
+    f.Kinf, f.Pinf = hold.d(np.asarray(fam["Kinf"]).reshape(nu, nx), True), hold.d(fam["Pinf"], True)
+    f.Quu_inv, f.AmBKt = hold.d(np.asarray(fam["Quu_inv"]).reshape(nu, nu), True), hold.d(fam["AmBKt"], True)
+    f.APf, f.BPf = hold.d(fam.get("APf", np.zeros(nx))), hold.d(fam.get("BPf", np.zeros(nu)))
+    if fam.get("dKinf_drho") is not None:
+        f.dKinf_drho = hold.d(np.asarray(fam["dKinf_drho"]).reshape(nu, nx), True)
+        f.dPinf_drho = hold.d(fam["dPinf_drho"], True)
+    for k, default in (("abs_pri_tol", 1e-3), ("abs_dua_tol", 1e-3), ("max_iter", 1000), ("check_termination", 1),
+                       ("en_state_bound", 0), ("en_input_bound", 0), ("en_state_soc", 0), ("en_input_soc", 0),
+                       ("en_state_linear", 0), ("en_input_linear", 0), ("adaptive_rho", 0), ("adaptive_rho_min", 1.0),
+                       ("adaptive_rho_max", 100.0), ("adaptive_rho_enable_clipping", 1)):
+        setattr(f, k, type(default)(fam.get(k, default)))
+    f.x_min, f.x_max = hold.d(fam.get("x_min")), hold.d(fam.get("x_max"))
+    f.u_min, f.u_max = hold.d(fam.get("u_min")), hold.d(fam.get("u_max"))
+    Acx, Acu = np.asarray(fam.get("Acx", []), np.int32), np.asarray(fam.get("Acu", []), np.int32)
+    f.numStateCones, f.numInputCones = len(Acx), len(Acu)
+    if len(Acx):
+        f.Acx, f.qcx, f.cx = hold.i(Acx), hold.i(fam["qcx"]), hold.d(fam["cx"])
+    if len(Acu):
+        f.Acu, f.qcu, f.cu = hold.i(Acu), hold.i(fam["qcu"]), hold.d(fam["cu"])
+    Alx, Alu = np.asarray(fam.get("Alin_x", np.zeros((0, nx)))), np.asarray(fam.get("Alin_u", np.zeros((0, nu))))
+    f.numStateLinear = int(Alx.shape[0]) if Alx.size else 0
+    f.numInputLinear = int(Alu.shape[0]) if Alu.size else 0
+    if f.numStateLinear:
+        f.Alin_x, f.blin_x = hold.d(Alx, True), hold.d(fam["blin_x"])
+    if f.numInputLinear:
+        f.Alin_u, f.blin_u = hold.d(Alu, True), hold.d(fam["blin_u"])
+    return f
+
+
+class CudaSolver:
+    """Thin object wrapper over the opaque tinympc_cuda_solver handle."""
+
+    def __init__(self, devices=None):
+        self.L = load()
+        self.h = C.c_void_p()
+        if devices:
+            arr = (C.c_int * len(devices))(*devices)
+            rc = self.L.tinympc_cuda_create(C.byref(self.h), arr, len(devices))
+        else:
+            rc = self.L.tinympc_cuda_create(C.byref(self.h), None, 0)
+        if rc:
+            raise TinympcCudaError(rc, "tinympc_cuda_create failed (no CUDA device?)")
+        self.dims = None
+
+    def _check(self, rc):
+        if rc:
+            raise TinympcCudaError(rc, self.L.tinympc_cuda_last_error(self.h).decode())
+
+    def close(self):
+        if self.h:
+            self.L.tinympc_cuda_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_option(self, name: str, value: float):
+        self._check(self.L.tinympc_cuda_set_option(self.h, name.encode(), float(value)))
+
+    def set_family(self, fam: dict):
+        hold = _Hold()
+        cf = family_struct(fam, hold)
+        self._check(self.L.tinympc_cuda_set_family(self.h, C.byref(cf)))
+        self.dims = (cf.nx, cf.nu, cf.N)
+
+    @property
+    def last_kernel(self) -> str:
+        return self.L.tinympc_cuda_last_kernel(self.h).decode()
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.L.tinympc_cuda_launch_count(self.h))
+
+    def last_timing(self):
+        ms = (C.c_double * 3)()
+        self.L.tinympc_cuda_last_timing(self.h, ms)
+        return dict(total_ms=ms[0], kernel_ms=ms[1], chunks=int(ms[2]))
+
+    # ---- host buffers (numpy) ---------------------------------------------------------------
+    def solve_batch(self, x0, Xref=None, Uref=None, x_min=None, x_max=None, u_min=None, u_max=None,
+                    want_residuals=True, want_rho=True, out=None) -> dict:
+        nx, nu, N = self.dims
+        keep = []
+
+        def fptr(a, shape):
+            if a is None:
+                return None
+            a = np.ascontiguousarray(a, np.float32)
+            if a.shape != shape:
+                raise ValueError(f"expected shape {shape}, got {a.shape}")
+            keep.append(a)
+            return a.ctypes.data
+
+        x0 = np.ascontiguousarray(x0, np.float32)
+        B = x0.shape[0]
+        cin = CBatchIn(B, fptr(x0, (B, nx)), fptr(Xref, (B, N, nx)), fptr(Uref, (B, N - 1, nu)),
+                       fptr(x_min, (B, N, nx)), fptr(x_max, (B, N, nx)), fptr(u_min, (B, N - 1, nu)), fptr(u_max, (B, N - 1, nu)))
+        if out is None:
+            out = dict(x=np.empty((B, N, nx), np.float32), u=np.empty((B, N - 1, nu), np.float32),
+                       iter=np.empty(B, np.int32), status=np.empty(B, np.int32))
+            if want_residuals:
+                out["residuals"] = np.empty((B, 4), np.float32)
+            if want_rho:
+                out["rho"] = np.empty(B, np.float32)
+        co = CBatchOut(out["x"].ctypes.data, out["u"].ctypes.data, out["iter"].ctypes.data, out["status"].ctypes.data,
+                       out["residuals"].ctypes.data if "residuals" in out else None,
+                       out["rho"].ctypes.data if "rho" in out else None)
+        self._check(self.L.tinympc_cuda_solve_batch(self.h, C.byref(cin), C.byref(co)))
+        return out
+
+    # ---- device buffers (raw pointers, e.g. torch.Tensor.data_ptr()) ---------------------------
+    def solve_batch_device(self, batch: int, x0, Xref, Uref, x, u, iters, status, residuals=None, rho=None,
+                           x_min=None, x_max=None, u_min=None, u_max=None, stream=None, dev_index=0):
+        cin = CBatchIn(batch, x0, Xref, Uref, x_min, x_max, u_min, u_max)
+        co = CBatchOut(x, u, iters, status, residuals, rho)
+        self._check(self.L.tinympc_cuda_solve_batch_device(self.h, dev_index, C.byref(cin), C.byref(co), stream))

@@ -1,0 +1,570 @@
+// tmpc_capi.cu -- implementation of the C ABI declared in include/tinympc_b200.h.
+//
+// Host side of the drop-in boundary: validates and packs the family data a TinySolver holds
+// (reference types.hpp:43-187), shards batches contiguously by problem index over the devices of
+// one box (no collective: problems are independent), moves host buffers through pinned-speed
+// async copies in a chunked H2D -> kernel -> D2H pipeline, and launches the sm_100a kernels.
+// There is no CPU fallback anywhere in this file: without a device every call fails.
+#include "../../include/tinympc_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "tmpc_common.h"
+#include "tmpc_registry.h"
+
+using namespace tmpc;
+
+namespace {
+
+constexpr int kFeatBox = 0, kFeatConstr = 1, kFeatAdapt = 2;
+constexpr int kMaxChunks = 64;
+constexpr int kStreams = 3;
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct DeviceCtx {
+    int device = 0;
+    int sm_count = 0;
+    void* pack32 = nullptr;
+    void* pack64 = nullptr;
+    int* counters = nullptr;            // kMaxChunks work counters
+    cudaStream_t streams[kStreams] = {nullptr, nullptr, nullptr};
+    cudaEvent_t k0[kMaxChunks], k1[kMaxChunks];
+    bool events = false;
+    DevBuf x0, Xref, Uref, xmin, xmax, umin, umax, x, u, iter, status, res, rho;
+};
+
+struct Family {
+    bool set = false;
+    int nx = 0, nu = 0, N = 0;
+    int feat = kFeatBox;
+    bool shared_bounds_ok = false;     // every enabled bound has shared arrays
+    PackLayout L{};
+    std::vector<double> pack;          // double master copy
+    SolveParams base{};                // settings + cone specs, pointers empty
+};
+
+}  // namespace
+
+struct tinympc_cuda_solver {
+    std::vector<DeviceCtx> devs;
+    Family fam;
+    int precision = 32;
+    int ctas_per_sm = 0;
+    int chunks = 0;                    // 0 = auto
+    int variant = 0;
+    std::string err;
+    std::string last_kernel;
+    long long launches = 0;
+    double t_total_ms = 0, t_kernel_ms = 0;
+    int t_chunks = 0;
+};
+
+namespace {
+
+int fail(tinympc_cuda_solver* s, int code, const std::string& msg) {
+    if (s) s->err = msg;
+    return code;
+}
+int cuda_fail(tinympc_cuda_solver* s, cudaError_t e, const char* what) {
+    return fail(s, TINYMPC_CUDA_ECUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define CU(s, call)                                              \
+    do {                                                         \
+        cudaError_t e__ = (call);                                \
+        if (e__ != cudaSuccess) return cuda_fail(s, e__, #call); \
+    } while (0)
+
+// column-major (rows x cols) double -> row-major into the pack
+void put_rowmajor(std::vector<double>& pk, int at, const double* src, int rows, int cols) {
+    for (int r = 0; r < rows; ++r)
+        for (int c = 0; c < cols; ++c) pk[at + r * cols + c] = src ? src[(size_t)c * rows + r] : 0.0;
+}
+void put_vec(std::vector<double>& pk, int at, const double* src, int n) {
+    for (int i = 0; i < n; ++i) pk[at + i] = src ? src[i] : 0.0;
+}
+
+const KernelEntry* find_kernel(const Family& f, int bits, bool ppb, int variant) {
+    int n = 0;
+    const KernelEntry* const* tab = kernel_table(&n);
+    for (int i = 0; i < n; ++i) {
+        const KernelEntry* e = tab[i];
+        if (e->family == KF_TPP && e->nx == f.nx && e->nu == f.nu && e->N == f.N && e->feat == f.feat && e->dtype_bits == bits &&
+            e->ppb == (ppb ? 1 : 0) && e->variant == variant)
+            return e;
+    }
+    if (variant != 0) return find_kernel(f, bits, ppb, 0);
+    return nullptr;
+}
+
+int upload_family(tinympc_cuda_solver* s) {
+    const Family& f = s->fam;
+    std::vector<float> p32(f.pack.size());
+    for (size_t i = 0; i < f.pack.size(); ++i) p32[i] = static_cast<float>(f.pack[i]);
+    for (auto& d : s->devs) {
+        CU(s, cudaSetDevice(d.device));
+        if (d.pack32) cudaFree(d.pack32);
+        if (d.pack64) cudaFree(d.pack64);
+        d.pack32 = d.pack64 = nullptr;
+        CU(s, cudaMalloc(&d.pack32, p32.size() * sizeof(float)));
+        CU(s, cudaMalloc(&d.pack64, f.pack.size() * sizeof(double)));
+        CU(s, cudaMemcpy(d.pack32, p32.data(), p32.size() * sizeof(float), cudaMemcpyHostToDevice));
+        CU(s, cudaMemcpy(d.pack64, f.pack.data(), f.pack.size() * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    return TINYMPC_CUDA_OK;
+}
+
+// Enqueue one kernel over `in`/`out` (device pointers) on `st`.  counter must be a zeroed device int.
+int enqueue(tinympc_cuda_solver* s, DeviceCtx& d, const tinympc_cuda_batch_in& in, const tinympc_cuda_batch_out& out, int* counter,
+            cudaStream_t st) {
+    const Family& f = s->fam;
+    const bool ppb = in.x_min || in.x_max || in.u_min || in.u_max;
+    if (ppb && !(in.x_min && in.x_max && in.u_min && in.u_max))
+        return fail(s, TINYMPC_CUDA_EINVAL, "per-problem bounds need all four of x_min, x_max, u_min, u_max");
+    if (!ppb && !f.shared_bounds_ok)
+        return fail(s, TINYMPC_CUDA_EINVAL, "bound constraints are enabled but neither the family nor the batch supplies bounds");
+    const KernelEntry* ke = find_kernel(f, s->precision, ppb, s->variant);
+    if (!ke) {
+        char b[256];
+        snprintf(b, sizeof b, "no compiled kernel for nx=%d nu=%d N=%d feat=%d precision=%d per_problem_bounds=%d", f.nx, f.nu, f.N, f.feat,
+                 s->precision, (int)ppb);
+        return fail(s, TINYMPC_CUDA_EUNSUPPORTED, b);
+    }
+    SolveParams p = f.base;
+    p.pack = s->precision == 64 ? d.pack64 : d.pack32;
+    p.pack_elems = f.L.size;
+    p.batch = in.batch;
+    p.work_counter = counter;
+    p.x0 = in.x0; p.Xref = in.Xref; p.Uref = in.Uref;
+    p.x_min = in.x_min; p.x_max = in.x_max; p.u_min = in.u_min; p.u_max = in.u_max;
+    p.x = out.x; p.u = out.u; p.iter = out.iter; p.status = out.status; p.residuals = out.residuals; p.rho_out = out.rho;
+
+    const size_t smem = ke->smem_bytes(f.L.size);
+    CU(s, ke->prepare(smem));
+    int occ = 0;
+    CU(s, ke->occupancy(&occ, smem));
+    if (occ < 1) return fail(s, TINYMPC_CUDA_EUNSUPPORTED, std::string("kernel ") + ke->name + " does not fit on an SM");
+    if (s->ctas_per_sm > 0 && s->ctas_per_sm < occ) occ = s->ctas_per_sm;
+    int grid = d.sm_count * occ;                       // persistent CTAs: a multiple of the SM count
+    const int need = (in.batch + ke->block - 1) / ke->block;
+    if (grid > need) grid = need;
+    if (grid < 1) grid = 1;
+    CU(s, cudaMemsetAsync(counter, 0, sizeof(int), st));
+    CU(s, ke->launch(p, grid, smem, st));
+    s->last_kernel = ke->name;
+    s->launches += 1;
+    return TINYMPC_CUDA_OK;
+}
+
+int check_ptr16(tinympc_cuda_solver* s, const void* p, const char* name) {
+    if (p && (reinterpret_cast<uintptr_t>(p) & 15u)) return fail(s, TINYMPC_CUDA_EINVAL, std::string(name) + " must be 16-byte aligned");
+    return TINYMPC_CUDA_OK;
+}
+
+// max_iter <= 0: the reference loop body never runs (admm.cpp:312); solution = zero workspace, iter 0, status 11
+int zero_iteration_result(tinympc_cuda_solver* s, const Family& f, const tinympc_cuda_batch_out& out, int batch, cudaStream_t st, bool device) {
+    const size_t sx = (size_t)f.nx * f.N, su = (size_t)f.nu * (f.N - 1);
+    if (device) {
+        CU(s, cudaMemsetAsync(out.x, 0, sizeof(float) * sx * batch, st));
+        CU(s, cudaMemsetAsync(out.u, 0, sizeof(float) * su * batch, st));
+        CU(s, cudaMemsetAsync(out.iter, 0, sizeof(int) * batch, st));
+        std::vector<int> st11(batch, 11);
+        CU(s, cudaMemcpyAsync(out.status, st11.data(), sizeof(int) * batch, cudaMemcpyHostToDevice, st));
+        CU(s, cudaStreamSynchronize(st));
+        if (out.residuals) CU(s, cudaMemsetAsync(out.residuals, 0, sizeof(float) * 4 * batch, st));
+        if (out.rho) {
+            std::vector<float> r(batch, (float)f.base.rho);
+            CU(s, cudaMemcpyAsync(out.rho, r.data(), sizeof(float) * batch, cudaMemcpyHostToDevice, st));
+            CU(s, cudaStreamSynchronize(st));
+        }
+    } else {
+        std::memset(out.x, 0, sizeof(float) * sx * batch);
+        std::memset(out.u, 0, sizeof(float) * su * batch);
+        for (int b = 0; b < batch; ++b) { out.iter[b] = 0; out.status[b] = 11; }
+        if (out.residuals) std::memset(out.residuals, 0, sizeof(float) * 4 * batch);
+        if (out.rho) for (int b = 0; b < batch; ++b) out.rho[b] = (float)f.base.rho;
+    }
+    return TINYMPC_CUDA_OK;
+}
+
+// One device's share of a host batch: chunked H2D -> kernel -> D2H pipeline over kStreams streams.
+int run_shard(tinympc_cuda_solver* s, DeviceCtx& d, const tinympc_cuda_batch_in& in, const tinympc_cuda_batch_out& out, int lo, int hi,
+              double* kernel_ms, int* nchunks_out) {
+    const Family& f = s->fam;
+    const int n = hi - lo;
+    *kernel_ms = 0; *nchunks_out = 0;
+    if (n <= 0) return TINYMPC_CUDA_OK;
+    CU(s, cudaSetDevice(d.device));
+    const size_t sx = (size_t)f.nx * f.N, su = (size_t)f.nu * (f.N - 1);
+    const bool ppb = in.x_min != nullptr;
+    CU(s, d.x0.reserve(sizeof(float) * f.nx * (size_t)n));
+    if (in.Xref) CU(s, d.Xref.reserve(sizeof(float) * sx * n));
+    if (in.Uref) CU(s, d.Uref.reserve(sizeof(float) * su * n));
+    if (ppb) {
+        CU(s, d.xmin.reserve(sizeof(float) * sx * n)); CU(s, d.xmax.reserve(sizeof(float) * sx * n));
+        CU(s, d.umin.reserve(sizeof(float) * su * n)); CU(s, d.umax.reserve(sizeof(float) * su * n));
+    }
+    CU(s, d.x.reserve(sizeof(float) * sx * n)); CU(s, d.u.reserve(sizeof(float) * su * n));
+    CU(s, d.iter.reserve(sizeof(int) * (size_t)n)); CU(s, d.status.reserve(sizeof(int) * (size_t)n));
+    if (out.residuals) CU(s, d.res.reserve(sizeof(float) * 4 * (size_t)n));
+    if (out.rho) CU(s, d.rho.reserve(sizeof(float) * (size_t)n));
+
+    // chunking: enough chunks to overlap copies with compute, each still many waves of the GPU
+    int nch = s->chunks > 0 ? s->chunks : (n >= (1 << 17) ? 8 : (n >= (1 << 15) ? 4 : 1));
+    nch = std::min(nch, kMaxChunks);
+    int per = (n + nch - 1) / nch;
+    per = (per + 3) & ~3;                     // keeps every chunk's arrays 16 B aligned for all shapes
+    nch = (n + per - 1) / per;
+    for (int c = 0; c < nch; ++c) {
+        const int c0 = c * per, c1 = std::min(n, c0 + per), cn = c1 - c0;
+        cudaStream_t st = d.streams[c % kStreams];
+        const size_t g0 = (size_t)lo + c0;    // global problem index of the chunk start
+        auto h2d = [&](DevBuf& dst, const float* src, size_t per_problem) -> cudaError_t {
+            return cudaMemcpyAsync((float*)dst.p + per_problem * c0, src + per_problem * g0, sizeof(float) * per_problem * cn,
+                                   cudaMemcpyHostToDevice, st);
+        };
+        CU(s, h2d(d.x0, in.x0, f.nx));
+        if (in.Xref) CU(s, h2d(d.Xref, in.Xref, sx));
+        if (in.Uref) CU(s, h2d(d.Uref, in.Uref, su));
+        if (ppb) { CU(s, h2d(d.xmin, in.x_min, sx)); CU(s, h2d(d.xmax, in.x_max, sx)); CU(s, h2d(d.umin, in.u_min, su)); CU(s, h2d(d.umax, in.u_max, su)); }
+        tinympc_cuda_batch_in din{};
+        din.batch = cn;
+        din.x0 = (float*)d.x0.p + (size_t)f.nx * c0;
+        din.Xref = in.Xref ? (float*)d.Xref.p + sx * c0 : nullptr;
+        din.Uref = in.Uref ? (float*)d.Uref.p + su * c0 : nullptr;
+        if (ppb) {
+            din.x_min = (float*)d.xmin.p + sx * c0; din.x_max = (float*)d.xmax.p + sx * c0;
+            din.u_min = (float*)d.umin.p + su * c0; din.u_max = (float*)d.umax.p + su * c0;
+        }
+        tinympc_cuda_batch_out dout{};
+        dout.x = (float*)d.x.p + sx * c0; dout.u = (float*)d.u.p + su * c0;
+        dout.iter = (int*)d.iter.p + c0; dout.status = (int*)d.status.p + c0;
+        dout.residuals = out.residuals ? (float*)d.res.p + 4 * (size_t)c0 : nullptr;
+        dout.rho = out.rho ? (float*)d.rho.p + c0 : nullptr;
+        CU(s, cudaEventRecord(d.k0[c], st));
+        int rc = enqueue(s, d, din, dout, d.counters + c, st);
+        if (rc) return rc;
+        CU(s, cudaEventRecord(d.k1[c], st));
+        CU(s, cudaMemcpyAsync(out.x + sx * g0, dout.x, sizeof(float) * sx * cn, cudaMemcpyDeviceToHost, st));
+        CU(s, cudaMemcpyAsync(out.u + su * g0, dout.u, sizeof(float) * su * cn, cudaMemcpyDeviceToHost, st));
+        CU(s, cudaMemcpyAsync(out.iter + g0, dout.iter, sizeof(int) * cn, cudaMemcpyDeviceToHost, st));
+        CU(s, cudaMemcpyAsync(out.status + g0, dout.status, sizeof(int) * cn, cudaMemcpyDeviceToHost, st));
+        if (out.residuals) CU(s, cudaMemcpyAsync(out.residuals + 4 * g0, dout.residuals, sizeof(float) * 4 * cn, cudaMemcpyDeviceToHost, st));
+        if (out.rho) CU(s, cudaMemcpyAsync(out.rho + g0, dout.rho, sizeof(float) * cn, cudaMemcpyDeviceToHost, st));
+    }
+    for (int k = 0; k < kStreams; ++k) CU(s, cudaStreamSynchronize(d.streams[k]));
+    for (int c = 0; c < nch; ++c) {
+        float ms = 0;
+        CU(s, cudaEventElapsedTime(&ms, d.k0[c], d.k1[c]));
+        *kernel_ms += ms;
+    }
+    *nchunks_out = nch;
+    return TINYMPC_CUDA_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int tinympc_cuda_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+const char* tinympc_cuda_version(void) { return "tinympc-b200 0.1 (sm_100a)"; }
+
+int tinympc_cuda_create(tinympc_cuda_solver** out, const int* devices, int n_devices) {
+    if (!out) return TINYMPC_CUDA_EINVAL;
+    *out = nullptr;
+    const int have = tinympc_cuda_device_count();
+    if (have <= 0) return TINYMPC_CUDA_ENODEVICE;
+    auto* s = new tinympc_cuda_solver();
+    std::vector<int> ids;
+    if (n_devices <= 0 || !devices) {
+        int cur = 0;
+        cudaGetDevice(&cur);
+        ids.push_back(cur);
+    } else {
+        for (int i = 0; i < n_devices; ++i) {
+            if (devices[i] < 0 || devices[i] >= have) { delete s; return TINYMPC_CUDA_EINVAL; }
+            ids.push_back(devices[i]);
+        }
+    }
+    int prev = 0;
+    cudaGetDevice(&prev);
+    for (int id : ids) {
+        DeviceCtx d;
+        d.device = id;
+        if (cudaSetDevice(id) != cudaSuccess) { delete s; return TINYMPC_CUDA_ECUDA; }
+        cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, id);
+        if (cudaMalloc(&d.counters, sizeof(int) * kMaxChunks) != cudaSuccess) { delete s; return TINYMPC_CUDA_ECUDA; }
+        for (int k = 0; k < kStreams; ++k) cudaStreamCreateWithFlags(&d.streams[k], cudaStreamNonBlocking);
+        for (int c = 0; c < kMaxChunks; ++c) { cudaEventCreate(&d.k0[c]); cudaEventCreate(&d.k1[c]); }
+        d.events = true;
+        s->devs.push_back(d);
+    }
+    cudaSetDevice(prev);
+    *out = s;
+    return TINYMPC_CUDA_OK;
+}
+
+int tinympc_cuda_destroy(tinympc_cuda_solver* s) {
+    if (!s) return TINYMPC_CUDA_OK;
+    int prev = 0;
+    cudaGetDevice(&prev);
+    for (auto& d : s->devs) {
+        cudaSetDevice(d.device);
+        for (int k = 0; k < kStreams; ++k) if (d.streams[k]) { cudaStreamSynchronize(d.streams[k]); cudaStreamDestroy(d.streams[k]); }
+        if (d.events) for (int c = 0; c < kMaxChunks; ++c) { cudaEventDestroy(d.k0[c]); cudaEventDestroy(d.k1[c]); }
+        if (d.pack32) cudaFree(d.pack32);
+        if (d.pack64) cudaFree(d.pack64);
+        if (d.counters) cudaFree(d.counters);
+        for (DevBuf* b : {&d.x0, &d.Xref, &d.Uref, &d.xmin, &d.xmax, &d.umin, &d.umax, &d.x, &d.u, &d.iter, &d.status, &d.res, &d.rho}) b->release();
+    }
+    cudaSetDevice(prev);
+    delete s;
+    return TINYMPC_CUDA_OK;
+}
+
+int tinympc_cuda_set_family(tinympc_cuda_solver* s, const tinympc_cuda_family* fm) {
+    if (!s || !fm) return TINYMPC_CUDA_EINVAL;
+    const int nx = fm->nx, nu = fm->nu, N = fm->N;
+    if (nx < 1 || nu < 1 || N < 2) return fail(s, TINYMPC_CUDA_EINVAL, "need nx >= 1, nu >= 1, N >= 2");
+    if (!fm->Adyn || !fm->Bdyn || !fm->Q || !fm->R || !fm->Kinf || !fm->Pinf || !fm->Quu_inv || !fm->AmBKt)
+        return fail(s, TINYMPC_CUDA_EINVAL, "Adyn, Bdyn, Q, R, Kinf, Pinf, Quu_inv, AmBKt are required");
+    if (fm->check_termination <= 0)
+        return fail(s, TINYMPC_CUDA_EINVAL, "check_termination must be >= 1 (the reference divides by it, admm.cpp:255)");
+    if (fm->numStateCones < 0 || fm->numInputCones < 0 || fm->numStateCones > TINYMPC_MAX_CONES || fm->numInputCones > TINYMPC_MAX_CONES)
+        return fail(s, TINYMPC_CUDA_EINVAL, "at most TINYMPC_MAX_CONES cones per kind");
+    for (int k = 0; k < fm->numStateCones; ++k)
+        if (fm->qcx[k] < 1 || fm->Acx[k] < 0 || fm->Acx[k] + fm->qcx[k] > nx) return fail(s, TINYMPC_CUDA_EINVAL, "state cone outside [0, nx)");
+    for (int k = 0; k < fm->numInputCones; ++k)
+        if (fm->qcu[k] < 1 || fm->Acu[k] < 0 || fm->Acu[k] + fm->qcu[k] > nu) return fail(s, TINYMPC_CUDA_EINVAL, "input cone outside [0, nu)");
+    if (fm->numStateLinear < 0 || fm->numInputLinear < 0) return fail(s, TINYMPC_CUDA_EINVAL, "negative linear row count");
+    if (fm->en_state_linear && fm->numStateLinear > 0 && (!fm->Alin_x || !fm->blin_x)) return fail(s, TINYMPC_CUDA_EINVAL, "Alin_x/blin_x missing");
+    if (fm->en_input_linear && fm->numInputLinear > 0 && (!fm->Alin_u || !fm->blin_u)) return fail(s, TINYMPC_CUDA_EINVAL, "Alin_u/blin_u missing");
+    if (fm->adaptive_rho && (!fm->dKinf_drho || !fm->dPinf_drho)) return fail(s, TINYMPC_CUDA_EINVAL, "adaptive_rho needs dKinf_drho and dPinf_drho");
+
+    Family f;
+    f.nx = nx; f.nu = nu; f.N = N;
+    const int nsl = fm->en_state_linear ? fm->numStateLinear : 0, nil = fm->en_input_linear ? fm->numInputLinear : 0;
+    f.L = PackLayout::make(nx, nu, N, nsl, nil);
+    const PackLayout& L = f.L;
+    f.pack.assign(L.size, 0.0);
+    put_rowmajor(f.pack, L.A, fm->Adyn, nx, nx);
+    put_rowmajor(f.pack, L.B, fm->Bdyn, nx, nu);
+    put_rowmajor(f.pack, L.Kinf, fm->Kinf, nu, nx);
+    put_rowmajor(f.pack, L.AmBKt, fm->AmBKt, nx, nx);
+    put_rowmajor(f.pack, L.Quu_inv, fm->Quu_inv, nu, nu);
+    put_rowmajor(f.pack, L.Pinf, fm->Pinf, nx, nx);
+    put_vec(f.pack, L.f, fm->fdyn, nx);
+    put_vec(f.pack, L.APf, fm->APf, nx);
+    put_vec(f.pack, L.BPf, fm->BPf, nu);
+    put_vec(f.pack, L.Qd, fm->Q, nx);
+    put_vec(f.pack, L.Rd, fm->R, nu);
+    if (fm->adaptive_rho) {
+        put_rowmajor(f.pack, L.dKinf, fm->dKinf_drho, nu, nx);
+        put_rowmajor(f.pack, L.dPinf, fm->dPinf_drho, nx, nx);
+    }
+    // d0: backward_pass_grad (admm.cpp:13-20) on the zero workspace tiny_setup leaves (q = r = p = 0)
+    {
+        std::vector<double> p(nx, 0.0), pn(nx), t(nu);
+        for (int i = N - 2; i >= 0; --i) {
+            for (int a = 0; a < nu; ++a) {
+                double acc = 0;
+                for (int r = 0; r < nx; ++r) acc += f.pack[L.B + r * nu + a] * p[r];
+                t[a] = acc + f.pack[L.BPf + a];
+            }
+            for (int a = 0; a < nu; ++a) {
+                double acc = 0;
+                for (int b = 0; b < nu; ++b) acc += f.pack[L.Quu_inv + a * nu + b] * t[b];
+                f.pack[L.d0 + i * nu + a] = acc;
+            }
+            for (int c = 0; c < nx; ++c) {
+                double acc = 0;
+                for (int r = 0; r < nx; ++r) acc += f.pack[L.AmBKt + c * nx + r] * p[r];
+                pn[c] = acc + f.pack[L.APf + c];
+            }
+            p = pn;
+        }
+    }
+    // bounds: a disabled bound is an infinite box (clamping with +-inf is the identity)
+    const double inf = std::numeric_limits<double>::infinity();
+    const bool sb = fm->en_state_bound != 0, ib = fm->en_input_bound != 0;
+    const bool have_sb = fm->x_min && fm->x_max, have_ib = fm->u_min && fm->u_max;
+    for (int e = 0; e < nx * N; ++e) {
+        f.pack[L.xmin + e] = (sb && have_sb) ? fm->x_min[e] : -inf;
+        f.pack[L.xmax + e] = (sb && have_sb) ? fm->x_max[e] : inf;
+    }
+    for (int e = 0; e < nu * (N - 1); ++e) {
+        f.pack[L.umin + e] = (ib && have_ib) ? fm->u_min[e] : -inf;
+        f.pack[L.umax + e] = (ib && have_ib) ? fm->u_max[e] : inf;
+    }
+    f.shared_bounds_ok = (!sb || have_sb) && (!ib || have_ib);
+    // linear rows + squared norms (project_hyperplane, admm.cpp:70-73)
+    for (int k = 0; k < nsl; ++k) {
+        double nr = 0;
+        for (int j = 0; j < nx; ++j) { double a = fm->Alin_x[(size_t)j * fm->numStateLinear + k]; f.pack[L.Alin_x + k * nx + j] = a; nr += a * a; }
+        f.pack[L.blin_x + k] = fm->blin_x[k];
+        f.pack[L.nrm_x + k] = nr;
+    }
+    for (int k = 0; k < nil; ++k) {
+        double nr = 0;
+        for (int j = 0; j < nu; ++j) { double a = fm->Alin_u[(size_t)j * fm->numInputLinear + k]; f.pack[L.Alin_u + k * nu + j] = a; nr += a * a; }
+        f.pack[L.blin_u + k] = fm->blin_u[k];
+        f.pack[L.nrm_u + k] = nr;
+    }
+
+    SolveParams& b = f.base;
+    b = SolveParams{};
+    b.rho = fm->rho;
+    b.abs_pri_tol = fm->abs_pri_tol; b.abs_dua_tol = fm->abs_dua_tol;
+    b.max_iter = fm->max_iter; b.check_termination = fm->check_termination;
+    b.en_state_bound = fm->en_state_bound; b.en_input_bound = fm->en_input_bound;
+    b.en_state_soc = fm->en_state_soc; b.en_input_soc = fm->en_input_soc;
+    b.adaptive_rho = fm->adaptive_rho;
+    b.rho_min = fm->adaptive_rho_min; b.rho_max = fm->adaptive_rho_max; b.rho_clip = fm->adaptive_rho_enable_clipping;
+    b.n_state_cones = fm->numStateCones; b.n_input_cones = fm->numInputCones;
+    for (int k = 0; k < fm->numStateCones; ++k) { b.Acx[k] = fm->Acx[k]; b.qcx[k] = fm->qcx[k]; b.cx[k] = (float)fm->cx[k]; }
+    for (int k = 0; k < fm->numInputCones; ++k) { b.Acu[k] = fm->Acu[k]; b.qcu[k] = fm->qcu[k]; b.cu[k] = (float)fm->cu[k]; }
+    b.nsl = nsl; b.nil = nil;
+    // NB: with en_*_linear set but zero rows the reference still adds the (vl - gl) = x term to q
+    // (admm.cpp:138-140, 223-225); keep that by leaving the flag on with zero rows.
+    b.en_state_linear = fm->en_state_linear; b.en_input_linear = fm->en_input_linear;
+
+    const bool soc = (fm->en_state_soc && fm->numStateCones > 0) || (fm->en_input_soc && fm->numInputCones > 0);
+    const bool lin = fm->en_state_linear || fm->en_input_linear;
+    if (fm->adaptive_rho && (soc || lin))
+        return fail(s, TINYMPC_CUDA_EUNSUPPORTED, "adaptive_rho together with cone/linear constraints has no compiled kernel yet");
+    f.feat = fm->adaptive_rho ? kFeatAdapt : ((soc || lin) ? kFeatConstr : kFeatBox);
+    f.set = true;
+    s->fam = std::move(f);
+    return upload_family(s);
+}
+
+int tinympc_cuda_solve_batch_device(tinympc_cuda_solver* s, int dev_index, const tinympc_cuda_batch_in* in, const tinympc_cuda_batch_out* out,
+                                    void* stream) {
+    if (!s || !in || !out) return TINYMPC_CUDA_EINVAL;
+    if (!s->fam.set) return fail(s, TINYMPC_CUDA_ENOTREADY, "tinympc_cuda_set_family has not been called");
+    if (dev_index < 0 || dev_index >= (int)s->devs.size()) return fail(s, TINYMPC_CUDA_EINVAL, "dev_index out of range");
+    if (in->batch < 0) return fail(s, TINYMPC_CUDA_EINVAL, "negative batch");
+    if (in->batch == 0) return TINYMPC_CUDA_OK;
+    if (!in->x0 || !out->x || !out->u || !out->iter || !out->status) return fail(s, TINYMPC_CUDA_EINVAL, "x0, x, u, iter, status are required");
+    int rc = 0;
+    rc |= check_ptr16(s, in->x0, "x0"); rc |= check_ptr16(s, in->Xref, "Xref"); rc |= check_ptr16(s, in->Uref, "Uref");
+    rc |= check_ptr16(s, in->x_min, "x_min"); rc |= check_ptr16(s, in->x_max, "x_max"); rc |= check_ptr16(s, in->u_min, "u_min");
+    rc |= check_ptr16(s, in->u_max, "u_max"); rc |= check_ptr16(s, out->x, "x"); rc |= check_ptr16(s, out->u, "u");
+    rc |= check_ptr16(s, out->residuals, "residuals");
+    if (rc) return TINYMPC_CUDA_EINVAL;
+    DeviceCtx& d = s->devs[dev_index];
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int prev = 0;
+    cudaGetDevice(&prev);
+    CU(s, cudaSetDevice(d.device));
+    if (s->fam.base.max_iter <= 0) {
+        rc = zero_iteration_result(s, s->fam, *out, in->batch, st, true);
+    } else {
+        // the last counter slot is reserved for the device-resident entry point
+        rc = enqueue(s, d, *in, *out, d.counters + (kMaxChunks - 1), st);
+    }
+    cudaSetDevice(prev);
+    return rc;
+}
+
+int tinympc_cuda_solve_batch(tinympc_cuda_solver* s, const tinympc_cuda_batch_in* in, const tinympc_cuda_batch_out* out) {
+    if (!s || !in || !out) return TINYMPC_CUDA_EINVAL;
+    if (!s->fam.set) return fail(s, TINYMPC_CUDA_ENOTREADY, "tinympc_cuda_set_family has not been called");
+    if (in->batch < 0) return fail(s, TINYMPC_CUDA_EINVAL, "negative batch");
+    if (in->batch == 0) return TINYMPC_CUDA_OK;
+    if (!in->x0 || !out->x || !out->u || !out->iter || !out->status) return fail(s, TINYMPC_CUDA_EINVAL, "x0, x, u, iter, status are required");
+    const bool ppb = in->x_min || in->x_max || in->u_min || in->u_max;
+    if (ppb && !(in->x_min && in->x_max && in->u_min && in->u_max))
+        return fail(s, TINYMPC_CUDA_EINVAL, "per-problem bounds need all four of x_min, x_max, u_min, u_max");
+    if (s->fam.base.max_iter <= 0) return zero_iteration_result(s, s->fam, *out, in->batch, nullptr, false);
+
+    const auto t0 = std::chrono::steady_clock::now();
+    const int G = (int)s->devs.size();
+    int prev = 0;
+    cudaGetDevice(&prev);
+    std::vector<int> rcs(G, 0), nch(G, 0);
+    std::vector<double> kms(G, 0.0);
+    // contiguous split by problem index (multiples of 4 keep every shard 16 B aligned), remainder to the last
+    int per = ((in->batch + G - 1) / G + 3) & ~3;
+    auto work = [&](int g) {
+        const int lo = std::min(in->batch, g * per), hi = (g == G - 1) ? in->batch : std::min(in->batch, lo + per);
+        rcs[g] = run_shard(s, s->devs[g], *in, *out, lo, hi, &kms[g], &nch[g]);
+    };
+    if (G == 1) {
+        work(0);
+    } else {
+        std::vector<std::thread> th;
+        for (int g = 0; g < G; ++g) th.emplace_back(work, g);
+        for (auto& t : th) t.join();
+    }
+    cudaSetDevice(prev);
+    for (int g = 0; g < G; ++g) if (rcs[g]) return rcs[g];
+    s->t_kernel_ms = *std::max_element(kms.begin(), kms.end());
+    s->t_chunks = *std::max_element(nch.begin(), nch.end());
+    s->t_total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    return TINYMPC_CUDA_OK;
+}
+
+int tinympc_cuda_set_option(tinympc_cuda_solver* s, const char* name, double value) {
+    if (!s || !name) return TINYMPC_CUDA_EINVAL;
+    const std::string n(name);
+    if (n == "precision") {
+        if (value != 32 && value != 64) return fail(s, TINYMPC_CUDA_EINVAL, "precision must be 32 or 64");
+        s->precision = (int)value;
+    } else if (n == "ctas_per_sm") {
+        s->ctas_per_sm = (int)value;
+    } else if (n == "chunks") {
+        s->chunks = (int)value;
+    } else if (n == "variant") {
+        s->variant = (int)value;
+    } else {
+        return fail(s, TINYMPC_CUDA_EINVAL, "unknown option " + n);
+    }
+    return TINYMPC_CUDA_OK;
+}
+
+int tinympc_cuda_num_devices(const tinympc_cuda_solver* s) { return s ? (int)s->devs.size() : 0; }
+const char* tinympc_cuda_last_kernel(const tinympc_cuda_solver* s) { return s ? s->last_kernel.c_str() : ""; }
+long long tinympc_cuda_launch_count(const tinympc_cuda_solver* s) { return s ? s->launches : 0; }
+int tinympc_cuda_last_timing(const tinympc_cuda_solver* s, double ms[3]) {
+    if (!s || !ms) return TINYMPC_CUDA_EINVAL;
+    ms[0] = s->t_total_ms; ms[1] = s->t_kernel_ms; ms[2] = (double)s->t_chunks;
+    return TINYMPC_CUDA_OK;
+}
+const char* tinympc_cuda_last_error(const tinympc_cuda_solver* s) { return s ? s->err.c_str() : "null solver"; }
+
+void* tinympc_cuda_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+void tinympc_cuda_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+}  // extern "C"

@@ -1,0 +1,108 @@
+// tmpc_common.h -- data shared by the host C-ABI layer and the sm_100a kernels.
+//
+// "Family" data = everything a TinySolver holds that is identical for every problem of a batch
+// (reference: TinyCache types.hpp:43-59, the matrices/bounds/constraint specs of TinyWorkspace
+// types.hpp:114-173 and TinySettings types.hpp:63-80).  The host converts it once to the kernel's
+// scalar type and lays it out as one contiguous "pack" that every CTA stages into shared memory
+// with a single TMA bulk copy.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+
+namespace tmpc {
+
+constexpr int kMaxCones = 4;     // per family (state cones) and (input cones)
+
+// Offsets (in elements of the kernel scalar type) of the tables inside the pack.
+// All small matrices are stored ROW-major: M[r * cols + c].
+struct PackLayout {
+    int nx, nu, N;
+    int nsl, nil;                 // linear rows (state / input)
+    int A, B, Kinf, AmBKt, Quu_inv, Pinf, f, APf, BPf, Qd, Rd;
+    int d0;                       // nu*(N-1): d of the first backward pass on a zero workspace
+    int xmin, xmax, umin, umax;   // shared bounds nx*N / nu*(N-1) (time-major)
+    int dKinf, dPinf;             // adaptive-rho sensitivities
+    int Alin_x, blin_x, nrm_x;    // nsl*nx, nsl, nsl (||a||^2)
+    int Alin_u, blin_u, nrm_u;
+    int size;                     // total elements, padded so that size*sizeof(T) % 16 == 0
+
+    static PackLayout make(int nx, int nu, int N, int nsl, int nil) {
+        PackLayout L{};
+        L.nx = nx; L.nu = nu; L.N = N; L.nsl = nsl; L.nil = nil;
+        int o = 0;
+        auto take = [&](int n) { int at = o; o += n; return at; };
+        L.A = take(nx * nx); L.B = take(nx * nu); L.Kinf = take(nu * nx); L.AmBKt = take(nx * nx);
+        L.Quu_inv = take(nu * nu); L.Pinf = take(nx * nx); L.f = take(nx); L.APf = take(nx); L.BPf = take(nu);
+        L.Qd = take(nx); L.Rd = take(nu); L.d0 = take(nu * (N - 1));
+        L.xmin = take(nx * N); L.xmax = take(nx * N); L.umin = take(nu * (N - 1)); L.umax = take(nu * (N - 1));
+        L.dKinf = take(nu * nx); L.dPinf = take(nx * nx);
+        L.Alin_x = take(nsl * nx); L.blin_x = take(nsl); L.nrm_x = take(nsl);
+        L.Alin_u = take(nil * nu); L.blin_u = take(nil); L.nrm_u = take(nil);
+        L.size = (o + 3) & ~3;    // multiple of 4 elements -> 16 B multiple for float and double
+        return L;
+    }
+};
+
+// compile-time version of the fixed part (no linear rows) used by the specialised kernels
+template <int NX, int NU, int NH>
+struct StaticPack {
+    static constexpr int A = 0;
+    static constexpr int B = A + NX * NX;
+    static constexpr int Kinf = B + NX * NU;
+    static constexpr int AmBKt = Kinf + NU * NX;
+    static constexpr int Quu_inv = AmBKt + NX * NX;
+    static constexpr int Pinf = Quu_inv + NU * NU;
+    static constexpr int f = Pinf + NX * NX;
+    static constexpr int APf = f + NX;
+    static constexpr int BPf = APf + NX;
+    static constexpr int Qd = BPf + NU;
+    static constexpr int Rd = Qd + NX;
+    static constexpr int d0 = Rd + NU;
+    static constexpr int xmin = d0 + NU * (NH - 1);
+    static constexpr int xmax = xmin + NX * NH;
+    static constexpr int umin = xmax + NX * NH;
+    static constexpr int umax = umin + NU * (NH - 1);
+    static constexpr int dKinf = umax + NU * (NH - 1);
+    static constexpr int dPinf = dKinf + NU * NX;
+    static constexpr int lin = dPinf + NX * NX;   // linear rows start here (runtime sized)
+};
+
+// Kernel launch parameters (passed by value; plain data only).
+struct SolveParams {
+    const void* pack;          // device pointer, 16 B aligned
+    int pack_elems;            // PackLayout::size
+    int batch;
+    int* work_counter;         // device int, zeroed before launch: next unclaimed problem index
+    // per-problem inputs (device pointers, float32); NULL where noted
+    const float* x0;           // batch*nx
+    const float* Xref;         // batch*nx*N      or NULL (zeros)
+    const float* Uref;         // batch*nu*(N-1)  or NULL (zeros)
+    const float* x_min;        // per-problem bounds or NULL (use the family's shared bounds)
+    const float* x_max;
+    const float* u_min;
+    const float* u_max;
+    // outputs
+    float* x;                  // batch*nx*N      solution->x (= vnew)
+    float* u;                  // batch*nu*(N-1)  solution->u (= znew)
+    int* iter;                 // batch
+    int* status;               // batch (1 solved / 11 unsolved)
+    float* residuals;          // batch*4 or NULL  (pri_state, dua_state, pri_input, dua_input)
+    float* rho_out;            // batch or NULL
+    // settings (TinySettings) + cache->rho
+    double rho;
+    double abs_pri_tol, abs_dua_tol;
+    int max_iter, check_termination;
+    int en_state_bound, en_input_bound;
+    int en_state_soc, en_input_soc;
+    int en_state_linear, en_input_linear;
+    int adaptive_rho;
+    double rho_min, rho_max;
+    int rho_clip;
+    // cones as they sit in the workspace
+    int n_state_cones, n_input_cones;
+    int Acx[kMaxCones], qcx[kMaxCones], Acu[kMaxCones], qcu[kMaxCones];
+    float cx[kMaxCones], cu[kMaxCones];     // the reference's project_soc takes `float mu` (admm.cpp:39)
+    int nsl, nil;
+};
+
+}  // namespace tmpc

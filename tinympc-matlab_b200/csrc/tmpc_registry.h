@@ -1,0 +1,48 @@
+// tmpc_registry.h -- table of compiled kernel instances the C-ABI layer dispatches over.
+// Each instance lives in its own generated translation unit (csrc/gen/*.cu, written by
+// tinympc-matlab_b200/build.py from the INSTANCES list) so that nvcc can compile them in parallel.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "tmpc_common.h"
+
+namespace tmpc {
+
+enum KernelFamily : int { KF_TPP = 0, KF_WPP = 1 };
+
+struct KernelEntry {
+    const char* name;
+    int family;          // KF_TPP: thread per problem (throughput);  KF_WPP: warp per problem (latency / generic shapes)
+    int nx, nu, N;       // 0 = any (runtime-sized kernel)
+    int feat;            // FEAT_BOX / FEAT_CONSTR / FEAT_ADAPT
+    int dtype_bits;      // 32 or 64
+    int ppb;             // per-problem bounds variant
+    int block;           // threads per CTA
+    int variant;         // tuning variant (0 = default); selected with the "variant" option
+    size_t (*smem_bytes)(int pack_elems);
+    cudaError_t (*prepare)(size_t smem);                                   // cudaFuncSetAttribute(max dynamic smem)
+    cudaError_t (*occupancy)(int* ctas_per_sm, size_t smem);
+    cudaError_t (*launch)(const SolveParams& p, int grid, size_t smem, cudaStream_t st);
+};
+
+const KernelEntry* const* kernel_table(int* count);   // defined in gen/tmpc_table.cu
+
+}  // namespace tmpc
+
+// one of these per generated translation unit
+#define TMPC_DEFINE_TPP_ENTRY(SYM, CFG, FEATV, BITS, VAR)                                                              \
+    namespace tmpc {                                                                                                \
+    static size_t SYM##_smem(int pe) { return tpp_smem_bytes<CFG>(pe); }                                            \
+    static cudaError_t SYM##_prepare(size_t smem) {                                                                 \
+        return cudaFuncSetAttribute(tpp_kernel<CFG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);       \
+    }                                                                                                               \
+    static cudaError_t SYM##_occ(int* n, size_t smem) {                                                             \
+        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(n, tpp_kernel<CFG>, CFG::BLOCK, smem);                 \
+    }                                                                                                               \
+    static cudaError_t SYM##_launch(const SolveParams& p, int grid, size_t smem, cudaStream_t st) {                 \
+        tpp_kernel<CFG><<<grid, CFG::BLOCK, smem, st>>>(p);                                                         \
+        return cudaGetLastError();                                                                                  \
+    }                                                                                                               \
+    extern const KernelEntry SYM = {#SYM, KF_TPP, CFG::NX, CFG::NU, CFG::NH, FEATV, BITS, CFG::PPB ? 1 : 0,         \
+                                    CFG::BLOCK, VAR, SYM##_smem, SYM##_prepare, SYM##_occ, SYM##_launch};                \
+    }
