@@ -106,16 +106,18 @@ void put_vec(std::vector<double>& pk, int at, const double* src, int n) {
     for (int i = 0; i < n; ++i) pk[at + i] = src ? src[i] : 0.0;
 }
 
-const KernelEntry* find_kernel(const Family& f, int bits, bool ppb, int variant) {
+const KernelEntry* find_kernel(const Family& f, int bits, bool ppb, bool refs, int variant) {
     int n = 0;
     const KernelEntry* const* tab = kernel_table(&n);
-    for (int i = 0; i < n; ++i) {
-        const KernelEntry* e = tab[i];
-        if (e->family == KF_TPP && e->nx == f.nx && e->nu == f.nu && e->N == f.N && e->feat == f.feat && e->dtype_bits == bits &&
-            e->ppb == (ppb ? 1 : 0) && e->variant == variant)
-            return e;
+    for (int pass = 0; pass < 2; ++pass) {   // pass 1: a reference-storing kernel also serves a reference-free batch
+        for (int i = 0; i < n; ++i) {
+            const KernelEntry* e = tab[i];
+            if (e->family == KF_TPP && e->nx == f.nx && e->nu == f.nu && e->N == f.N && e->feat == f.feat && e->dtype_bits == bits &&
+                e->ppb == (ppb ? 1 : 0) && e->variant == variant && (e->refs == (refs ? 1 : 0) || (pass == 1 && e->refs == 1)))
+                return e;
+        }
     }
-    if (variant != 0) return find_kernel(f, bits, ppb, 0);
+    if (variant != 0) return find_kernel(f, bits, ppb, refs, 0);
     return nullptr;
 }
 
@@ -145,7 +147,7 @@ int enqueue(tinympc_cuda_solver* s, DeviceCtx& d, const tinympc_cuda_batch_in& i
         return fail(s, TINYMPC_CUDA_EINVAL, "per-problem bounds need all four of x_min, x_max, u_min, u_max");
     if (!ppb && !f.shared_bounds_ok)
         return fail(s, TINYMPC_CUDA_EINVAL, "bound constraints are enabled but neither the family nor the batch supplies bounds");
-    const KernelEntry* ke = find_kernel(f, s->precision, ppb, s->variant);
+    const KernelEntry* ke = find_kernel(f, s->precision, ppb, in.Xref || in.Uref, s->variant);
     if (!ke) {
         char b[256];
         snprintf(b, sizeof b, "no compiled kernel for nx=%d nu=%d N=%d feat=%d precision=%d per_problem_bounds=%d", f.nx, f.nu, f.N, f.feat,
@@ -153,15 +155,16 @@ int enqueue(tinympc_cuda_solver* s, DeviceCtx& d, const tinympc_cuda_batch_in& i
         return fail(s, TINYMPC_CUDA_EUNSUPPORTED, b);
     }
     SolveParams p = f.base;
-    p.pack = s->precision == 64 ? d.pack64 : d.pack32;
-    p.pack_elems = f.L.size;
+    p.pack = s->precision == 64 ? (const void*)((const double*)d.pack64 + f.L.cold) : (const void*)((const float*)d.pack32 + f.L.cold);
+    p.pack_elems = f.L.cold_size;
     p.batch = in.batch;
     p.work_counter = counter;
     p.x0 = in.x0; p.Xref = in.Xref; p.Uref = in.Uref;
     p.x_min = in.x_min; p.x_max = in.x_max; p.u_min = in.u_min; p.u_max = in.u_max;
     p.x = out.x; p.u = out.u; p.iter = out.iter; p.status = out.status; p.residuals = out.residuals; p.rho_out = out.rho;
 
-    const size_t smem = ke->smem_bytes(f.L.size);
+    const size_t smem = ke->smem_bytes(f.L.cold_size);
+    if (smem > 227u * 1024u) return fail(s, TINYMPC_CUDA_EUNSUPPORTED, std::string("kernel ") + ke->name + " needs more shared memory than an SM has");
     CU(s, ke->prepare(smem));
     int occ = 0;
     CU(s, ke->occupancy(&occ, smem));
@@ -172,7 +175,7 @@ int enqueue(tinympc_cuda_solver* s, DeviceCtx& d, const tinympc_cuda_batch_in& i
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
     CU(s, cudaMemsetAsync(counter, 0, sizeof(int), st));
-    CU(s, ke->launch(p, grid, smem, st));
+    CU(s, ke->launch(p, grid, smem, st, f.pack.data(), f.L));
     s->last_kernel = ke->name;
     s->launches += 1;
     return TINYMPC_CUDA_OK;

@@ -13,18 +13,25 @@ namespace tmpc {
 
 constexpr int kMaxCones = 4;     // per family (state cones) and (input cones)
 
-// Offsets (in elements of the kernel scalar type) of the tables inside the pack.
-// All small matrices are stored ROW-major: M[r * cols + c].
+// Offsets (in elements) of the tables inside the family's master pack (host, double).
+// All small matrices are stored ROW-major: M[r * cols + c].  The "hot" tables are converted into the
+// kernel-parameter constant pack at launch; the "cold" tail [cold, cold + cold_size) is what each CTA
+// stages into shared memory with one TMA bulk copy.
 struct PackLayout {
     int nx, nu, N;
     int nsl, nil;                 // linear rows (state / input)
-    int A, B, Kinf, AmBKt, Quu_inv, Pinf, f, APf, BPf, Qd, Rd;
-    int d0;                       // nu*(N-1): d of the first backward pass on a zero workspace
+    // hot
+    int A, B, Kinf, AmBKt, Quu_inv, f, APf, BPf, Qd, Rd;
     int xmin, xmax, umin, umax;   // shared bounds nx*N / nu*(N-1) (time-major)
-    int dKinf, dPinf;             // adaptive-rho sensitivities
+    int dKinf;
+    // cold (shared-memory staged)
+    int cold;                     // start of the cold tail (multiple of 4 elements)
+    int Pinf, dPinf;
+    int d0;                       // nu*(N-1): d of the first backward pass on a zero workspace
     int Alin_x, blin_x, nrm_x;    // nsl*nx, nsl, nsl (||a||^2)
     int Alin_u, blin_u, nrm_u;
-    int size;                     // total elements, padded so that size*sizeof(T) % 16 == 0
+    int cold_size;                // elements in the cold tail, multiple of 4
+    int size;                     // total elements
 
     static PackLayout make(int nx, int nu, int N, int nsl, int nil) {
         PackLayout L{};
@@ -32,45 +39,35 @@ struct PackLayout {
         int o = 0;
         auto take = [&](int n) { int at = o; o += n; return at; };
         L.A = take(nx * nx); L.B = take(nx * nu); L.Kinf = take(nu * nx); L.AmBKt = take(nx * nx);
-        L.Quu_inv = take(nu * nu); L.Pinf = take(nx * nx); L.f = take(nx); L.APf = take(nx); L.BPf = take(nu);
-        L.Qd = take(nx); L.Rd = take(nu); L.d0 = take(nu * (N - 1));
+        L.Quu_inv = take(nu * nu); L.f = take(nx); L.APf = take(nx); L.BPf = take(nu);
+        L.Qd = take(nx); L.Rd = take(nu);
         L.xmin = take(nx * N); L.xmax = take(nx * N); L.umin = take(nu * (N - 1)); L.umax = take(nu * (N - 1));
-        L.dKinf = take(nu * nx); L.dPinf = take(nx * nx);
+        L.dKinf = take(nu * nx);
+        o = (o + 3) & ~3;
+        L.cold = o;
+        L.Pinf = take(nx * nx); L.dPinf = take(nx * nx); L.d0 = take(nu * (N - 1));
         L.Alin_x = take(nsl * nx); L.blin_x = take(nsl); L.nrm_x = take(nsl);
         L.Alin_u = take(nil * nu); L.blin_u = take(nil); L.nrm_u = take(nil);
-        L.size = (o + 3) & ~3;    // multiple of 4 elements -> 16 B multiple for float and double
+        o = (o + 3) & ~3;         // multiple of 4 elements -> 16 B multiple for float and double
+        L.cold_size = o - L.cold;
+        L.size = o;
         return L;
     }
 };
 
-// compile-time version of the fixed part (no linear rows) used by the specialised kernels
+// compile-time offsets inside the COLD tail (relative to PackLayout::cold) used by the kernels
 template <int NX, int NU, int NH>
 struct StaticPack {
-    static constexpr int A = 0;
-    static constexpr int B = A + NX * NX;
-    static constexpr int Kinf = B + NX * NU;
-    static constexpr int AmBKt = Kinf + NU * NX;
-    static constexpr int Quu_inv = AmBKt + NX * NX;
-    static constexpr int Pinf = Quu_inv + NU * NU;
-    static constexpr int f = Pinf + NX * NX;
-    static constexpr int APf = f + NX;
-    static constexpr int BPf = APf + NX;
-    static constexpr int Qd = BPf + NU;
-    static constexpr int Rd = Qd + NX;
-    static constexpr int d0 = Rd + NU;
-    static constexpr int xmin = d0 + NU * (NH - 1);
-    static constexpr int xmax = xmin + NX * NH;
-    static constexpr int umin = xmax + NX * NH;
-    static constexpr int umax = umin + NU * (NH - 1);
-    static constexpr int dKinf = umax + NU * (NH - 1);
-    static constexpr int dPinf = dKinf + NU * NX;
-    static constexpr int lin = dPinf + NX * NX;   // linear rows start here (runtime sized)
+    static constexpr int Pinf = 0;
+    static constexpr int dPinf = Pinf + NX * NX;
+    static constexpr int d0 = dPinf + NX * NX;
+    static constexpr int lin = d0 + NU * (NH - 1);   // linear rows start here (runtime sized)
 };
 
 // Kernel launch parameters (passed by value; plain data only).
 struct SolveParams {
-    const void* pack;          // device pointer, 16 B aligned
-    int pack_elems;            // PackLayout::size
+    const void* pack;          // device pointer to the cold tail of the pack, 16 B aligned
+    int pack_elems;            // PackLayout::cold_size
     int batch;
     int* work_counter;         // device int, zeroed before launch: next unclaimed problem index
     // per-problem inputs (device pointers, float32); NULL where noted

@@ -1,6 +1,6 @@
 // tmpc_registry.h -- table of compiled kernel instances the C-ABI layer dispatches over.
 // Each instance lives in its own generated translation unit (csrc/gen/*.cu, written by
-// tinympc-matlab_b200/build.py from the INSTANCES list) so that nvcc can compile them in parallel.
+// tinympc-matlab_b200/build.py from its instance list) so that nvcc can compile them in parallel.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -16,13 +16,16 @@ struct KernelEntry {
     int nx, nu, N;       // 0 = any (runtime-sized kernel)
     int feat;            // FEAT_BOX / FEAT_CONSTR / FEAT_ADAPT
     int dtype_bits;      // 32 or 64
+    int refs;            // 1: stores per-problem Xref/Uref terms; 0: reference-free variant (Xref = Uref = NULL)
     int ppb;             // per-problem bounds variant
     int block;           // threads per CTA
     int variant;         // tuning variant (0 = default); selected with the "variant" option
     size_t (*smem_bytes)(int pack_elems);
     cudaError_t (*prepare)(size_t smem);                                   // cudaFuncSetAttribute(max dynamic smem)
     cudaError_t (*occupancy)(int* ctas_per_sm, size_t smem);
-    cudaError_t (*launch)(const SolveParams& p, int grid, size_t smem, cudaStream_t st);
+    // master_pack: the family's double-precision pack (PackLayout L) on the host; the launcher
+    // converts the hot tables into the kernel-parameter constant pack
+    cudaError_t (*launch)(const SolveParams& p, int grid, size_t smem, cudaStream_t st, const double* master_pack, const PackLayout& L);
 };
 
 const KernelEntry* const* kernel_table(int* count);   // defined in gen/tmpc_table.cu
@@ -30,7 +33,7 @@ const KernelEntry* const* kernel_table(int* count);   // defined in gen/tmpc_tab
 }  // namespace tmpc
 
 // one of these per generated translation unit
-#define TMPC_DEFINE_TPP_ENTRY(SYM, CFG, FEATV, BITS, VAR)                                                              \
+#define TMPC_DEFINE_TPP_ENTRY(SYM, CFG, FEATV, BITS, VAR)                                                           \
     namespace tmpc {                                                                                                \
     static size_t SYM##_smem(int pe) { return tpp_smem_bytes<CFG>(pe); }                                            \
     static cudaError_t SYM##_prepare(size_t smem) {                                                                 \
@@ -39,10 +42,14 @@ const KernelEntry* const* kernel_table(int* count);   // defined in gen/tmpc_tab
     static cudaError_t SYM##_occ(int* n, size_t smem) {                                                             \
         return cudaOccupancyMaxActiveBlocksPerMultiprocessor(n, tpp_kernel<CFG>, CFG::BLOCK, smem);                 \
     }                                                                                                               \
-    static cudaError_t SYM##_launch(const SolveParams& p, int grid, size_t smem, cudaStream_t st) {                 \
-        tpp_kernel<CFG><<<grid, CFG::BLOCK, smem, st>>>(p);                                                         \
+    static cudaError_t SYM##_launch(const SolveParams& p, int grid, size_t smem, cudaStream_t st, const double* mp, \
+                                    const PackLayout& L) {                                                          \
+        typename CFG::CPack cpk;                                                                                    \
+        fill_const_pack(cpk, mp, L);                                                                                \
+        tpp_kernel<CFG><<<grid, CFG::BLOCK, smem, st>>>(p, cpk);                                                    \
         return cudaGetLastError();                                                                                  \
     }                                                                                                               \
-    extern const KernelEntry SYM = {#SYM, KF_TPP, CFG::NX, CFG::NU, CFG::NH, FEATV, BITS, CFG::PPB ? 1 : 0,         \
-                                    CFG::BLOCK, VAR, SYM##_smem, SYM##_prepare, SYM##_occ, SYM##_launch};                \
+    extern const KernelEntry SYM = {#SYM, KF_TPP, CFG::NX, CFG::NU, CFG::NH, FEATV, BITS, CFG::REFS ? 1 : 0,        \
+                                    CFG::PPB ? 1 : 0, CFG::BLOCK, VAR, SYM##_smem, SYM##_prepare, SYM##_occ,        \
+                                    SYM##_launch};                                                                  \
     }

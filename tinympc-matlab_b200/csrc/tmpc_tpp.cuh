@@ -10,22 +10,29 @@
 //   termination_condition :253-271
 //   adaptive rho          rho_benchmark.cpp:44-250 in closed block form
 //
-// Mapping.  One CUDA thread owns one MPC problem for all of its ADMM iterations.  The mat-vec
-// operands (A, B, Kinf, AmBKt, Quu_inv, ...) are identical for the whole batch: every CTA stages
-// the family "pack" into shared memory once with a TMA bulk copy (cp.async.bulk + mbarrier) and all
-// lanes read the same coefficient at the same time (a shared-memory broadcast), so a mat-vec is a
-// pure FFMA stream with no shuffles.  Per-problem trajectories (duals g,y, slacks v,z, reference
-// terms, d) live in registers or in conflict-free shared-memory columns ([element][thread]) for the
-// whole solve; HBM is touched only to read x0/Xref/Uref once and to write the solution once.
-// Problems need 1..max_iter iterations, so lanes are refilled: a lane that finishes claims the
-// next unsolved problem from a global counter (warp-aggregated atomic) while its neighbours keep
-// iterating -- no lane waits for the slowest problem of a warp.
+// Mapping.  One CUDA thread owns one MPC problem for all of its ADMM iterations; a mat-vec is then a
+// pure FMA stream with no shuffles.  Operand delivery decides the speed of that stream
+// (profiles/microbench/RESULTS.md): a shared-memory broadcast returns at most one coefficient per
+// clock per SM (<= 25 % of the FP32 pipe), so the family matrices A, B, Kinf, AmBKt, Quu_inv and the
+// shared bounds travel in the kernel-parameter constant bank and reach the FMA pipe through uniform
+// registers (LDCU), paired two columns at a time into packed FFMA2 (fma.rn.f32x2).  The cold tables
+// (Pinf, d0, cost diagonals, linear rows) are staged once per CTA into shared memory with a TMA bulk
+// copy (cp.async.bulk + mbarrier).  Per-problem state lives in conflict-free shared-memory columns
+// ([element][thread]) for the whole solve; HBM is touched only to read x0/Xref/Uref once and to write
+// the solution once.  Problems need 1..max_iter iterations, so lanes are refilled: a lane that
+// finishes claims the next problem from a global counter (warp-aggregated atomic) while its
+// neighbours keep iterating.
+//
+// State compression.  For the box constraint the reference keeps four arrays per variable: slack
+// vnew, previous slack v, dual g (and the trajectory x).  Since vnew = clamp(x + g) and
+// g_new = (g + x) - vnew (admm.cpp:85,92,184), the single pre-clamp value t = x + g determines both:
+// vnew = clamp(t), g_new = t - vnew.  Only t is stored (TV / TZ), which halves shared-memory traffic
+// and doubles the number of resident problems per SM.
 //
 // Loop rotation.  The reference runs backward -> forward -> slack -> dual -> linear cost -> check.
-// On a cold workspace (q = r = p = 0) the first backward pass is problem independent, so its
-// result d0 is precomputed on the host; each iteration here is forward+slack+dual -> check ->
-// backward (for the next iteration), which is the same sequence of values and skips the backward
-// pass of the final iteration.
+// On a cold workspace (q = r = p = 0) the first backward pass is problem independent, so its result
+// d0 is precomputed on the host; each iteration here is forward+slack+dual -> check -> backward (for
+// the next iteration): the same sequence of values, without the backward pass of the last iteration.
 #pragma once
 #include <cuda_runtime.h>
 #include <math_constants.h>
@@ -37,10 +44,9 @@ namespace tmpc {
 enum : int { FEAT_BOX = 0, FEAT_CONSTR = 1, FEAT_ADAPT = 2 };
 
 // ----------------------------------------------------------------------------------------------
-// small PTX helpers: mbarrier + TMA bulk copy (global -> shared), sm_90+/sm_100a
+// PTX helpers: mbarrier + TMA bulk copy (global -> shared)
 // ----------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
-
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
@@ -68,61 +74,73 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gme
 }
 
 // ----------------------------------------------------------------------------------------------
-// per-thread arrays: registers (static indexing only) or a shared-memory column [elem][thread]
+// family tables that ride in the kernel-parameter constant bank (row-major, plus transposed copies
+// so that every dot product reads its coefficients as adjacent pairs)
 // ----------------------------------------------------------------------------------------------
-template <typename T, int LEN, bool SM, int OFF, int BLOCK>
-struct Col;
-template <typename T, int LEN, int OFF, int BLOCK>
-struct Col<T, LEN, true, OFF, BLOCK> {
-    T* base;  // thread's column origin (already + threadIdx.x)
+template <typename T, int NX, int NU, int NH, bool ADAPT>
+struct ConstPack {
+    T A[NX * NX];      // x_next rows
+    T B[NX * NU];
+    T BT[NU * NX];     // B'  (backward: B' p)
+    T K[NU * NX];      // Kinf (forward)
+    T KT[NX * NU];     // Kinf' (backward: Kinf' r)
+    T AK[NX * NX];     // AmBKt
+    T Quu[NU * NU];
+    T f[NX], APf[NX], BPf[NU];
+    T Qd[NX], Rd[NU];
+    T xmin[NX * NH], xmax[NX * NH], umin[NU * (NH - 1)], umax[NU * (NH - 1)];
+    T dK[ADAPT ? NU * NX : 2], dKT[ADAPT ? NX * NU : 2];
+    T AT[ADAPT ? NX * NX : 2];   // A' (adaptive rho: A' g)
+};
+
+template <typename T, int NX, int NU, int NH, bool ADAPT>
+inline void fill_const_pack(ConstPack<T, NX, NU, NH, ADAPT>& c, const double* pk, const PackLayout& L) {
+    auto cp = [&](T* dst, int at, int n) { for (int i = 0; i < n; ++i) dst[i] = static_cast<T>(pk[at + i]); };
+    auto tr = [&](T* dst, int at, int rows, int cols) {   // dst (cols x rows) = transpose of row-major (rows x cols)
+        for (int r = 0; r < rows; ++r) for (int k = 0; k < cols; ++k) dst[k * rows + r] = static_cast<T>(pk[at + r * cols + k]);
+    };
+    cp(c.A, L.A, NX * NX); cp(c.B, L.B, NX * NU); tr(c.BT, L.B, NX, NU);
+    cp(c.K, L.Kinf, NU * NX); tr(c.KT, L.Kinf, NU, NX);
+    cp(c.AK, L.AmBKt, NX * NX); cp(c.Quu, L.Quu_inv, NU * NU);
+    cp(c.f, L.f, NX); cp(c.APf, L.APf, NX); cp(c.BPf, L.BPf, NU); cp(c.Qd, L.Qd, NX); cp(c.Rd, L.Rd, NU);
+    cp(c.xmin, L.xmin, NX * NH); cp(c.xmax, L.xmax, NX * NH); cp(c.umin, L.umin, NU * (NH - 1)); cp(c.umax, L.umax, NU * (NH - 1));
+    if (ADAPT) { cp(c.dK, L.dKinf, NU * NX); tr(c.dKT, L.dKinf, NU, NX); tr(c.AT, L.A, NX, NX); }
+}
+
+// ----------------------------------------------------------------------------------------------
+// per-thread state: a shared-memory column [elem][thread]
+// ----------------------------------------------------------------------------------------------
+template <typename T, int OFF, int BLOCK>
+struct Col {
+    T* base;
     __device__ __forceinline__ explicit Col(T* colbase) : base(colbase + OFF * BLOCK) {}
     __device__ __forceinline__ T get(int i) const { return base[i * BLOCK]; }
     __device__ __forceinline__ void set(int i, T v) { base[i * BLOCK] = v; }
 };
-template <typename T, int LEN, int OFF, int BLOCK>
-struct Col<T, LEN, false, OFF, BLOCK> {
-    T v[LEN > 0 ? LEN : 1];
-    __device__ __forceinline__ explicit Col(T*) {}
-    __device__ __forceinline__ T get(int i) const { return v[i]; }
-    __device__ __forceinline__ void set(int i, T val) { v[i] = val; }
-};
 
-// placement bits: 1 = shared memory column, 0 = registers
-enum : unsigned {
-    P_G = 1u << 0, P_V = 1u << 1, P_XRQ = 1u << 2, P_Y = 1u << 3, P_Z = 1u << 4, P_URR = 1u << 5, P_D = 1u << 6,
-    P_X0 = 1u << 7, P_PT = 1u << 8, P_GC = 1u << 9, P_GL = 1u << 10, P_SX = 1u << 11, P_YC = 1u << 12, P_YL = 1u << 13,
-    P_SU = 1u << 14, P_ALL = 0x7fffu
-};
-
-template <typename T_, int NX_, int NU_, int NH_, int FEAT_, int BLOCK_, bool UNROLL_, unsigned PLACE_, bool PPB_>
+template <typename T_, int NX_, int NU_, int NH_, int FEAT_, int BLOCK_, bool REFS_, bool PPB_, int MINB_ = 1>
 struct TppCfg {
     using T = T_;
-    static constexpr int NX = NX_, NU = NU_, NH = NH_, FEAT = FEAT_, BLOCK = BLOCK_;
-    static constexpr bool UNROLL = UNROLL_;
+    static constexpr int NX = NX_, NU = NU_, NH = NH_, FEAT = FEAT_, BLOCK = BLOCK_, MINB = MINB_;
+    static constexpr bool REFS = REFS_;                     // per-problem Xref/Uref present
     static constexpr bool PPB = PPB_;                       // per-problem bounds read from global memory
-    static constexpr unsigned PLACE = UNROLL_ ? PLACE_ : P_ALL;  // a rolled time loop needs dynamic indexing
     static constexpr bool CONSTR = FEAT_ == FEAT_CONSTR;
     static constexpr bool ADAPT = FEAT_ == FEAT_ADAPT;
     static constexpr int SX = NX * NH, SU = NU * (NH - 1);
-    static constexpr int TU = UNROLL_ ? NH : 1;             // time-loop unroll factor
+    using CPack = ConstPack<T_, NX_, NU_, NH_, ADAPT>;
     // element offsets of the shared-memory columns
-    static constexpr int sz(unsigned bit, int len, bool enabled = true) { return (enabled && (PLACE & bit)) ? len : 0; }
-    static constexpr int oG = 0;
-    static constexpr int oV = oG + sz(P_G, SX);
-    static constexpr int oXRQ = oV + sz(P_V, SX);
-    static constexpr int oY = oXRQ + sz(P_XRQ, SX);
-    static constexpr int oZ = oY + sz(P_Y, SU);
-    static constexpr int oURR = oZ + sz(P_Z, SU);
-    static constexpr int oD = oURR + sz(P_URR, SU);
-    static constexpr int oX0 = oD + sz(P_D, SU);
-    static constexpr int oPT = oX0 + sz(P_X0, NX);
-    static constexpr int oGC = oPT + sz(P_PT, ADAPT ? 2 * NX : NX);
-    static constexpr int oGL = oGC + sz(P_GC, SX, CONSTR);
-    static constexpr int oSX = oGL + sz(P_GL, SX, CONSTR);
-    static constexpr int oYC = oSX + sz(P_SX, SX, CONSTR);
-    static constexpr int oYL = oYC + sz(P_YC, SU, CONSTR);
-    static constexpr int oSU = oYL + sz(P_YL, SU, CONSTR);
-    static constexpr int oSCR = oSU + sz(P_SU, SU, CONSTR);
+    static constexpr int oTV = 0;
+    static constexpr int oTZ = oTV + SX;
+    static constexpr int oD = oTZ + SU;
+    static constexpr int oXRQ = oD + SU;
+    static constexpr int oURR = oXRQ + (REFS ? SX : 0);
+    static constexpr int oGC = oURR + (REFS ? SU : 0);
+    static constexpr int oGL = oGC + (CONSTR ? SX : 0);
+    static constexpr int oSX = oGL + (CONSTR ? SX : 0);
+    static constexpr int oYC = oSX + (CONSTR ? SX : 0);
+    static constexpr int oYL = oYC + (CONSTR ? SU : 0);
+    static constexpr int oSU = oYL + (CONSTR ? SU : 0);
+    static constexpr int oSCR = oSU + (CONSTR ? SU : 0);
     static constexpr int COLS = oSCR + (CONSTR ? (NX > NU ? NX : NU) : 0);   // + cone scratch column
 };
 
@@ -133,6 +151,7 @@ template <> struct Num<float> {
     static __device__ __forceinline__ float max(float a, float b) { return fmaxf(a, b); }
     static __device__ __forceinline__ float min(float a, float b) { return fminf(a, b); }
     static __device__ __forceinline__ float sqrt(float a) { return sqrtf(a); }
+    static __device__ __forceinline__ float inf() { return CUDART_INF_F; }
 };
 template <> struct Num<double> {
     static __device__ __forceinline__ double fma(double a, double b, double c) { return ::fma(a, b, c); }
@@ -140,7 +159,30 @@ template <> struct Num<double> {
     static __device__ __forceinline__ double max(double a, double b) { return ::fmax(a, b); }
     static __device__ __forceinline__ double min(double a, double b) { return ::fmin(a, b); }
     static __device__ __forceinline__ double sqrt(double a) { return ::sqrt(a); }
+    static __device__ __forceinline__ double inf() { return CUDART_INF; }
 };
+
+// init + sum_c m(c) * x[c]; fp32 pairs adjacent columns into packed FFMA2 (two partial sums)
+template <int C, typename FM>
+__device__ __forceinline__ float dot(FM&& m, const float (&x)[C], float init) {
+    if constexpr (C >= 2) {
+        float2 acc = make_float2(init, 0.f);
+#pragma unroll
+        for (int c = 0; c + 1 < C; c += 2) acc = __ffma2_rn(make_float2(m(c), m(c + 1)), make_float2(x[c], x[c + 1]), acc);
+        float r = acc.x + acc.y;
+        if constexpr (C & 1) r = fmaf(m(C - 1), x[C - 1], r);
+        return r;
+    } else {
+        return fmaf(m(0), x[0], init);
+    }
+}
+template <int C, typename FM>
+__device__ __forceinline__ double dot(FM&& m, const double (&x)[C], double init) {
+    double acc = init;
+#pragma unroll
+    for (int c = 0; c < C; ++c) acc = ::fma(m(c), x[c], acc);
+    return acc;
+}
 
 // vectorised, read-only loads of one problem's contiguous float chunk (LEN floats at src)
 template <int LEN, typename F>
@@ -204,12 +246,12 @@ __device__ __forceinline__ void project_soc_col(T* scr, int start, int dim, floa
 }
 
 template <class C>
-__global__ void __launch_bounds__(C::BLOCK, 1) tpp_kernel(const SolveParams prm) {
+__global__ void __launch_bounds__(C::BLOCK, C::MINB)
+tpp_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ typename C::CPack cp) {
     using T = typename C::T;
     using N = Num<T>;
     using SP = StaticPack<C::NX, C::NU, C::NH>;
     constexpr int NX = C::NX, NU = C::NU, NH = C::NH, BLOCK = C::BLOCK, SXL = C::SX, SUL = C::SU;
-    constexpr unsigned PL = C::PLACE;
     constexpr unsigned FULL = 0xffffffffu;
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -217,7 +259,7 @@ __global__ void __launch_bounds__(C::BLOCK, 1) tpp_kernel(const SolveParams prm)
     T* pack = reinterpret_cast<T*>(smem_raw);
     const uint32_t pack_bytes = static_cast<uint32_t>(prm.pack_elems) * sizeof(T);
 
-    // ---- stage the family pack into shared memory: one TMA bulk copy per CTA ----
+    // ---- stage the cold family tables into shared memory: one TMA bulk copy per CTA ----
     if (threadIdx.x == 0) {
         mbar_init(&pack_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -228,34 +270,20 @@ __global__ void __launch_bounds__(C::BLOCK, 1) tpp_kernel(const SolveParams prm)
     mbar_wait(&pack_bar, 0);
 
     T* colbase = pack + ((prm.pack_elems + 31) & ~31) + threadIdx.x;
+    Col<T, C::oTV, BLOCK> TV(colbase);      // t = x + g   (pre-clamp state slack)
+    Col<T, C::oTZ, BLOCK> TZ(colbase);      // t = u + y   (pre-clamp input slack)
+    Col<T, C::oD, BLOCK> D(colbase);        // d of the backward pass
+    Col<T, C::oXRQ, BLOCK> XRQ(colbase);    // Xref .* Q
+    Col<T, C::oURR, BLOCK> URR(colbase);    // Uref .* R
+    Col<T, C::oGC, BLOCK> GC(colbase);      // cone duals (state)
+    Col<T, C::oGL, BLOCK> GL(colbase);      // linear duals (state)
+    Col<T, C::oSX, BLOCK> SXT(colbase);     // (vc - gc) + (vl - gl)
+    Col<T, C::oYC, BLOCK> YC(colbase);
+    Col<T, C::oYL, BLOCK> YL(colbase);
+    Col<T, C::oSU, BLOCK> SUT(colbase);
+    T* scr = colbase + C::oSCR * BLOCK;     // cone scratch column (CONSTR only)
 
-    Col<T, SXL, (PL & P_G) != 0, C::oG, BLOCK> G(colbase);
-    Col<T, SXL, (PL & P_V) != 0, C::oV, BLOCK> V(colbase);
-    Col<T, SXL, (PL & P_XRQ) != 0, C::oXRQ, BLOCK> XRQ(colbase);
-    Col<T, SUL, (PL & P_Y) != 0, C::oY, BLOCK> Y(colbase);
-    Col<T, SUL, (PL & P_Z) != 0, C::oZ, BLOCK> Z(colbase);
-    Col<T, SUL, (PL & P_URR) != 0, C::oURR, BLOCK> URR(colbase);
-    Col<T, SUL, (PL & P_D) != 0, C::oD, BLOCK> D(colbase);
-    Col<T, NX, (PL & P_X0) != 0, C::oX0, BLOCK> X0(colbase);
-    Col<T, C::ADAPT ? 2 * NX : NX, (PL & P_PT) != 0, C::oPT, BLOCK> PT(colbase);
-    Col<T, C::CONSTR ? SXL : 0, (PL & P_GC) != 0, C::oGC, BLOCK> GC(colbase);
-    Col<T, C::CONSTR ? SXL : 0, (PL & P_GL) != 0, C::oGL, BLOCK> GL(colbase);
-    Col<T, C::CONSTR ? SXL : 0, (PL & P_SX) != 0, C::oSX, BLOCK> SXT(colbase);
-    Col<T, C::CONSTR ? SUL : 0, (PL & P_YC) != 0, C::oYC, BLOCK> YC(colbase);
-    Col<T, C::CONSTR ? SUL : 0, (PL & P_YL) != 0, C::oYL, BLOCK> YL(colbase);
-    Col<T, C::CONSTR ? SUL : 0, (PL & P_SU) != 0, C::oSU, BLOCK> SUT(colbase);
-    T* scr = colbase + C::oSCR * BLOCK;   // cone scratch column (CONSTR only)
-
-    const T* cA = pack + SP::A;
-    const T* cB = pack + SP::B;
-    const T* cK = pack + SP::Kinf;
-    const T* cAK = pack + SP::AmBKt;
-    const T* cQuu = pack + SP::Quu_inv;
     const T* cP = pack + SP::Pinf;
-    const T* cf = pack + SP::f;
-    const T* cAPf = pack + SP::APf;
-    const T* cBPf = pack + SP::BPf;
-    const T* cdK = pack + SP::dKinf;
     const T* cdP = pack + SP::dPinf;
 
     const T rho0 = static_cast<T>(prm.rho);
@@ -272,16 +300,35 @@ __global__ void __launch_bounds__(C::BLOCK, 1) tpp_kernel(const SolveParams prm)
     const T* cAlu = cnrx + nsl;
     const T* cblu = cAlu + nil * NU;
     const T* cnru = cblu + nil;
+    const bool en_sb = prm.en_state_bound != 0, en_ib = prm.en_input_bound != 0;
+    (void)en_sb; (void)en_ib;
 
     const int lane = threadIdx.x & 31;
-    int prob = -1;          // problem owned by this lane
+    int prob = 0;           // problem owned by this lane
     bool active = false;    // lane holds an unfinished problem
     bool exhausted = false; // the work counter ran past the batch
     int k = 0;              // ADMM iterations done on the current problem
     T res_px = 0, res_dx = 0, res_pu = 0, res_du = 0;   // last evaluated residuals (admm.cpp:257-260)
-    // adaptive rho state (cache->rho, and the Taylor offset of Kinf/Pinf): rho_lc/dl_lc are the
-    // values update_linear_cost saw (it runs BEFORE the adaptation inside an iteration)
+    // adaptive rho state (cache->rho and the Taylor offset of Kinf/Pinf); *_lc are the values
+    // update_linear_cost saw (it runs BEFORE the adaptation inside an iteration)
     T rho = rho0, rho_lc = rho0, dlt = 0, dlt_lc = 0;
+    T x0r[NX], ptr_[C::ADAPT ? 2 * NX : NX];            // x0 and the terminal term -(xref_N' Pinf)'
+#pragma unroll
+    for (int r = 0; r < NX; ++r) { x0r[r] = 0; ptr_[r] = 0; if constexpr (C::ADAPT) ptr_[NX + r] = 0; }
+
+    // box bounds of trajectory element e (state) / (input)
+    auto xbounds = [&](int e, size_t pb, T& lo, T& hi) {
+        if constexpr (C::PPB) {
+            lo = en_sb ? static_cast<T>(__ldg(prm.x_min + pb + e)) : -N::inf();
+            hi = en_sb ? static_cast<T>(__ldg(prm.x_max + pb + e)) : N::inf();
+        } else { lo = cp.xmin[e]; hi = cp.xmax[e]; }
+    };
+    auto ubounds = [&](int e, size_t pb, T& lo, T& hi) {
+        if constexpr (C::PPB) {
+            lo = en_ib ? static_cast<T>(__ldg(prm.u_min + pb + e)) : -N::inf();
+            hi = en_ib ? static_cast<T>(__ldg(prm.u_max + pb + e)) : N::inf();
+        } else { lo = cp.umin[e]; hi = cp.umax[e]; }
+    };
 
     for (;;) {
         // ------------------------------------------------------------------ refill idle lanes
@@ -297,55 +344,56 @@ __global__ void __launch_bounds__(C::BLOCK, 1) tpp_kernel(const SolveParams prm)
                     prob = base + __popc(m & ((1u << lane) - 1u));
                     if (prob >= prm.batch) {
                         exhausted = true;
-                        prob = 0;   // keeps the (unused) per-problem bound reads of an idle lane in range
+                        prob = 0;   // keeps the (unused) per-problem reads of an idle lane in range
                     } else {
                         active = true;
                         k = 0;
                         res_px = res_dx = res_pu = res_du = 0;
                         rho = rho_lc = rho0; dlt = dlt_lc = 0;
-                        // x0
-                        load_chunk<NX>(prm.x0 + (size_t)prob * NX, [&](int i, float v) { X0.set(i, static_cast<T>(v)); });
+                        load_chunk<NX>(prm.x0 + (size_t)prob * NX, [&](int i, float v) { x0r[i] = static_cast<T>(v); });
                         // Xref -> XRQ = Xref .* Q (work->Q = diag(Q)+rho, admm.cpp:218) and the terminal
                         // term PT = -(xref_N' Pinf)' (admm.cpp:238)
-                        T xr_last[NX];
+                        if constexpr (C::REFS) {
+                            T xr_last[NX];
 #pragma unroll
-                        for (int r = 0; r < NX; ++r) xr_last[r] = 0;
-                        if (prm.Xref) {
-                            load_chunk<SXL>(prm.Xref + (size_t)prob * SXL, [&](int e, float v) {
-                                XRQ.set(e, static_cast<T>(v) * pack[SP::Qd + e % NX]);
-                                if (e >= SXL - NX) xr_last[e - (SXL - NX)] = static_cast<T>(v);
-                            });
-                        } else {
-#pragma unroll
-                            for (int e = 0; e < SXL; ++e) XRQ.set(e, T(0));
-                        }
-#pragma unroll
-                        for (int c = 0; c < NX; ++c) {
-                            T acc = 0, acc1 = 0;
-#pragma unroll
-                            for (int r = 0; r < NX; ++r) {
-                                acc = N::fma(xr_last[r], cP[r * NX + c], acc);
-                                if constexpr (C::ADAPT) acc1 = N::fma(xr_last[r], cdP[r * NX + c], acc1);
+                            for (int r = 0; r < NX; ++r) xr_last[r] = 0;
+                            if (prm.Xref) {
+                                load_chunk<SXL>(prm.Xref + (size_t)prob * SXL, [&](int e, float v) {
+                                    XRQ.set(e, static_cast<T>(v) * cp.Qd[e % NX]);
+                                    if (e >= SXL - NX) xr_last[e - (SXL - NX)] = static_cast<T>(v);
+                                });
+                            } else {
+#pragma unroll 4
+                                for (int e = 0; e < SXL; ++e) XRQ.set(e, T(0));
                             }
-                            PT.set(c, -acc);
-                            if constexpr (C::ADAPT) PT.set(NX + c, -acc1);
-                        }
-                        if (prm.Uref) {
-                            load_chunk<SUL>(prm.Uref + (size_t)prob * SUL,
-                                            [&](int e, float v) { URR.set(e, static_cast<T>(v) * pack[SP::Rd + e % NU]); });
-                        } else {
 #pragma unroll
-                            for (int e = 0; e < SUL; ++e) URR.set(e, T(0));
+                            for (int c = 0; c < NX; ++c) {
+                                T acc = 0, acc1 = 0;
+#pragma unroll
+                                for (int r = 0; r < NX; ++r) {
+                                    acc = N::fma(xr_last[r], cP[r * NX + c], acc);
+                                    if constexpr (C::ADAPT) acc1 = N::fma(xr_last[r], cdP[r * NX + c], acc1);
+                                }
+                                ptr_[c] = -acc;
+                                if constexpr (C::ADAPT) ptr_[NX + c] = -acc1;
+                            }
+                            if (prm.Uref) {
+                                load_chunk<SUL>(prm.Uref + (size_t)prob * SUL,
+                                                [&](int e, float v) { URR.set(e, static_cast<T>(v) * cp.Rd[e % NU]); });
+                            } else {
+#pragma unroll 4
+                                for (int e = 0; e < SUL; ++e) URR.set(e, T(0));
+                            }
                         }
                         // cold workspace (tiny_api.cpp:68-105): duals and slacks zero, d = d0
-#pragma unroll
-                        for (int e = 0; e < SXL; ++e) { G.set(e, T(0)); V.set(e, T(0)); }
-#pragma unroll
-                        for (int e = 0; e < SUL; ++e) { Y.set(e, T(0)); Z.set(e, T(0)); D.set(e, pack[SP::d0 + e]); }
+#pragma unroll 4
+                        for (int e = 0; e < SXL; ++e) TV.set(e, T(0));
+#pragma unroll 4
+                        for (int e = 0; e < SUL; ++e) { TZ.set(e, T(0)); D.set(e, pack[SP::d0 + e]); }
                         if constexpr (C::CONSTR) {
-#pragma unroll
+#pragma unroll 4
                             for (int e = 0; e < SXL; ++e) { GC.set(e, T(0)); GL.set(e, T(0)); SXT.set(e, T(0)); }
-#pragma unroll
+#pragma unroll 4
                             for (int e = 0; e < SUL; ++e) { YC.set(e, T(0)); YL.set(e, T(0)); SUT.set(e, T(0)); }
                         }
                     }
@@ -360,45 +408,38 @@ __global__ void __launch_bounds__(C::BLOCK, 1) tpp_kernel(const SolveParams prm)
         // lane of the warp is at an adaptation iteration (i > 0 && i % 5 == 0, admm.cpp:339)
         const bool do_adapt = C::ADAPT && prm.adaptive_rho && __any_sync(FULL, active && k > 0 && k % 5 == 0);
         T a_pri = 0, a_prin = 0, a_dua = 0, a_duan = 0;
+        const bool first = (k == 0);   // cold start: v = 0, g = 0 whatever the bounds are
         T x[NX];
         T xprev[NX], gprev[NX], uprev[NU], yprev[NU];   // ADAPT: lagged column for the A'g terms
 #pragma unroll
-        for (int r = 0; r < NX; ++r) { x[r] = X0.get(r); xprev[r] = 0; gprev[r] = 0; }
+        for (int r = 0; r < NX; ++r) { x[r] = x0r[r]; xprev[r] = 0; gprev[r] = 0; }
 #pragma unroll
         for (int a = 0; a < NU; ++a) { uprev[a] = 0; yprev[a] = 0; }
-        const T* pxmin = pack + SP::xmin;
-        const T* pxmax = pack + SP::xmax;
-        const T* pumin = pack + SP::umin;
-        const T* pumax = pack + SP::umax;
-        const size_t pbx = (size_t)(prob < 0 ? 0 : prob) * SXL, pbu = (size_t)(prob < 0 ? 0 : prob) * SUL;
-        (void)pbx; (void)pbu;
+        const size_t pbx = (size_t)prob * SXL, pbu = (size_t)prob * SUL;
 
-#pragma unroll(C::TU)
+#pragma unroll 1
         for (int i = 0; i < NH; ++i) {
             // ---- state column i: vnew = clamp(x + g), g += x - vnew (admm.cpp:85,92,184)
             T gnew[NX];
 #pragma unroll
             for (int r = 0; r < NX; ++r) {
                 const int e = i * NX + r;
-                const T g = G.get(e), vo = V.get(e);
                 T lo, hi;
-                if constexpr (C::PPB) {
-                    lo = prm.en_state_bound ? static_cast<T>(__ldg(prm.x_min + pbx + e)) : -CUDART_INF_F;
-                    hi = prm.en_state_bound ? static_cast<T>(__ldg(prm.x_max + pbx + e)) : CUDART_INF_F;
-                }
-                else { lo = pxmin[e]; hi = pxmax[e]; }
-                T vn = x[r] + g;
-                vn = N::min(hi, N::max(lo, vn));
-                const T gn = (g + x[r]) - vn;
+                xbounds(e, pbx, lo, hi);
+                const T tvo = TV.get(e);
+                T vo = N::min(hi, N::max(lo, tvo));
+                T g = tvo - vo;
+                if (first) { vo = 0; g = 0; }
+                const T tvn = x[r] + g;
+                const T vn = N::min(hi, N::max(lo, tvn));
                 rpx = N::max(rpx, N::abs(x[r] - vn));
                 rdx = N::max(rdx, N::abs(vo - vn));
-                V.set(e, vn);
-                G.set(e, gn);
-                gnew[r] = gn;
+                TV.set(e, tvn);
+                gnew[r] = tvn - vn;
                 if constexpr (C::ADAPT) {
                     if (do_adapt && i > 0) {   // dynamics rows of A_matrix: (A x + B u - x_next) - vnew_next = -f - vnew
-                        a_pri = N::max(a_pri, N::abs(cf[r] + vn));
-                        a_prin = N::max(a_prin, N::max(N::abs(vn), N::abs(cf[r])));
+                        a_pri = N::max(a_pri, N::abs(cp.f[r] + vn));
+                        a_prin = N::max(a_prin, N::max(N::abs(vn), N::abs(cp.f[r])));
                     }
                 }
             }
@@ -447,20 +488,16 @@ __global__ void __launch_bounds__(C::BLOCK, 1) tpp_kernel(const SolveParams prm)
                 if (do_adapt && i > 0) {
 #pragma unroll
                     for (int c = 0; c < NX; ++c) {
-                        T aty = 0;
-#pragma unroll
-                        for (int r = 0; r < NX; ++r) aty = N::fma(cA[r * NX + c], gnew[r], aty);
+                        T aty = dot<NX>([&](int r) { return cp.AT[c * NX + r]; }, gnew, T(0));
                         if (i > 1) aty -= gprev[c];
-                        const T qx = pack[SP::Qd + c] * xprev[c];   // Px = qv = Q .* x for columns < N-1
+                        const T qx = cp.Qd[c] * xprev[c];   // Px = qv = Q .* x for columns < N-1
                         a_dua = N::max(a_dua, N::abs(qx + qx + aty));
                         a_duan = N::max(a_duan, N::max(N::abs(qx), N::abs(aty)));
                     }
 #pragma unroll
                     for (int a = 0; a < NU; ++a) {
-                        T aty = yprev[a];
-#pragma unroll
-                        for (int r = 0; r < NX; ++r) aty = N::fma(cB[r * NU + a], gnew[r], aty);
-                        const T ru = pack[SP::Rd + a] * uprev[a];
+                        const T aty = dot<NX>([&](int r) { return cp.BT[a * NX + r]; }, gnew, yprev[a]);
+                        const T ru = cp.Rd[a] * uprev[a];
                         a_dua = N::max(a_dua, N::abs(ru + ru + aty));
                         a_duan = N::max(a_duan, N::max(N::abs(ru), N::abs(aty)));
                     }
@@ -471,7 +508,7 @@ __global__ void __launch_bounds__(C::BLOCK, 1) tpp_kernel(const SolveParams prm)
                         T px = 0;
 #pragma unroll
                         for (int c = 0; c < NX; ++c) px = N::fma(N::fma(dlt, cdP[r * NX + c], cP[r * NX + c]), x[c], px);
-                        const T qx = pack[SP::Qd + r] * x[r];
+                        const T qx = cp.Qd[r] * x[r];
                         const T aty = -gnew[r];
                         a_dua = N::max(a_dua, N::abs(px + qx + aty));
                         a_duan = N::max(a_duan, N::max(N::max(N::abs(px), N::abs(qx)), N::abs(aty)));
@@ -483,15 +520,8 @@ __global__ void __launch_bounds__(C::BLOCK, 1) tpp_kernel(const SolveParams prm)
                 T u[NU];
 #pragma unroll
                 for (int a = 0; a < NU; ++a) {
-                    T acc = 0;
-#pragma unroll
-                    for (int c = 0; c < NX; ++c) acc = N::fma(cK[a * NX + c], x[c], acc);
-                    if constexpr (C::ADAPT) {
-                        T acc1 = 0;
-#pragma unroll
-                        for (int c = 0; c < NX; ++c) acc1 = N::fma(cdK[a * NX + c], x[c], acc1);
-                        acc = N::fma(dlt, acc1, acc);
-                    }
+                    T acc = dot<NX>([&](int c) { return cp.K[a * NX + c]; }, x, T(0));
+                    if constexpr (C::ADAPT) acc = N::fma(dlt, dot<NX>([&](int c) { return cp.dK[a * NX + c]; }, x, T(0)), acc);
                     u[a] = -acc - D.get(i * NU + a);
                 }
                 // ---- input column i: znew = clamp(u + y), y += u - znew (admm.cpp:88,97,187)
@@ -499,21 +529,18 @@ __global__ void __launch_bounds__(C::BLOCK, 1) tpp_kernel(const SolveParams prm)
 #pragma unroll
                 for (int a = 0; a < NU; ++a) {
                     const int e = i * NU + a;
-                    const T yv = Y.get(e), zo = Z.get(e);
                     T lo, hi;
-                    if constexpr (C::PPB) {
-                        lo = prm.en_input_bound ? static_cast<T>(__ldg(prm.u_min + pbu + e)) : -CUDART_INF_F;
-                        hi = prm.en_input_bound ? static_cast<T>(__ldg(prm.u_max + pbu + e)) : CUDART_INF_F;
-                    }
-                    else { lo = pumin[e]; hi = pumax[e]; }
-                    T zn = u[a] + yv;
-                    zn = N::min(hi, N::max(lo, zn));
-                    const T yn = (yv + u[a]) - zn;
+                    ubounds(e, pbu, lo, hi);
+                    const T tzo = TZ.get(e);
+                    T zo = N::min(hi, N::max(lo, tzo));
+                    T yv = tzo - zo;
+                    if (first) { zo = 0; yv = 0; }
+                    const T tzn = u[a] + yv;
+                    const T zn = N::min(hi, N::max(lo, tzn));
                     rpu = N::max(rpu, N::abs(u[a] - zn));
                     rdu = N::max(rdu, N::abs(zo - zn));
-                    Z.set(e, zn);
-                    Y.set(e, yn);
-                    ynew[a] = yn;
+                    TZ.set(e, tzn);
+                    ynew[a] = tzn - zn;
                     if constexpr (C::ADAPT) { if (do_adapt) a_prin = N::max(a_prin, N::max(N::abs(u[a]), N::abs(zn))); }
                 }
                 if constexpr (C::CONSTR) {
@@ -560,12 +587,8 @@ __global__ void __launch_bounds__(C::BLOCK, 1) tpp_kernel(const SolveParams prm)
                 T xn[NX];
 #pragma unroll
                 for (int r = 0; r < NX; ++r) {
-                    T acc = 0;
-#pragma unroll
-                    for (int c = 0; c < NX; ++c) acc = N::fma(cA[r * NX + c], x[c], acc);
-#pragma unroll
-                    for (int a = 0; a < NU; ++a) acc = N::fma(cB[r * NU + a], u[a], acc);
-                    xn[r] = acc + cf[r];
+                    T acc = dot<NX>([&](int c) { return cp.A[r * NX + c]; }, x, cp.f[r]);
+                    xn[r] = dot<NU>([&](int a) { return cp.B[r * NU + a]; }, u, acc);
                 }
                 if constexpr (C::ADAPT) {
 #pragma unroll
@@ -602,8 +625,15 @@ __global__ void __launch_bounds__(C::BLOCK, 1) tpp_kernel(const SolveParams prm)
         }
         if (k >= max_iter) finish = true;
         if (active && finish) {
-            store_chunk<SXL>(prm.x + (size_t)prob * SXL, [&](int e) { return static_cast<float>(V.get(e)); });
-            store_chunk<SUL>(prm.u + (size_t)prob * SUL, [&](int e) { return static_cast<float>(Z.get(e)); });
+            // solution = (vnew, znew) = clamp of the stored pre-clamp values
+            store_chunk<SXL>(prm.x + pbx, [&](int e) {
+                T lo, hi; xbounds(e, pbx, lo, hi);
+                return static_cast<float>(N::min(hi, N::max(lo, TV.get(e))));
+            });
+            store_chunk<SUL>(prm.u + pbu, [&](int e) {
+                T lo, hi; ubounds(e, pbu, lo, hi);
+                return static_cast<float>(N::min(hi, N::max(lo, TZ.get(e))));
+            });
             prm.iter[prob] = k;
             prm.status[prob] = st;
             if (prm.residuals) {
@@ -618,55 +648,58 @@ __global__ void __launch_bounds__(C::BLOCK, 1) tpp_kernel(const SolveParams prm)
         // ------------------------------------------------- backward Riccati sweep for the next iteration
         // q, r, p_N of update_linear_cost (admm.cpp:214-247) are formed on the fly with the rho / Pinf
         // that update_linear_cost saw; Kinf' uses the current (possibly adapted) Kinf.
+        // v - g = 2 clamp(t) - t for the box slack/dual pair.
         T p[NX];
 #pragma unroll
         for (int c = 0; c < NX; ++c) {
             const int e = (NH - 1) * NX + c;
-            T w = V.get(e) - G.get(e);
+            T lo, hi;
+            xbounds(e, pbx, lo, hi);
+            const T tv = TV.get(e);
+            const T v = N::min(hi, N::max(lo, tv));
+            T w = (v + v) - tv;
             if constexpr (C::CONSTR) w += SXT.get(e);
-            T pt = PT.get(c);
-            if constexpr (C::ADAPT) pt = N::fma(dlt_lc, PT.get(NX + c), pt);
+            T pt = ptr_[c];
+            if constexpr (C::ADAPT) pt = N::fma(dlt_lc, ptr_[NX + c], pt);
             p[c] = pt - rho_lc * w;
         }
-#pragma unroll(C::TU)
+#pragma unroll 1
         for (int i = NH - 2; i >= 0; --i) {
             T rr[NU], t[NU];
 #pragma unroll
             for (int a = 0; a < NU; ++a) {
                 const int e = i * NU + a;
-                T w = Z.get(e) - Y.get(e);
+                T lo, hi;
+                ubounds(e, pbu, lo, hi);
+                const T tz = TZ.get(e);
+                const T z = N::min(hi, N::max(lo, tz));
+                T w = (z + z) - tz;
                 if constexpr (C::CONSTR) w += SUT.get(e);
-                rr[a] = -URR.get(e) - rho_lc * w;
-                T acc = 0;
-#pragma unroll
-                for (int r = 0; r < NX; ++r) acc = N::fma(cB[r * NU + a], p[r], acc);
-                t[a] = acc + rr[a] + cBPf[a];
+                T ur = T(0);
+                if constexpr (C::REFS) ur = URR.get(e);
+                rr[a] = -ur - rho_lc * w;
             }
 #pragma unroll
-            for (int a = 0; a < NU; ++a) {
-                T acc = 0;
+            for (int a = 0; a < NU; ++a) t[a] = dot<NX>([&](int r) { return cp.BT[a * NX + r]; }, p, rr[a] + cp.BPf[a]);
 #pragma unroll
-                for (int b = 0; b < NU; ++b) acc = N::fma(cQuu[a * NU + b], t[b], acc);
-                D.set(i * NU + a, acc);
-            }
+            for (int a = 0; a < NU; ++a) D.set(i * NU + a, dot<NU>([&](int b) { return cp.Quu[a * NU + b]; }, t, T(0)));
             T pn[NX];
 #pragma unroll
             for (int c = 0; c < NX; ++c) {
                 const int e = i * NX + c;
-                T w = V.get(e) - G.get(e);
+                T lo, hi;
+                xbounds(e, pbx, lo, hi);
+                const T tv = TV.get(e);
+                const T v = N::min(hi, N::max(lo, tv));
+                T w = (v + v) - tv;
                 if constexpr (C::CONSTR) w += SXT.get(e);
-                const T q = -XRQ.get(e) - rho_lc * w;
-                T acc = 0;
-#pragma unroll
-                for (int r = 0; r < NX; ++r) acc = N::fma(cAK[c * NX + r], p[r], acc);
-                T kr = 0;
-#pragma unroll
-                for (int a = 0; a < NU; ++a) {
-                    T kc = cK[a * NX + c];
-                    if constexpr (C::ADAPT) kc = N::fma(dlt, cdK[a * NX + c], kc);
-                    kr = N::fma(kc, rr[a], kr);
-                }
-                pn[c] = (q + acc - kr) + cAPf[c];
+                T xq = T(0);
+                if constexpr (C::REFS) xq = XRQ.get(e);
+                const T q = -xq - rho_lc * w;
+                T acc = dot<NX>([&](int r) { return cp.AK[c * NX + r]; }, p, q + cp.APf[c]);
+                T kr = dot<NU>([&](int a) { return cp.KT[c * NU + a]; }, rr, T(0));
+                if constexpr (C::ADAPT) kr = N::fma(dlt, dot<NU>([&](int a) { return cp.dKT[c * NU + a]; }, rr, T(0)), kr);
+                pn[c] = acc - kr;
             }
 #pragma unroll
             for (int c = 0; c < NX; ++c) p[c] = pn[c];
