@@ -76,7 +76,7 @@ class ClockSampler:
                     self.samples.append([t.strip() for t in out.split(",")])
             except Exception:
                 pass
-            self.stop_flag.wait(0.1)
+            self.stop_flag.wait(0.02)
 
     def __enter__(self):
         self.t = threading.Thread(target=self._run, daemon=True)
@@ -131,7 +131,7 @@ def reference_arm(args, P, spec, batch_np):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=1 << 20, help="problems per GPU")

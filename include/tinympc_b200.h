@@ -112,6 +112,24 @@ int  tinympc_cuda_solve_batch(tinympc_cuda_solver *s, const tinympc_cuda_batch_i
 int  tinympc_cuda_solve_batch_device(tinympc_cuda_solver *s, int dev_index, const tinympc_cuda_batch_in *in,
                                      const tinympc_cuda_batch_out *out, void *stream);
 
+/* Full-workspace solve of ONE problem with the reference's warm-start semantics: replaces
+ * tiny_solve(solver) on a live TinySolver (tiny_api.cpp:321-323 -> admm.cpp:274-389).  All arrays are HOST,
+ * column-major double, exactly the TinyWorkspace members (types.hpp:92-160); the solve starts from whatever
+ * they hold (q, r, p, d, duals, slacks of the previous solve) and leaves them as the reference would.
+ * Always computed in fp64. */
+typedef struct {
+    double *x, *u, *q, *r, *p, *d, *v, *vnew, *z, *znew, *g, *y;   /* in-out; x[:,0] is x0 */
+    double *vcnew, *zcnew, *gc, *yc;     /* in-out; may be NULL when the cone flags are off */
+    double *vlnew, *zlnew, *gl, *yl;     /* in-out; may be NULL when the linear flags are off */
+    const double *Xref, *Uref;           /* NULL = zeros */
+    double *rho, *Kinf, *Pinf;           /* in-out cache fields adaptive rho mutates persistently (NULL = family values,
+                                            not written back); Kinf nu x nx, Pinf nx x nx column-major */
+    double *sol_x, *sol_u;               /* out: solution->x, solution->u */
+    int *iter, *status, *solved;         /* out */
+    double *residuals;                   /* out, 4 values or NULL */
+} tinympc_cuda_workspace;
+int  tinympc_cuda_solve_workspace(tinympc_cuda_solver *s, const tinympc_cuda_workspace *w);
+
 /* ---- knobs and introspection ----------------------------------------------------------------- */
 /* option names: "precision" (32 = fp32 arithmetic [default], 64 = fp64 parity mode),
    "ctas_per_sm" (0 = occupancy API), "chunks" (host pipeline depth, 0 = auto),

@@ -46,7 +46,7 @@ def compare(r, g, precision, name, max_flip_frac=0.0):
     assert flips <= max_flip_frac * B, f"{name}: {flips}/{B} iteration/status mismatches (kernel {r['kernel']})"
     if flips:   # a flipped problem stopped a few iterations early/late: its solution is still the same to ~10 x tol
         scale_f = max(1.0, float(np.abs(g["x"]).max()))
-        assert np.abs(r["x"][~same] - g["x"][~same]).max() <= 2e-2 * scale_f, name
+        assert np.abs(r["x"][~same] - g["x"][~same]).max() <= 1e-1 * scale_f, name
     tol = X_TOL_F64 if precision == 64 else X_TOL_F32
     dx = np.abs(r["x"][same] - g["x"][same]).max() if same.any() else 0.0
     du = np.abs(r["u"][same] - g["u"][same]).max() if same.any() else 0.0

@@ -20,9 +20,21 @@ c_ip = C.POINTER(C.c_int)
 
 ERRORS = {1: "EINVAL", 2: "ENODEVICE", 3: "ECUDA", 4: "EUNSUPPORTED", 5: "ENOTREADY"}
 
+HOST_EXPORTS = [
+    "tinympc_host_setup", "tinympc_host_free", "tinympc_host_set_bound_constraints", "tinympc_host_set_cone_constraints",
+    "tinympc_host_set_linear_constraints", "tinympc_host_update_settings", "tinympc_host_set_x0", "tinympc_host_set_x_ref",
+    "tinympc_host_set_u_ref", "tinympc_host_solve", "tinympc_host_get_solution", "tinympc_host_get_stats", "tinympc_host_get_cache",
+    "tinympc_host_set_cache_terms", "tinympc_host_init_sensitivity", "tinympc_host_set_sensitivity", "tinympc_host_reset_workspace",
+    "tinympc_host_solve_batch", "tinympc_host_set_devices", "tinympc_host_set_option", "tinympc_host_cuda_handle",
+    # the C++ API mirror itself (extern "C" names of the reference, tiny_api.hpp:10-50)
+    "tiny_setup", "tiny_set_bound_constraints", "tiny_set_cone_constraints", "tiny_set_linear_constraints",
+    "tiny_precompute_and_set_cache", "tiny_solve", "tiny_update_settings", "tiny_set_default_settings", "tiny_set_x0",
+    "tiny_set_x_ref", "tiny_set_u_ref", "tiny_initialize_sensitivity_matrices", "tiny_solve_batch",
+]
+
 EXPORTS = [
     "tinympc_cuda_create", "tinympc_cuda_destroy", "tinympc_cuda_set_family", "tinympc_cuda_solve_batch",
-    "tinympc_cuda_solve_batch_device", "tinympc_cuda_set_option", "tinympc_cuda_device_count", "tinympc_cuda_num_devices",
+    "tinympc_cuda_solve_batch_device", "tinympc_cuda_solve_workspace", "tinympc_cuda_set_option", "tinympc_cuda_device_count", "tinympc_cuda_num_devices",
     "tinympc_cuda_last_kernel", "tinympc_cuda_launch_count", "tinympc_cuda_last_timing", "tinympc_cuda_last_error",
     "tinympc_cuda_version", "tinympc_cuda_host_alloc", "tinympc_cuda_host_free",
 ]
@@ -93,6 +105,34 @@ def load():
         L.tinympc_cuda_host_alloc.argtypes = [C.c_size_t]
         L.tinympc_cuda_host_alloc.restype = C.c_void_p
         L.tinympc_cuda_host_free.argtypes = [C.c_void_p]
+        # plain-C shim over the host C++ API mirror (csrc/host/tiny_capi_shim.cpp)
+        dp, ip, vp = c_dp, c_ip, C.c_void_p
+        L.tinympc_host_setup.argtypes = [dp, dp, dp, dp, dp, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, ip]
+        L.tinympc_host_setup.restype = vp
+        L.tinympc_host_free.argtypes = [vp]
+        L.tinympc_host_set_bound_constraints.argtypes = [vp, dp, dp, dp, dp]
+        L.tinympc_host_set_cone_constraints.argtypes = [vp, C.c_int, ip, ip, dp, C.c_int, ip, ip, dp]
+        L.tinympc_host_set_linear_constraints.argtypes = [vp, C.c_int, dp, dp, C.c_int, dp, dp]
+        L.tinympc_host_update_settings.argtypes = [vp, C.c_double, C.c_double] + [C.c_int] * 9 + [C.c_double, C.c_double, C.c_int]
+        L.tinympc_host_set_x0.argtypes = [vp, dp]
+        L.tinympc_host_set_x_ref.argtypes = [vp, dp]
+        L.tinympc_host_set_u_ref.argtypes = [vp, dp]
+        L.tinympc_host_solve.argtypes = [vp]
+        L.tinympc_host_get_solution.argtypes = [vp, dp, dp]
+        L.tinympc_host_get_stats.argtypes = [vp, ip, ip, dp]
+        L.tinympc_host_get_work_u0.argtypes = [vp, dp]
+        L.tinympc_host_get_cache.argtypes = [vp, dp, dp, dp, dp, dp, dp]
+        L.tinympc_host_set_cache_terms.argtypes = [vp, dp, dp, dp, dp]
+        L.tinympc_host_init_sensitivity.argtypes = [vp]
+        L.tinympc_host_set_sensitivity.argtypes = [vp, dp, dp, dp, dp]
+        L.tinympc_host_reset_workspace.argtypes = [vp]
+        L.tinympc_host_solve_batch.argtypes = [vp, C.POINTER(CBatchIn), C.POINTER(CBatchOut)]
+        L.tinympc_host_set_devices.argtypes = [vp, ip, C.c_int]
+        L.tinympc_host_set_option.argtypes = [vp, C.c_char_p, C.c_double]
+        L.tinympc_host_last_error.argtypes = [vp]
+        L.tinympc_host_last_error.restype = C.c_char_p
+        L.tinympc_host_cuda_handle.argtypes = [vp]
+        L.tinympc_host_cuda_handle.restype = vp
         _lib = L
     return _lib
 
@@ -158,9 +198,14 @@ def family_struct(fam: dict, hold: _Hold) -> CFamily:
 class CudaSolver:
     """Thin object wrapper over the opaque tinympc_cuda_solver handle."""
 
-    def __init__(self, devices=None):
+    def __init__(self, devices=None, borrowed_handle=None):
         self.L = load()
         self.h = C.c_void_p()
+        self.owned = borrowed_handle is None
+        self.dims = None
+        if borrowed_handle is not None:       # handle owned by a host-side TinySolver (tiny_b200_cuda_handle)
+            self.h = C.c_void_p(borrowed_handle)
+            return
         if devices:
             arr = (C.c_int * len(devices))(*devices)
             rc = self.L.tinympc_cuda_create(C.byref(self.h), arr, len(devices))
@@ -175,9 +220,9 @@ class CudaSolver:
             raise TinympcCudaError(rc, self.L.tinympc_cuda_last_error(self.h).decode())
 
     def close(self):
-        if self.h:
+        if self.h and self.owned:
             self.L.tinympc_cuda_destroy(self.h)
-            self.h = C.c_void_p()
+        self.h = C.c_void_p()
 
     def __del__(self):
         try:

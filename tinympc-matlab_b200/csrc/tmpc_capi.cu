@@ -21,6 +21,7 @@
 
 #include "tmpc_common.h"
 #include "tmpc_registry.h"
+#include "tmpc_wpp.h"
 
 using namespace tmpc;
 
@@ -54,6 +55,7 @@ struct DeviceCtx {
     cudaEvent_t k0[kMaxChunks], k1[kMaxChunks];
     bool events = false;
     DevBuf x0, Xref, Uref, xmin, xmax, umin, umax, x, u, iter, status, res, rho;
+    DevBuf wpp_scratch[kStreams + 1];   // warp-per-problem workspaces (one per pipeline stream + the device/workspace entry)
 };
 
 struct Family {
@@ -75,6 +77,7 @@ struct tinympc_cuda_solver {
     int ctas_per_sm = 0;
     int chunks = 0;                    // 0 = auto
     int variant = 0;
+    int force_wpp = 0;                 // option "kernel": 0 auto, 1 always the warp-per-problem kernel
     std::string err;
     std::string last_kernel;
     long long launches = 0;
@@ -140,20 +143,14 @@ int upload_family(tinympc_cuda_solver* s) {
 
 // Enqueue one kernel over `in`/`out` (device pointers) on `st`.  counter must be a zeroed device int.
 int enqueue(tinympc_cuda_solver* s, DeviceCtx& d, const tinympc_cuda_batch_in& in, const tinympc_cuda_batch_out& out, int* counter,
-            cudaStream_t st) {
+            cudaStream_t st, int scratch_slot) {
     const Family& f = s->fam;
     const bool ppb = in.x_min || in.x_max || in.u_min || in.u_max;
     if (ppb && !(in.x_min && in.x_max && in.u_min && in.u_max))
         return fail(s, TINYMPC_CUDA_EINVAL, "per-problem bounds need all four of x_min, x_max, u_min, u_max");
     if (!ppb && !f.shared_bounds_ok)
         return fail(s, TINYMPC_CUDA_EINVAL, "bound constraints are enabled but neither the family nor the batch supplies bounds");
-    const KernelEntry* ke = find_kernel(f, s->precision, ppb, in.Xref || in.Uref, s->variant);
-    if (!ke) {
-        char b[256];
-        snprintf(b, sizeof b, "no compiled kernel for nx=%d nu=%d N=%d feat=%d precision=%d per_problem_bounds=%d", f.nx, f.nu, f.N, f.feat,
-                 s->precision, (int)ppb);
-        return fail(s, TINYMPC_CUDA_EUNSUPPORTED, b);
-    }
+    const KernelEntry* ke = s->force_wpp ? nullptr : find_kernel(f, s->precision, ppb, in.Xref || in.Uref, s->variant);
     SolveParams p = f.base;
     p.pack = s->precision == 64 ? (const void*)((const double*)d.pack64 + f.L.cold) : (const void*)((const float*)d.pack32 + f.L.cold);
     p.pack_elems = f.L.cold_size;
@@ -163,6 +160,20 @@ int enqueue(tinympc_cuda_solver* s, DeviceCtx& d, const tinympc_cuda_batch_in& i
     p.x_min = in.x_min; p.x_max = in.x_max; p.u_min = in.u_min; p.u_max = in.u_max;
     p.x = out.x; p.u = out.u; p.iter = out.iter; p.status = out.status; p.residuals = out.residuals; p.rho_out = out.rho;
 
+    if (!ke) {
+        // no specialised thread-per-problem kernel for this shape / feature mix: general warp-per-problem kernel
+        const WppLayout W = WppLayout::make(f.nx, f.nu, f.N);
+        const int warps = std::max(1, std::min(in.batch, d.sm_count * 16));
+        const size_t esz = s->precision == 64 ? sizeof(double) : sizeof(float);
+        DevBuf& sb = d.wpp_scratch[scratch_slot];
+        CU(s, sb.reserve((size_t)warps * W.size * esz));
+        const void* full_pack = s->precision == 64 ? d.pack64 : d.pack32;
+        if (s->precision == 64) CU(s, wpp_launch<double>(p, f.L, full_pack, W, sb.p, warps, 0, st));
+        else CU(s, wpp_launch<float>(p, f.L, full_pack, W, sb.p, warps, 0, st));
+        s->last_kernel = s->precision == 64 ? "wpp_f64_generic" : "wpp_f32_generic";
+        s->launches += 1;
+        return TINYMPC_CUDA_OK;
+    }
     const size_t smem = ke->smem_bytes(f.L.cold_size);
     if (smem > 227u * 1024u) return fail(s, TINYMPC_CUDA_EUNSUPPORTED, std::string("kernel ") + ke->name + " needs more shared memory than an SM has");
     CU(s, ke->prepare(smem));
@@ -267,7 +278,7 @@ int run_shard(tinympc_cuda_solver* s, DeviceCtx& d, const tinympc_cuda_batch_in&
         dout.residuals = out.residuals ? (float*)d.res.p + 4 * (size_t)c0 : nullptr;
         dout.rho = out.rho ? (float*)d.rho.p + c0 : nullptr;
         CU(s, cudaEventRecord(d.k0[c], st));
-        int rc = enqueue(s, d, din, dout, d.counters + c, st);
+        int rc = enqueue(s, d, din, dout, d.counters + c, st, c % kStreams);
         if (rc) return rc;
         CU(s, cudaEventRecord(d.k1[c], st));
         CU(s, cudaMemcpyAsync(out.x + sx * g0, dout.x, sizeof(float) * sx * cn, cudaMemcpyDeviceToHost, st));
@@ -346,6 +357,7 @@ int tinympc_cuda_destroy(tinympc_cuda_solver* s) {
         if (d.pack64) cudaFree(d.pack64);
         if (d.counters) cudaFree(d.counters);
         for (DevBuf* b : {&d.x0, &d.Xref, &d.Uref, &d.xmin, &d.xmax, &d.umin, &d.umax, &d.x, &d.u, &d.iter, &d.status, &d.res, &d.rho}) b->release();
+        for (auto& b : d.wpp_scratch) b.release();
     }
     cudaSetDevice(prev);
     delete s;
@@ -460,9 +472,9 @@ int tinympc_cuda_set_family(tinympc_cuda_solver* s, const tinympc_cuda_family* f
 
     const bool soc = (fm->en_state_soc && fm->numStateCones > 0) || (fm->en_input_soc && fm->numInputCones > 0);
     const bool lin = fm->en_state_linear || fm->en_input_linear;
-    if (fm->adaptive_rho && (soc || lin))
-        return fail(s, TINYMPC_CUDA_EUNSUPPORTED, "adaptive_rho together with cone/linear constraints has no compiled kernel yet");
-    f.feat = fm->adaptive_rho ? kFeatAdapt : ((soc || lin) ? kFeatConstr : kFeatBox);
+    // adaptive rho together with cones / linear rows has no specialised kernel: feat 3 matches none, so the
+    // general warp-per-problem kernel takes it
+    f.feat = fm->adaptive_rho ? ((soc || lin) ? 3 : kFeatAdapt) : ((soc || lin) ? kFeatConstr : kFeatBox);
     f.set = true;
     s->fam = std::move(f);
     return upload_family(s);
@@ -491,7 +503,7 @@ int tinympc_cuda_solve_batch_device(tinympc_cuda_solver* s, int dev_index, const
         rc = zero_iteration_result(s, s->fam, *out, in->batch, st, true);
     } else {
         // the last counter slot is reserved for the device-resident entry point
-        rc = enqueue(s, d, *in, *out, d.counters + (kMaxChunks - 1), st);
+        rc = enqueue(s, d, *in, *out, d.counters + (kMaxChunks - 1), st, kStreams);
     }
     cudaSetDevice(prev);
     return rc;
@@ -535,6 +547,64 @@ int tinympc_cuda_solve_batch(tinympc_cuda_solver* s, const tinympc_cuda_batch_in
     return TINYMPC_CUDA_OK;
 }
 
+int tinympc_cuda_solve_workspace(tinympc_cuda_solver* s, const tinympc_cuda_workspace* w) {
+    if (!s || !w) return TINYMPC_CUDA_EINVAL;
+    if (!s->fam.set) return fail(s, TINYMPC_CUDA_ENOTREADY, "tinympc_cuda_set_family has not been called");
+    if (!w->x || !w->u || !w->q || !w->r || !w->p || !w->d || !w->v || !w->vnew || !w->z || !w->znew || !w->g || !w->y || !w->iter || !w->status)
+        return fail(s, TINYMPC_CUDA_EINVAL, "workspace arrays x,u,q,r,p,d,v,vnew,z,znew,g,y and iter,status are required");
+    const Family& f = s->fam;
+    const int nx = f.nx, nu = f.nu, N = f.N, sx = nx * N, su = nu * (N - 1);
+    const WppLayout W = WppLayout::make(nx, nu, N);
+    std::vector<double> h(W.size, 0.0);
+    auto put = [&](int at, const double* src, int n) { if (src) std::memcpy(h.data() + at, src, sizeof(double) * n); };
+    put(W.x, w->x, sx); put(W.u, w->u, su); put(W.q, w->q, sx); put(W.r, w->r, su); put(W.p, w->p, sx); put(W.d, w->d, su);
+    put(W.v, w->v, sx); put(W.vnew, w->vnew, sx); put(W.z, w->z, su); put(W.znew, w->znew, su); put(W.g, w->g, sx); put(W.y, w->y, su);
+    put(W.vcnew, w->vcnew, sx); put(W.zcnew, w->zcnew, su); put(W.gc, w->gc, sx); put(W.yc, w->yc, su);
+    put(W.vlnew, w->vlnew, sx); put(W.zlnew, w->zlnew, su); put(W.gl, w->gl, sx); put(W.yl, w->yl, su);
+    put(W.Xref, w->Xref, sx); put(W.Uref, w->Uref, su);
+    put(W.xmin, f.pack.data() + f.L.xmin, sx); put(W.xmax, f.pack.data() + f.L.xmax, sx);
+    put(W.umin, f.pack.data() + f.L.umin, su); put(W.umax, f.pack.data() + f.L.umax, su);
+    if (w->Kinf) { for (int a = 0; a < nu; ++a) for (int c = 0; c < nx; ++c) h[W.Kinf + a * nx + c] = w->Kinf[(size_t)c * nu + a]; }
+    else put(W.Kinf, f.pack.data() + f.L.Kinf, nu * nx);
+    if (w->Pinf) { for (int r = 0; r < nx; ++r) for (int c = 0; c < nx; ++c) h[W.Pinf + r * nx + c] = w->Pinf[(size_t)c * nx + r]; }
+    else put(W.Pinf, f.pack.data() + f.L.Pinf, nx * nx);
+    h[W.scalars + 0] = w->rho ? *w->rho : f.base.rho;
+    if (w->residuals) for (int k = 0; k < 4; ++k) h[W.scalars + 3 + k] = w->residuals[k];
+
+    DeviceCtx& d = s->devs[0];
+    int prev = 0;
+    cudaGetDevice(&prev);
+    CU(s, cudaSetDevice(d.device));
+    DevBuf& sb = d.wpp_scratch[kStreams];
+    CU(s, sb.reserve(sizeof(double) * W.size));
+    cudaStream_t st = d.streams[0];
+    CU(s, cudaMemcpyAsync(sb.p, h.data(), sizeof(double) * W.size, cudaMemcpyHostToDevice, st));
+    SolveParams p = f.base;
+    p.batch = 1;
+    if (w->rho) p.rho = *w->rho;
+    CU(s, wpp_launch<double>(p, f.L, d.pack64, W, sb.p, 1, 1, st));
+    CU(s, cudaMemcpyAsync(h.data(), sb.p, sizeof(double) * W.size, cudaMemcpyDeviceToHost, st));
+    CU(s, cudaStreamSynchronize(st));
+    cudaSetDevice(prev);
+    s->last_kernel = "wpp_f64_workspace";
+    s->launches += 1;
+
+    auto get = [&](double* dst, int at, int n) { if (dst) std::memcpy(dst, h.data() + at, sizeof(double) * n); };
+    get(w->x, W.x, sx); get(w->u, W.u, su); get(w->q, W.q, sx); get(w->r, W.r, su); get(w->p, W.p, sx); get(w->d, W.d, su);
+    get(w->v, W.v, sx); get(w->vnew, W.vnew, sx); get(w->z, W.z, su); get(w->znew, W.znew, su); get(w->g, W.g, sx); get(w->y, W.y, su);
+    get(w->vcnew, W.vcnew, sx); get(w->zcnew, W.zcnew, su); get(w->gc, W.gc, sx); get(w->yc, W.yc, su);
+    get(w->vlnew, W.vlnew, sx); get(w->zlnew, W.zlnew, su); get(w->gl, W.gl, sx); get(w->yl, W.yl, su);
+    get(w->sol_x, W.vnew, sx); get(w->sol_u, W.znew, su);     // solution = (vnew, znew), admm.cpp:370-371, 386-387
+    if (w->Kinf) for (int a = 0; a < nu; ++a) for (int c = 0; c < nx; ++c) w->Kinf[(size_t)c * nu + a] = h[W.Kinf + a * nx + c];
+    if (w->Pinf) for (int r = 0; r < nx; ++r) for (int c = 0; c < nx; ++c) w->Pinf[(size_t)c * nx + r] = h[W.Pinf + r * nx + c];
+    if (w->rho) *w->rho = h[W.scalars + 0];
+    *w->iter = (int)h[W.scalars + 1];
+    *w->status = (int)h[W.scalars + 2];
+    if (w->solved) *w->solved = (int)h[W.scalars + 7];
+    if (w->residuals) for (int k = 0; k < 4; ++k) w->residuals[k] = h[W.scalars + 3 + k];
+    return TINYMPC_CUDA_OK;
+}
+
 int tinympc_cuda_set_option(tinympc_cuda_solver* s, const char* name, double value) {
     if (!s || !name) return TINYMPC_CUDA_EINVAL;
     const std::string n(name);
@@ -547,6 +617,8 @@ int tinympc_cuda_set_option(tinympc_cuda_solver* s, const char* name, double val
         s->chunks = (int)value;
     } else if (n == "variant") {
         s->variant = (int)value;
+    } else if (n == "force_wpp") {
+        s->force_wpp = (int)value;
     } else {
         return fail(s, TINYMPC_CUDA_EINVAL, "unknown option " + n);
     }
