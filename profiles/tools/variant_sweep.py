@@ -46,8 +46,8 @@ def run(p, scale, B, variants, precision=32, reps=3):
 
 if __name__ == "__main__":
     B = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 20
-    run(P.quadrotor(), 0.3, B, [0])
-    run(P.quadrotor(), 1.0, B, [0])
+    run(P.quadrotor(), 0.3, B, [0, 1])
+    run(P.quadrotor(), 1.0, B, [0, 1])
     run(P.cartpole(), 0.3, B, [0])
     run(P.cartpole(), 1.0, B, [0])
     run(P.rocket(), 1.0, B // 4, [0])

@@ -55,6 +55,7 @@ struct DeviceCtx {
     cudaEvent_t k0[kMaxChunks], k1[kMaxChunks];
     bool events = false;
     DevBuf x0, Xref, Uref, xmin, xmax, umin, umax, x, u, iter, status, res, rho;
+    DevBuf ref_scratch[kStreams + 1];   // REFS_L2 kernels: per-slot reference terms
     DevBuf wpp_scratch[kStreams + 1];   // warp-per-problem workspaces (one per pipeline stream + the device/workspace entry)
 };
 
@@ -63,6 +64,7 @@ struct Family {
     int nx = 0, nu = 0, N = 0;
     int feat = kFeatBox;
     bool shared_bounds_ok = false;     // every enabled bound has shared arrays
+    bool fastbox = false;              // shared bounds are constant over the horizon and contain 0
     PackLayout L{};
     std::vector<double> pack;          // double master copy
     SolveParams base{};                // settings + cone specs, pointers empty
@@ -115,8 +117,9 @@ const KernelEntry* find_kernel(const Family& f, int bits, bool ppb, bool refs, i
     for (int pass = 0; pass < 2; ++pass) {   // pass 1: a reference-storing kernel also serves a reference-free batch
         for (int i = 0; i < n; ++i) {
             const KernelEntry* e = tab[i];
+            if (e->fastbox && (!f.fastbox || ppb)) continue;      // table order puts the fast-box instances first
             if (e->family == KF_TPP && e->nx == f.nx && e->nu == f.nu && e->N == f.N && e->feat == f.feat && e->dtype_bits == bits &&
-                e->ppb == (ppb ? 1 : 0) && e->variant == variant && (e->refs == (refs ? 1 : 0) || (pass == 1 && e->refs == 1)))
+                e->ppb == (ppb ? 1 : 0) && e->variant == variant && ((e->refs != 0) == refs || (pass == 1 && e->refs != 0)))
                 return e;
         }
     }
@@ -185,6 +188,12 @@ int enqueue(tinympc_cuda_solver* s, DeviceCtx& d, const tinympc_cuda_batch_in& i
     const int need = (in.batch + ke->block - 1) / ke->block;
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
+    if (ke->refs == 2) {   // reference terms live in a lane-interleaved global scratch that stays L2 resident
+        DevBuf& rb = d.ref_scratch[scratch_slot];
+        const size_t esz = s->precision == 64 ? sizeof(double) : sizeof(float);
+        CU(s, rb.reserve((size_t)grid * ke->block * ((size_t)f.nx * f.N + (size_t)f.nu * (f.N - 1)) * esz));
+        p.ref_scratch = rb.p;
+    }
     CU(s, cudaMemsetAsync(counter, 0, sizeof(int), st));
     CU(s, ke->launch(p, grid, smem, st, f.pack.data(), f.L));
     s->last_kernel = ke->name;
@@ -358,6 +367,7 @@ int tinympc_cuda_destroy(tinympc_cuda_solver* s) {
         if (d.counters) cudaFree(d.counters);
         for (DevBuf* b : {&d.x0, &d.Xref, &d.Uref, &d.xmin, &d.xmax, &d.umin, &d.umax, &d.x, &d.u, &d.iter, &d.status, &d.res, &d.rho}) b->release();
         for (auto& b : d.wpp_scratch) b.release();
+        for (auto& b : d.ref_scratch) b.release();
     }
     cudaSetDevice(prev);
     delete s;
@@ -439,6 +449,13 @@ int tinympc_cuda_set_family(tinympc_cuda_solver* s, const tinympc_cuda_family* f
         f.pack[L.umax + e] = (ib && have_ib) ? fm->u_max[e] : inf;
     }
     f.shared_bounds_ok = (!sb || have_sb) && (!ib || have_ib);
+    f.fastbox = true;
+    for (int e = 0; e < nx * N && f.fastbox; ++e)
+        f.fastbox = f.pack[L.xmin + e] == f.pack[L.xmin + e % nx] && f.pack[L.xmax + e] == f.pack[L.xmax + e % nx] &&
+                    f.pack[L.xmin + e] <= 0.0 && f.pack[L.xmax + e] >= 0.0;
+    for (int e = 0; e < nu * (N - 1) && f.fastbox; ++e)
+        f.fastbox = f.pack[L.umin + e] == f.pack[L.umin + e % nu] && f.pack[L.umax + e] == f.pack[L.umax + e % nu] &&
+                    f.pack[L.umin + e] <= 0.0 && f.pack[L.umax + e] >= 0.0;
     // linear rows + squared norms (project_hyperplane, admm.cpp:70-73)
     for (int k = 0; k < nsl; ++k) {
         double nr = 0;

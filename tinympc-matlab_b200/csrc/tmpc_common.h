@@ -70,6 +70,7 @@ struct SolveParams {
     int pack_elems;            // PackLayout::cold_size
     int batch;
     int* work_counter;         // device int, zeroed before launch: next unclaimed problem index
+    void* ref_scratch;         // REFS_L2 kernels: grid*block*(nx*N+nu*(N-1)) elements of the kernel scalar type
     // per-problem inputs (device pointers, float32); NULL where noted
     const float* x0;           // batch*nx
     const float* Xref;         // batch*nx*N      or NULL (zeros)

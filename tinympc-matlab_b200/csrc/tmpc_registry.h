@@ -16,8 +16,9 @@ struct KernelEntry {
     int nx, nu, N;       // 0 = any (runtime-sized kernel)
     int feat;            // FEAT_BOX / FEAT_CONSTR / FEAT_ADAPT
     int dtype_bits;      // 32 or 64
-    int refs;            // 1: stores per-problem Xref/Uref terms; 0: reference-free variant (Xref = Uref = NULL)
+    int refs;            // 0: reference-free variant (Xref = Uref = NULL); 1: reference terms in shared memory; 2: in an L2-resident scratch
     int ppb;             // per-problem bounds variant
+    int fastbox;         // 1: requires shared bounds that are constant over the horizon and contain 0
     int block;           // threads per CTA
     int variant;         // tuning variant (0 = default); selected with the "variant" option
     size_t (*smem_bytes)(int pack_elems);
@@ -49,7 +50,7 @@ const KernelEntry* const* kernel_table(int* count);   // defined in gen/tmpc_tab
         tpp_kernel<CFG><<<grid, CFG::BLOCK, smem, st>>>(p, cpk);                                                    \
         return cudaGetLastError();                                                                                  \
     }                                                                                                               \
-    extern const KernelEntry SYM = {#SYM, KF_TPP, CFG::NX, CFG::NU, CFG::NH, FEATV, BITS, CFG::REFS ? 1 : 0,        \
-                                    CFG::PPB ? 1 : 0, CFG::BLOCK, VAR, SYM##_smem, SYM##_prepare, SYM##_occ,        \
+    extern const KernelEntry SYM = {#SYM, KF_TPP, CFG::NX, CFG::NU, CFG::NH, FEATV, BITS, CFG::REFMODE,             \
+                                    CFG::PPB ? 1 : 0, CFG::FB ? 1 : 0, CFG::BLOCK, VAR, SYM##_smem, SYM##_prepare, SYM##_occ,        \
                                     SYM##_launch};                                                                  \
     }

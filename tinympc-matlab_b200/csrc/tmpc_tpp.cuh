@@ -83,7 +83,7 @@ struct ConstPack {
     T B[NX * NU];
     T BT[NU * NX];     // B'  (backward: B' p)
     T K[NU * NX];      // Kinf (forward)
-    T KT[NX * NU];     // Kinf' (backward: Kinf' r)
+    T KT[NX * NU];     // -Kinf' (backward: - Kinf' r, negated so that it chains into the AmBKt accumulation)
     T AK[NX * NX];     // AmBKt
     T Quu[NU * NU];
     T f[NX], APf[NX], BPf[NU];
@@ -101,10 +101,11 @@ inline void fill_const_pack(ConstPack<T, NX, NU, NH, ADAPT>& c, const double* pk
     };
     cp(c.A, L.A, NX * NX); cp(c.B, L.B, NX * NU); tr(c.BT, L.B, NX, NU);
     cp(c.K, L.Kinf, NU * NX); tr(c.KT, L.Kinf, NU, NX);
+    for (int i = 0; i < NX * NU; ++i) c.KT[i] = -c.KT[i];
     cp(c.AK, L.AmBKt, NX * NX); cp(c.Quu, L.Quu_inv, NU * NU);
     cp(c.f, L.f, NX); cp(c.APf, L.APf, NX); cp(c.BPf, L.BPf, NU); cp(c.Qd, L.Qd, NX); cp(c.Rd, L.Rd, NU);
     cp(c.xmin, L.xmin, NX * NH); cp(c.xmax, L.xmax, NX * NH); cp(c.umin, L.umin, NU * (NH - 1)); cp(c.umax, L.umax, NU * (NH - 1));
-    if (ADAPT) { cp(c.dK, L.dKinf, NU * NX); tr(c.dKT, L.dKinf, NU, NX); tr(c.AT, L.A, NX, NX); }
+    if (ADAPT) { cp(c.dK, L.dKinf, NU * NX); tr(c.dKT, L.dKinf, NU, NX); tr(c.AT, L.A, NX, NX); for (int i = 0; i < NX * NU; ++i) c.dKT[i] = -c.dKT[i]; }
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -118,23 +119,31 @@ struct Col {
     __device__ __forceinline__ void set(int i, T v) { base[i * BLOCK] = v; }
 };
 
-template <typename T_, int NX_, int NU_, int NH_, int FEAT_, int BLOCK_, bool REFS_, bool PPB_, int MINB_ = 1>
+enum : int { REFS_NONE = 0, REFS_SMEM = 1, REFS_L2 = 2 };
+
+template <typename T_, int NX_, int NU_, int NH_, int FEAT_, int BLOCK_, int REFS_, bool PPB_, int MINB_ = 1, bool FB_ = false>
 struct TppCfg {
     using T = T_;
     static constexpr int NX = NX_, NU = NU_, NH = NH_, FEAT = FEAT_, BLOCK = BLOCK_, MINB = MINB_;
-    static constexpr bool REFS = REFS_;                     // per-problem Xref/Uref present
+    static constexpr int REFMODE = REFS_;                   // where the per-problem reference terms live
+    static constexpr bool REFS = REFS_ != REFS_NONE;        // per-problem Xref/Uref present
+    static constexpr bool REFS_SM = REFS_ == REFS_SMEM;     // ... in shared-memory columns
+    static constexpr bool REFS_G = REFS_ == REFS_L2;        // ... in an L2-resident, lane-interleaved global scratch
     static constexpr bool PPB = PPB_;                       // per-problem bounds read from global memory
+    static constexpr bool FB = FB_ && !PPB_;                // "fast box": shared bounds are time-invariant and contain 0
     static constexpr bool CONSTR = FEAT_ == FEAT_CONSTR;
     static constexpr bool ADAPT = FEAT_ == FEAT_ADAPT;
     static constexpr int SX = NX * NH, SU = NU * (NH - 1);
     using CPack = ConstPack<T_, NX_, NU_, NH_, ADAPT>;
+    static constexpr int VX = (NX_ % 4 == 0) ? 4 : ((NX_ % 2 == 0) ? 2 : 1);   // REFS_L2: elements per vector load
+    static constexpr int VU = (NU_ % 4 == 0) ? 4 : ((NU_ % 2 == 0) ? 2 : 1);
     // element offsets of the shared-memory columns
     static constexpr int oTV = 0;
     static constexpr int oTZ = oTV + SX;
     static constexpr int oD = oTZ + SU;
     static constexpr int oXRQ = oD + SU;
-    static constexpr int oURR = oXRQ + (REFS ? SX : 0);
-    static constexpr int oGC = oURR + (REFS ? SU : 0);
+    static constexpr int oURR = oXRQ + (REFS_SM ? SX : 0);
+    static constexpr int oGC = oURR + (REFS_SM ? SU : 0);
     static constexpr int oGL = oGC + (CONSTR ? SX : 0);
     static constexpr int oSX = oGL + (CONSTR ? SX : 0);
     static constexpr int oYC = oSX + (CONSTR ? SX : 0);
@@ -181,6 +190,28 @@ __device__ __forceinline__ double dot(FM&& m, const double (&x)[C], double init)
     double acc = init;
 #pragma unroll
     for (int c = 0; c < C; ++c) acc = ::fma(m(c), x[c], acc);
+    return acc;
+}
+
+// init + sum_c m1(c) x1[c] + sum_c m2(c) x2[c] in ONE accumulation chain (one pair-sum instead of two)
+template <int C1, int C2, typename F1, typename F2>
+__device__ __forceinline__ float dot2(F1&& m1, const float (&x1)[C1], F2&& m2, const float (&x2)[C2], float init) {
+    float2 acc = make_float2(init, 0.f);
+#pragma unroll
+    for (int c = 0; c + 1 < C1; c += 2) acc = __ffma2_rn(make_float2(m1(c), m1(c + 1)), make_float2(x1[c], x1[c + 1]), acc);
+#pragma unroll
+    for (int c = 0; c + 1 < C2; c += 2) acc = __ffma2_rn(make_float2(m2(c), m2(c + 1)), make_float2(x2[c], x2[c + 1]), acc);
+    if constexpr (C1 & 1) acc.x = fmaf(m1(C1 - 1), x1[C1 - 1], acc.x);
+    if constexpr (C2 & 1) acc.y = fmaf(m2(C2 - 1), x2[C2 - 1], acc.y);
+    return acc.x + acc.y;
+}
+template <int C1, int C2, typename F1, typename F2>
+__device__ __forceinline__ double dot2(F1&& m1, const double (&x1)[C1], F2&& m2, const double (&x2)[C2], double init) {
+    double acc = init;
+#pragma unroll
+    for (int c = 0; c < C1; ++c) acc = ::fma(m1(c), x1[c], acc);
+#pragma unroll
+    for (int c = 0; c < C2; ++c) acc = ::fma(m2(c), x2[c], acc);
     return acc;
 }
 
@@ -245,6 +276,15 @@ __device__ __forceinline__ void project_soc_col(T* scr, int start, int dim, floa
     }
 }
 
+// vector type of V elements of T for the lane-interleaved scratch
+template <typename T, int V> struct VecOf;
+template <> struct VecOf<float, 4> { using type = float4; static __device__ __forceinline__ void unpack(const float4& v, float* d) { d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w; } };
+template <> struct VecOf<float, 2> { using type = float2; static __device__ __forceinline__ void unpack(const float2& v, float* d) { d[0] = v.x; d[1] = v.y; } };
+template <> struct VecOf<float, 1> { using type = float; static __device__ __forceinline__ void unpack(const float& v, float* d) { d[0] = v; } };
+template <> struct VecOf<double, 4> { using type = double4; static __device__ __forceinline__ void unpack(const double4& v, double* d) { d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w; } };
+template <> struct VecOf<double, 2> { using type = double2; static __device__ __forceinline__ void unpack(const double2& v, double* d) { d[0] = v.x; d[1] = v.y; } };
+template <> struct VecOf<double, 1> { using type = double; static __device__ __forceinline__ void unpack(const double& v, double* d) { d[0] = v; } };
+
 template <class C>
 __global__ void __launch_bounds__(C::BLOCK, C::MINB)
 tpp_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ typename C::CPack cp) {
@@ -283,6 +323,43 @@ tpp_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ type
     Col<T, C::oSU, BLOCK> SUT(colbase);
     T* scr = colbase + C::oSCR * BLOCK;     // cone scratch column (CONSTR only)
 
+    // REFS_L2: reference terms in a global scratch laid out [element / V][slot][V] (V = 4/2/1 elements per lane and
+    // load): coalesced across lanes, one vector load per V elements, re-read every iteration out of L2
+    const size_t slots = (size_t)gridDim.x * BLOCK;
+    const size_t slot = (size_t)blockIdx.x * BLOCK + threadIdx.x;
+    T* const gxr = static_cast<T*>(prm.ref_scratch) + slot * C::VX;
+    T* const gur = static_cast<T*>(prm.ref_scratch) + (size_t)SXL * slots + slot * C::VU;
+    auto xrq_set = [&](int e, T v) { if constexpr (C::REFS_G) gxr[(size_t)(e / C::VX) * slots * C::VX + (e % C::VX)] = v; else XRQ.set(e, v); };
+    auto urr_set = [&](int e, T v) { if constexpr (C::REFS_G) gur[(size_t)(e / C::VU) * slots * C::VU + (e % C::VU)] = v; else URR.set(e, v); };
+    // fetch the NX (NU) reference terms of time step i
+    auto xrq_step = [&](int i, T (&dst)[NX]) {
+        if constexpr (C::REFS_G) {
+            using V = typename VecOf<T, C::VX>::type;
+#pragma unroll
+            for (int k = 0; k < NX / C::VX; ++k) {
+                const V v = *reinterpret_cast<const V*>(gxr + (size_t)(i * (NX / C::VX) + k) * slots * C::VX);
+                VecOf<T, C::VX>::unpack(v, &dst[k * C::VX]);
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < NX; ++c) dst[c] = XRQ.get(i * NX + c);
+        }
+    };
+    auto urr_step = [&](int i, T (&dst)[NU]) {
+        if constexpr (C::REFS_G) {
+            using V = typename VecOf<T, C::VU>::type;
+#pragma unroll
+            for (int k = 0; k < NU / C::VU; ++k) {
+                const V v = *reinterpret_cast<const V*>(gur + (size_t)(i * (NU / C::VU) + k) * slots * C::VU);
+                VecOf<T, C::VU>::unpack(v, &dst[k * C::VU]);
+            }
+        } else {
+#pragma unroll
+            for (int a = 0; a < NU; ++a) dst[a] = URR.get(i * NU + a);
+        }
+    };
+    (void)slots; (void)slot;
+
     const T* cP = pack + SP::Pinf;
     const T* cdP = pack + SP::dPinf;
 
@@ -317,17 +394,21 @@ tpp_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ type
     for (int r = 0; r < NX; ++r) { x0r[r] = 0; ptr_[r] = 0; if constexpr (C::ADAPT) ptr_[NX + r] = 0; }
 
     // box bounds of trajectory element e (state) / (input)
-    auto xbounds = [&](int e, size_t pb, T& lo, T& hi) {
+    auto xbounds = [&](int i, int r, size_t pb, T& lo, T& hi) {
+        const int e = i * NX + r; (void)e;
         if constexpr (C::PPB) {
             lo = en_sb ? static_cast<T>(__ldg(prm.x_min + pb + e)) : -N::inf();
             hi = en_sb ? static_cast<T>(__ldg(prm.x_max + pb + e)) : N::inf();
-        } else { lo = cp.xmin[e]; hi = cp.xmax[e]; }
+        } else if constexpr (C::FB) { lo = cp.xmin[r]; hi = cp.xmax[r]; }
+        else { lo = cp.xmin[e]; hi = cp.xmax[e]; }
     };
-    auto ubounds = [&](int e, size_t pb, T& lo, T& hi) {
+    auto ubounds = [&](int i, int a, size_t pb, T& lo, T& hi) {
+        const int e = i * NU + a; (void)e;
         if constexpr (C::PPB) {
             lo = en_ib ? static_cast<T>(__ldg(prm.u_min + pb + e)) : -N::inf();
             hi = en_ib ? static_cast<T>(__ldg(prm.u_max + pb + e)) : N::inf();
-        } else { lo = cp.umin[e]; hi = cp.umax[e]; }
+        } else if constexpr (C::FB) { lo = cp.umin[a]; hi = cp.umax[a]; }
+        else { lo = cp.umin[e]; hi = cp.umax[e]; }
     };
 
     for (;;) {
@@ -354,17 +435,21 @@ tpp_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ type
                         // Xref -> XRQ = Xref .* Q (work->Q = diag(Q)+rho, admm.cpp:218) and the terminal
                         // term PT = -(xref_N' Pinf)' (admm.cpp:238)
                         if constexpr (C::REFS) {
+                            // one time step per (rolled) trip keeps the number of loads in flight -- and registers -- small
                             T xr_last[NX];
 #pragma unroll
                             for (int r = 0; r < NX; ++r) xr_last[r] = 0;
                             if (prm.Xref) {
-                                load_chunk<SXL>(prm.Xref + (size_t)prob * SXL, [&](int e, float v) {
-                                    XRQ.set(e, static_cast<T>(v) * cp.Qd[e % NX]);
-                                    if (e >= SXL - NX) xr_last[e - (SXL - NX)] = static_cast<T>(v);
-                                });
+                                const float* src = prm.Xref + (size_t)prob * SXL;
+#pragma unroll 1
+                                for (int i = 0; i < NH; ++i)
+                                    load_chunk<NX>(src + i * NX, [&](int r, float v) {
+                                        xrq_set(i * NX + r, static_cast<T>(v) * cp.Qd[r]);
+                                        xr_last[r] = static_cast<T>(v);      // after the last trip: xref_N
+                                    });
                             } else {
 #pragma unroll 4
-                                for (int e = 0; e < SXL; ++e) XRQ.set(e, T(0));
+                                for (int e = 0; e < SXL; ++e) xrq_set(e, T(0));
                             }
 #pragma unroll
                             for (int c = 0; c < NX; ++c) {
@@ -378,11 +463,13 @@ tpp_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ type
                                 if constexpr (C::ADAPT) ptr_[NX + c] = -acc1;
                             }
                             if (prm.Uref) {
-                                load_chunk<SUL>(prm.Uref + (size_t)prob * SUL,
-                                                [&](int e, float v) { URR.set(e, static_cast<T>(v) * cp.Rd[e % NU]); });
+                                const float* src = prm.Uref + (size_t)prob * SUL;
+#pragma unroll 1
+                                for (int i = 0; i < NH - 1; ++i)
+                                    load_chunk<NU>(src + i * NU, [&](int a, float v) { urr_set(i * NU + a, static_cast<T>(v) * cp.Rd[a]); });
                             } else {
 #pragma unroll 4
-                                for (int e = 0; e < SUL; ++e) URR.set(e, T(0));
+                                for (int e = 0; e < SUL; ++e) urr_set(e, T(0));
                             }
                         }
                         // cold workspace (tiny_api.cpp:68-105): duals and slacks zero, d = d0
@@ -425,11 +512,11 @@ tpp_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ type
             for (int r = 0; r < NX; ++r) {
                 const int e = i * NX + r;
                 T lo, hi;
-                xbounds(e, pbx, lo, hi);
+                xbounds(i, r, pbx, lo, hi);
                 const T tvo = TV.get(e);
                 T vo = N::min(hi, N::max(lo, tvo));
                 T g = tvo - vo;
-                if (first) { vo = 0; g = 0; }
+                if constexpr (!C::FB) { if (first) { vo = 0; g = 0; } }   // FB: 0 is inside the box, clamp(0) = 0 already
                 const T tvn = x[r] + g;
                 const T vn = N::min(hi, N::max(lo, tvn));
                 rpx = N::max(rpx, N::abs(x[r] - vn));
@@ -530,11 +617,11 @@ tpp_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ type
                 for (int a = 0; a < NU; ++a) {
                     const int e = i * NU + a;
                     T lo, hi;
-                    ubounds(e, pbu, lo, hi);
+                    ubounds(i, a, pbu, lo, hi);
                     const T tzo = TZ.get(e);
                     T zo = N::min(hi, N::max(lo, tzo));
                     T yv = tzo - zo;
-                    if (first) { zo = 0; yv = 0; }
+                    if constexpr (!C::FB) { if (first) { zo = 0; yv = 0; } }
                     const T tzn = u[a] + yv;
                     const T zn = N::min(hi, N::max(lo, tzn));
                     rpu = N::max(rpu, N::abs(u[a] - zn));
@@ -587,8 +674,7 @@ tpp_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ type
                 T xn[NX];
 #pragma unroll
                 for (int r = 0; r < NX; ++r) {
-                    T acc = dot<NX>([&](int c) { return cp.A[r * NX + c]; }, x, cp.f[r]);
-                    xn[r] = dot<NU>([&](int a) { return cp.B[r * NU + a]; }, u, acc);
+                    xn[r] = dot2<NX, NU>([&](int c) { return cp.A[r * NX + c]; }, x, [&](int a) { return cp.B[r * NU + a]; }, u, cp.f[r]);
                 }
                 if constexpr (C::ADAPT) {
 #pragma unroll
@@ -626,14 +712,18 @@ tpp_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ type
         if (k >= max_iter) finish = true;
         if (active && finish) {
             // solution = (vnew, znew) = clamp of the stored pre-clamp values
-            store_chunk<SXL>(prm.x + pbx, [&](int e) {
-                T lo, hi; xbounds(e, pbx, lo, hi);
-                return static_cast<float>(N::min(hi, N::max(lo, TV.get(e))));
-            });
-            store_chunk<SUL>(prm.u + pbu, [&](int e) {
-                T lo, hi; ubounds(e, pbu, lo, hi);
-                return static_cast<float>(N::min(hi, N::max(lo, TZ.get(e))));
-            });
+#pragma unroll 1
+            for (int i = 0; i < NH; ++i)
+                store_chunk<NX>(prm.x + pbx + i * NX, [&](int r) {
+                    T lo, hi; xbounds(i, r, pbx, lo, hi);
+                    return static_cast<float>(N::min(hi, N::max(lo, TV.get(i * NX + r))));
+                });
+#pragma unroll 1
+            for (int i = 0; i < NH - 1; ++i)
+                store_chunk<NU>(prm.u + pbu + i * NU, [&](int a) {
+                    T lo, hi; ubounds(i, a, pbu, lo, hi);
+                    return static_cast<float>(N::min(hi, N::max(lo, TZ.get(i * NU + a))));
+                });
             prm.iter[prob] = k;
             prm.status[prob] = st;
             if (prm.residuals) {
@@ -654,30 +744,43 @@ tpp_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ type
         for (int c = 0; c < NX; ++c) {
             const int e = (NH - 1) * NX + c;
             T lo, hi;
-            xbounds(e, pbx, lo, hi);
+            xbounds(NH - 1, c, pbx, lo, hi);
             const T tv = TV.get(e);
             const T v = N::min(hi, N::max(lo, tv));
-            T w = (v + v) - tv;
+            T w = N::fma(T(2), v, -tv);
             if constexpr (C::CONSTR) w += SXT.get(e);
             T pt = ptr_[c];
             if constexpr (C::ADAPT) pt = N::fma(dlt_lc, ptr_[NX + c], pt);
             p[c] = pt - rho_lc * w;
         }
+        // reference terms of step i are fetched one step ahead (they may live in L2)
+        T xq_nx[NX], ur_nx[NU];
+#pragma unroll
+        for (int c = 0; c < NX; ++c) xq_nx[c] = T(0);
+#pragma unroll
+        for (int a = 0; a < NU; ++a) ur_nx[a] = T(0);
+        if constexpr (C::REFS) { xrq_step(NH - 2, xq_nx); urr_step(NH - 2, ur_nx); }
 #pragma unroll 1
         for (int i = NH - 2; i >= 0; --i) {
             T rr[NU], t[NU];
+            T xq_cur[NX], ur_cur[NU];
+#pragma unroll
+            for (int c = 0; c < NX; ++c) xq_cur[c] = xq_nx[c];
+#pragma unroll
+            for (int a = 0; a < NU; ++a) ur_cur[a] = ur_nx[a];
+            if constexpr (C::REFS) {
+                if (i > 0) { xrq_step(i - 1, xq_nx); urr_step(i - 1, ur_nx); }
+            }
 #pragma unroll
             for (int a = 0; a < NU; ++a) {
                 const int e = i * NU + a;
                 T lo, hi;
-                ubounds(e, pbu, lo, hi);
+                ubounds(i, a, pbu, lo, hi);
                 const T tz = TZ.get(e);
                 const T z = N::min(hi, N::max(lo, tz));
-                T w = (z + z) - tz;
+                T w = N::fma(T(2), z, -tz);
                 if constexpr (C::CONSTR) w += SUT.get(e);
-                T ur = T(0);
-                if constexpr (C::REFS) ur = URR.get(e);
-                rr[a] = -ur - rho_lc * w;
+                rr[a] = -ur_cur[a] - rho_lc * w;
             }
 #pragma unroll
             for (int a = 0; a < NU; ++a) t[a] = dot<NX>([&](int r) { return cp.BT[a * NX + r]; }, p, rr[a] + cp.BPf[a]);
@@ -688,18 +791,16 @@ tpp_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ type
             for (int c = 0; c < NX; ++c) {
                 const int e = i * NX + c;
                 T lo, hi;
-                xbounds(e, pbx, lo, hi);
+                xbounds(i, c, pbx, lo, hi);
                 const T tv = TV.get(e);
                 const T v = N::min(hi, N::max(lo, tv));
-                T w = (v + v) - tv;
+                T w = N::fma(T(2), v, -tv);
                 if constexpr (C::CONSTR) w += SXT.get(e);
-                T xq = T(0);
-                if constexpr (C::REFS) xq = XRQ.get(e);
-                const T q = -xq - rho_lc * w;
-                T acc = dot<NX>([&](int r) { return cp.AK[c * NX + r]; }, p, q + cp.APf[c]);
-                T kr = dot<NU>([&](int a) { return cp.KT[c * NU + a]; }, rr, T(0));
-                if constexpr (C::ADAPT) kr = N::fma(dlt, dot<NU>([&](int a) { return cp.dKT[c * NU + a]; }, rr, T(0)), kr);
-                pn[c] = acc - kr;
+                const T q = -xq_cur[c] - rho_lc * w;
+                // q + APf + AmBKt p - Kinf' r in one chain (the pack holds -Kinf')
+                T acc = dot2<NX, NU>([&](int r) { return cp.AK[c * NX + r]; }, p, [&](int a) { return cp.KT[c * NU + a]; }, rr, q + cp.APf[c]);
+                if constexpr (C::ADAPT) acc = N::fma(dlt, dot<NU>([&](int a) { return cp.dKT[c * NU + a]; }, rr, T(0)), acc);
+                pn[c] = acc;
             }
 #pragma unroll
             for (int c = 0; c < NX; ++c) p[c] = pn[c];
