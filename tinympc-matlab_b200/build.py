@@ -30,14 +30,16 @@ FEAT_ENUM = {BOX: "FEAT_BOX", CON: "FEAT_CONSTR", ADP: "FEAT_ADAPT"}
 REFS_NONE, REFS_SMEM, REFS_L2 = 0, 1, 2
 
 
-def inst(bits, nx, nu, N, feat, refs=REFS_SMEM, ppb=False, variant=0, block=None, minb=None, budget_kb=226, fb=False):
-    b, m = plan_block(nx, nu, N, feat, bits, refs, budget_kb)
-    return dict(bits=bits, nx=nx, nu=nu, N=N, feat=feat, refs=refs, ppb=ppb, variant=variant, block=block or b, minb=minb or m, fb=fb)
+def inst(bits, nx, nu, N, feat, refs=REFS_SMEM, ppb=False, variant=0, block=None, minb=None, budget_kb=226, fb=False, gen=2, aff=None, tm=False):
+    tm = tm and bits == 32 and gen == 2
+    b, m = plan_block(nx, nu, N, feat, bits, refs, budget_kb, tm)
+    aff = ((nx, nu) == (6, 3)) if aff is None else aff   # affine-term instances only where a shipped config needs them (rocket: gravity)
+    return dict(aff=aff, tm=tm, bits=bits, nx=nx, nu=nu, N=N, feat=feat, refs=refs, ppb=ppb, variant=variant, block=block or b, minb=minb or m, fb=fb, gen=gen)
 
 
-def cols_per_thread(nx, nu, N, feat, refs):
+def cols_per_thread(nx, nu, N, feat, refs, tm=False):
     sx, su = nx * N, nu * (N - 1)
-    cols = sx + 2 * su + ((sx + su) if refs == REFS_SMEM else 0)
+    cols = (0 if tm else sx) + 2 * su + ((sx + su) if refs == REFS_SMEM else 0)   # tm: TV lives in tensor memory
     if feat == CON:
         cols += 3 * sx + 3 * su + max(nx, nu)
     return cols
@@ -49,8 +51,14 @@ def pack_elems(nx, nu, N):
     return n + 4 * (nx + 2) + 4 * (nu + 2) + 40           # + room for a few linear rows and padding
 
 
-def plan_block(nx, nu, N, feat, bits, refs, budget_kb=226):
+def plan_block(nx, nu, N, feat, bits, refs, budget_kb=226, tm=False):
     """(threads per CTA, CTAs per SM) maximising resident problems per SM for the all-in-shared-memory state columns"""
+    if tm:
+        # one CTA per SM owns the 512 tensor-memory columns; warps w, w+4, ... share a lane quarter
+        per_thread = cols_per_thread(nx, nu, N, feat, refs, True) * 4
+        avail = budget_kb * 1024 - (1024 + pack_elems(nx, nu, N) * 4)
+        warps = min(16, avail // per_thread // 32, 4 * (512 // (nx * N)))
+        return max(4, (warps // 4) * 4) * 32, 1
     per_thread = cols_per_thread(nx, nu, N, feat, refs) * bits // 8
     best = (32, 1, 0)
     for ctas in range(1, 9):
@@ -71,23 +79,27 @@ def default_instances():
     for bits in (32, 64):
         for (nx, nu, N) in shapes:
             for fb in (True, False):      # fb: bounds constant over the horizon and containing 0 (the common case)
-                out.append(inst(bits, nx, nu, N, BOX, refs=REFS_L2, fb=fb))
-                out.append(inst(bits, nx, nu, N, BOX, refs=REFS_NONE, fb=fb))
-            out.append(inst(bits, nx, nu, N, BOX, refs=REFS_L2, ppb=True))
+                out.append(inst(bits, nx, nu, N, BOX, refs=REFS_L2, fb=fb, tm=True))
+                out.append(inst(bits, nx, nu, N, BOX, refs=REFS_NONE, fb=fb, tm=True))
+            out.append(inst(bits, nx, nu, N, BOX, refs=REFS_L2, ppb=True, tm=True))
             out.append(inst(bits, nx, nu, N, CON, refs=REFS_L2, fb=True))
             out.append(inst(bits, nx, nu, N, CON, refs=REFS_L2))
             if (nx, nu) == (12, 4):
                 out.append(inst(bits, nx, nu, N, ADP, refs=REFS_L2, fb=True))
                 out.append(inst(bits, nx, nu, N, ADP, refs=REFS_L2))
-    # tuning variant 1 of the headline shape: reference terms in shared memory (fewer resident warps, no L2 traffic)
-    out.append(inst(32, 12, 4, 10, BOX, refs=REFS_SMEM, variant=1, fb=True))
+    # A/B baseline: the shared-memory-only (8 warps/SM) form of the headline shapes, option variant=2
+    out.append(inst(32, 12, 4, 10, BOX, refs=REFS_L2, variant=2, fb=True))
+    out.append(inst(32, 4, 1, 20, BOX, refs=REFS_NONE, variant=2, fb=True))
+    # A/B baseline: the first-generation (column-pair) kernel on the two headline shapes, option variant=1
+    out.append(inst(32, 12, 4, 10, BOX, refs=REFS_L2, variant=1, fb=True, gen=1))
+    out.append(inst(32, 4, 1, 20, BOX, refs=REFS_NONE, variant=1, fb=True, gen=1))
     return out
 
 
 def name_of(i):
     t = "f32" if i["bits"] == 32 else "f64"
-    return (f"tpp_{t}_{i['nx']}x{i['nu']}x{i['N']}_{FEAT_NAME[i['feat']]}{['_noref', '_refsm', ''][i['refs']]}"
-            f"{'_ppb' if i['ppb'] else ''}{'_fb' if i['fb'] else ''}_v{i['variant']}")
+    return (f"tpp{'' if i['gen'] == 1 else '2'}_{t}_{i['nx']}x{i['nu']}x{i['N']}_{FEAT_NAME[i['feat']]}{['_noref', '_refsm', ''][i['refs']]}"
+            f"{'_ppb' if i['ppb'] else ''}{'_fb' if i['fb'] else ''}{'_aff' if (i['aff'] and i['gen'] == 2) else ''}{'_tm' if i['tm'] else ''}_v{i['variant']}")
 
 
 def gen_sources(instances):
@@ -98,12 +110,14 @@ def gen_sources(instances):
         n = name_of(i)
         names.append(n)
         T = "float" if i["bits"] == 32 else "double"
+        g = "" if i["gen"] == 1 else "2"
         src = (
             "// generated by tinympc-matlab_b200/build.py -- do not edit\n"
-            '#include "../tmpc_tpp.cuh"\n#include "../tmpc_registry.h"\nusing namespace tmpc;\n'
-            f"using Cfg_{n} = TppCfg<{T}, {i['nx']}, {i['nu']}, {i['N']}, {FEAT_ENUM[i['feat']]}, {i['block']}, "
-            f"{i['refs']}, {'true' if i['ppb'] else 'false'}, {i['minb']}, {'true' if i['fb'] else 'false'}>;\n"
-            f"TMPC_DEFINE_TPP_ENTRY({n}, Cfg_{n}, {i['feat']}, {i['bits']}, {i['variant']})\n"
+            f'#include "../tmpc_tpp{g}.cuh"\n#include "../tmpc_registry.h"\nusing namespace tmpc;\n'
+            f"using Cfg_{n} = Tpp{g}Cfg<{T}, {i['nx']}, {i['nu']}, {i['N']}, {FEAT_ENUM[i['feat']]}, {i['block']}, "
+            f"{i['refs']}, {'true' if i['ppb'] else 'false'}, {i['minb']}, {'true' if i['fb'] else 'false'}"
+            f"{((', true' if i['aff'] else ', false') + (', true' if i['tm'] else ', false')) if g else ''}>;\n"
+            f"TMPC_DEFINE_TPP{g}_ENTRY({n}, Cfg_{n}, {i['feat']}, {i['bits']}, {i['variant']})\n"
         )
         path = GEN / f"{n}.cu"
         wanted.add(path.name)

@@ -65,6 +65,7 @@ struct Family {
     int feat = kFeatBox;
     bool shared_bounds_ok = false;     // every enabled bound has shared arrays
     bool fastbox = false;              // shared bounds are constant over the horizon and contain 0
+    bool affine = false;               // fdyn (hence APf, BPf) is not identically zero
     PackLayout L{};
     std::vector<double> pack;          // double master copy
     SolveParams base{};                // settings + cone specs, pointers empty
@@ -118,6 +119,7 @@ const KernelEntry* find_kernel(const Family& f, int bits, bool ppb, bool refs, i
         for (int i = 0; i < n; ++i) {
             const KernelEntry* e = tab[i];
             if (e->fastbox && (!f.fastbox || ppb)) continue;      // table order puts the fast-box instances first
+            if (f.affine && !e->affine) continue;
             if (e->family == KF_TPP && e->nx == f.nx && e->nu == f.nu && e->N == f.N && e->feat == f.feat && e->dtype_bits == bits &&
                 e->ppb == (ppb ? 1 : 0) && e->variant == variant && ((e->refs != 0) == refs || (pass == 1 && e->refs != 0)))
                 return e;
@@ -449,6 +451,8 @@ int tinympc_cuda_set_family(tinympc_cuda_solver* s, const tinympc_cuda_family* f
         f.pack[L.umax + e] = (ib && have_ib) ? fm->u_max[e] : inf;
     }
     f.shared_bounds_ok = (!sb || have_sb) && (!ib || have_ib);
+    for (int r = 0; r < nx; ++r) f.affine = f.affine || f.pack[L.f + r] != 0.0 || f.pack[L.APf + r] != 0.0;
+    for (int a = 0; a < nu; ++a) f.affine = f.affine || f.pack[L.BPf + a] != 0.0;
     f.fastbox = true;
     for (int e = 0; e < nx * N && f.fastbox; ++e)
         f.fastbox = f.pack[L.xmin + e] == f.pack[L.xmin + e % nx] && f.pack[L.xmax + e] == f.pack[L.xmax + e % nx] &&

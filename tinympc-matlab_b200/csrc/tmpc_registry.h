@@ -19,6 +19,7 @@ struct KernelEntry {
     int refs;            // 0: reference-free variant (Xref = Uref = NULL); 1: reference terms in shared memory; 2: in an L2-resident scratch
     int ppb;             // per-problem bounds variant
     int fastbox;         // 1: requires shared bounds that are constant over the horizon and contain 0
+    int affine;          // 1: handles a non-zero affine term (fdyn, APf, BPf); 0: requires f = 0
     int block;           // threads per CTA
     int variant;         // tuning variant (0 = default); selected with the "variant" option
     size_t (*smem_bytes)(int pack_elems);
@@ -51,6 +52,28 @@ const KernelEntry* const* kernel_table(int* count);   // defined in gen/tmpc_tab
         return cudaGetLastError();                                                                                  \
     }                                                                                                               \
     extern const KernelEntry SYM = {#SYM, KF_TPP, CFG::NX, CFG::NU, CFG::NH, FEATV, BITS, CFG::REFMODE,             \
-                                    CFG::PPB ? 1 : 0, CFG::FB ? 1 : 0, CFG::BLOCK, VAR, SYM##_smem, SYM##_prepare, SYM##_occ,        \
+                                    CFG::PPB ? 1 : 0, CFG::FB ? 1 : 0, 1, CFG::BLOCK, VAR, SYM##_smem, SYM##_prepare, SYM##_occ,     \
                                     SYM##_launch};                                                                  \
+    }
+
+// packed-pair kernel (tmpc_tpp2.cuh)
+#define TMPC_DEFINE_TPP2_ENTRY(SYM, CFG, FEATV, BITS, VAR)                                                          \
+    namespace tmpc {                                                                                                \
+    static size_t SYM##_smem(int pe) { return tpp2_smem_bytes<CFG>(pe); }                                           \
+    static cudaError_t SYM##_prepare(size_t smem) {                                                                 \
+        return cudaFuncSetAttribute(tpp2_kernel<CFG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
+    }                                                                                                               \
+    static cudaError_t SYM##_occ(int* n, size_t smem) {                                                             \
+        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(n, tpp2_kernel<CFG>, CFG::BLOCK, smem);                \
+    }                                                                                                               \
+    static cudaError_t SYM##_launch(const SolveParams& p, int grid, size_t smem, cudaStream_t st, const double* mp, \
+                                    const PackLayout& L) {                                                          \
+        typename CFG::CPack cpk;                                                                                    \
+        fill_const_pack2(cpk, mp, L);                                                                               \
+        tpp2_kernel<CFG><<<grid, CFG::BLOCK, smem, st>>>(p, cpk);                                                   \
+        return cudaGetLastError();                                                                                  \
+    }                                                                                                               \
+    extern const KernelEntry SYM = {#SYM, KF_TPP, CFG::NX, CFG::NU, CFG::NH, FEATV, BITS, CFG::REFMODE,             \
+                                    CFG::PPB ? 1 : 0, CFG::FB ? 1 : 0, CFG::AFF ? 1 : 0, CFG::BLOCK, VAR, SYM##_smem, SYM##_prepare, \
+                                    SYM##_occ, SYM##_launch};                                                       \
     }
