@@ -6,6 +6,9 @@ this module; the product (tinympc-matlab_b200/) never does.
   impl="ref"  -> oracle/_ref/libtinympc_ref.so : the unmodified reference C++ (built from
                  /root/reference by oracle/Makefile) behind oracle/ref_driver.cpp
   impl="port" -> oracle/liboracle_port.so      : the C restatement oracle/tinympc_oracle.c
+  impl="refhost_b200" -> oracle/_ref/libtinympc_refhost_b200.so : the drop-in proof -- the unmodified reference
+                 tiny_api.cpp behind the same driver, with ONLY solve() (admm.cpp) replaced by the B200 C ABI
+                 (oracle/ref_b200_binding.cpp).  This one needs a GPU; it is the thing under test, not a checker.
 """
 from __future__ import annotations
 
@@ -16,8 +19,9 @@ from pathlib import Path
 import numpy as np
 
 HERE = Path(__file__).resolve().parent
-_LIBS = {"ref": HERE / "_ref" / "libtinympc_ref.so", "port": HERE / "liboracle_port.so"}
-_PREFIX = {"ref": "ref", "port": "port"}
+_LIBS = {"ref": HERE / "_ref" / "libtinympc_ref.so", "port": HERE / "liboracle_port.so",
+         "refhost_b200": HERE / "_ref" / "libtinympc_refhost_b200.so"}
+_PREFIX = {"ref": "ref", "port": "port", "refhost_b200": "ref"}
 _loaded = {}
 
 c_dp = C.POINTER(C.c_double)

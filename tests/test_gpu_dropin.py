@@ -179,3 +179,48 @@ def test_edge_cases(tm):
     fam["check_termination"] = 0
     with pytest.raises(tm.TinympcCudaError):
         s2.set_family(fam)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# The reference's own host code on top of the GPU hot path: oracle/_ref/libtinympc_refhost_b200.so is the UNMODIFIED
+# reference tiny_api.cpp (tiny_setup, Riccati cache precompute, setters; Eigen) linked WITHOUT admm.cpp /
+# rho_benchmark.cpp -- its solve() is oracle/ref_b200_binding.cpp, the binding of INTEGRATION.md option B, which
+# forwards the live TinySolver to tinympc_cuda_solve_workspace.  Same driver, same inputs as the golden files.
+# ------------------------------------------------------------------------------------------------------------
+REFHOST_CASES = ["G1_cartpole_unconstrained", "G2_cartpole_ubound", "G3_quadrotor_hover", "G4_rocket_soc",
+                 "G4_rocket_soc_linear", "G5_quadrotor_adaptive", "batch_cartpole", "batch_quadrotor", "batch_rocket",
+                 "batch_quadrotor_adaptive", "batch_quadrotor_perproblem_bounds", "batch_quadrotor_check3_max20"]
+
+
+@pytest.mark.parametrize("name", REFHOST_CASES)
+def test_reference_host_code_with_gpu_hot_path(name, oracle_mod):
+    O = oracle_mod
+    if not O.available("refhost_b200"):
+        pytest.skip("oracle/_ref/libtinympc_refhost_b200.so not built (needs /root/reference at build time)")
+    p, b, g = cases.load(name)
+    n = min(b.size, 16)
+    r = O.solve_batch(p, b.slice(0, n), "refhost_b200", threads=1)
+    assert np.array_equal(r["iter"], g["iter"][:n]), (r["iter"], g["iter"][:n])
+    assert np.array_equal(r["status"], g["status"][:n])
+    sx, su = max(1.0, np.abs(g["x"][:n]).max()), max(1.0, np.abs(g["u"][:n]).max())
+    assert np.abs(r["x"] - g["x"][:n]).max() < 1e-9 * sx
+    assert np.abs(r["u"] - g["u"][:n]).max() < 1e-9 * su
+
+
+@pytest.mark.parametrize("name", ["mpc_quadrotor", "mpc_cartpole"])
+def test_reference_host_closed_loop_with_gpu_hot_path(name, oracle_mod):
+    """Warm-started closed loop (quadrotor_hovering.cpp:73-93) through the reference's API, hot path on the GPU."""
+    O = oracle_mod
+    if not O.available("refhost_b200"):
+        pytest.skip("oracle/_ref/libtinympc_refhost_b200.so not built")
+    g = np.load(cases.GOLDEN / f"{name}.npz")
+    p = P.quadrotor() if "quad" in name else P.cartpole(N=10)
+    s = O.Session(p, "refhost_b200")
+    s.set_x_ref(g["Xref"])
+    for k in range(len(g["iter"])):
+        s.set_x0(g["x0"][k])
+        r = s.solve()
+        assert r["iter"] == g["iter"][k] and r["status"] == g["status"][k], (k, r["iter"], g["iter"][k])
+        assert np.abs(r["x"] - g["x"][k]).max() < 1e-9
+        assert np.abs(r["work_u0"] - g["work_u0"][k]).max() < 1e-9
+    s.close()

@@ -461,7 +461,7 @@ struct SmemTraj : Traj<T, N, S, OFF, BLOCK> {
     __device__ __forceinline__ void stores_done() const {}
 };
 
-template <typename T_, int NX_, int NU_, int NH_, int FEAT_, int BLOCK_, int REFS_, bool PPB_, int MINB_ = 1, bool FB_ = false, bool AFF_ = true, bool TM_ = false>
+template <typename T_, int NX_, int NU_, int NH_, int FEAT_, int BLOCK_, int REFS_, bool PPB_, int MINB_ = 1, bool FB_ = false, bool AFF_ = true, bool TM_ = false, bool OPQ_ = true>
 struct Tpp2Cfg {
     using T = T_;
     static constexpr int NX = NX_, NU = NU_, NH = NH_, FEAT = FEAT_, BLOCK = BLOCK_, MINB = MINB_;
@@ -470,6 +470,7 @@ struct Tpp2Cfg {
     static constexpr bool PPB = PPB_;                       // per-problem bounds read from global memory
     static constexpr bool FB = FB_ && !PPB_;                // "fast box": every shared box contains 0 (cold start needs no special case)
     static constexpr bool AFF = AFF_;                       // affine dynamics term: f, APf, BPf may be non-zero
+    static constexpr bool OPQ = OPQ_;                       // loop-variant (opaque) constant-bank offsets: see opaque_zero4()
     static constexpr bool TM = TM_ && sizeof(T_) == 4;      // TV lives in tensor memory (one CTA per SM, BLOCK up to 512 * 128 / SX threads)
     static constexpr bool CONSTR = FEAT_ == FEAT_CONSTR;
     static constexpr bool ADAPT = FEAT_ == FEAT_ADAPT;
@@ -858,7 +859,7 @@ tpp2_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ typ
 
 #pragma unroll 1
         for (int i = 0; i < NH; ++i) {
-            const int zf = opaque_zero4();
+            const int zf = C::OPQ ? opaque_zero4() : 0;
             // ---- state column i
             VX gnew, vnx, tvo, tvn;
             TV.load(i, tvo);
@@ -1162,7 +1163,7 @@ tpp2_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ typ
         }
 #pragma unroll 1
         for (int i = NH - 2; i >= 0; --i) {
-            const int zb = opaque_zero4();
+            const int zb = C::OPQ ? opaque_zero4() : 0;
             TV.load(i, tvv);
             const VX sq_cur = sq_nx;
             const VU sr_cur = sr_nx;
