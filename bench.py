@@ -189,8 +189,12 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     tm = importlib.import_module("tinympc-matlab_b200")
+    S = importlib.import_module("tinympc-matlab_b200.sharding")
     B = args.batch
-    batch_np = P.make_batch(spec, B, args.scale, seed=1234 + 3 + 1000 * rank)   # each rank owns its shard
+    # weak scaling: the job is world*B problems, rank r owns the contiguous index range [lo, hi) of it
+    lo, hi = S.shard_range(world * B, rank, world)
+    assert hi - lo == B
+    batch_np = P.make_batch(spec, B, args.scale, seed=1234 + 3 + 1000 * rank)   # each rank generates its own shard
     solver = tm.TinyMPC()
     solver.setup_from_spec(spec, devices=[local])
     solver.cuda.set_option("precision", args.precision)
@@ -226,13 +230,8 @@ def main():
     launches = solver.cuda.launch_count - launches0
     iters_one = int(it.sum().item())                 # identical every step (same inputs)
     unsolved = float((st == 11).float().mean().item())
-    tmax = torch.tensor([ms], device=dev)
-    tot = torch.tensor([float(iters_one), float(launches)], device=dev, dtype=torch.float64)
-    if dist is not None:
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-    ms_all = float(tmax.item())
-    iters_all, launches_all = float(tot[0].item()), int(tot[1].item())
+    ms_all, (iters_all, launches_all) = S.reduce_report(ms, [iters_one, launches], dist, dev)   # max of times, sum of work
+    launches_all = int(launches_all)
     value = world * B * args.steps / (ms_all * 1e-3)
     ns_iter = ms_all * 1e6 / (iters_all * args.steps)
 
@@ -276,9 +275,14 @@ def main():
             "traffic": None, "peak_source": peak_how, "flops_per_admm_iter": F, "kernel": solver.cuda.last_kernel,
             "hbm": {"achieved": ach_gbs, "peak": hbm_pk, "unit": "GB/s", "frac": ach_gbs / hbm_pk, "peak_source": hbm_how,
                     "bytes_per_solve": bytes_per_solve(n, m, N)}}
-    prof = ROOT / "profiles" / "r01_traffic.json"
+    # DRAM traffic of the same kernel on the same workload from the committed `ncu --set full` capture
+    # (profiles/r01/traffic.json: dram__bytes_read.sum + dram__bytes_write.sum per launch)
+    prof = ROOT / "profiles" / "r01" / "traffic.json"
     if prof.exists():
-        roof["traffic"] = json.loads(prof.read_text()).get("dram_bytes_per_launch")
+        t = json.loads(prof.read_text()).get(f"{args.config}_b{B}_s{args.scale:g}")
+        if t and t.get("kernel") == solver.cuda.last_kernel:
+            roof["traffic"] = t["dram_bytes_per_launch"]
+            roof["traffic_algorithmic"] = bytes_per_solve(n, m, N) * B
 
     line = {"metric": "solves_per_sec", "value": value, "unit": "solves/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_all / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
