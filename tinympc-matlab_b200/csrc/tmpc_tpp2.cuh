@@ -579,6 +579,42 @@ template <> struct VecOf<double, 4> { using type = double4; };
 template <> struct VecOf<double, 2> { using type = double2; };
 template <> struct VecOf<double, 1> { using type = double; };
 
+// A register copy the compiler cannot coalesce away (volatile mov): keeps the destination of a prefetch and the
+// value still in use in DIFFERENT registers, so that the prefetch can be issued at the top of a loop body.
+__device__ __forceinline__ float pinned_copy(float s) { float d; asm volatile("mov.b32 %0, %1;" : "=f"(d) : "f"(s)); return d; }
+__device__ __forceinline__ double pinned_copy(double s) { double d; asm volatile("mov.b64 %0, %1;" : "=d"(d) : "d"(s)); return d; }
+template <typename T, int N>
+__device__ __forceinline__ void pinned_copy(Vec<T, N>& d, const Vec<T, N>& s) {
+#pragma unroll
+    for (int j = 0; j < N / 2; ++j) d.p[j] = mk2(pinned_copy(s.p[j].x), pinned_copy(s.p[j].y));
+    d.t = (N & 1) ? pinned_copy(s.t) : s.t;
+}
+
+// store V consecutive elements as one vector (two 16-byte halves for four doubles)
+template <typename T, int V>
+__device__ __forceinline__ void store_vec(T* dst, const T (&v)[V]) {
+    if constexpr (V == 1) dst[0] = v[0];
+    else if constexpr (V == 2) *reinterpret_cast<typename PairOf<T>::type*>(dst) = mk2(v[0], v[1]);
+    else if constexpr (sizeof(T) == 4) *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+    else { *reinterpret_cast<double2*>(dst) = make_double2(v[0], v[1]); *reinterpret_cast<double2*>(dst + 2) = make_double2(v[2], v[3]); }
+}
+
+// Load LEN contiguous floats (aligned to AL), transform element e with f(e, value) and store the results as
+// LEN / V vectors of V elements, vector g at dst + g * stride (the lane-interleaved scratch layout).
+template <int LEN, int AL, int V, typename T, typename F>
+__device__ __forceinline__ void load_transform_scatter(const float* __restrict__ src, T* dst, uint32_t stride, F&& f) {
+    static_assert(LEN % V == 0, "block length must be a whole number of vectors");
+    float buf[LEN];
+    load_span<LEN, AL>(src, [&](int e, float v) { buf[e] = v; });
+#pragma unroll
+    for (int g = 0; g < LEN / V; ++g) {
+        T out[V];
+#pragma unroll
+        for (int k = 0; k < V; ++k) out[k] = f(g * V + k, buf[g * V + k]);
+        store_vec<T, V>(dst + (size_t)g * stride, out);
+    }
+}
+
 template <class C>
 __global__ void __launch_bounds__(C::BLOCK, C::MINB)
 tpp2_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ typename C::CPack cp) {
@@ -639,17 +675,17 @@ tpp2_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ typ
     // Reference terms in a global scratch laid out [element / V][slot][V] (V = 4/2/1 elements per lane and
     // load): coalesced across lanes, one vector load per V elements, re-read every iteration out of L2.
     // Stored pre-combined: SQ = APf - Xref .* Q (state) and SR = -(Uref .* R) (input).
-    const size_t slots = (size_t)gridDim.x * BLOCK;
-    const size_t slot = (size_t)blockIdx.x * BLOCK + tid;
+    // All index arithmetic is 32 bit (the scratch has gridDim * BLOCK * (SX + SU) < 2^32 elements).
+    const uint32_t slots = gridDim.x * BLOCK;
+    const uint32_t slot = blockIdx.x * BLOCK + tid;
+    const uint32_t qstride = slots * C::VX, ustride = slots * C::VU;   // elements between consecutive vectors of a lane
     T* const gxr = static_cast<T*>(prm.ref_scratch) + slot * C::VX;
     T* const gur = static_cast<T*>(prm.ref_scratch) + (size_t)SXL * slots + slot * C::VU;
-    auto sq_set = [&](int e, T v) { gxr[(size_t)(e / C::VX) * slots * C::VX + (e % C::VX)] = v; };
-    auto sr_set = [&](int e, T v) { gur[(size_t)(e / C::VU) * slots * C::VU + (e % C::VU)] = v; };
     auto sq_step = [&](int i, VX& dst) {   // fetch the NX state reference terms of time step i
         using V = typename VecOf<T, C::VX>::type;
 #pragma unroll
         for (int k = 0; k < NX / C::VX; ++k) {
-            const V v = *reinterpret_cast<const V*>(gxr + (size_t)(i * (NX / C::VX) + k) * slots * C::VX);
+            const V v = *reinterpret_cast<const V*>(gxr + static_cast<uint32_t>(i * (NX / C::VX) + k) * qstride);
             if constexpr (C::VX == 4) { dst.p[2 * k] = mk2(v.x, v.y); dst.p[2 * k + 1] = mk2(v.z, v.w); }
             else if constexpr (C::VX == 2) { dst.p[k] = mk2(v.x, v.y); }
             else { dst.set(k, v); }
@@ -659,13 +695,13 @@ tpp2_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ typ
         using V = typename VecOf<T, C::VU>::type;
 #pragma unroll
         for (int k = 0; k < NU / C::VU; ++k) {
-            const V v = *reinterpret_cast<const V*>(gur + (size_t)(i * (NU / C::VU) + k) * slots * C::VU);
+            const V v = *reinterpret_cast<const V*>(gur + static_cast<uint32_t>(i * (NU / C::VU) + k) * ustride);
             if constexpr (C::VU == 4) { dst.p[2 * k] = mk2(v.x, v.y); dst.p[2 * k + 1] = mk2(v.z, v.w); }
             else if constexpr (C::VU == 2) { dst.p[k] = mk2(v.x, v.y); }
             else { dst.set(k, v); }
         }
     };
-    (void)slots; (void)slot;
+    (void)qstride; (void)ustride;
 
     const T* cP = pack + SP::Pinf;
     const T* cdP = pack + SP::dPinf;
@@ -780,34 +816,61 @@ tpp2_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ typ
                                 const float* src = prm.Xref + (size_t)prob * SXL;
 #pragma unroll 1
                                 for (int b = 0; b < NH / GX; ++b)
-                                    load_span<GX * NX, vec_width(SXL, GX * NX)>(src + b * GX * NX, [&](int e, float v) {
-                                        const int r = e % NX;
-                                        sq_set(b * GX * NX + e, (C::AFF ? cp.APf[r] : T(0)) - static_cast<T>(v) * cp.Qd[r]);
-                                        if (e / NX == GX - 1) xr_last[r] = static_cast<T>(v);   // after the last block: xref_N
-                                    });
+                                    load_transform_scatter<GX * NX, vec_width(SXL, GX * NX), C::VX>(
+                                        src + b * GX * NX, gxr + static_cast<uint32_t>(b * (GX * NX / C::VX)) * qstride, qstride, [&](int e, float v) {
+                                            const int r = e % NX;
+                                            if (e / NX == GX - 1) xr_last[r] = static_cast<T>(v);   // after the last block: xref_N
+                                            return (C::AFF ? cp.APf[r] : T(0)) - static_cast<T>(v) * cp.Qd[r];
+                                        });
                             } else {
-#pragma unroll 4
-                                for (int e = 0; e < SXL; ++e) sq_set(e, C::AFF ? cp.APf[e % NX] : T(0));
-                            }
+#pragma unroll 1
+                                for (int i = 0; i < NH; ++i) {
 #pragma unroll
-                            for (int c = 0; c < NX; ++c) {
-                                T acc = 0, acc1 = 0;
+                                    for (int g = 0; g < NX / C::VX; ++g) {
+                                        T out[C::VX];
+#pragma unroll
+                                        for (int k = 0; k < C::VX; ++k) out[k] = C::AFF ? cp.APf[g * C::VX + k] : T(0);
+                                        store_vec<T, C::VX>(gxr + static_cast<uint32_t>(i * (NX / C::VX) + g) * qstride, out);
+                                    }
+                                }
+                            }
+                            {   // PT = -(xref_N' Pinf)' as row pairs of Pinf' (Pinf is row-major in the staged pack)
+                                VX acc, acc1;
+                                acc.fill(T(0)); acc1.fill(T(0));
 #pragma unroll
                                 for (int r = 0; r < NX; ++r) {
-                                    acc = N::fma(xr_last[r], cP[r * NX + c], acc);
-                                    if constexpr (C::ADAPT) acc1 = N::fma(xr_last[r], cdP[r * NX + c], acc1);
+                                    const T nxr = -xr_last[r];
+#pragma unroll
+                                    for (int j = 0; j < NX / 2; ++j) {
+                                        acc.p[j] = fmas(mk2(cP[r * NX + 2 * j], cP[r * NX + 2 * j + 1]), nxr, acc.p[j]);
+                                        if constexpr (C::ADAPT) acc1.p[j] = fmas(mk2(cdP[r * NX + 2 * j], cdP[r * NX + 2 * j + 1]), nxr, acc1.p[j]);
+                                    }
+                                    if constexpr (NX & 1) {
+                                        acc.t = fmas(cP[r * NX + NX - 1], nxr, acc.t);
+                                        if constexpr (C::ADAPT) acc1.t = fmas(cdP[r * NX + NX - 1], nxr, acc1.t);
+                                    }
                                 }
-                                ptv.set(c, -acc);
-                                if constexpr (C::ADAPT) ptv1.set(c, -acc1);
+                                ptv = acc;
+                                if constexpr (C::ADAPT) ptv1 = acc1;
                             }
                             if (prm.Uref) {
                                 const float* src = prm.Uref + (size_t)prob * SUL;
 #pragma unroll 1
                                 for (int b = 0; b < (NH - 1) / GU; ++b)
-                                    load_span<GU * NU, vec_width(SUL, GU * NU)>(src + b * GU * NU, [&](int e, float v) { sr_set(b * GU * NU + e, -(static_cast<T>(v) * cp.Rd[e % NU])); });
+                                    load_transform_scatter<GU * NU, vec_width(SUL, GU * NU), C::VU>(
+                                        src + b * GU * NU, gur + static_cast<uint32_t>(b * (GU * NU / C::VU)) * ustride, ustride,
+                                        [&](int e, float v) { return -(static_cast<T>(v) * cp.Rd[e % NU]); });
                             } else {
-#pragma unroll 4
-                                for (int e = 0; e < SUL; ++e) sr_set(e, T(0));
+#pragma unroll 1
+                                for (int i = 0; i < NH - 1; ++i) {
+#pragma unroll
+                                    for (int g = 0; g < NU / C::VU; ++g) {
+                                        T out[C::VU];
+#pragma unroll
+                                        for (int k = 0; k < C::VU; ++k) out[k] = T(0);
+                                        store_vec<T, C::VU>(gur + static_cast<uint32_t>(i * (NU / C::VU) + g) * ustride, out);
+                                    }
+                                }
                             }
                         }
                         // cold workspace (tiny_api.cpp:68-105): duals and slacks zero, d = d0 (TV: below, warp-wide)
@@ -1165,10 +1228,17 @@ tpp2_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ typ
         for (int i = NH - 2; i >= 0; --i) {
             const int zb = C::OPQ ? opaque_zero4() : 0;
             TV.load(i, tvv);
-            const VX sq_cur = sq_nx;
-            const VU sr_cur = sr_nx;
+            // The terms of step i move to their own registers with copies the compiler cannot remove, and the fetch
+            // for step i-1 is issued at once: a whole step of distance to the L2.  (With plain copies the register
+            // allocator coalesces both buffers and sinks the loads to the end of the loop body: distance zero, 8 % of
+            // all stall samples on the first consumer.)
+            VX sq_cur; VU sr_cur;
             if constexpr (C::REFS) {
-                if (i > 0) { sq_step(i - 1, sq_nx); sr_step(i - 1, sr_nx); }
+                pinned_copy(sq_cur, sq_nx); pinned_copy(sr_cur, sr_nx);
+                const int inx = i > 0 ? i - 1 : 0;   // no branch: a conditional fetch block gets laid out at the loop end
+                sq_step(inx, sq_nx); sr_step(inx, sr_nx);
+            } else {
+                sq_cur = sq_nx; sr_cur = sr_nx;
             }
             // r_i = -(Uref .* R) - rho (znew - y) ...  (admm.cpp:227-236)
             VU rr;
