@@ -54,8 +54,8 @@ if __name__ == "__main__":
     B = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 20
     run(P.quadrotor(), 0.3, B, [0, 3, 2, 1])
     run(P.quadrotor(), 1.0, B, [0, 3, 2, 1])
-    run(P.cartpole(), 0.3, B, [0, 3, 2, 1])
-    run(P.cartpole(), 1.0, B, [0, 3, 2, 1])
+    run(P.cartpole(), 0.3, B, [0, 4, 3, 2, 1])
+    run(P.cartpole(), 1.0, B, [0, 4, 3, 2, 1])
     run(P.rocket(), 1.0, B // 4, [0])
     run(P.quadrotor(adaptive=True), 1.0, B // 4, [0])
     run(P.quadrotor(), 1.0, B // 8, [0], precision=64)

@@ -30,21 +30,28 @@ FEAT_ENUM = {BOX: "FEAT_BOX", CON: "FEAT_CONSTR", ADP: "FEAT_ADAPT"}
 REFS_NONE, REFS_SMEM, REFS_L2 = 0, 1, 2
 
 
-def inst(bits, nx, nu, N, feat, refs=REFS_SMEM, ppb=False, variant=0, block=None, minb=None, budget_kb=226, fb=False, gen=2, aff=None, tm=False, opq=None):
+def inst(bits, nx, nu, N, feat, refs=REFS_SMEM, ppb=False, variant=0, block=None, minb=None, budget_kb=226, fb=False, gen=2, aff=None, tm=False, opq=None, max_warps=None, tib=None):
+    max_warps = (24 if nx * N <= 80 else 16) if max_warps is None else max_warps   # small shapes: 6 warps per tensor-memory lane quarter
+    tib = (not (nx == 12 and feat == BOX)) if tib is None else tib
     tm = tm and bits == 32 and gen == 2
-    b, m = plan_block(nx, nu, N, feat, bits, refs, budget_kb, tm)
+    b, m = plan_block(nx, nu, N, feat, bits, refs, budget_kb, tm, max_warps)
+    ntm = m if tm else 0      # tensor-memory instances: plan_block returns (block, arrays in tensor memory); always 1 CTA/SM
+    if tm:
+        m = 1
     aff = ((nx, nu) == (6, 3)) if aff is None else aff   # affine-term instances only where a shipped config needs them (rocket: gravity)
     # opaque (loop-variant) constant offsets pay off only where few warps hide the LDCU latency: measured +27 % on the
     # fp64 instances (8 warps/SM), -14 % on the fp32 tensor-memory instances (16 warps/SM, LDCU issue-rate bound)
     opq = (bits == 64) if opq is None else opq
-    return dict(aff=aff, tm=tm, opq=opq, bits=bits, nx=nx, nu=nu, N=N, feat=feat, refs=refs, ppb=ppb, variant=variant, block=block or b, minb=minb or m, fb=fb, gen=gen)
+    return dict(aff=aff, tm=tm, ntm=ntm, opq=opq, tib=tib, bits=bits, nx=nx, nu=nu, N=N, feat=feat, refs=refs, ppb=ppb, variant=variant, block=block or b, minb=minb or m, fb=fb, gen=gen)
 
 
-def cols_per_thread(nx, nu, N, feat, refs, tm=False):
+def cols_per_thread(nx, nu, N, feat, refs, ntm=0):
+    """shared-memory scalar columns per thread; ntm = number of state-sized arrays (TV, GC, GL, SXT) in tensor memory"""
     sx, su = nx * N, nu * (N - 1)
-    cols = (0 if tm else sx) + 2 * su + ((sx + su) if refs == REFS_SMEM else 0)   # tm: TV lives in tensor memory
+    nstate = 4 if feat == CON else 1
+    cols = (nstate - min(ntm, nstate)) * sx + 2 * su + ((sx + su) if refs == REFS_SMEM else 0)
     if feat == CON:
-        cols += 3 * sx + 3 * su + max(nx, nu)
+        cols += 3 * su + max(nx, nu)
     return cols
 
 
@@ -54,14 +61,20 @@ def pack_elems(nx, nu, N):
     return n + 4 * (nx + 2) + 4 * (nu + 2) + 40           # + room for a few linear rows and padding
 
 
-def plan_block(nx, nu, N, feat, bits, refs, budget_kb=226, tm=False):
+def plan_block(nx, nu, N, feat, bits, refs, budget_kb=226, tm=False, max_warps=16):
     """(threads per CTA, CTAs per SM) maximising resident problems per SM for the all-in-shared-memory state columns"""
     if tm:
-        # one CTA per SM owns the 512 tensor-memory columns; warps w, w+4, ... share a lane quarter
-        per_thread = cols_per_thread(nx, nu, N, feat, refs, True) * 4
-        avail = budget_kb * 1024 - (1024 + pack_elems(nx, nu, N) * 4)
-        warps = min(16, avail // per_thread // 32, 4 * (512 // (nx * N)))
-        return max(4, (warps // 4) * 4) * 32, 1
+        # one CTA per SM owns the 512 tensor-memory columns; warps w, w+4, ... share a lane quarter.  Pick the number
+        # of state arrays to keep there (1 for box kernels, 1..4 with cones / linear rows) that maximises the residency.
+        best = (0, 0)
+        for ntm in range(1, (4 if feat == CON else 1) + 1):
+            per_thread = cols_per_thread(nx, nu, N, feat, refs, ntm) * 4
+            avail = budget_kb * 1024 - (1024 + pack_elems(nx, nu, N) * 4)
+            warps = min(max_warps, avail // per_thread // 32, 4 * (512 // (ntm * nx * N)))
+            warps = (warps // 4) * 4
+            if warps > best[0]:
+                best = (warps, ntm)
+        return max(4, best[0]) * 32, max(1, best[1])
     per_thread = cols_per_thread(nx, nu, N, feat, refs) * bits // 8
     best = (32, 1, 0)
     for ctas in range(1, 9):
@@ -85,14 +98,16 @@ def default_instances():
                 out.append(inst(bits, nx, nu, N, BOX, refs=REFS_L2, fb=fb, tm=True))
                 out.append(inst(bits, nx, nu, N, BOX, refs=REFS_NONE, fb=fb, tm=True))
             out.append(inst(bits, nx, nu, N, BOX, refs=REFS_L2, ppb=True, tm=True))
-            out.append(inst(bits, nx, nu, N, CON, refs=REFS_L2, fb=True))
-            out.append(inst(bits, nx, nu, N, CON, refs=REFS_L2))
+            out.append(inst(bits, nx, nu, N, CON, refs=REFS_L2, fb=True, tm=True))
+            out.append(inst(bits, nx, nu, N, CON, refs=REFS_L2, tm=True))
             if (nx, nu) == (12, 4):
                 out.append(inst(bits, nx, nu, N, ADP, refs=REFS_L2, fb=True, tm=True))
                 out.append(inst(bits, nx, nu, N, ADP, refs=REFS_L2, tm=True))
     # A/B: hoistable (immediate-offset, LDCU.128) constant loads on the tensor-memory instances, option variant=3
     out.append(inst(32, 12, 4, 10, BOX, refs=REFS_L2, variant=3, fb=True, tm=True, opq=True))
     out.append(inst(32, 4, 1, 20, BOX, refs=REFS_NONE, variant=3, fb=True, tm=True, opq=True))
+    # A/B: 16 warps/SM on the small shape, option variant=4
+    out.append(inst(32, 4, 1, 20, BOX, refs=REFS_NONE, variant=4, fb=True, tm=True, max_warps=16))
     # A/B baseline: the shared-memory-only (8 warps/SM) form of the headline shapes, option variant=2
     out.append(inst(32, 12, 4, 10, BOX, refs=REFS_L2, variant=2, fb=True))
     out.append(inst(32, 4, 1, 20, BOX, refs=REFS_NONE, variant=2, fb=True))
@@ -122,7 +137,7 @@ def gen_sources(instances):
             f'#include "../tmpc_tpp{g}.cuh"\n#include "../tmpc_registry.h"\nusing namespace tmpc;\n'
             f"using Cfg_{n} = Tpp{g}Cfg<{T}, {i['nx']}, {i['nu']}, {i['N']}, {FEAT_ENUM[i['feat']]}, {i['block']}, "
             f"{i['refs']}, {'true' if i['ppb'] else 'false'}, {i['minb']}, {'true' if i['fb'] else 'false'}"
-            f"{((', true' if i['aff'] else ', false') + (', true' if i['tm'] else ', false') + (', true' if i['opq'] else ', false')) if g else ''}>;\n"
+            f"{((', true' if i['aff'] else ', false') + (', %d' % i['ntm']) + (', true' if i['opq'] else ', false') + (', true' if i['tib'] else ', false')) if g else ''}>;\n"
             f"TMPC_DEFINE_TPP{g}_ENTRY({n}, Cfg_{n}, {i['feat']}, {i['bits']}, {i['variant']})\n"
         )
         path = GEN / f"{n}.cu"

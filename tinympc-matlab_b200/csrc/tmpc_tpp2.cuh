@@ -461,7 +461,7 @@ struct SmemTraj : Traj<T, N, S, OFF, BLOCK> {
     __device__ __forceinline__ void stores_done() const {}
 };
 
-template <typename T_, int NX_, int NU_, int NH_, int FEAT_, int BLOCK_, int REFS_, bool PPB_, int MINB_ = 1, bool FB_ = false, bool AFF_ = true, bool TM_ = false, bool OPQ_ = true>
+template <typename T_, int NX_, int NU_, int NH_, int FEAT_, int BLOCK_, int REFS_, bool PPB_, int MINB_ = 1, bool FB_ = false, bool AFF_ = true, int NTM_ = 0, bool OPQ_ = true, bool TIB_ = false>
 struct Tpp2Cfg {
     using T = T_;
     static constexpr int NX = NX_, NU = NU_, NH = NH_, FEAT = FEAT_, BLOCK = BLOCK_, MINB = MINB_;
@@ -470,8 +470,12 @@ struct Tpp2Cfg {
     static constexpr bool PPB = PPB_;                       // per-problem bounds read from global memory
     static constexpr bool FB = FB_ && !PPB_;                // "fast box": every shared box contains 0 (cold start needs no special case)
     static constexpr bool AFF = AFF_;                       // affine dynamics term: f, APf, BPf may be non-zero
+    static constexpr bool TIB = TIB_ && FB_ && !PPB_ && !OPQ_;   // fast-box bounds read from time row 0 with immediate addresses
     static constexpr bool OPQ = OPQ_;                       // loop-variant (opaque) constant-bank offsets: see opaque_zero4()
-    static constexpr bool TM = TM_ && sizeof(T_) == 4;      // TV lives in tensor memory (one CTA per SM, BLOCK up to 512 * 128 / SX threads)
+    // number of state-sized arrays held in tensor memory instead of shared memory, in the order TV, GC, GL, SXT
+    // (the last three exist only with cones / linear rows); one CTA per SM owns all 512 columns
+    static constexpr int NTM = (sizeof(T_) == 4) ? ((FEAT_ == FEAT_CONSTR) ? NTM_ : (NTM_ > 0 ? 1 : 0)) : 0;
+    static constexpr bool TM = NTM > 0;
     static constexpr bool CONSTR = FEAT_ == FEAT_CONSTR;
     static constexpr bool ADAPT = FEAT_ == FEAT_ADAPT;
     static constexpr int SX = NX * NH, SU = NU * (NH - 1);
@@ -480,19 +484,19 @@ struct Tpp2Cfg {
     static constexpr int VU = (NU_ % 4 == 0) ? 4 : ((NU_ % 2 == 0) ? 2 : 1);
     // scalar-column offsets of the shared-memory state
     static constexpr int oTV = 0;
-    static constexpr int oTZ = oTV + (TM ? 0 : SX);
+    static constexpr int oTZ = oTV + (NTM >= 1 ? 0 : SX);
     static constexpr int oD = oTZ + SU;
     static constexpr int oGC = oD + SU;
-    static constexpr int oGL = oGC + (CONSTR ? SX : 0);
-    static constexpr int oSX = oGL + (CONSTR ? SX : 0);
-    static constexpr int oYC = oSX + (CONSTR ? SX : 0);
+    static constexpr int oGL = oGC + (CONSTR && NTM < 2 ? SX : 0);
+    static constexpr int oSX = oGL + (CONSTR && NTM < 3 ? SX : 0);
+    static constexpr int oYC = oSX + (CONSTR && NTM < 4 ? SX : 0);
     static constexpr int oYL = oYC + (CONSTR ? SU : 0);
     static constexpr int oSU = oYL + (CONSTR ? SU : 0);
     static constexpr int oSCR = oSU + (CONSTR ? SU : 0);
     static constexpr int COLS = oSCR + (CONSTR ? (NX > NU ? NX : NU) : 0);   // + cone scratch column
     // tensor-memory columns per thread: warps w, w+4, w+8, ... share a lane quarter
-    static constexpr int TM_COLS_PER_THREAD = SX;
-    static_assert(!TM || ((BLOCK_ / 32 + 3) / 4) * SX <= 512, "TV does not fit the 512 tensor-memory columns");
+    static constexpr int TM_COLS_PER_THREAD = NTM * SX;
+    static_assert(((BLOCK_ / 32 + 3) / 4) * TM_COLS_PER_THREAD <= 512, "the state does not fit the 512 tensor-memory columns");
 };
 
 // second-order-cone projection of scr[start .. start+dim) in place (admm.cpp:39-60).
@@ -653,20 +657,26 @@ tpp2_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ typ
     T* cta_cols = pack + ((prm.pack_elems + 31) & ~31);
     const int tid = threadIdx.x;
     // t = x + g (pre-clamp state slack): shared-memory pair columns, or this thread's tensor-memory columns
-    using TVT = std::conditional_t<C::TM, TmemTraj<NX, NH>, SmemTraj<T, NX, NH, C::oTV, BLOCK>>;
-    TVT TV = [&]() {
+    // array number A of the state-sized arrays (TV, GC, GL, SXT) lives in tensor memory iff A < NTM
+    const uint32_t tm_thread_base = [&]() -> uint32_t {
         if constexpr (C::TM) {
             const uint32_t w = static_cast<uint32_t>(tid) >> 5;
-            return TVT{tmem_base_s + ((32u * (w & 3u)) << 16) + (w >> 2) * SXL};
+            return tmem_base_s + ((32u * (w & 3u)) << 16) + (w >> 2) * C::TM_COLS_PER_THREAD;
         } else {
-            return TVT(cta_cols, tid);
+            return 0u;
         }
     }();
+    auto make_x = [&](auto a_tag, auto off_tag) {
+        constexpr int A = decltype(a_tag)::value, OFF = decltype(off_tag)::value;
+        if constexpr (A < C::NTM) return TmemTraj<NX, NH>{tm_thread_base + A * SXL};
+        else return SmemTraj<T, NX, NH, OFF, BLOCK>(cta_cols, tid);
+    };
+    auto TV = make_x(std::integral_constant<int, 0>{}, std::integral_constant<int, C::oTV>{});
+    auto GC = make_x(std::integral_constant<int, 1>{}, std::integral_constant<int, C::oGC>{});    // cone duals (state)
+    auto GL = make_x(std::integral_constant<int, 2>{}, std::integral_constant<int, C::oGL>{});    // linear duals (state)
+    auto SXT = make_x(std::integral_constant<int, 3>{}, std::integral_constant<int, C::oSX>{});   // (vc - gc) + (vl - gl)
     Traj<T, NU, NH - 1, C::oTZ, BLOCK> TZ(cta_cols, tid);    // t = u + y   (pre-clamp input slack)
     Traj<T, NU, NH - 1, C::oD, BLOCK> ND(cta_cols, tid);     // -d of the backward pass
-    Col<T, C::oGC, BLOCK> GC(cta_cols, tid);      // cone duals (state)
-    Col<T, C::oGL, BLOCK> GL(cta_cols, tid);      // linear duals (state)
-    Col<T, C::oSX, BLOCK> SXT(cta_cols, tid);     // (vc - gc) + (vl - gl)
     Col<T, C::oYC, BLOCK> YC(cta_cols, tid);
     Col<T, C::oYL, BLOCK> YL(cta_cols, tid);
     Col<T, C::oSU, BLOCK> SUT(cta_cols, tid);
@@ -737,13 +747,18 @@ tpp2_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ typ
     x0v.fill(T(0)); ptv.fill(T(0)); ptv1.fill(T(0));
 
     // box bounds of state pair j (elements 2j, 2j+1) / tail element of time step i
+    // time row of the shared bound tables: fast-box families have time-invariant bounds (tmpc_capi.cu); TIB instances
+    // read row 0 with immediate addresses (LDCU.128, hoistable).  Measured: +10 % cartpole, +5 % adaptive quadrotor,
+    // -7 % on the plain quadrotor kernel (the bounds then compete with the matrix coefficients for the uniform
+    // registers), so build.py sets it per instance.
+    auto bt = [](int i) { return C::TIB ? 0 : i; };
     auto xb_pair = [&](int i, int j, size_t pb, P& lo, P& hi) {
         if constexpr (C::PPB) {
             const size_t e = pb + (size_t)i * NX + 2 * j;
             lo = en_sb ? mk2(static_cast<T>(__ldg(prm.x_min + e)), static_cast<T>(__ldg(prm.x_min + e + 1))) : mk2(-N::inf(), -N::inf());
             hi = en_sb ? mk2(static_cast<T>(__ldg(prm.x_max + e)), static_cast<T>(__ldg(prm.x_max + e + 1))) : mk2(N::inf(), N::inf());
         } else {
-            lo = mk2(cp.xmin[i * NXP + 2 * j], cp.xmin[i * NXP + 2 * j + 1]); hi = mk2(cp.xmax[i * NXP + 2 * j], cp.xmax[i * NXP + 2 * j + 1]);
+            lo = mk2(cp.xmin[bt(i) * NXP + 2 * j], cp.xmin[bt(i) * NXP + 2 * j + 1]); hi = mk2(cp.xmax[bt(i) * NXP + 2 * j], cp.xmax[bt(i) * NXP + 2 * j + 1]);
         }
     };
     auto xb_tail = [&](int i, size_t pb, T& lo, T& hi) {
@@ -751,7 +766,7 @@ tpp2_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ typ
             const size_t e = pb + (size_t)i * NX + NX - 1;
             lo = en_sb ? static_cast<T>(__ldg(prm.x_min + e)) : -N::inf();
             hi = en_sb ? static_cast<T>(__ldg(prm.x_max + e)) : N::inf();
-        } else { lo = cp.xmin[i * NXP + NX - 1]; hi = cp.xmax[i * NXP + NX - 1]; }
+        } else { lo = cp.xmin[bt(i) * NXP + NX - 1]; hi = cp.xmax[bt(i) * NXP + NX - 1]; }
     };
     auto ub_pair = [&](int i, int j, size_t pb, P& lo, P& hi) {
         if constexpr (C::PPB) {
@@ -759,7 +774,7 @@ tpp2_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ typ
             lo = en_ib ? mk2(static_cast<T>(__ldg(prm.u_min + e)), static_cast<T>(__ldg(prm.u_min + e + 1))) : mk2(-N::inf(), -N::inf());
             hi = en_ib ? mk2(static_cast<T>(__ldg(prm.u_max + e)), static_cast<T>(__ldg(prm.u_max + e + 1))) : mk2(N::inf(), N::inf());
         } else {
-            lo = mk2(cp.umin[i * NUP + 2 * j], cp.umin[i * NUP + 2 * j + 1]); hi = mk2(cp.umax[i * NUP + 2 * j], cp.umax[i * NUP + 2 * j + 1]);
+            lo = mk2(cp.umin[bt(i) * NUP + 2 * j], cp.umin[bt(i) * NUP + 2 * j + 1]); hi = mk2(cp.umax[bt(i) * NUP + 2 * j], cp.umax[bt(i) * NUP + 2 * j + 1]);
         }
     };
     auto ub_tail = [&](int i, size_t pb, T& lo, T& hi) {
@@ -767,7 +782,7 @@ tpp2_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ typ
             const size_t e = pb + (size_t)i * NU + NU - 1;
             lo = en_ib ? static_cast<T>(__ldg(prm.u_min + e)) : -N::inf();
             hi = en_ib ? static_cast<T>(__ldg(prm.u_max + e)) : N::inf();
-        } else { lo = cp.umin[i * NUP + NU - 1]; hi = cp.umax[i * NUP + NU - 1]; }
+        } else { lo = cp.umin[bt(i) * NUP + NU - 1]; hi = cp.umax[bt(i) * NUP + NU - 1]; }
     };
 
     for (;;) {
@@ -885,13 +900,12 @@ tpp2_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ typ
                         }
                         if constexpr (C::CONSTR) {
 #pragma unroll 4
-                            for (int e = 0; e < SXL; ++e) { GC.set(e, T(0)); GL.set(e, T(0)); SXT.set(e, T(0)); }
-#pragma unroll 4
                             for (int e = 0; e < SUL; ++e) { YC.set(e, T(0)); YL.set(e, T(0)); SUT.set(e, T(0)); }
                         }
                     }
                 }
                 TV.reset(want && active);   // warp-collective when TV lives in tensor memory
+                if constexpr (C::CONSTR) { GC.reset(want && active); GL.reset(want && active); }   // SXT is written before it is read
             }
             if (!__any_sync(FULL, active)) break;
         }
@@ -950,25 +964,29 @@ tpp2_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ typ
                 }
             }
             if constexpr (C::CONSTR) {
-                T extra[NX];
-#pragma unroll
-                for (int r = 0; r < NX; ++r) extra[r] = 0;
+                VX extra;
+                extra.fill(T(0));
                 if (soc_x) {   // admm.cpp:103,112-122,191
+                    VX gcv;
+                    GC.load(i, gcv);
 #pragma unroll
-                    for (int r = 0; r < NX; ++r) scr[r * BLOCK] = x.get(r) + GC.get(i * NX + r);
+                    for (int r = 0; r < NX; ++r) scr[r * BLOCK] = x.get(r) + gcv.get(r);
                     for (int c = 0; c < prm.n_state_cones; ++c) project_soc_col2<T, BLOCK>(scr, prm.Acx[c], prm.qcx[c], prm.cx[c]);
 #pragma unroll
                     for (int r = 0; r < NX; ++r) {
                         const T vc = scr[r * BLOCK];
-                        const T gcn = (GC.get(i * NX + r) + x.get(r)) - vc;
-                        GC.set(i * NX + r, gcn);
-                        extra[r] += vc - gcn;
+                        const T gcn = (gcv.get(r) + x.get(r)) - vc;
+                        gcv.set(r, gcn);
+                        extra.set(r, extra.get(r) + (vc - gcn));
                     }
+                    GC.store(i, gcv);
                 }
                 if (lin_x) {   // admm.cpp:139,148-159,201
                     T vl[NX];
+                    VX glv;
+                    GL.load(i, glv);
 #pragma unroll
-                    for (int r = 0; r < NX; ++r) vl[r] = x.get(r) + GL.get(i * NX + r);
+                    for (int r = 0; r < NX; ++r) vl[r] = x.get(r) + glv.get(r);
                     for (int c = 0; c < nsl; ++c) {
                         T val = 0;
 #pragma unroll
@@ -981,13 +999,13 @@ tpp2_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ typ
                     }
 #pragma unroll
                     for (int r = 0; r < NX; ++r) {
-                        const T gln = (GL.get(i * NX + r) + x.get(r)) - vl[r];
-                        GL.set(i * NX + r, gln);
-                        extra[r] += vl[r] - gln;
+                        const T gln = (glv.get(r) + x.get(r)) - vl[r];
+                        glv.set(r, gln);
+                        extra.set(r, extra.get(r) + (vl[r] - gln));
                     }
+                    GL.store(i, glv);
                 }
-#pragma unroll
-                for (int r = 0; r < NX; ++r) SXT.set(i * NX + r, extra[r]);
+                SXT.store(i, extra);
             }
             if constexpr (C::ADAPT) {
                 // dual residual blocks of column i-1 need g_i (post update): x-block A'g_i - g_{i-1}, u-block y_{i-1} + B'g_i
@@ -1201,15 +1219,16 @@ tpp2_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ typ
         // box slack minus dual of one element: w = 2 clamp(t) - t (+ cone / linear terms)
         auto w_of = [&](auto t, auto lo, auto hi) { return twice_minus(clampv(t, lo, hi), t); };
 
-        VX p, tvv;
+        VX p, tvv, sxv;
         {   // p_N = -(xref_N' Pinf)' - rho (vnew_N - g_N) ...  (admm.cpp:238-246)
             TV.load(NH - 1, tvv);
+            if constexpr (C::CONSTR) SXT.load(NH - 1, sxv);
 #pragma unroll
             for (int j = 0; j < NX / 2; ++j) {
                 P lo, hi;
                 xb_pair(NH - 1, j, pbx, lo, hi);
                 P w = w_of(tvv.p[j], lo, hi);
-                if constexpr (C::CONSTR) w = addv(w, mk2(SXT.get((NH - 1) * NX + 2 * j), SXT.get((NH - 1) * NX + 2 * j + 1)));
+                if constexpr (C::CONSTR) w = addv(w, sxv.p[j]);
                 P pt = ptv.p[j];
                 if constexpr (C::ADAPT) pt = fmas(ptv1.p[j], dlt_lc, pt);
                 p.p[j] = fmas(w, nrho, pt);
@@ -1218,7 +1237,7 @@ tpp2_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ typ
                 T lo, hi;
                 xb_tail(NH - 1, pbx, lo, hi);
                 T w = w_of(tvv.t, lo, hi);
-                if constexpr (C::CONSTR) w += SXT.get((NH - 1) * NX + NX - 1);
+                if constexpr (C::CONSTR) w += sxv.t;
                 T pt = ptv.t;
                 if constexpr (C::ADAPT) pt = fmas(ptv1.t, dlt_lc, pt);
                 p.t = fmas(w, nrho, pt);
@@ -1228,6 +1247,7 @@ tpp2_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ typ
         for (int i = NH - 2; i >= 0; --i) {
             const int zb = C::OPQ ? opaque_zero4() : 0;
             TV.load(i, tvv);
+            if constexpr (C::CONSTR) SXT.load(i, sxv);
             // The terms of step i move to their own registers with copies the compiler cannot remove, and the fetch
             // for step i-1 is issued at once: a whole step of distance to the L2.  (With plain copies the register
             // allocator coalesces both buffers and sinks the loads to the end of the loop body: distance zero, 8 % of
@@ -1281,14 +1301,14 @@ tpp2_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ typ
                 P lo, hi;
                 xb_pair(i, j, pbx, lo, hi);
                 P w = w_of(tvv.p[j], lo, hi);
-                if constexpr (C::CONSTR) w = addv(w, mk2(SXT.get(i * NX + 2 * j), SXT.get(i * NX + 2 * j + 1)));
+                if constexpr (C::CONSTR) w = addv(w, sxv.p[j]);
                 pn.p[j] = fmas(w, nrho, sq_cur.p[j]);
             }
             if constexpr (NX & 1) {
                 T lo, hi;
                 xb_tail(i, pbx, lo, hi);
                 T w = w_of(tvv.t, lo, hi);
-                if constexpr (C::CONSTR) w += SXT.get(i * NX + NX - 1);
+                if constexpr (C::CONSTR) w += sxv.t;
                 pn.t = fmas(w, nrho, sq_cur.t);
             }
             mv_acc<NX, NX>(cp.AK, zb, p, pn);
