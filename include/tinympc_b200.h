@@ -130,6 +130,32 @@ typedef struct {
 } tinympc_cuda_workspace;
 int  tinympc_cuda_solve_workspace(tinympc_cuda_solver *s, const tinympc_cuda_workspace *w);
 
+/* ---- sessions: a batch of warm-started solvers resident on the device ------------------------- */
+/* The closed-loop pattern of the reference (tinympc/TinyMPC/examples/quadrotor_hovering.cpp:73-93,
+ * examples/cartpole_example_mpc.m:36-44): { tiny_set_x0; tiny_solve; x0 = A x0 + B u0 } repeated on ONE solver whose
+ * workspace persists between solves (admm.cpp starts from the q, r, p, d, duals and slacks of the previous solve).
+ * A session is `batch` such solvers of the family, each with its own complete TinyWorkspace and cache copy
+ * (types.hpp:43-187) in device memory; every call below acts on all of them.  Arithmetic follows the "precision" option
+ * at creation (64 reproduces the reference's iteration counts exactly).  All array arguments are HOST pointers. */
+typedef struct tinympc_cuda_session tinympc_cuda_session;
+/* `batch` solvers as tiny_setup + the constraint setters leave them (cold workspaces, pristine cache), on device `dev_index` */
+int  tinympc_cuda_session_create(tinympc_cuda_solver *s, int dev_index, int batch, tinympc_cuda_session **out);
+int  tinympc_cuda_session_destroy(tinympc_cuda_session *ss);
+/* tiny_set_x0 / tiny_set_x_ref / tiny_set_u_ref on every solver (tiny_api.cpp:375-409).  x0: batch*nx doubles.
+ * Xref: batch*nx*N (broadcast 0) or one nx*N array shared by all (broadcast 1); Uref likewise with nu*(N-1). */
+int  tinympc_cuda_session_set_x0(tinympc_cuda_session *ss, const double *x0);
+int  tinympc_cuda_session_set_x_ref(tinympc_cuda_session *ss, const double *Xref, int broadcast);
+int  tinympc_cuda_session_set_u_ref(tinympc_cuda_session *ss, const double *Uref, int broadcast);
+/* tiny_solve on every solver, warm start (tiny_api.cpp:321-323 -> admm.cpp:274-389) */
+int  tinympc_cuda_session_solve(tinympc_cuda_session *ss);
+/* x0 <- Adyn x0 + Bdyn u0 + fdyn on the device; u0 = work->u.col(0) (use_solution 0, quadrotor_hovering.cpp:91) or
+ * solution->u.col(0) (use_solution 1, cartpole_example_mpc.m:40-41) */
+int  tinympc_cuda_session_step(tinympc_cuda_session *ss, int use_solution);
+/* read one member of every solver into host memory (doubles; iter/status as doubles too):
+ * "x0" batch*nx | "x", "sol_x" batch*nx*N (work->x, solution->x) | "u", "sol_u" batch*nu*(N-1) |
+ * "iter", "status", "rho" batch | "residuals" batch*4 */
+int  tinympc_cuda_session_read(tinympc_cuda_session *ss, const char *field, double *host);
+
 /* ---- knobs and introspection ----------------------------------------------------------------- */
 /* option names: "precision" (32 = fp32 arithmetic [default], 64 = fp64 parity mode),
    "ctas_per_sm" (0 = occupancy API), "chunks" (host pipeline depth, 0 = auto),

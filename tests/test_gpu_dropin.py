@@ -224,3 +224,73 @@ def test_reference_host_closed_loop_with_gpu_hot_path(name, oracle_mod):
         assert np.abs(r["x"] - g["x"][k]).max() < 1e-9
         assert np.abs(r["work_u0"] - g["work_u0"][k]).max() < 1e-9
     s.close()
+
+
+# ------------------------------------------------------------------------------------------------------------
+# Sessions: a batch of warm-started solvers resident on the device
+# ------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("cfg", ["quadrotor", "cartpole", "rocket", "quadrotor_adaptive"])
+def test_session_closed_loop_matches_reference_per_problem(cfg, tm, oracle_mod):
+    """{set_x0; solve; x0 = A x0 + B u0 + f} for 12 steps on 24 independent systems at once (fp64): every solver of the
+    session must take exactly the iterations, and produce the trajectory, of a reference solver driven the same way."""
+    O = oracle_mod
+    p = {"quadrotor": P.quadrotor, "cartpole": lambda: P.cartpole(N=10), "rocket": P.rocket,
+         "quadrotor_adaptive": lambda: P.quadrotor(adaptive=True)}[cfg]()
+    impl = "ref" if O.available("ref") else "port"
+    B, steps = 24, 12
+    b = P.make_batch(p, B, 0.6, seed=11)
+    s = tm.TinyMPC().setup_from_spec(p, devices=[0])
+    s.cuda.set_option("precision", 64)
+    ses = s.cuda.session(B)
+    Xref = b.Xref.astype(np.float64) if b.Xref is not None else np.zeros((B, p.N, p.nx))
+    Uref = b.Uref.astype(np.float64) if b.Uref is not None else np.zeros((B, p.N - 1, p.nu))
+    ses.set_x_ref(Xref); ses.set_u_ref(Uref)
+    x0 = b.x0.astype(np.float64)
+    ses.set_x0(x0)
+    refs = [O.Session(p, impl) for _ in range(B)]
+    for k in range(B):
+        refs[k].set_x_ref(Xref[k]); refs[k].set_u_ref(Uref[k])
+    Bm = np.asarray(p.B).reshape(p.nx, p.nu)
+    xr = x0.copy()
+    for t in range(steps):
+        ses.solve()
+        it, st, sx, wu = ses.read("iter"), ses.read("status"), ses.read("sol_x"), ses.read("u")
+        for k in range(B):
+            refs[k].set_x0(xr[k])
+            r = refs[k].solve()
+            assert it[k] == r["iter"] and st[k] == r["status"], (cfg, t, k, it[k], r["iter"])
+            assert np.abs(sx[k] - r["x"]).max() < 1e-8 * max(1.0, np.abs(r["x"]).max())
+            assert np.abs(wu[k, 0] - r["work_u0"]).max() < 1e-8 * max(1.0, np.abs(r["work_u0"]).max())
+            xr[k] = p.A @ xr[k] + Bm @ r["work_u0"] + p.f
+        ses.step()                                        # on the device
+        assert np.abs(ses.read("x0") - xr).max() < 1e-8 * max(1.0, np.abs(xr).max())
+    for r in refs:
+        r.close()
+    ses.close()
+
+
+def test_session_fp32_tracks_the_reference(tm, oracle_mod):
+    """fp32 session: same closed loop within the fp32 tolerance of the north star (1e-4 on states / controls)."""
+    O = oracle_mod
+    p = P.quadrotor()
+    impl = "ref" if O.available("ref") else "port"
+    B, steps = 16, 8
+    b = P.make_batch(p, B, 0.3, seed=5)
+    s = tm.TinyMPC().setup_from_spec(p, devices=[0])
+    ses = s.cuda.session(B)                      # precision option 32 (default)
+    ses.set_x_ref(b.Xref.astype(np.float64)); ses.set_x0(b.x0.astype(np.float64))
+    refs = [O.Session(p, impl) for _ in range(B)]
+    xr = b.x0.astype(np.float64)
+    Bm = np.asarray(p.B).reshape(p.nx, p.nu)
+    for k in range(B):
+        refs[k].set_x_ref(b.Xref[k].astype(np.float64))
+    for t in range(steps):
+        ses.solve()
+        sx = ses.read("sol_x")
+        for k in range(B):
+            refs[k].set_x0(xr[k]); r = refs[k].solve()
+            assert np.abs(sx[k] - r["x"]).max() < 2e-3        # a flipped iteration count moves the iterate by O(tol)
+            xr[k] = p.A @ xr[k] + Bm @ r["work_u0"] + p.f
+        ses.step()
+        assert np.abs(ses.read("x0") - xr).max() < 2e-3
+    ses.close()

@@ -37,6 +37,8 @@ EXPORTS = [
     "tinympc_cuda_solve_batch_device", "tinympc_cuda_solve_workspace", "tinympc_cuda_set_option", "tinympc_cuda_device_count", "tinympc_cuda_num_devices",
     "tinympc_cuda_last_kernel", "tinympc_cuda_launch_count", "tinympc_cuda_last_timing", "tinympc_cuda_last_error",
     "tinympc_cuda_version", "tinympc_cuda_host_alloc", "tinympc_cuda_host_free",
+    "tinympc_cuda_session_create", "tinympc_cuda_session_destroy", "tinympc_cuda_session_set_x0", "tinympc_cuda_session_set_x_ref",
+    "tinympc_cuda_session_set_u_ref", "tinympc_cuda_session_solve", "tinympc_cuda_session_step", "tinympc_cuda_session_read",
 ]
 
 
@@ -105,6 +107,14 @@ def load():
         L.tinympc_cuda_host_alloc.argtypes = [C.c_size_t]
         L.tinympc_cuda_host_alloc.restype = C.c_void_p
         L.tinympc_cuda_host_free.argtypes = [C.c_void_p]
+        L.tinympc_cuda_session_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+        L.tinympc_cuda_session_destroy.argtypes = [C.c_void_p]
+        L.tinympc_cuda_session_set_x0.argtypes = [C.c_void_p, c_dp]
+        L.tinympc_cuda_session_set_x_ref.argtypes = [C.c_void_p, c_dp, C.c_int]
+        L.tinympc_cuda_session_set_u_ref.argtypes = [C.c_void_p, c_dp, C.c_int]
+        L.tinympc_cuda_session_solve.argtypes = [C.c_void_p]
+        L.tinympc_cuda_session_step.argtypes = [C.c_void_p, C.c_int]
+        L.tinympc_cuda_session_read.argtypes = [C.c_void_p, C.c_char_p, c_dp]
         # plain-C shim over the host C++ API mirror (csrc/host/tiny_capi_shim.cpp)
         dp, ip, vp = c_dp, c_ip, C.c_void_p
         L.tinympc_host_setup.argtypes = [dp, dp, dp, dp, dp, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, ip]
@@ -284,9 +294,75 @@ class CudaSolver:
         self._check(self.L.tinympc_cuda_solve_batch(self.h, C.byref(cin), C.byref(co)))
         return out
 
+    def session(self, batch: int, dev_index: int = 0) -> "CudaSession":
+        """`batch` warm-started solvers of the family, resident on the device (tinympc_cuda_session_*)."""
+        return CudaSession(self, batch, dev_index)
+
     # ---- device buffers (raw pointers, e.g. torch.Tensor.data_ptr()) ---------------------------
     def solve_batch_device(self, batch: int, x0, Xref, Uref, x, u, iters, status, residuals=None, rho=None,
                            x_min=None, x_max=None, u_min=None, u_max=None, stream=None, dev_index=0):
         cin = CBatchIn(batch, x0, Xref, Uref, x_min, x_max, u_min, u_max)
         co = CBatchOut(x, u, iters, status, residuals, rho)
         self._check(self.L.tinympc_cuda_solve_batch_device(self.h, dev_index, C.byref(cin), C.byref(co), stream))
+
+
+class CudaSession:
+    """A batch of warm-started solvers on the device: the closed-loop pattern of the reference
+    (tinympc/TinyMPC/examples/quadrotor_hovering.cpp:73-93) for `batch` independent systems at once."""
+
+    def __init__(self, solver: CudaSolver, batch: int, dev_index: int = 0):
+        self.solver, self.L, self.batch = solver, solver.L, int(batch)
+        self.nx, self.nu, self.N = solver.dims
+        self.h = C.c_void_p()
+        solver._check(self.L.tinympc_cuda_session_create(solver.h, dev_index, self.batch, C.byref(self.h)))
+
+    def close(self):
+        if self.h:
+            self.L.tinympc_cuda_session_destroy(self.h)
+        self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _arr(self, a, shape_batch, shape_one):
+        """(pointer, broadcast flag, keep-alive array) for a per-solver array or one array shared by all solvers"""
+        if a is None:
+            return None, 0, None
+        a = np.ascontiguousarray(a, np.float64)
+        if a.shape == shape_one:
+            return a.ctypes.data_as(c_dp), 1, a
+        if a.shape != shape_batch:
+            raise ValueError(f"expected shape {shape_batch} or {shape_one}, got {a.shape}")
+        return a.ctypes.data_as(c_dp), 0, a
+
+    def set_x0(self, x0):
+        x0 = np.ascontiguousarray(x0, np.float64)
+        if x0.shape != (self.batch, self.nx):
+            raise ValueError(f"expected shape {(self.batch, self.nx)}, got {x0.shape}")
+        self.solver._check(self.L.tinympc_cuda_session_set_x0(self.h, x0.ctypes.data_as(c_dp)))
+
+    def set_x_ref(self, Xref):
+        p, bc, keep = self._arr(Xref, (self.batch, self.N, self.nx), (self.N, self.nx))
+        self.solver._check(self.L.tinympc_cuda_session_set_x_ref(self.h, p, bc))
+
+    def set_u_ref(self, Uref):
+        p, bc, keep = self._arr(Uref, (self.batch, self.N - 1, self.nu), (self.N - 1, self.nu))
+        self.solver._check(self.L.tinympc_cuda_session_set_u_ref(self.h, p, bc))
+
+    def solve(self):
+        self.solver._check(self.L.tinympc_cuda_session_solve(self.h))
+
+    def step(self, use_solution: bool = False):
+        """x0 <- A x0 + B u0 + f on the device; u0 = work->u[:, 0] (default) or solution->u[:, 0]"""
+        self.solver._check(self.L.tinympc_cuda_session_step(self.h, 1 if use_solution else 0))
+
+    def read(self, field: str) -> np.ndarray:
+        nx, nu, N, B = self.nx, self.nu, self.N, self.batch
+        shape = {"x0": (B, nx), "x": (B, N, nx), "sol_x": (B, N, nx), "u": (B, N - 1, nu), "sol_u": (B, N - 1, nu),
+                 "iter": (B,), "status": (B,), "rho": (B,), "residuals": (B, 4)}[field]
+        out = np.empty(shape, np.float64)
+        self.solver._check(self.L.tinympc_cuda_session_read(self.h, field.encode(), out.ctypes.data_as(c_dp)))
+        return out.astype(np.int32) if field in ("iter", "status") else out

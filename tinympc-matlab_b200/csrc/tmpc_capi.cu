@@ -88,6 +88,15 @@ struct tinympc_cuda_solver {
     int t_chunks = 0;
 };
 
+struct tinympc_cuda_session {
+    tinympc_cuda_solver* s = nullptr;
+    int dev = 0, batch = 0, bits = 64;
+    Family fam;                        // the family at creation time (a later set_family does not disturb a live session)
+    WppLayout W{};
+    DevBuf ws, pack, x, u, iter, status;
+    std::vector<unsigned char> stage;
+};
+
 namespace {
 
 int fail(tinympc_cuda_solver* s, int code, const std::string& msg) {
@@ -624,6 +633,173 @@ int tinympc_cuda_solve_workspace(tinympc_cuda_solver* s, const tinympc_cuda_work
     if (w->solved) *w->solved = (int)h[W.scalars + 7];
     if (w->residuals) for (int k = 0; k < 4; ++k) w->residuals[k] = h[W.scalars + 3 + k];
     return TINYMPC_CUDA_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// sessions: persistent per-problem workspaces iterated in place by the warp-per-problem kernel (exact tiny_solve
+// warm-start semantics, tmpc_wpp.cu mode 2)
+// ---------------------------------------------------------------------------------------------------------------
+int tinympc_cuda_session_create(tinympc_cuda_solver* s, int dev_index, int batch, tinympc_cuda_session** out) {
+    if (!s || !out) return TINYMPC_CUDA_EINVAL;
+    *out = nullptr;
+    if (!s->fam.set) return fail(s, TINYMPC_CUDA_ENOTREADY, "tinympc_cuda_set_family has not been called");
+    if (dev_index < 0 || dev_index >= (int)s->devs.size()) return fail(s, TINYMPC_CUDA_EINVAL, "dev_index out of range");
+    if (batch < 1) return fail(s, TINYMPC_CUDA_EINVAL, "session batch must be >= 1");
+    if (!s->fam.shared_bounds_ok) return fail(s, TINYMPC_CUDA_EINVAL, "bound constraints are enabled but the family has no bounds");
+    auto* ss = new tinympc_cuda_session();
+    ss->s = s; ss->dev = dev_index; ss->batch = batch; ss->bits = s->precision;
+    ss->fam = s->fam;
+    ss->W = WppLayout::make(ss->fam.nx, ss->fam.nu, ss->fam.N);
+    DeviceCtx& d = s->devs[dev_index];
+    int prev = 0;
+    cudaGetDevice(&prev);
+    auto bail = [&](cudaError_t e, const char* what) { cudaSetDevice(prev); tinympc_cuda_session_destroy(ss); return cuda_fail(s, e, what); };
+    cudaError_t e = cudaSetDevice(d.device);
+    if (e != cudaSuccess) return bail(e, "cudaSetDevice");
+    const size_t esz = ss->bits == 64 ? sizeof(double) : sizeof(float);
+    const size_t sx = (size_t)ss->fam.nx * ss->fam.N, su = (size_t)ss->fam.nu * (ss->fam.N - 1);
+    if ((e = ss->ws.reserve((size_t)batch * ss->W.size * esz)) != cudaSuccess) return bail(e, "session workspace allocation");
+    if ((e = ss->x.reserve(sizeof(float) * sx * batch)) != cudaSuccess) return bail(e, "session buffer");
+    if ((e = ss->u.reserve(sizeof(float) * su * batch)) != cudaSuccess) return bail(e, "session buffer");
+    if ((e = ss->iter.reserve(sizeof(int) * (size_t)batch)) != cudaSuccess) return bail(e, "session buffer");
+    if ((e = ss->status.reserve(sizeof(int) * (size_t)batch)) != cudaSuccess) return bail(e, "session buffer");
+    // the family pack in the session's precision lives with the solver (re-uploaded by set_family); keep our own copy
+    if ((e = ss->pack.reserve(ss->fam.pack.size() * esz)) != cudaSuccess) return bail(e, "session pack");
+    if (ss->bits == 64) {
+        e = cudaMemcpy(ss->pack.p, ss->fam.pack.data(), ss->fam.pack.size() * sizeof(double), cudaMemcpyHostToDevice);
+    } else {
+        std::vector<float> p32(ss->fam.pack.size());
+        for (size_t i = 0; i < p32.size(); ++i) p32[i] = static_cast<float>(ss->fam.pack[i]);
+        e = cudaMemcpy(ss->pack.p, p32.data(), p32.size() * sizeof(float), cudaMemcpyHostToDevice);
+    }
+    if (e != cudaSuccess) return bail(e, "session pack upload");
+    cudaStream_t st = d.streams[0];
+    e = ss->bits == 64 ? wpp_session_init<double>(ss->fam.base, ss->fam.L, ss->pack.p, ss->W, ss->ws.p, batch, st)
+                       : wpp_session_init<float>(ss->fam.base, ss->fam.L, ss->pack.p, ss->W, ss->ws.p, batch, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return bail(e, "session init");
+    s->launches += 1;
+    cudaSetDevice(prev);
+    *out = ss;
+    return TINYMPC_CUDA_OK;
+}
+
+int tinympc_cuda_session_destroy(tinympc_cuda_session* ss) {
+    if (!ss) return TINYMPC_CUDA_OK;
+    int prev = 0;
+    cudaGetDevice(&prev);
+    cudaSetDevice(ss->s->devs[ss->dev].device);
+    for (DevBuf* b : {&ss->ws, &ss->pack, &ss->x, &ss->u, &ss->iter, &ss->status}) b->release();
+    cudaSetDevice(prev);
+    delete ss;
+    return TINYMPC_CUDA_OK;
+}
+
+namespace {
+// host doubles (rows of `width` elements, `rows_src` of them or ONE broadcast row) -> member `at` of every workspace
+int session_scatter(tinympc_cuda_session* ss, int at, int width, const double* src, bool broadcast) {
+    tinympc_cuda_solver* s = ss->s;
+    const size_t esz = ss->bits == 64 ? sizeof(double) : sizeof(float);
+    const size_t n = (size_t)ss->batch * width;
+    ss->stage.resize(n * esz);
+    for (size_t k = 0; k < n; ++k) {
+        const double v = src ? src[broadcast ? k % width : k] : 0.0;
+        if (ss->bits == 64) reinterpret_cast<double*>(ss->stage.data())[k] = v;
+        else reinterpret_cast<float*>(ss->stage.data())[k] = static_cast<float>(v);
+    }
+    int prev = 0;
+    cudaGetDevice(&prev);
+    CU(s, cudaSetDevice(s->devs[ss->dev].device));
+    CU(s, cudaMemcpy2D(static_cast<char*>(ss->ws.p) + (size_t)at * esz, (size_t)ss->W.size * esz, ss->stage.data(), (size_t)width * esz,
+                       (size_t)width * esz, ss->batch, cudaMemcpyHostToDevice));
+    cudaSetDevice(prev);
+    return TINYMPC_CUDA_OK;
+}
+int session_gather(tinympc_cuda_session* ss, int at, int width, double* dst) {
+    tinympc_cuda_solver* s = ss->s;
+    const size_t esz = ss->bits == 64 ? sizeof(double) : sizeof(float);
+    const size_t n = (size_t)ss->batch * width;
+    ss->stage.resize(n * esz);
+    int prev = 0;
+    cudaGetDevice(&prev);
+    CU(s, cudaSetDevice(s->devs[ss->dev].device));
+    CU(s, cudaMemcpy2D(ss->stage.data(), (size_t)width * esz, static_cast<char*>(ss->ws.p) + (size_t)at * esz, (size_t)ss->W.size * esz,
+                       (size_t)width * esz, ss->batch, cudaMemcpyDeviceToHost));
+    cudaSetDevice(prev);
+    for (size_t k = 0; k < n; ++k)
+        dst[k] = ss->bits == 64 ? reinterpret_cast<double*>(ss->stage.data())[k] : static_cast<double>(reinterpret_cast<float*>(ss->stage.data())[k]);
+    return TINYMPC_CUDA_OK;
+}
+}  // namespace
+
+int tinympc_cuda_session_set_x0(tinympc_cuda_session* ss, const double* x0) {
+    if (!ss || !x0) return TINYMPC_CUDA_EINVAL;
+    return session_scatter(ss, ss->W.x, ss->fam.nx, x0, false);     // work->x.col(0) = x0, tiny_api.cpp:383
+}
+int tinympc_cuda_session_set_x_ref(tinympc_cuda_session* ss, const double* Xref, int broadcast) {
+    if (!ss) return TINYMPC_CUDA_EINVAL;
+    return session_scatter(ss, ss->W.Xref, ss->fam.nx * ss->fam.N, Xref, broadcast != 0);
+}
+int tinympc_cuda_session_set_u_ref(tinympc_cuda_session* ss, const double* Uref, int broadcast) {
+    if (!ss) return TINYMPC_CUDA_EINVAL;
+    return session_scatter(ss, ss->W.Uref, ss->fam.nu * (ss->fam.N - 1), Uref, broadcast != 0);
+}
+
+int tinympc_cuda_session_solve(tinympc_cuda_session* ss) {
+    if (!ss) return TINYMPC_CUDA_EINVAL;
+    tinympc_cuda_solver* s = ss->s;
+    DeviceCtx& d = s->devs[ss->dev];
+    int prev = 0;
+    cudaGetDevice(&prev);
+    CU(s, cudaSetDevice(d.device));
+    SolveParams p = ss->fam.base;
+    p.batch = ss->batch;
+    p.x = static_cast<float*>(ss->x.p); p.u = static_cast<float*>(ss->u.p);
+    p.iter = static_cast<int*>(ss->iter.p); p.status = static_cast<int*>(ss->status.p);
+    const int warps = std::max(1, std::min(ss->batch, d.sm_count * 16));
+    cudaStream_t st = d.streams[0];
+    if (ss->fam.base.max_iter > 0) {
+        CU(s, ss->bits == 64 ? wpp_launch<double>(p, ss->fam.L, ss->pack.p, ss->W, ss->ws.p, warps, 2, st)
+                             : wpp_launch<float>(p, ss->fam.L, ss->pack.p, ss->W, ss->ws.p, warps, 2, st));
+        s->launches += 1;
+        s->last_kernel = ss->bits == 64 ? "wpp_f64_session" : "wpp_f32_session";
+    }
+    CU(s, cudaStreamSynchronize(st));
+    cudaSetDevice(prev);
+    return TINYMPC_CUDA_OK;
+}
+
+int tinympc_cuda_session_step(tinympc_cuda_session* ss, int use_solution) {
+    if (!ss) return TINYMPC_CUDA_EINVAL;
+    tinympc_cuda_solver* s = ss->s;
+    DeviceCtx& d = s->devs[ss->dev];
+    int prev = 0;
+    cudaGetDevice(&prev);
+    CU(s, cudaSetDevice(d.device));
+    cudaStream_t st = d.streams[0];
+    CU(s, ss->bits == 64 ? wpp_session_step<double>(ss->fam.L, ss->pack.p, ss->W, ss->ws.p, ss->batch, use_solution, st)
+                         : wpp_session_step<float>(ss->fam.L, ss->pack.p, ss->W, ss->ws.p, ss->batch, use_solution, st));
+    s->launches += 1;
+    CU(s, cudaStreamSynchronize(st));
+    cudaSetDevice(prev);
+    return TINYMPC_CUDA_OK;
+}
+
+int tinympc_cuda_session_read(tinympc_cuda_session* ss, const char* field, double* host) {
+    if (!ss || !field || !host) return TINYMPC_CUDA_EINVAL;
+    const std::string f(field);
+    const WppLayout& W = ss->W;
+    const int nx = ss->fam.nx, nu = ss->fam.nu, N = ss->fam.N;
+    if (f == "x0") return session_gather(ss, W.x, nx, host);
+    if (f == "x") return session_gather(ss, W.x, nx * N, host);
+    if (f == "u") return session_gather(ss, W.u, nu * (N - 1), host);
+    if (f == "sol_x") return session_gather(ss, W.vnew, nx * N, host);       // solution->x = work->vnew, admm.cpp:370, 386
+    if (f == "sol_u") return session_gather(ss, W.znew, nu * (N - 1), host);
+    if (f == "rho") return session_gather(ss, W.scalars + 0, 1, host);
+    if (f == "iter") return session_gather(ss, W.scalars + 1, 1, host);
+    if (f == "status") return session_gather(ss, W.scalars + 2, 1, host);
+    if (f == "residuals") return session_gather(ss, W.scalars + 3, 4, host);
+    return fail(ss->s, TINYMPC_CUDA_EINVAL, "unknown session field " + f);
 }
 
 int tinympc_cuda_set_option(tinympc_cuda_solver* s, const char* name, double value) {

@@ -80,7 +80,6 @@ __global__ void __launch_bounds__(128) wpp_kernel(const SolveParams prm, const P
     const int n_warps = (gridDim.x * blockDim.x) >> 5;
     const int nx = L.nx, nu = L.nu, N = L.N;
     const int sx = nx * N, su = nu * (N - 1);
-    T* ws = scratch + (size_t)warp_global * W.size;
 
     const T* A = pack + L.A;   const T* B = pack + L.B;   const T* AK = pack + L.AmBKt; const T* Quu = pack + L.Quu_inv;
     const T* f = pack + L.f;   const T* APf = pack + L.APf; const T* BPf = pack + L.BPf;
@@ -89,22 +88,25 @@ __global__ void __launch_bounds__(128) wpp_kernel(const SolveParams prm, const P
     const T* Alx = pack + L.Alin_x; const T* blx = pack + L.blin_x; const T* nrx = pack + L.nrm_x;
     const T* Alu = pack + L.Alin_u; const T* blu = pack + L.blin_u; const T* nru = pack + L.nrm_u;
 
-    T *x = ws + W.x, *u = ws + W.u, *q = ws + W.q, *r = ws + W.r, *p = ws + W.p, *d = ws + W.d;
-    T *v = ws + W.v, *vnew = ws + W.vnew, *z = ws + W.z, *znew = ws + W.znew, *g = ws + W.g, *y = ws + W.y;
-    T *vcnew = ws + W.vcnew, *zcnew = ws + W.zcnew, *gc = ws + W.gc, *yc = ws + W.yc;
-    T *vlnew = ws + W.vlnew, *zlnew = ws + W.zlnew, *gl = ws + W.gl, *yl = ws + W.yl;
-    T *Xref = ws + W.Xref, *Uref = ws + W.Uref;
-    T *xmin = ws + W.xmin, *xmax = ws + W.xmax, *umin = ws + W.umin, *umax = ws + W.umax;
-    T *K = ws + W.Kinf, *P = ws + W.Pinf;        // per-problem copies: adaptive rho mutates them
-    T *tmp = ws + W.tmp;                          // nu scratch
-    T *sc = ws + W.scalars;                       // [0] rho, [1] iter, [2] status, [3..6] residuals, [7] solved
-
     const bool en_sb = prm.en_state_bound, en_ib = prm.en_input_bound;
     const bool soc_x = prm.en_state_soc && prm.n_state_cones > 0, soc_u = prm.en_input_soc && prm.n_input_cones > 0;
     const bool lin_x = prm.en_state_linear, lin_u = prm.en_input_linear;
     const T tol_pri = static_cast<T>(prm.abs_pri_tol), tol_dua = static_cast<T>(prm.abs_dua_tol);
 
     for (int prob = warp_global; prob < prm.batch; prob += n_warps) {
+        // explicit_workspace 0: one scratch workspace per warp, cold start per problem; 1: ONE live workspace (tiny_solve);
+        // 2: a persistent workspace per PROBLEM (a session of warm-started solvers), iterated in place
+        T* ws = scratch + (size_t)(explicit_workspace == 2 ? prob : warp_global) * W.size;
+        T *x = ws + W.x, *u = ws + W.u, *q = ws + W.q, *r = ws + W.r, *p = ws + W.p, *d = ws + W.d;
+        T *v = ws + W.v, *vnew = ws + W.vnew, *z = ws + W.z, *znew = ws + W.znew, *g = ws + W.g, *y = ws + W.y;
+        T *vcnew = ws + W.vcnew, *zcnew = ws + W.zcnew, *gc = ws + W.gc, *yc = ws + W.yc;
+        T *vlnew = ws + W.vlnew, *zlnew = ws + W.zlnew, *gl = ws + W.gl, *yl = ws + W.yl;
+        T *Xref = ws + W.Xref, *Uref = ws + W.Uref;
+        T *xmin = ws + W.xmin, *xmax = ws + W.xmax, *umin = ws + W.umin, *umax = ws + W.umax;
+        T *K = ws + W.Kinf, *P = ws + W.Pinf;        // per-problem copies: adaptive rho mutates them
+        T *tmp = ws + W.tmp;                          // nu scratch
+        T *sc = ws + W.scalars;                       // [0] rho, [1] iter, [2] status, [3..6] residuals, [7] solved
+
         if (!explicit_workspace) {
             // ---- cold workspace (tiny_api.cpp:68-105) + this problem's inputs
             for (int e = lane; e < W.zero_end; e += 32) ws[e] = 0;
@@ -283,7 +285,7 @@ __global__ void __launch_bounds__(128) wpp_kernel(const SolveParams prm, const P
         }
         // ---------------- results
         if (lane == 0) { sc[0] = rho; sc[1] = static_cast<T>(iter); sc[2] = static_cast<T>(status); sc[3] = r_px; sc[4] = r_dx; sc[5] = r_pu; sc[6] = r_du; sc[7] = static_cast<T>(solved); }
-        if (!explicit_workspace) {
+        if (explicit_workspace != 1 && prm.x) {
             for (int e = lane; e < sx; e += 32) prm.x[(size_t)prob * sx + e] = static_cast<float>(vnew[e]);
             for (int e = lane; e < su; e += 32) prm.u[(size_t)prob * su + e] = static_cast<float>(znew[e]);
             if (lane == 0) {
@@ -295,6 +297,59 @@ __global__ void __launch_bounds__(128) wpp_kernel(const SolveParams prm, const P
         __syncwarp();
     }
 }
+
+// ---- session helpers (persistent per-problem workspaces) -------------------------------------------------------
+// cold workspaces as tiny_setup + the constraint setters leave them (tiny_api.cpp:68-105) with the pristine cache
+template <typename T>
+__global__ void wpp_session_init_kernel(const SolveParams prm, const PackLayout L, const T* __restrict__ pack, const WppLayout W,
+                                        T* __restrict__ wsp, int batch) {
+    const int sx = L.nx * L.N, su = L.nu * (L.N - 1);
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < (size_t)batch * W.size; k += (size_t)gridDim.x * blockDim.x) {
+        const int e = static_cast<int>(k % W.size);
+        T v = 0;
+        if (e >= W.xmin && e < W.xmin + sx) v = pack[L.xmin + (e - W.xmin)];
+        else if (e >= W.xmax && e < W.xmax + sx) v = pack[L.xmax + (e - W.xmax)];
+        else if (e >= W.umin && e < W.umin + su) v = pack[L.umin + (e - W.umin)];
+        else if (e >= W.umax && e < W.umax + su) v = pack[L.umax + (e - W.umax)];
+        else if (e >= W.Kinf && e < W.Kinf + L.nu * L.nx) v = pack[L.Kinf + (e - W.Kinf)];
+        else if (e >= W.Pinf && e < W.Pinf + L.nx * L.nx) v = pack[L.Pinf + (e - W.Pinf)];
+        else if (e == W.scalars) v = static_cast<T>(prm.rho);
+        else if (e == W.scalars + 2) v = T(11);
+        wsp[k] = v;
+    }
+}
+// x0 <- A x0 + B u0 + f for every problem (the "simulate forward" line of quadrotor_hovering.cpp:91); u0 = work->u.col(0)
+// (use_solution 0) or solution->u.col(0) = znew.col(0) (use_solution 1, cartpole_example_mpc.m:40-41)
+template <typename T>
+__global__ void wpp_session_step_kernel(const PackLayout L, const T* __restrict__ pack, const WppLayout W, T* __restrict__ wsp, int batch,
+                                        int use_solution) {
+    const int nx = L.nx, nu = L.nu;
+    const int prob = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (prob >= batch) return;
+    T* ws = wsp + (size_t)prob * W.size;
+    const T* x0 = ws + W.x;
+    const T* u0 = ws + (use_solution ? W.znew : W.u);
+    T xn = 0;
+    if (lane < nx) xn = row_dot(pack + L.A, lane, nx, x0) + row_dot(pack + L.B, lane, nu, u0) + pack[L.f + lane];
+    __syncwarp();
+    if (lane < nx) ws[W.x + lane] = xn;
+}
+
+template <typename T>
+cudaError_t wpp_session_init(const SolveParams& p, const PackLayout& L, const void* pack, const WppLayout& W, void* wsp, int batch, cudaStream_t st) {
+    wpp_session_init_kernel<T><<<592, 256, 0, st>>>(p, L, static_cast<const T*>(pack), W, static_cast<T*>(wsp), batch);
+    return cudaGetLastError();
+}
+template <typename T>
+cudaError_t wpp_session_step(const PackLayout& L, const void* pack, const WppLayout& W, void* wsp, int batch, int use_solution, cudaStream_t st) {
+    if (L.nx > 32) return cudaErrorInvalidValue;
+    wpp_session_step_kernel<T><<<(batch + 3) / 4, 128, 0, st>>>(L, static_cast<const T*>(pack), W, static_cast<T*>(wsp), batch, use_solution);
+    return cudaGetLastError();
+}
+template cudaError_t wpp_session_init<float>(const SolveParams&, const PackLayout&, const void*, const WppLayout&, void*, int, cudaStream_t);
+template cudaError_t wpp_session_init<double>(const SolveParams&, const PackLayout&, const void*, const WppLayout&, void*, int, cudaStream_t);
+template cudaError_t wpp_session_step<float>(const PackLayout&, const void*, const WppLayout&, void*, int, int, cudaStream_t);
+template cudaError_t wpp_session_step<double>(const PackLayout&, const void*, const WppLayout&, void*, int, int, cudaStream_t);
 
 WppLayout WppLayout::make(int nx, int nu, int N) {
     WppLayout W{};

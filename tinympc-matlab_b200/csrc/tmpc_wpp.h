@@ -19,9 +19,16 @@ struct WppLayout {
 };
 
 // explicit_workspace = 1: `scratch` holds ONE fully initialised workspace that is iterated in place
-// (tiny_solve semantics); 0: cold start per problem from p.x0/Xref/Uref, `warps` scratch workspaces.
+// (tiny_solve semantics); 0: cold start per problem from p.x0/Xref/Uref, `warps` scratch workspaces;
+// 2: `scratch` holds p.batch persistent workspaces (a session of warm-started solvers), each iterated in place.
 template <typename T>
 cudaError_t wpp_launch(const SolveParams& p, const PackLayout& L, const void* pack, const WppLayout& W, void* scratch, int warps,
                        int explicit_workspace, cudaStream_t st);
+
+// session helpers: cold workspaces for `batch` solvers; x0 <- A x0 + B u0 + f on every workspace
+template <typename T>
+cudaError_t wpp_session_init(const SolveParams& p, const PackLayout& L, const void* pack, const WppLayout& W, void* wsp, int batch, cudaStream_t st);
+template <typename T>
+cudaError_t wpp_session_step(const PackLayout& L, const void* pack, const WppLayout& W, void* wsp, int batch, int use_solution, cudaStream_t st);
 
 }  // namespace tmpc
