@@ -158,6 +158,9 @@ int  tinympc_cuda_session_read(tinympc_cuda_session *ss, const char *field, doub
 
 /* ---- knobs and introspection ----------------------------------------------------------------- */
 /* option names: "precision" (32 = fp32 arithmetic [default], 64 = fp64 parity mode),
+   "mixed" (relative band b in [0,1), 0 = off [default]; with precision 32 and b > 0 the fp32 kernel stops and marks every
+   problem whose termination decision (admm.cpp:262-265) has its largest residual/tolerance ratio inside [1-b, 1+b], and an
+   fp64 pass re-solves exactly the marked problems: the reference's iteration counts and status codes at close to fp32 speed),
    "ctas_per_sm" (0 = occupancy API), "chunks" (host pipeline depth, 0 = auto),
    "variant" (kernel tuning variant, 0 = default) */
 int  tinympc_cuda_set_option(tinympc_cuda_solver *s, const char *name, double value);
@@ -169,6 +172,8 @@ long long tinympc_cuda_launch_count(const tinympc_cuda_solver *s);
 /* last tinympc_cuda_solve_batch(): ms[0] host wall time of the call, ms[1] summed device time of its kernels
    (CUDA events, max over devices), ms[2] number of pipeline chunks */
 int  tinympc_cuda_last_timing(const tinympc_cuda_solver *s, double ms[3]);
+/* number of problems the last "mixed" solve re-solved in fp64 (after a device-resident solve this synchronises the device) */
+long long tinympc_cuda_last_marked(tinympc_cuda_solver *s);
 const char *tinympc_cuda_last_error(const tinympc_cuda_solver *s);
 const char *tinympc_cuda_version(void);
 

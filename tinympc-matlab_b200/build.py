@@ -45,6 +45,17 @@ def inst(bits, nx, nu, N, feat, refs=REFS_SMEM, ppb=False, variant=0, block=None
     return dict(aff=aff, tm=tm, ntm=ntm, opq=opq, tib=tib, bits=bits, nx=nx, nu=nu, N=N, feat=feat, refs=refs, ppb=ppb, variant=variant, block=block or b, minb=minb or m, fb=fb, gen=gen)
 
 
+def inst3(nx, nu, N, refs=True, ppb=False, fb=False, variant=0, max_warps=24, opq=False, tib=None, aff=None):
+    """incremental-form kernel (tmpc_tpp3.cuh): x and t in tensor memory (2 nx N columns per thread), u, u + y, -dd in shared memory"""
+    sx, su = nx * N, nu * (N - 1)
+    warps = min(max_warps, 4 * (512 // (2 * sx)), ((226 * 1024 - 1024 - pack_elems(nx, nu, N) * 4) // (3 * su * 4 * 32) // 4) * 4)
+    assert warps >= 4, "shape does not fit the incremental-form kernel"
+    aff = ((nx, nu) == (6, 3)) if aff is None else aff
+    tib = (not (nx == 12)) if tib is None else tib
+    return dict(gen=3, bits=32, nx=nx, nu=nu, N=N, feat=BOX, refs=3 if refs else 0, ppb=ppb, fb=fb, variant=variant, block=warps * 32, aff=aff,
+                opq=opq, tib=tib, tm=True, minb=1, ntm=2)
+
+
 def cols_per_thread(nx, nu, N, feat, refs, ntm=0):
     """shared-memory scalar columns per thread; ntm = number of state-sized arrays (TV, GC, GL, SXT) in tensor memory"""
     sx, su = nx * N, nu * (N - 1)
@@ -92,23 +103,31 @@ def plan_block(nx, nu, N, feat, bits, refs, budget_kb=226, tm=False, max_warps=1
 def default_instances():
     out = []
     shapes = [(12, 4, 10), (4, 1, 20), (4, 1, 10), (6, 3, 10)]
+    # fp32 box-constrained batches: the incremental ("delta") form, tmpc_tpp3.cuh -- the default (variant 0)
+    for (nx, nu, N) in shapes:
+        for fb in (True, False):      # fb: bounds constant over the horizon and containing 0 (the common case)
+            out.append(inst3(nx, nu, N, refs=True, fb=fb))
+            out.append(inst3(nx, nu, N, refs=False, fb=fb))
+        out.append(inst3(nx, nu, N, refs=True, ppb=True))
     for bits in (32, 64):
         for (nx, nu, N) in shapes:
-            for fb in (True, False):      # fb: bounds constant over the horizon and containing 0 (the common case)
-                out.append(inst(bits, nx, nu, N, BOX, refs=REFS_L2, fb=fb, tm=True))
-                out.append(inst(bits, nx, nu, N, BOX, refs=REFS_NONE, fb=fb, tm=True))
-            out.append(inst(bits, nx, nu, N, BOX, refs=REFS_L2, ppb=True, tm=True))
+            if bits == 64:            # fp64 parity mode: direct form (admm.cpp order), tmpc_tpp2.cuh
+                for fb in (True, False):
+                    out.append(inst(bits, nx, nu, N, BOX, refs=REFS_L2, fb=fb, tm=True))
+                    out.append(inst(bits, nx, nu, N, BOX, refs=REFS_NONE, fb=fb, tm=True))
+                out.append(inst(bits, nx, nu, N, BOX, refs=REFS_L2, ppb=True, tm=True))
             out.append(inst(bits, nx, nu, N, CON, refs=REFS_L2, fb=True, tm=True))
             out.append(inst(bits, nx, nu, N, CON, refs=REFS_L2, tm=True))
             if (nx, nu) == (12, 4):
                 out.append(inst(bits, nx, nu, N, ADP, refs=REFS_L2, fb=True, tm=True))
                 out.append(inst(bits, nx, nu, N, ADP, refs=REFS_L2, tm=True))
-    # A/B: hoistable (immediate-offset, LDCU.128) constant loads on the tensor-memory instances, option variant=3
-    out.append(inst(32, 12, 4, 10, BOX, refs=REFS_L2, variant=3, fb=True, tm=True, opq=True))
-    out.append(inst(32, 4, 1, 20, BOX, refs=REFS_NONE, variant=3, fb=True, tm=True, opq=True))
-    # A/B: 16 warps/SM on the small shape, option variant=4
-    out.append(inst(32, 4, 1, 20, BOX, refs=REFS_NONE, variant=4, fb=True, tm=True, max_warps=16))
-    # A/B baseline: the shared-memory-only (8 warps/SM) form of the headline shapes, option variant=2
+    # A/B: the direct-form fp32 box kernels (16 / 24 warps per SM, tensor-memory TV) on the headline shapes, option variant=5
+    out.append(inst(32, 12, 4, 10, BOX, refs=REFS_L2, variant=5, fb=True, tm=True))
+    out.append(inst(32, 12, 4, 10, BOX, refs=REFS_L2, variant=5, tm=True))
+    out.append(inst(32, 12, 4, 10, BOX, refs=REFS_L2, variant=5, ppb=True, tm=True))
+    out.append(inst(32, 4, 1, 20, BOX, refs=REFS_NONE, variant=5, fb=True, tm=True))
+    out.append(inst(32, 4, 1, 20, BOX, refs=REFS_L2, variant=5, fb=True, tm=True))
+    # A/B baseline: the shared-memory-only (8 warps/SM) direct form of the headline shapes, option variant=2
     out.append(inst(32, 12, 4, 10, BOX, refs=REFS_L2, variant=2, fb=True))
     out.append(inst(32, 4, 1, 20, BOX, refs=REFS_NONE, variant=2, fb=True))
     # A/B baseline: the first-generation (column-pair) kernel on the two headline shapes, option variant=1
@@ -119,6 +138,9 @@ def default_instances():
 
 def name_of(i):
     t = "f32" if i["bits"] == 32 else "f64"
+    if i["gen"] == 3:
+        return (f"tpp3_f32_{i['nx']}x{i['nu']}x{i['N']}_box{'' if i['refs'] else '_noref'}{'_ppb' if i['ppb'] else ''}{'_fb' if i['fb'] else ''}"
+                f"{'_aff' if i['aff'] else ''}_v{i['variant']}")
     return (f"tpp{'' if i['gen'] == 1 else '2'}_{t}_{i['nx']}x{i['nu']}x{i['N']}_{FEAT_NAME[i['feat']]}{['_noref', '_refsm', ''][i['refs']]}"
             f"{'_ppb' if i['ppb'] else ''}{'_fb' if i['fb'] else ''}{'_aff' if (i['aff'] and i['gen'] == 2) else ''}{'_tm' if i['tm'] else ''}_v{i['variant']}")
 
@@ -132,7 +154,17 @@ def gen_sources(instances):
         names.append(n)
         T = "float" if i["bits"] == 32 else "double"
         g = "" if i["gen"] == 1 else "2"
-        src = (
+        b = lambda v: "true" if v else "false"
+        if i["gen"] == 3:
+            src = (
+                "// generated by tinympc-matlab_b200/build.py -- do not edit\n"
+                '#include "../tmpc_tpp3.cuh"\n#include "../tmpc_registry.h"\nusing namespace tmpc;\n'
+                f"using Cfg_{n} = Tpp3Cfg<{i['nx']}, {i['nu']}, {i['N']}, {i['block']}, {b(i['refs'])}, {b(i['ppb'])}, {b(i['fb'])}, {b(i['aff'])}, "
+                f"{b(i['opq'])}, {b(i['tib'])}>;\n"
+                f"TMPC_DEFINE_TPP3_ENTRY({n}, Cfg_{n}, {i['feat']}, 32, {i['variant']})\n"
+            )
+        else:
+          src = (
             "// generated by tinympc-matlab_b200/build.py -- do not edit\n"
             f'#include "../tmpc_tpp{g}.cuh"\n#include "../tmpc_registry.h"\nusing namespace tmpc;\n'
             f"using Cfg_{n} = Tpp{g}Cfg<{T}, {i['nx']}, {i['nu']}, {i['N']}, {FEAT_ENUM[i['feat']]}, {i['block']}, "

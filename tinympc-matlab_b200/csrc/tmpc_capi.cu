@@ -50,13 +50,15 @@ struct DeviceCtx {
     int sm_count = 0;
     void* pack32 = nullptr;
     void* pack64 = nullptr;
-    int* counters = nullptr;            // kMaxChunks work counters
+    int* counters = nullptr;            // 3 * kMaxChunks ints: work counters of the first pass, of the fp64 re-solve pass, marked-problem counts
     cudaStream_t streams[kStreams] = {nullptr, nullptr, nullptr};
     cudaEvent_t k0[kMaxChunks], k1[kMaxChunks];
     bool events = false;
     DevBuf x0, Xref, Uref, xmin, xmax, umin, umax, x, u, iter, status, res, rho;
     DevBuf ref_scratch[kStreams + 1];   // REFS_L2 kernels: per-slot reference terms
     DevBuf wpp_scratch[kStreams + 1];   // warp-per-problem workspaces (one per pipeline stream + the device/workspace entry)
+    DevBuf ref_scratch64[kStreams + 1]; // mixed mode: reference terms of the fp64 re-solve pass
+    DevBuf marked[kStreams + 1];        // mixed mode: indices of the problems the fp32 pass marked ambiguous
 };
 
 struct Family {
@@ -81,6 +83,10 @@ struct tinympc_cuda_solver {
     int chunks = 0;                    // 0 = auto
     int variant = 0;
     int force_wpp = 0;                 // option "kernel": 0 auto, 1 always the warp-per-problem kernel
+    double mixed_band = 0;             // option "mixed": > 0 = fp32 pass + fp64 re-solve of the problems whose termination decision
+                                       // falls within this relative band of the tolerances (exact iteration counts at ~fp32 speed)
+    long long mixed_marked = 0;        // problems re-solved in fp64 by the last mixed solve (host entry: filled by the call)
+    int mixed_pending_dev = -1;        // device entry: the count still sits in that device's counter slot
     std::string err;
     std::string last_kernel;
     long long launches = 0;
@@ -138,6 +144,19 @@ const KernelEntry* find_kernel(const Family& f, int bits, bool ppb, bool refs, i
     return nullptr;
 }
 
+// mixed mode: gather the indices of the problems whose status carries kAmbiguousBit (order is irrelevant)
+__global__ void collect_marked_kernel(const int* __restrict__ status, int n, int* __restrict__ list, int* __restrict__ count) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool hit = i < n && (status[i] & kAmbiguousBit);
+    const unsigned m = __ballot_sync(0xffffffffu, hit);
+    if (!m) return;
+    const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(count, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (hit) list[base + __popc(m & ((1u << lane) - 1u))] = i;
+}
+
 int upload_family(tinympc_cuda_solver* s) {
     const Family& f = s->fam;
     std::vector<float> p32(f.pack.size());
@@ -155,39 +174,9 @@ int upload_family(tinympc_cuda_solver* s) {
     return TINYMPC_CUDA_OK;
 }
 
-// Enqueue one kernel over `in`/`out` (device pointers) on `st`.  counter must be a zeroed device int.
-int enqueue(tinympc_cuda_solver* s, DeviceCtx& d, const tinympc_cuda_batch_in& in, const tinympc_cuda_batch_out& out, int* counter,
-            cudaStream_t st, int scratch_slot) {
+// Launch one thread-per-problem kernel instance (persistent grid, a multiple of the SM count).
+int launch_tpp(tinympc_cuda_solver* s, DeviceCtx& d, const KernelEntry* ke, SolveParams& p, DevBuf& rb, int bits, int* counter, cudaStream_t st) {
     const Family& f = s->fam;
-    const bool ppb = in.x_min || in.x_max || in.u_min || in.u_max;
-    if (ppb && !(in.x_min && in.x_max && in.u_min && in.u_max))
-        return fail(s, TINYMPC_CUDA_EINVAL, "per-problem bounds need all four of x_min, x_max, u_min, u_max");
-    if (!ppb && !f.shared_bounds_ok)
-        return fail(s, TINYMPC_CUDA_EINVAL, "bound constraints are enabled but neither the family nor the batch supplies bounds");
-    const KernelEntry* ke = s->force_wpp ? nullptr : find_kernel(f, s->precision, ppb, in.Xref || in.Uref, s->variant);
-    SolveParams p = f.base;
-    p.pack = s->precision == 64 ? (const void*)((const double*)d.pack64 + f.L.cold) : (const void*)((const float*)d.pack32 + f.L.cold);
-    p.pack_elems = f.L.cold_size;
-    p.batch = in.batch;
-    p.work_counter = counter;
-    p.x0 = in.x0; p.Xref = in.Xref; p.Uref = in.Uref;
-    p.x_min = in.x_min; p.x_max = in.x_max; p.u_min = in.u_min; p.u_max = in.u_max;
-    p.x = out.x; p.u = out.u; p.iter = out.iter; p.status = out.status; p.residuals = out.residuals; p.rho_out = out.rho;
-
-    if (!ke) {
-        // no specialised thread-per-problem kernel for this shape / feature mix: general warp-per-problem kernel
-        const WppLayout W = WppLayout::make(f.nx, f.nu, f.N);
-        const int warps = std::max(1, std::min(in.batch, d.sm_count * 16));
-        const size_t esz = s->precision == 64 ? sizeof(double) : sizeof(float);
-        DevBuf& sb = d.wpp_scratch[scratch_slot];
-        CU(s, sb.reserve((size_t)warps * W.size * esz));
-        const void* full_pack = s->precision == 64 ? d.pack64 : d.pack32;
-        if (s->precision == 64) CU(s, wpp_launch<double>(p, f.L, full_pack, W, sb.p, warps, 0, st));
-        else CU(s, wpp_launch<float>(p, f.L, full_pack, W, sb.p, warps, 0, st));
-        s->last_kernel = s->precision == 64 ? "wpp_f64_generic" : "wpp_f32_generic";
-        s->launches += 1;
-        return TINYMPC_CUDA_OK;
-    }
     const size_t smem = ke->smem_bytes(f.L.cold_size);
     if (smem > 227u * 1024u) return fail(s, TINYMPC_CUDA_EUNSUPPORTED, std::string("kernel ") + ke->name + " needs more shared memory than an SM has");
     CU(s, ke->prepare(smem));
@@ -196,19 +185,90 @@ int enqueue(tinympc_cuda_solver* s, DeviceCtx& d, const tinympc_cuda_batch_in& i
     if (occ < 1) return fail(s, TINYMPC_CUDA_EUNSUPPORTED, std::string("kernel ") + ke->name + " does not fit on an SM");
     if (s->ctas_per_sm > 0 && s->ctas_per_sm < occ) occ = s->ctas_per_sm;
     int grid = d.sm_count * occ;                       // persistent CTAs: a multiple of the SM count
-    const int need = (in.batch + ke->block - 1) / ke->block;
+    const int need = (p.batch + ke->block - 1) / ke->block;
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
     if (ke->refs == 2) {   // reference terms live in a lane-interleaved global scratch that stays L2 resident
-        DevBuf& rb = d.ref_scratch[scratch_slot];
-        const size_t esz = s->precision == 64 ? sizeof(double) : sizeof(float);
+        const size_t esz = bits == 64 ? sizeof(double) : sizeof(float);
         CU(s, rb.reserve((size_t)grid * ke->block * ((size_t)f.nx * f.N + (size_t)f.nu * (f.N - 1)) * esz));
         p.ref_scratch = rb.p;
     }
+    p.work_counter = counter;
     CU(s, cudaMemsetAsync(counter, 0, sizeof(int), st));
     CU(s, ke->launch(p, grid, smem, st, f.pack.data(), f.L));
-    s->last_kernel = ke->name;
     s->launches += 1;
+    return TINYMPC_CUDA_OK;
+}
+
+// Enqueue the solve of `in`/`out` (device pointers) on `st`.  slot selects the work counters and scratch buffers
+// (one set per pipeline stream + one for the device-resident entry point).
+int enqueue(tinympc_cuda_solver* s, DeviceCtx& d, const tinympc_cuda_batch_in& in, const tinympc_cuda_batch_out& out, int counter_slot,
+            cudaStream_t st, int scratch_slot) {
+    const Family& f = s->fam;
+    const bool ppb = in.x_min || in.x_max || in.u_min || in.u_max;
+    if (ppb && !(in.x_min && in.x_max && in.u_min && in.u_max))
+        return fail(s, TINYMPC_CUDA_EINVAL, "per-problem bounds need all four of x_min, x_max, u_min, u_max");
+    if (!ppb && !f.shared_bounds_ok)
+        return fail(s, TINYMPC_CUDA_EINVAL, "bound constraints are enabled but neither the family nor the batch supplies bounds");
+    const bool refs = in.Xref || in.Uref;
+    int bits = s->precision;
+    const KernelEntry* ke = s->force_wpp ? nullptr : find_kernel(f, bits, ppb, refs, s->variant);
+    // mixed mode needs the specialised kernels in both precisions; any other shape runs entirely in fp64 (exact as well)
+    const KernelEntry* ke64 = nullptr;
+    const bool mixed = s->mixed_band > 0 && bits == 32;
+    if (mixed) {
+        ke64 = s->force_wpp ? nullptr : find_kernel(f, 64, ppb, refs, 0);
+        if (!ke || !ke64) { ke = nullptr; bits = 64; }
+    }
+    SolveParams p = f.base;
+    p.pack = bits == 64 ? (const void*)((const double*)d.pack64 + f.L.cold) : (const void*)((const float*)d.pack32 + f.L.cold);
+    p.pack_elems = f.L.cold_size;
+    p.batch = in.batch;
+    p.x0 = in.x0; p.Xref = in.Xref; p.Uref = in.Uref;
+    p.x_min = in.x_min; p.x_max = in.x_max; p.u_min = in.u_min; p.u_max = in.u_max;
+    p.x = out.x; p.u = out.u; p.iter = out.iter; p.status = out.status; p.residuals = out.residuals; p.rho_out = out.rho;
+
+    if (!ke) {
+        // no specialised thread-per-problem kernel for this shape / feature mix: general warp-per-problem kernel
+        const WppLayout W = WppLayout::make(f.nx, f.nu, f.N);
+        const int warps = std::max(1, std::min(in.batch, d.sm_count * 16));
+        const size_t esz = bits == 64 ? sizeof(double) : sizeof(float);
+        DevBuf& sb = d.wpp_scratch[scratch_slot];
+        CU(s, sb.reserve((size_t)warps * W.size * esz));
+        const void* full_pack = bits == 64 ? d.pack64 : d.pack32;
+        if (bits == 64) CU(s, wpp_launch<double>(p, f.L, full_pack, W, sb.p, warps, 0, st));
+        else CU(s, wpp_launch<float>(p, f.L, full_pack, W, sb.p, warps, 0, st));
+        s->last_kernel = bits == 64 ? "wpp_f64_generic" : "wpp_f32_generic";
+        s->launches += 1;
+        return TINYMPC_CUDA_OK;
+    }
+    int* const counter = d.counters + counter_slot;
+    if (!mixed) {
+        int rc = launch_tpp(s, d, ke, p, d.ref_scratch[scratch_slot], bits, counter, st);
+        if (rc) return rc;
+        s->last_kernel = ke->name;
+        return TINYMPC_CUDA_OK;
+    }
+    // ---- mixed mode: fp32 pass that marks the ambiguous problems, compaction, fp64 re-solve of the marked ones ----
+    int* const counter2 = d.counters + kMaxChunks + counter_slot;
+    int* const n_marked = d.counters + 2 * kMaxChunks + counter_slot;
+    DevBuf& list = d.marked[scratch_slot];
+    CU(s, list.reserve(sizeof(int) * (size_t)in.batch));
+    p.amb_band = static_cast<float>(s->mixed_band);
+    int rc = launch_tpp(s, d, ke, p, d.ref_scratch[scratch_slot], 32, counter, st);
+    if (rc) return rc;
+    CU(s, cudaMemsetAsync(n_marked, 0, sizeof(int), st));
+    collect_marked_kernel<<<(in.batch + 255) / 256, 256, 0, st>>>(out.status, in.batch, static_cast<int*>(list.p), n_marked);
+    CU(s, cudaGetLastError());
+    s->launches += 1;
+    SolveParams p2 = p;
+    p2.pack = (const void*)((const double*)d.pack64 + f.L.cold);
+    p2.amb_band = 0.f;
+    p2.index_list = static_cast<const int*>(list.p);
+    p2.batch_ptr = n_marked;
+    rc = launch_tpp(s, d, ke64, p2, d.ref_scratch64[scratch_slot], 64, counter2, st);
+    if (rc) return rc;
+    s->last_kernel = std::string(ke->name) + "+" + ke64->name;
     return TINYMPC_CUDA_OK;
 }
 
@@ -245,10 +305,10 @@ int zero_iteration_result(tinympc_cuda_solver* s, const Family& f, const tinympc
 
 // One device's share of a host batch: chunked H2D -> kernel -> D2H pipeline over kStreams streams.
 int run_shard(tinympc_cuda_solver* s, DeviceCtx& d, const tinympc_cuda_batch_in& in, const tinympc_cuda_batch_out& out, int lo, int hi,
-              double* kernel_ms, int* nchunks_out) {
+              double* kernel_ms, int* nchunks_out, long long* marked_out) {
     const Family& f = s->fam;
     const int n = hi - lo;
-    *kernel_ms = 0; *nchunks_out = 0;
+    *kernel_ms = 0; *nchunks_out = 0; *marked_out = 0;
     if (n <= 0) return TINYMPC_CUDA_OK;
     CU(s, cudaSetDevice(d.device));
     const size_t sx = (size_t)f.nx * f.N, su = (size_t)f.nu * (f.N - 1);
@@ -298,7 +358,7 @@ int run_shard(tinympc_cuda_solver* s, DeviceCtx& d, const tinympc_cuda_batch_in&
         dout.residuals = out.residuals ? (float*)d.res.p + 4 * (size_t)c0 : nullptr;
         dout.rho = out.rho ? (float*)d.rho.p + c0 : nullptr;
         CU(s, cudaEventRecord(d.k0[c], st));
-        int rc = enqueue(s, d, din, dout, d.counters + c, st, c % kStreams);
+        int rc = enqueue(s, d, din, dout, c, st, c % kStreams);
         if (rc) return rc;
         CU(s, cudaEventRecord(d.k1[c], st));
         CU(s, cudaMemcpyAsync(out.x + sx * g0, dout.x, sizeof(float) * sx * cn, cudaMemcpyDeviceToHost, st));
@@ -315,6 +375,13 @@ int run_shard(tinympc_cuda_solver* s, DeviceCtx& d, const tinympc_cuda_batch_in&
         *kernel_ms += ms;
     }
     *nchunks_out = nch;
+    if (s->mixed_band > 0 && s->precision == 32) {
+        int counts[kMaxChunks];
+        CU(s, cudaMemcpy(counts, d.counters + 2 * kMaxChunks, sizeof(int) * nch, cudaMemcpyDeviceToHost));
+        long long tot = 0;
+        for (int c = 0; c < nch; ++c) tot += counts[c];
+        *marked_out = tot;
+    }
     return TINYMPC_CUDA_OK;
 }
 
@@ -354,7 +421,7 @@ int tinympc_cuda_create(tinympc_cuda_solver** out, const int* devices, int n_dev
         d.device = id;
         if (cudaSetDevice(id) != cudaSuccess) { delete s; return TINYMPC_CUDA_ECUDA; }
         cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, id);
-        if (cudaMalloc(&d.counters, sizeof(int) * kMaxChunks) != cudaSuccess) { delete s; return TINYMPC_CUDA_ECUDA; }
+        if (cudaMalloc(&d.counters, sizeof(int) * 3 * kMaxChunks) != cudaSuccess) { delete s; return TINYMPC_CUDA_ECUDA; }
         for (int k = 0; k < kStreams; ++k) cudaStreamCreateWithFlags(&d.streams[k], cudaStreamNonBlocking);
         for (int c = 0; c < kMaxChunks; ++c) { cudaEventCreate(&d.k0[c]); cudaEventCreate(&d.k1[c]); }
         d.events = true;
@@ -379,6 +446,8 @@ int tinympc_cuda_destroy(tinympc_cuda_solver* s) {
         for (DevBuf* b : {&d.x0, &d.Xref, &d.Uref, &d.xmin, &d.xmax, &d.umin, &d.umax, &d.x, &d.u, &d.iter, &d.status, &d.res, &d.rho}) b->release();
         for (auto& b : d.wpp_scratch) b.release();
         for (auto& b : d.ref_scratch) b.release();
+        for (auto& b : d.ref_scratch64) b.release();
+        for (auto& b : d.marked) b.release();
     }
     cudaSetDevice(prev);
     delete s;
@@ -533,7 +602,8 @@ int tinympc_cuda_solve_batch_device(tinympc_cuda_solver* s, int dev_index, const
         rc = zero_iteration_result(s, s->fam, *out, in->batch, st, true);
     } else {
         // the last counter slot is reserved for the device-resident entry point
-        rc = enqueue(s, d, *in, *out, d.counters + (kMaxChunks - 1), st, kStreams);
+        rc = enqueue(s, d, *in, *out, kMaxChunks - 1, st, kStreams);
+        s->mixed_pending_dev = (s->mixed_band > 0 && s->precision == 32) ? dev_index : -1;
     }
     cudaSetDevice(prev);
     return rc;
@@ -556,11 +626,12 @@ int tinympc_cuda_solve_batch(tinympc_cuda_solver* s, const tinympc_cuda_batch_in
     cudaGetDevice(&prev);
     std::vector<int> rcs(G, 0), nch(G, 0);
     std::vector<double> kms(G, 0.0);
+    std::vector<long long> marked(G, 0);
     // contiguous split by problem index (multiples of 4 keep every shard 16 B aligned), remainder to the last
     int per = ((in->batch + G - 1) / G + 3) & ~3;
     auto work = [&](int g) {
         const int lo = std::min(in->batch, g * per), hi = (g == G - 1) ? in->batch : std::min(in->batch, lo + per);
-        rcs[g] = run_shard(s, s->devs[g], *in, *out, lo, hi, &kms[g], &nch[g]);
+        rcs[g] = run_shard(s, s->devs[g], *in, *out, lo, hi, &kms[g], &nch[g], &marked[g]);
     };
     if (G == 1) {
         work(0);
@@ -571,6 +642,9 @@ int tinympc_cuda_solve_batch(tinympc_cuda_solver* s, const tinympc_cuda_batch_in
     }
     cudaSetDevice(prev);
     for (int g = 0; g < G; ++g) if (rcs[g]) return rcs[g];
+    s->mixed_marked = 0;
+    for (int g = 0; g < G; ++g) s->mixed_marked += marked[g];
+    s->mixed_pending_dev = -1;
     s->t_kernel_ms = *std::max_element(kms.begin(), kms.end());
     s->t_chunks = *std::max_element(nch.begin(), nch.end());
     s->t_total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
@@ -814,6 +888,9 @@ int tinympc_cuda_set_option(tinympc_cuda_solver* s, const char* name, double val
         s->chunks = (int)value;
     } else if (n == "variant") {
         s->variant = (int)value;
+    } else if (n == "mixed") {
+        if (!(value >= 0 && value < 1)) return fail(s, TINYMPC_CUDA_EINVAL, "mixed (relative band) must be in [0, 1)");
+        s->mixed_band = value;
     } else if (n == "force_wpp") {
         s->force_wpp = (int)value;
     } else {
@@ -829,6 +906,21 @@ int tinympc_cuda_last_timing(const tinympc_cuda_solver* s, double ms[3]) {
     if (!s || !ms) return TINYMPC_CUDA_EINVAL;
     ms[0] = s->t_total_ms; ms[1] = s->t_kernel_ms; ms[2] = (double)s->t_chunks;
     return TINYMPC_CUDA_OK;
+}
+long long tinympc_cuda_last_marked(tinympc_cuda_solver* s) {
+    if (!s) return 0;
+    if (s->mixed_pending_dev >= 0) {   // device entry: blocking read of the count its fp64 pass consumed
+        DeviceCtx& d = s->devs[s->mixed_pending_dev];
+        int prev = 0, n = 0;
+        cudaGetDevice(&prev);
+        cudaSetDevice(d.device);
+        cudaDeviceSynchronize();
+        cudaMemcpy(&n, d.counters + 3 * kMaxChunks - 1, sizeof(int), cudaMemcpyDeviceToHost);
+        cudaSetDevice(prev);
+        s->mixed_marked = n;
+        s->mixed_pending_dev = -1;
+    }
+    return s->mixed_marked;
 }
 const char* tinympc_cuda_last_error(const tinympc_cuda_solver* s) { return s ? s->err.c_str() : "null solver"; }
 

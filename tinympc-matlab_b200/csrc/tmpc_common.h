@@ -101,6 +101,14 @@ struct SolveParams {
     int Acx[kMaxCones], qcx[kMaxCones], Acu[kMaxCones], qcu[kMaxCones];
     float cx[kMaxCones], cu[kMaxCones];     // the reference's project_soc takes `float mu` (admm.cpp:39)
     int nsl, nil;
+    // mixed-precision exact-count mode (tmpc_capi.cu, option "mixed"): the fp32 pass marks a problem whose termination
+    // decision falls inside the relative band around the tolerances (status |= kAmbiguousBit) and stops iterating it;
+    // the fp64 pass re-solves exactly the marked problems through index_list / batch_ptr.
+    float amb_band;            // 0 = off
+    const int* index_list;     // NULL, or problem index of work item k (the kernel then runs over *batch_ptr items)
+    const int* batch_ptr;      // NULL, or device int holding the number of work items (<= batch)
 };
+
+constexpr int kAmbiguousBit = 0x100;
 
 }  // namespace tmpc

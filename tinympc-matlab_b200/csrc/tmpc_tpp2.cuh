@@ -734,6 +734,7 @@ tpp2_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ typ
     (void)en_sb; (void)en_ib;
 
     const int lane = tid & 31;
+    const int n_items = prm.batch_ptr ? min(*prm.batch_ptr, prm.batch) : prm.batch;   // work items (mixed mode: the marked problems)
     int prob = 0;           // problem owned by this lane
     bool active = false;    // lane holds an unfinished problem
     bool exhausted = false; // the work counter ran past the batch
@@ -797,10 +798,11 @@ tpp2_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ typ
                 base = __shfl_sync(FULL, base, leader);
                 if (want) {
                     prob = base + __popc(m & ((1u << lane) - 1u));
-                    if (prob >= prm.batch) {
+                    if (prob >= n_items) {
                         exhausted = true;
                         prob = 0;   // keeps the (unused) per-problem reads of an idle lane in range
                     } else {
+                        if (prm.index_list) prob = __ldg(prm.index_list + prob);
                         active = true;
                         k = 0;
                         next_check = check_every;
@@ -1162,6 +1164,17 @@ tpp2_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ typ
             next_check += check_every;
             res_px = rpx; res_dx = rdx * rho; res_pu = rpu; res_du = rdu * rho;
             if (res_px < tol_pri && res_pu < tol_pri && res_dx < tol_dua && res_du < tol_dua) { finish = true; st = 1; }
+            if constexpr (sizeof(T) == 4) {
+                // Mixed mode: this decision is a threshold crossing on values carrying fp32 rounding noise.  If the largest
+                // residual/tolerance ratio lies inside [1 - band, 1 + band] the fp64 arithmetic of the reference may decide
+                // the other way: stop here and hand the problem to the fp64 pass.
+                if (prm.amb_band > 0.f) {
+                    const T up = T(1) + prm.amb_band, dn = T(1) - prm.amb_band;
+                    const bool below_up = res_px < tol_pri * up && res_pu < tol_pri * up && res_dx < tol_dua * up && res_du < tol_dua * up;
+                    const bool below_dn = res_px < tol_pri * dn && res_pu < tol_pri * dn && res_dx < tol_dua * dn && res_du < tol_dua * dn;
+                    if (below_up && !below_dn) { finish = true; st = kAmbiguousBit | 11; }
+                }
+            }
         }
         if (k >= max_iter) finish = true;
         const bool fin = active && finish;

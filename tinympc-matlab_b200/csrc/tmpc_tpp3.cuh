@@ -1,0 +1,469 @@
+// tmpc_tpp3.cuh -- batched ADMM throughput kernel for sm_100a, INCREMENTAL ("delta") form, fp32, box constraints.
+//
+// Same path and mapping as tmpc_tpp2.cuh (one thread = one problem, packed f32x2 arithmetic, family matrices in the
+// kernel-parameter constant bank, state in tensor memory + shared memory, lane refill); reference: admm.cpp:274-389.
+// What changes is the ALGEBRA of the Riccati sweeps, to take the fp32 rounding noise out of the termination test.
+//
+// Why.  backward_pass_grad / forward_pass (admm.cpp:13-32) are one fixed affine map  x = L(q, r, p_N) + x_free.
+// Evaluated from scratch every iteration (what the reference does, in double), the costates p ~ Pinf x reach 1e3..1e4
+// for the quadrotor; in fp32 their rounding (~5e-4) lands in u and x as FRESH noise of 1e-5..1e-4 at every iteration,
+// i.e. 1..10 % of a 1e-3 tolerance, and flips the threshold test of 1-2 % of the problems by one check interval
+// (profiles/tools/noise_model.py reproduces that on the CPU).  L is linear, so
+//     x(k+1) = x(k) + L_h( q(k) - q(k-1), r(k) - r(k-1), p_N(k) - p_N(k-1) ),      q(k) - q(k-1) = -rho (w(k) - w(k-1)),
+// with L_h the homogeneous part (no f, APf, BPf, no reference terms).  The sweeps then run on increments whose size shrinks
+// with the residuals, the fresh noise becomes proportional to the residual itself, and what was rounded earlier is a
+// constant offset of ~1e-5 in x -- a slightly perturbed problem, not noise on the test.  Same flop count.
+//
+// One iteration here (reference order: backward, forward, slack, dual, linear cost, check):
+//   forward : dx_0 = 0, du_i = -Kinf dx_i - dd_i, dx_{i+1} = A dx_i + B du_i;  X += dx, U += du          (admm.cpp:25-32)
+//   sweep   : columns N-1 .. 0, fused: slack + dual + residuals of the column (admm.cpp:81-208, 253-260), the increment
+//             dw of (slack - dual), then the Riccati step on (-rho dw) giving dd for the next forward    (admm.cpp:13-20, 214-247)
+//   check   : admm.cpp:262-265, solution = (vnew, znew)
+// The first iteration of a problem is the full affine map: forward with d0 (first backward pass on the zero workspace,
+// host-precomputed), x0, f; its sweep adds the reference terms -(Xref .* Q), -(Uref .* R), -(xref_N' Pinf)' ONCE (q(0) = 0).
+// Those terms are parked in the T / TZ state columns at refill time (the cold slack t(0) is 0 by definition, so the
+// columns are free until the first sweep overwrites them): no scratch buffer, no reference traffic per iteration.
+//
+// State per problem: X (x), T (t = x + g_prev, pre-clamp slack: v = clamp(t), g = t - v) in tensor memory (2 nx N columns
+// per thread), U, TZ, DD (u, u + y_prev, -dd) in shared memory.
+#pragma once
+#include "tmpc_tpp2.cuh"
+
+namespace tmpc {
+
+enum : int { REFS_STATE = 3 };   // registry "refs" code: reference terms parked in the state columns
+
+template <int NX_, int NU_, int NH_, int BLOCK_, bool REFS_, bool PPB_, bool FB_, bool AFF_, bool OPQ_, bool TIB_>
+struct Tpp3Cfg {
+    using T = float;
+    static constexpr int NX = NX_, NU = NU_, NH = NH_, FEAT = FEAT_BOX, BLOCK = BLOCK_, MINB = 1;
+    static constexpr int REFMODE = REFS_ ? REFS_STATE : REFS_NONE;
+    static constexpr bool REFS = REFS_;
+    static constexpr bool PPB = PPB_;
+    static constexpr bool FB = FB_ && !PPB_;
+    static constexpr bool AFF = AFF_;
+    static constexpr bool OPQ = OPQ_;
+    static constexpr bool TIB = TIB_ && FB_ && !PPB_ && !OPQ_;
+    static constexpr int SX = NX * NH, SU = NU * (NH - 1);
+    using CPack = ConstPack2<float, NX_, NU_, NH_, false>;
+    static constexpr int oU = 0, oTZ = SU, oD = 2 * SU, COLS = 3 * SU;
+    static constexpr int TM_COLS_PER_THREAD = 2 * SX;
+    static_assert(((BLOCK_ / 32 + 3) / 4) * TM_COLS_PER_THREAD <= 512, "the state does not fit the 512 tensor-memory columns");
+};
+
+__device__ __forceinline__ float2 sel0(bool c, float2 a) { return make_float2(c ? 0.f : a.x, c ? 0.f : a.y); }   // c ? 0 : a
+__device__ __forceinline__ float sel0(bool c, float a) { return c ? 0.f : a; }
+
+template <class C>
+__global__ void __launch_bounds__(C::BLOCK, 1)
+tpp3_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ typename C::CPack cp) {
+    using T = float;
+    using N = Num<T>;
+    using P = float2;
+    using SP = StaticPack<C::NX, C::NU, C::NH>;
+    using VX = Vec<T, C::NX>;
+    using VU = Vec<T, C::NU>;
+    constexpr int NX = C::NX, NU = C::NU, NH = C::NH, BLOCK = C::BLOCK, SXL = C::SX, SUL = C::SU;
+    constexpr int NXP = pad2(NX), NUP = pad2(NU);
+    constexpr unsigned FULL = 0xffffffffu;
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t pack_bar;
+    __shared__ uint32_t tmem_base_s;
+    T* pack = reinterpret_cast<T*>(smem_raw);
+    const uint32_t pack_bytes = static_cast<uint32_t>(prm.pack_elems) * sizeof(T);
+
+    // ---- cold family tables -> shared memory (one TMA bulk copy per CTA); all 512 tensor-memory columns for the state ----
+    if (threadIdx.x == 0) {
+        mbar_init(&pack_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_expect_tx(&pack_bar, pack_bytes);
+        tma_bulk_g2s(pack, prm.pack, pack_bytes, &pack_bar);
+    }
+    if (threadIdx.x < 32) tmem_alloc(&tmem_base_s, 512);
+    tmem_fence_before_sync();
+    __syncthreads();
+    tmem_fence_after_sync();
+    mbar_wait(&pack_bar, 0);
+
+    T* cta_cols = pack + ((prm.pack_elems + 31) & ~31);
+    const int tid = threadIdx.x;
+    const uint32_t w_id = static_cast<uint32_t>(tid) >> 5;
+    const uint32_t tm_base = tmem_base_s + ((32u * (w_id & 3u)) << 16) + (w_id >> 2) * C::TM_COLS_PER_THREAD;
+    const TmemTraj<NX, NH> X{tm_base};            // x(k)
+    const TmemTraj<NX, NH> TT{tm_base + SXL};     // t(k) = x(k) + g(k-1)
+    Traj<T, NU, NH - 1, C::oU, BLOCK> U(cta_cols, tid);      // u(k)
+    Traj<T, NU, NH - 1, C::oTZ, BLOCK> TZ(cta_cols, tid);    // u(k) + y(k-1)
+    Traj<T, NU, NH - 1, C::oD, BLOCK> ND(cta_cols, tid);     // -dd of the last sweep
+
+    const T* cP = pack + SP::Pinf;
+    const T rho0 = static_cast<T>(prm.rho);
+    const T tol_pri = static_cast<T>(prm.abs_pri_tol), tol_dua = static_cast<T>(prm.abs_dua_tol);
+    const int max_iter = prm.max_iter, check_every = prm.check_termination;
+    const bool en_sb = prm.en_state_bound != 0, en_ib = prm.en_input_bound != 0;
+    (void)en_sb; (void)en_ib;
+
+    const int lane = tid & 31;
+    const int n_items = prm.batch_ptr ? min(*prm.batch_ptr, prm.batch) : prm.batch;
+    int prob = 0;
+    bool active = false, exhausted = false;
+    int k = 0;
+    int next_check = check_every;
+    T res_px = 0, res_dx = 0, res_pu = 0, res_du = 0;
+    VX x0v;
+    x0v.fill(T(0));
+
+    auto bt = [](int i) { return C::TIB ? 0 : i; };
+    auto xb_pair = [&](int i, int j, size_t pb, P& lo, P& hi) {
+        if constexpr (C::PPB) {
+            const size_t e = pb + (size_t)i * NX + 2 * j;
+            lo = en_sb ? mk2(__ldg(prm.x_min + e), __ldg(prm.x_min + e + 1)) : mk2(-N::inf(), -N::inf());
+            hi = en_sb ? mk2(__ldg(prm.x_max + e), __ldg(prm.x_max + e + 1)) : mk2(N::inf(), N::inf());
+        } else {
+            lo = mk2(cp.xmin[bt(i) * NXP + 2 * j], cp.xmin[bt(i) * NXP + 2 * j + 1]); hi = mk2(cp.xmax[bt(i) * NXP + 2 * j], cp.xmax[bt(i) * NXP + 2 * j + 1]);
+        }
+    };
+    auto xb_tail = [&](int i, size_t pb, T& lo, T& hi) {
+        if constexpr (C::PPB) {
+            const size_t e = pb + (size_t)i * NX + NX - 1;
+            lo = en_sb ? __ldg(prm.x_min + e) : -N::inf();
+            hi = en_sb ? __ldg(prm.x_max + e) : N::inf();
+        } else { lo = cp.xmin[bt(i) * NXP + NX - 1]; hi = cp.xmax[bt(i) * NXP + NX - 1]; }
+    };
+    auto ub_pair = [&](int i, int j, size_t pb, P& lo, P& hi) {
+        if constexpr (C::PPB) {
+            const size_t e = pb + (size_t)i * NU + 2 * j;
+            lo = en_ib ? mk2(__ldg(prm.u_min + e), __ldg(prm.u_min + e + 1)) : mk2(-N::inf(), -N::inf());
+            hi = en_ib ? mk2(__ldg(prm.u_max + e), __ldg(prm.u_max + e + 1)) : mk2(N::inf(), N::inf());
+        } else {
+            lo = mk2(cp.umin[bt(i) * NUP + 2 * j], cp.umin[bt(i) * NUP + 2 * j + 1]); hi = mk2(cp.umax[bt(i) * NUP + 2 * j], cp.umax[bt(i) * NUP + 2 * j + 1]);
+        }
+    };
+    auto ub_tail = [&](int i, size_t pb, T& lo, T& hi) {
+        if constexpr (C::PPB) {
+            const size_t e = pb + (size_t)i * NU + NU - 1;
+            lo = en_ib ? __ldg(prm.u_min + e) : -N::inf();
+            hi = en_ib ? __ldg(prm.u_max + e) : N::inf();
+        } else { lo = cp.umin[bt(i) * NUP + NU - 1]; hi = cp.umax[bt(i) * NUP + NU - 1]; }
+    };
+
+    for (;;) {
+        // ------------------------------------------------------------------ refill idle lanes
+        {
+            const bool want = !active && !exhausted;
+            const unsigned m = __ballot_sync(FULL, want);
+            if (m) {
+                const int leader = __ffs(m) - 1;
+                int base = 0;
+                if (lane == leader) base = atomicAdd(prm.work_counter, __popc(m));
+                base = __shfl_sync(FULL, base, leader);
+                bool mine = false;
+                if (want) {
+                    prob = base + __popc(m & ((1u << lane) - 1u));
+                    if (prob >= n_items) {
+                        exhausted = true;
+                        prob = 0;
+                    } else {
+                        if (prm.index_list) prob = __ldg(prm.index_list + prob);
+                        active = mine = true;
+                        k = 0;
+                        next_check = check_every;
+                        res_px = res_dx = res_pu = res_du = 0;
+                    }
+                }
+                const bool have_xref = C::REFS && prm.Xref != nullptr, have_uref = C::REFS && prm.Uref != nullptr;
+                if (mine) {
+                    if (have_xref) {   // pull the whole problem towards L2 first: the blocks below then cost one DRAM round trip
+                        const char* s = reinterpret_cast<const char*>(prm.Xref + (size_t)prob * SXL);
+#pragma unroll
+                        for (int b = 0; b <= (SXL * 4 + 127) / 128; ++b) prefetch_l2(s + (b * 128 < SXL * 4 ? b * 128 : SXL * 4 - 4));
+                    }
+                    if (have_uref) {
+                        const char* s = reinterpret_cast<const char*>(prm.Uref + (size_t)prob * SUL);
+#pragma unroll
+                        for (int b = 0; b <= (SUL * 4 + 127) / 128; ++b) prefetch_l2(s + (b * 128 < SUL * 4 ? b * 128 : SUL * 4 - 4));
+                    }
+                    load_span<NX, vec_width(NX, NX)>(prm.x0 + (size_t)prob * NX, [&](int i, float v) { x0v.set(i, v); });
+                }
+                // T columns of the refilled lanes := -(Xref .* Q) (column N-1: -(xref_N' Pinf)'), all other lanes keep theirs
+                // (tcgen05.st has no lane mask: read - select - write, warp-wide)
+                if (have_xref) {
+                    constexpr int GX = steps_per_block(NH, NX, 64);
+                    const float* src = prm.Xref + (size_t)prob * SXL;
+                    T xr_last[NX];
+#pragma unroll
+                    for (int r = 0; r < NX; ++r) xr_last[r] = 0;
+#pragma unroll 1
+                    for (int b = 0; b < NH / GX; ++b) {
+                        float buf[GX * NX];
+#pragma unroll
+                        for (int e = 0; e < GX * NX; ++e) buf[e] = 0.f;
+                        if (mine) load_span<GX * NX, vec_width(SXL, GX * NX)>(src + b * GX * NX, [&](int e, float v) { buf[e] = v; });
+#pragma unroll
+                        for (int r = 0; r < NX; ++r) xr_last[r] = buf[(GX - 1) * NX + r];   // after the last block: xref_N
+#pragma unroll
+                        for (int g = 0; g < GX; ++g) {
+                            uint32_t r[NX];
+                            TmemSpan<NX>::ld(TT.base + (b * GX + g) * NX, r);
+                            TmemSpan<NX>::wait(r);
+#pragma unroll
+                            for (int e = 0; e < NX; ++e) r[e] = mine ? __float_as_uint(-(buf[g * NX + e] * cp.Qd[e])) : r[e];
+                            TmemSpan<NX>::st(TT.base + (b * GX + g) * NX, r);
+                        }
+                    }
+                    {   // PT = -(xref_N' Pinf)' as row pairs of Pinf' (Pinf is row-major in the staged pack)
+                        VX acc;
+                        acc.fill(T(0));
+#pragma unroll
+                        for (int r = 0; r < NX; ++r) {
+                            const T nxr = -xr_last[r];
+#pragma unroll
+                            for (int j = 0; j < NX / 2; ++j) acc.p[j] = fmas(mk2(cP[r * NX + 2 * j], cP[r * NX + 2 * j + 1]), nxr, acc.p[j]);
+                            if constexpr (NX & 1) acc.t = fmas(cP[r * NX + NX - 1], nxr, acc.t);
+                        }
+                        uint32_t r[NX];
+                        TmemSpan<NX>::ld(TT.base + (NH - 1) * NX, r);
+                        TmemSpan<NX>::wait(r);
+#pragma unroll
+                        for (int e = 0; e < NX; ++e) r[e] = mine ? __float_as_uint(acc.get(e)) : r[e];
+                        TmemSpan<NX>::st(TT.base + (NH - 1) * NX, r);
+                    }
+                    tmem_wait_st();
+                } else {
+                    TT.reset(mine);
+                }
+                if (mine) {
+                    // TZ := -(Uref .* R), -dd := -d0 (first backward pass on the zero workspace, tiny_api.cpp:68-105 + admm.cpp:13-20)
+                    if (have_uref) {
+                        constexpr int GU = steps_per_block(NH - 1, NU, 64);
+                        const float* src = prm.Uref + (size_t)prob * SUL;
+#pragma unroll 1
+                        for (int b = 0; b < (NH - 1) / GU; ++b) {
+                            float buf[GU * NU];
+                            load_span<GU * NU, vec_width(SUL, GU * NU)>(src + b * GU * NU, [&](int e, float v) { buf[e] = v; });
+#pragma unroll
+                            for (int g = 0; g < GU; ++g) {
+#pragma unroll
+                                for (int j = 0; j < NU / 2; ++j)
+                                    TZ.setp(b * GU + g, j, mk2(-(buf[g * NU + 2 * j] * cp.Rd[2 * j]), -(buf[g * NU + 2 * j + 1] * cp.Rd[2 * j + 1])));
+                                if constexpr (NU & 1) TZ.sett(b * GU + g, -(buf[g * NU + NU - 1] * cp.Rd[NU - 1]));
+                            }
+                        }
+                    }
+#pragma unroll 1
+                    for (int i = 0; i < NH - 1; ++i) {
+#pragma unroll
+                        for (int j = 0; j < NU / 2; ++j) {
+                            if (!have_uref) TZ.setp(i, j, mk2(T(0), T(0)));
+                            ND.setp(i, j, mk2(-pack[SP::d0 + i * NU + 2 * j], -pack[SP::d0 + i * NU + 2 * j + 1]));
+                        }
+                        if constexpr (NU & 1) {
+                            if (!have_uref) TZ.sett(i, T(0));
+                            ND.sett(i, -pack[SP::d0 + i * NU + NU - 1]);
+                        }
+                    }
+                }
+            }
+            if (!__any_sync(FULL, active)) break;
+        }
+
+        const size_t pbx = (size_t)prob * SXL, pbu = (size_t)prob * SUL;
+
+        // ------------------------------------------------- forward rollout of the increment: X += dx, U += du
+        {
+            const bool ff = (k == 0);                                  // first iteration: the full affine map from x0
+            const bool anyff = __any_sync(FULL, active && ff);
+            VX dx;
+#pragma unroll
+            for (int j = 0; j < NX / 2; ++j) dx.p[j] = ff ? x0v.p[j] : mk2(T(0), T(0));
+            dx.t = ff ? x0v.t : T(0);
+#pragma unroll 1
+            for (int i = 0; i < NH; ++i) {
+                const int zf = C::OPQ ? opaque_zero4() : 0;
+                VX xo;
+                X.load(i, xo);
+#pragma unroll
+                for (int j = 0; j < NX / 2; ++j) xo.p[j] = addv(sel0(ff, xo.p[j]), dx.p[j]);
+                if constexpr (NX & 1) xo.t = sel0(ff, xo.t) + dx.t;
+                X.store(i, xo);
+                if (i < NH - 1) {
+                    // du_i = -Kinf dx_i - dd_i (admm.cpp:29)
+                    VU du;
+                    ND.load(i, du);
+                    if (i > 0 || anyff) mv_acc<NU, NX>(cp.NK, zf, dx, du);     // dx_0 = 0 unless this is a first iteration
+                    VU un;
+                    U.load(i, un);
+#pragma unroll
+                    for (int j = 0; j < NU / 2; ++j) un.p[j] = addv(sel0(ff, un.p[j]), du.p[j]);
+                    if constexpr (NU & 1) un.t = sel0(ff, un.t) + du.t;
+                    U.store(i, un);
+                    // dx_{i+1} = A dx_i + B du_i (+ f on the first iteration, admm.cpp:30)
+                    VX dxn;
+                    if constexpr (C::AFF) {
+#pragma unroll
+                        for (int j = 0; j < NX / 2; ++j) dxn.p[j] = ff ? mk2(cp.f[2 * j], cp.f[2 * j + 1]) : mk2(T(0), T(0));
+                        if constexpr (NX & 1) dxn.t = ff ? cp.f[NX - 1] : T(0);
+                    } else {
+                        dxn.fill(T(0));
+                    }
+                    if (i > 0 || anyff) mv_acc<NX, NX>(cp.A, zf, dx, dxn);
+                    mv_acc<NX, NU>(cp.B, zf, du, dxn);
+                    dx = dxn;
+                }
+            }
+            X.stores_done();
+        }
+        k += 1;   // work->iter += 1 (admm.cpp:328)
+
+        // ------------------------------------------------- reverse sweep: slack + dual + residuals fused with the Riccati step
+        const bool first = (k == 1);
+        const T nrho = -rho0;
+        T rpx = 0, rdx = 0, rpu = 0, rdu = 0;
+        // one trajectory element (pair or scalar tail).  traw: stored pre-clamp slack t(k-1) (on the first sweep: the parked
+        // reference term, t(0) = 0).  vo = clamp(t_old), g = t_old - vo, t_new = x + g, vn = clamp(t_new)  (admm.cpp:85,92,184);
+        // increment of (slack - dual) = (2 vn - t_new) - (2 vo - t_old) = 2 (vn - vo) - (t_new - t_old); dq = ref - rho dw
+        auto slack = [&](auto traw, auto xv, auto lo, auto hi, T& rp, T& rd, auto& tnew, auto& dq) {
+            const auto told = sel0(first, traw);
+            const auto ref = subv(traw, told);                 // first ? traw : 0
+            auto vo = clampv(told, lo, hi);
+            if constexpr (!C::FB) vo = sel0(first, vo);        // cold start: v = 0 whatever the bounds are (FB: clamp(0) = 0 already)
+            const auto go = subv(told, vo);
+            tnew = addv(xv, go);
+            const auto vn = clampv(tnew, lo, hi);
+            rp = amaxv(rp, subv(xv, vn));
+            const auto e = subv(vn, vo);
+            rd = amaxv(rd, e);
+            const auto dw = twice_minus(e, subv(tnew, told));
+            dq = fmas(dw, nrho, ref);
+        };
+        VX dp;
+        {   // column N-1: dp_N = -(xref_N' Pinf)' [first sweep] - rho dw_N   (admm.cpp:238-246)
+            VX xv, traw, tnew;
+            X.load(NH - 1, xv);
+            TT.load(NH - 1, traw);
+#pragma unroll
+            for (int j = 0; j < NX / 2; ++j) {
+                P lo, hi;
+                xb_pair(NH - 1, j, pbx, lo, hi);
+                slack(traw.p[j], xv.p[j], lo, hi, rpx, rdx, tnew.p[j], dp.p[j]);
+            }
+            if constexpr (NX & 1) {
+                T lo, hi;
+                xb_tail(NH - 1, pbx, lo, hi);
+                slack(traw.t, xv.t, lo, hi, rpx, rdx, tnew.t, dp.t);
+            }
+            TT.store(NH - 1, tnew);
+        }
+#pragma unroll 1
+        for (int i = NH - 2; i >= 0; --i) {
+            const int zb = C::OPQ ? opaque_zero4() : 0;
+            // ---- input column i: dr_i = -(Uref .* R) [first sweep] - rho dw   (admm.cpp:227-236)
+            VU uv, dr;
+            U.load(i, uv);
+#pragma unroll
+            for (int j = 0; j < NU / 2; ++j) {
+                P lo, hi, tn;
+                ub_pair(i, j, pbu, lo, hi);
+                slack(TZ.getp(i, j), uv.p[j], lo, hi, rpu, rdu, tn, dr.p[j]);
+                TZ.setp(i, j, tn);
+            }
+            if constexpr (NU & 1) {
+                T lo, hi, tn;
+                ub_tail(i, pbu, lo, hi);
+                slack(TZ.gett(i), uv.t, lo, hi, rpu, rdu, tn, dr.t);
+                TZ.sett(i, tn);
+            }
+            // dd_i = Quu_inv (B' dp + dr)   (admm.cpp:17; BPf cancels in the increment)
+            VU t = dr;
+            mv_acc<NU, NX>(cp.BT, zb, dp, t);
+            VU d;
+            d.fill(T(0));
+            mv_acc<NU, NU>(cp.Quu, zb, t, d);
+            {
+                VU nd;
+#pragma unroll
+                for (int j = 0; j < NU / 2; ++j) nd.p[j] = negv(d.p[j]);
+                if constexpr (NU & 1) nd.t = -d.t;
+                ND.store(i, nd);
+            }
+            // ---- state column i: dq_i = -(Xref .* Q) [first sweep] - rho dw;  dp_i = dq_i + AmBKt dp - Kinf' dr   (admm.cpp:18)
+            VX xv, traw, tnew, dq;
+            X.load(i, xv);
+            TT.load(i, traw);
+#pragma unroll
+            for (int j = 0; j < NX / 2; ++j) {
+                P lo, hi;
+                xb_pair(i, j, pbx, lo, hi);
+                slack(traw.p[j], xv.p[j], lo, hi, rpx, rdx, tnew.p[j], dq.p[j]);
+            }
+            if constexpr (NX & 1) {
+                T lo, hi;
+                xb_tail(i, pbx, lo, hi);
+                slack(traw.t, xv.t, lo, hi, rpx, rdx, tnew.t, dq.t);
+            }
+            TT.store(i, tnew);
+            if (i > 0) {   // p_0 is never used (admm.cpp:17 reads p_{i+1})
+                mv_acc<NX, NX>(cp.AK, zb, dp, dq);
+                mv_acc<NX, NU>(cp.NKT, zb, dr, dq);
+                dp = dq;
+            }
+        }
+        TT.stores_done();
+
+        // ------------------------------------------------- termination (admm.cpp:253-271, 364-388)
+        bool finish = false;
+        int st = 11;
+        if (k == next_check) {   // iter % check_termination == 0
+            next_check += check_every;
+            res_px = rpx; res_dx = rdx * rho0; res_pu = rpu; res_du = rdu * rho0;
+            if (res_px < tol_pri && res_pu < tol_pri && res_dx < tol_dua && res_du < tol_dua) { finish = true; st = 1; }
+            if (prm.amb_band > 0.f) {   // mixed mode, see tmpc_tpp2.cuh
+                const T up = T(1) + prm.amb_band, dn = T(1) - prm.amb_band;
+                const bool below_up = res_px < tol_pri * up && res_pu < tol_pri * up && res_dx < tol_dua * up && res_du < tol_dua * up;
+                const bool below_dn = res_px < tol_pri * dn && res_pu < tol_pri * dn && res_dx < tol_dua * dn && res_du < tol_dua * dn;
+                if (below_up && !below_dn) { finish = true; st = kAmbiguousBit | 11; }
+            }
+        }
+        if (k >= max_iter) finish = true;
+        const bool fin = active && finish;
+        if (__any_sync(FULL, fin)) {
+            // solution = (vnew, znew) = clamp of the stored pre-clamp values (the T read is warp-collective)
+#pragma unroll 1
+            for (int i = 0; i < NH; ++i) {
+                VX v;
+                TT.load(i, v);
+                if (fin) {
+#pragma unroll
+                    for (int j = 0; j < NX / 2; ++j) { P lo, hi; xb_pair(i, j, pbx, lo, hi); v.p[j] = clampv(v.p[j], lo, hi); }
+                    if constexpr (NX & 1) { T lo, hi; xb_tail(i, pbx, lo, hi); v.t = clampv(v.t, lo, hi); }
+                    store_span<NX, vec_width(SXL, NX)>(prm.x + pbx + i * NX, [&](int r) { return v.get(r); });
+                }
+            }
+        }
+        if (fin) {
+#pragma unroll 1
+            for (int i = 0; i < NH - 1; ++i) {
+                VU z;
+#pragma unroll
+                for (int j = 0; j < NU / 2; ++j) { P lo, hi; ub_pair(i, j, pbu, lo, hi); z.p[j] = clampv(TZ.getp(i, j), lo, hi); }
+                if constexpr (NU & 1) { T lo, hi; ub_tail(i, pbu, lo, hi); z.t = clampv(TZ.gett(i), lo, hi); }
+                store_span<NU, vec_width(SUL, NU)>(prm.u + pbu + i * NU, [&](int a) { return z.get(a); });
+            }
+            prm.iter[prob] = k;
+            prm.status[prob] = st;
+            if (prm.residuals) *reinterpret_cast<float4*>(prm.residuals + 4 * (size_t)prob) = make_float4(res_px, res_dx, res_pu, res_du);
+            if (prm.rho_out) prm.rho_out[prob] = rho0;
+            active = false;
+        }
+    }
+    tmem_fence_before_sync();
+    __syncthreads();
+    if (threadIdx.x < 32) tmem_dealloc(tmem_base_s, 512);
+}
+
+template <class C>
+inline size_t tpp3_smem_bytes(int pack_elems) {
+    return ((size_t)((pack_elems + 31) & ~31) + (size_t)C::COLS * C::BLOCK) * sizeof(float);
+}
+
+}  // namespace tmpc
