@@ -138,6 +138,8 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0, help="difficulty of the synthetic batch (SURVEY 8d: 0.3 easy, 1.0 hard)")
     ap.add_argument("--config", default="quadrotor", choices=["quadrotor", "cartpole", "rocket", "quadrotor_adaptive"])
     ap.add_argument("--precision", type=int, default=32)
+    ap.add_argument("--mixed", type=float, default=0.0, help="relative band of the fp32+fp64 exact-count mode (0 = plain fp32)")
+    ap.add_argument("--variant", type=int, default=0, help="kernel variant (0 = default; A/B baselines 1, 2, 5)")
     ap.add_argument("--cpu-seconds", dest="cpu_seconds", type=float, default=8.0)
     ap.add_argument("--steps-cpu", dest="steps_cpu", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -198,6 +200,9 @@ def main():
     solver = tm.TinyMPC()
     solver.setup_from_spec(spec, devices=[local])
     solver.cuda.set_option("precision", args.precision)
+    solver.cuda.set_option("variant", args.variant)
+    solver.cuda.set_option("mixed", args.mixed)
+    config["mixed_band"] = args.mixed
 
     tdev = lambda a: None if a is None else torch.from_numpy(a).to(dev)
     x0, Xref, Uref = tdev(batch_np.x0), tdev(batch_np.Xref), tdev(batch_np.Uref)
@@ -228,6 +233,7 @@ def main():
         barrier()
     ms = e0.elapsed_time(e1)
     launches = solver.cuda.launch_count - launches0
+    marked = solver.cuda.last_marked if args.mixed > 0 else 0
     iters_one = int(it.sum().item())                 # identical every step (same inputs)
     unsolved = float((st == 11).float().mean().item())
     ms_all, (iters_all, launches_all) = S.reduce_report(ms, [iters_one, launches], dist, dev)   # max of times, sum of work
@@ -279,16 +285,16 @@ def main():
     # (profiles/r01/traffic.json: dram__bytes_read.sum + dram__bytes_write.sum per launch)
     prof = ROOT / "profiles" / "r01" / "traffic.json"
     if prof.exists():
-        t = json.loads(prof.read_text()).get(f"{args.config}_b{B}_s{args.scale:g}")
-        if t and t.get("kernel") == solver.cuda.last_kernel:
-            roof["traffic"] = t["dram_bytes_per_launch"]
-            roof["traffic_algorithmic"] = bytes_per_solve(n, m, N) * B
+        for key, t in json.loads(prof.read_text()).items():
+            if key.startswith(f"{args.config}_b{B}_s{args.scale:g}") and t.get("kernel") == solver.cuda.last_kernel:
+                roof["traffic"] = t["dram_bytes_per_launch"]
+                roof["traffic_algorithmic"] = bytes_per_solve(n, m, N) * B
 
     line = {"metric": "solves_per_sec", "value": value, "unit": "solves/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_all / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32" if args.precision == 32 else "f64", "data": "synthetic", "config": config,
             "ns_per_admm_iter": ns_iter, "mean_iters": iters_all / (world * B), "unsolved_frac": unsolved,
-            "clocks": clk.summary(), "e2e": e2e, "gpu_launches": launches_all, "roofline": roof}
+            "clocks": clk.summary(), "e2e": e2e, "fp64_resolved": int(marked), "gpu_launches": launches_all, "roofline": roof}
     if not args.no_cpu_baseline:
         try:
             cb = reference_arm(args, P, spec, batch_np.slice(0, min(B, 1 << 18)))

@@ -147,3 +147,47 @@ def test_mixed_mode_host_and_device_paths_agree(capi, oracle_mod, problems):
     assert m1 == m7 and m1 > 0
     assert np.array_equal(r1["iter"], r7["iter"]) and np.array_equal(r1["status"], r7["status"])
     assert np.array_equal(r1["x"], r7["x"]) and np.array_equal(r1["u"], r7["u"])
+
+
+@pytest.mark.parametrize("family,B,chunks,precision", [("quadrotor", 100003, 0, 32), ("quadrotor", 70000, 7, 32), ("cartpole", 131072, 0, 32),
+                                                       ("rocket", 50001, 3, 32), ("quadrotor_adaptive", 40000, 2, 32), ("quadrotor", 40000, 3, 64)])
+def test_streamed_pipeline_matches_chunked_launches(family, B, chunks, precision, capi, oracle_mod, problems):
+    """option "streamed" (default): one persistent launch consumes the batch while the H2D chunks are still arriving and
+    hands results back chunk by chunk (arrival watermark + per-chunk completion counters, tmpc_capi.cu run_shard_streamed).
+    Must return bit-for-bit what the one-launch-per-chunk pipeline returns, for ragged sizes and every kernel family."""
+    p = dict(cartpole=problems.cartpole, quadrotor=problems.quadrotor, rocket=problems.rocket,
+             quadrotor_adaptive=lambda: problems.quadrotor(adaptive=True))[family]()
+    b = problems.make_batch(p, B, 1.0, seed=11)
+    s = capi.CudaSolver()
+    s.set_option("precision", precision)
+    s.set_family(cases.family_from_spec(p, oracle_mod.get_cache(p, "port")))
+    s.set_option("streamed", 0)
+    s.set_option("chunks", 1)
+    r0 = s.solve_batch(b.x0, b.Xref, b.Uref)
+    assert s.last_timing()["chunks"] == 1
+    s.set_option("streamed", 1)
+    s.set_option("chunks", chunks)
+    for _ in range(2):   # twice: the control words are reused
+        r1 = s.solve_batch(b.x0, b.Xref, b.Uref)
+        assert s.last_timing()["chunks"] >= 2, "the streamed path was not taken"
+        for k in ("iter", "status", "x", "u", "residuals", "rho"):
+            assert np.array_equal(r0[k], r1[k]), f"{family}: streamed pipeline differs in {k}"
+    s.close()
+
+
+def test_streamed_pipeline_per_problem_bounds(capi, oracle_mod, problems):
+    name = "batch_quadrotor_perproblem_bounds"
+    p, b0, g = cases.load(name)
+    reps = 40000 // b0.size + 1
+    tile = lambda a: None if a is None else np.ascontiguousarray(np.concatenate([a] * reps, axis=0))
+    s = capi.CudaSolver()
+    s.set_option("precision", 64)
+    s.set_family(cases.family_from_spec(p, oracle_mod.get_cache(p, "port")))
+    s.set_option("chunks", 3)
+    r = s.solve_batch(tile(b0.x0), tile(b0.Xref), tile(b0.Uref), tile(b0.x_min), tile(b0.x_max), tile(b0.u_min), tile(b0.u_max))
+    assert s.last_timing()["chunks"] == 3
+    s.close()
+    n = b0.size
+    for k in range(0, reps * n, n * 7):
+        assert np.array_equal(r["iter"][k:k + n], g["iter"]) and np.array_equal(r["status"][k:k + n], g["status"])
+        assert np.abs(r["x"][k:k + n] - g["x"]).max() <= X_TOL_F64 * max(1.0, float(np.abs(g["x"]).max()))

@@ -121,6 +121,9 @@ def default_instances():
             if (nx, nu) == (12, 4):
                 out.append(inst(bits, nx, nu, N, ADP, refs=REFS_L2, fb=True, tm=True))
                 out.append(inst(bits, nx, nu, N, ADP, refs=REFS_L2, tm=True))
+    # A/B: the incremental form with opaque (loop-variant) constant offsets, option variant=6
+    out.append(inst3(12, 4, 10, refs=True, fb=True, variant=6, opq=True))
+    out.append(inst3(4, 1, 20, refs=False, fb=True, variant=6, opq=True))
     # A/B: the direct-form fp32 box kernels (16 / 24 warps per SM, tensor-memory TV) on the headline shapes, option variant=5
     out.append(inst(32, 12, 4, 10, BOX, refs=REFS_L2, variant=5, fb=True, tm=True))
     out.append(inst(32, 12, 4, 10, BOX, refs=REFS_L2, variant=5, tm=True))

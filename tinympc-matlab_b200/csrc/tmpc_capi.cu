@@ -7,6 +7,7 @@
 // There is no CPU fallback anywhere in this file: without a device every call fails.
 #include "../../include/tinympc_b200.h"
 
+#include <cuda.h>            // types of the two stream memory operations only; the entry points come from cudaGetDriverEntryPoint
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -30,6 +31,7 @@ namespace {
 constexpr int kFeatBox = 0, kFeatConstr = 1, kFeatAdapt = 2;
 constexpr int kMaxChunks = 64;
 constexpr int kStreams = 3;
+constexpr int kMaxStreamChunks = 256;    // streamed pipeline: [0] work counter, [1] arrival watermark, [2 + c] finished problems of chunk c
 
 struct DevBuf {
     void* p = nullptr;
@@ -50,6 +52,8 @@ struct DeviceCtx {
     int sm_count = 0;
     void* pack32 = nullptr;
     void* pack64 = nullptr;
+    int* stream_ctl = nullptr;          // 2 + kMaxStreamChunks ints (see kMaxStreamChunks)
+    cudaEvent_t ev_ctl = nullptr;
     int* counters = nullptr;            // 3 * kMaxChunks ints: work counters of the first pass, of the fp64 re-solve pass, marked-problem counts
     cudaStream_t streams[kStreams] = {nullptr, nullptr, nullptr};
     cudaEvent_t k0[kMaxChunks], k1[kMaxChunks];
@@ -83,6 +87,7 @@ struct tinympc_cuda_solver {
     int chunks = 0;                    // 0 = auto
     int variant = 0;
     int force_wpp = 0;                 // option "kernel": 0 auto, 1 always the warp-per-problem kernel
+    int streamed = 1;                  // option "streamed": 1 = single-launch streamed host pipeline where it applies, 0 = chunked launches
     double mixed_band = 0;             // option "mixed": > 0 = fp32 pass + fp64 re-solve of the problems whose termination decision
                                        // falls within this relative band of the tolerances (exact iteration counts at ~fp32 speed)
     long long mixed_marked = 0;        // problems re-solved in fp64 by the last mixed solve (host entry: filled by the call)
@@ -303,6 +308,125 @@ int zero_iteration_result(tinympc_cuda_solver* s, const Family& f, const tinympc
     return TINYMPC_CUDA_OK;
 }
 
+// ---- streamed pipeline -------------------------------------------------------------------------------------------------
+// The two stream memory operations of the driver API, resolved at run time (no link-time dependency on libcuda).
+using StreamMemOp32 = CUresult (*)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+struct StreamMemOps {
+    StreamMemOp32 wait = nullptr, write = nullptr;
+    bool ok = false;
+};
+const StreamMemOps& stream_memops() {
+    static const StreamMemOps ops = [] {
+        StreamMemOps o;
+        void* fw = nullptr; void* fr = nullptr;
+        cudaDriverEntryPointQueryResult q1, q2;
+        if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &fw, cudaEnableDefault, &q1) == cudaSuccess && q1 == cudaDriverEntryPointSuccess &&
+            cudaGetDriverEntryPoint("cuStreamWriteValue32", &fr, cudaEnableDefault, &q2) == cudaSuccess && q2 == cudaDriverEntryPointSuccess && fw && fr) {
+            o.wait = reinterpret_cast<StreamMemOp32>(fw);
+            o.write = reinterpret_cast<StreamMemOp32>(fr);
+            o.ok = true;
+        }
+        cudaGetLastError();
+        return o;
+    }();
+    return ops;
+}
+
+// One device's share of a host batch as ONE persistent launch that consumes the problems while the copy engine is still
+// delivering them: stream 0 carries the H2D chunks, each followed by a write of the arrival watermark; stream 1 carries the
+// kernel, whose lanes wait on the watermark before they read a claimed problem and count every finished problem per chunk;
+// stream 2 waits (cuStreamWaitValue32) for a chunk's count and copies its results back.  No launch boundaries, hence no
+// per-chunk tails of idle lanes, and the three engines (H2D DMA, SMs, D2H DMA) overlap for the whole batch.
+int run_shard_streamed(tinympc_cuda_solver* s, DeviceCtx& d, const KernelEntry* ke, const tinympc_cuda_batch_in& in, const tinympc_cuda_batch_out& out,
+                       int lo, int hi, int nch, double* kernel_ms, int* nchunks_out) {
+    const Family& f = s->fam;
+    const StreamMemOps& ops = stream_memops();
+    const int n = hi - lo;
+    const size_t sx = (size_t)f.nx * f.N, su = (size_t)f.nu * (f.N - 1);
+    const bool ppb = in.x_min != nullptr;
+    // chunks of a multiple of 32 problems: every array's chunk boundary then falls on a 128-byte line for any shape, so no
+    // line holds data of two chunks (a lane may read its problem with non-coherent loads as soon as the watermark covers it)
+    int per = (((n + nch - 1) / nch) + 31) & ~31;
+    nch = (n + per - 1) / per;
+    cudaStream_t s_in = d.streams[0], s_k = d.streams[1], s_out = d.streams[2];
+    int* ctl = d.stream_ctl;
+    CU(s, cudaMemsetAsync(ctl, 0, sizeof(int) * (2 + nch), s_k));
+    CU(s, cudaEventRecord(d.ev_ctl, s_k));
+    CU(s, cudaStreamWaitEvent(s_in, d.ev_ctl, 0));
+    CU(s, cudaStreamWaitEvent(s_out, d.ev_ctl, 0));
+
+    SolveParams p = f.base;
+    p.pack = (const void*)((const float*)d.pack32 + f.L.cold);
+    if (ke->dtype_bits == 64) p.pack = (const void*)((const double*)d.pack64 + f.L.cold);
+    p.pack_elems = f.L.cold_size;
+    p.batch = n;
+    p.x0 = (const float*)d.x0.p; p.Xref = in.Xref ? (const float*)d.Xref.p : nullptr; p.Uref = in.Uref ? (const float*)d.Uref.p : nullptr;
+    if (ppb) { p.x_min = (const float*)d.xmin.p; p.x_max = (const float*)d.xmax.p; p.u_min = (const float*)d.umin.p; p.u_max = (const float*)d.umax.p; }
+    p.x = (float*)d.x.p; p.u = (float*)d.u.p; p.iter = (int*)d.iter.p; p.status = (int*)d.status.p;
+    p.residuals = out.residuals ? (float*)d.res.p : nullptr;
+    p.rho_out = out.rho ? (float*)d.rho.p : nullptr;
+    p.avail_ptr = ctl + 1;
+    p.done_counters = ctl + 2;
+    p.done_chunk = per;
+    CU(s, cudaEventRecord(d.k0[0], s_k));
+    {
+        // launch_tpp zeroes the work counter itself (ctl[0], on s_k, before the kernel)
+        int rc = launch_tpp(s, d, ke, p, d.ref_scratch[0], ke->dtype_bits, ctl, s_k);
+        if (rc) return rc;
+    }
+    CU(s, cudaEventRecord(d.k1[0], s_k));
+    s->last_kernel = ke->name;
+
+    auto drv = [&](CUresult r, const char* what) -> int {
+        if (r == CUDA_SUCCESS) return TINYMPC_CUDA_OK;
+        // the kernel is already waiting for data: release it before reporting (watermark = everything; contents are then
+        // undefined but the call fails anyway)
+        ops.write(reinterpret_cast<CUstream>(s_in), reinterpret_cast<CUdeviceptr>(ctl + 1), (cuuint32_t)n, 0);
+        cudaDeviceSynchronize();
+        return fail(s, TINYMPC_CUDA_ECUDA, std::string(what) + " failed with CUresult " + std::to_string((int)r));
+    };
+    auto rt = [&](cudaError_t e, const char* what) -> int {
+        if (e == cudaSuccess) return TINYMPC_CUDA_OK;
+        ops.write(reinterpret_cast<CUstream>(s_in), reinterpret_cast<CUdeviceptr>(ctl + 1), (cuuint32_t)n, 0);
+        cudaDeviceSynchronize();
+        return cuda_fail(s, e, what);
+    };
+#define RT(call) do { int rc__ = rt((call), #call); if (rc__) return rc__; } while (0)
+    for (int c = 0; c < nch; ++c) {
+        const int c0 = c * per, c1 = std::min(n, c0 + per), cn = c1 - c0;
+        const size_t g0 = (size_t)lo + c0;
+        auto h2d = [&](DevBuf& dst, const float* src, size_t per_problem) -> cudaError_t {
+            return cudaMemcpyAsync((float*)dst.p + per_problem * c0, src + per_problem * g0, sizeof(float) * per_problem * cn, cudaMemcpyHostToDevice, s_in);
+        };
+        RT(h2d(d.x0, in.x0, f.nx));
+        if (in.Xref) RT(h2d(d.Xref, in.Xref, sx));
+        if (in.Uref) RT(h2d(d.Uref, in.Uref, su));
+        if (ppb) { RT(h2d(d.xmin, in.x_min, sx)); RT(h2d(d.xmax, in.x_max, sx)); RT(h2d(d.umin, in.u_min, su)); RT(h2d(d.umax, in.u_max, su)); }
+        int rc = drv(ops.write(reinterpret_cast<CUstream>(s_in), reinterpret_cast<CUdeviceptr>(ctl + 1), (cuuint32_t)c1, 0), "cuStreamWriteValue32");
+        if (rc) return rc;
+    }
+    for (int c = 0; c < nch; ++c) {
+        const int c0 = c * per, c1 = std::min(n, c0 + per), cn = c1 - c0;
+        const size_t g0 = (size_t)lo + c0;
+        int rc = drv(ops.wait(reinterpret_cast<CUstream>(s_out), reinterpret_cast<CUdeviceptr>(ctl + 2 + c), (cuuint32_t)cn, CU_STREAM_WAIT_VALUE_GEQ),
+                     "cuStreamWaitValue32");
+        if (rc) return rc;
+        RT(cudaMemcpyAsync(out.x + sx * g0, (float*)d.x.p + sx * c0, sizeof(float) * sx * cn, cudaMemcpyDeviceToHost, s_out));
+        RT(cudaMemcpyAsync(out.u + su * g0, (float*)d.u.p + su * c0, sizeof(float) * su * cn, cudaMemcpyDeviceToHost, s_out));
+        RT(cudaMemcpyAsync(out.iter + g0, (int*)d.iter.p + c0, sizeof(int) * cn, cudaMemcpyDeviceToHost, s_out));
+        RT(cudaMemcpyAsync(out.status + g0, (int*)d.status.p + c0, sizeof(int) * cn, cudaMemcpyDeviceToHost, s_out));
+        if (out.residuals) RT(cudaMemcpyAsync(out.residuals + 4 * g0, (float*)d.res.p + 4 * (size_t)c0, sizeof(float) * 4 * cn, cudaMemcpyDeviceToHost, s_out));
+        if (out.rho) RT(cudaMemcpyAsync(out.rho + g0, (float*)d.rho.p + c0, sizeof(float) * cn, cudaMemcpyDeviceToHost, s_out));
+    }
+#undef RT
+    for (int k = 0; k < kStreams; ++k) CU(s, cudaStreamSynchronize(d.streams[k]));
+    float ms = 0;
+    CU(s, cudaEventElapsedTime(&ms, d.k0[0], d.k1[0]));
+    *kernel_ms = ms;
+    *nchunks_out = nch;
+    return TINYMPC_CUDA_OK;
+}
+
 // One device's share of a host batch: chunked H2D -> kernel -> D2H pipeline over kStreams streams.
 int run_shard(tinympc_cuda_solver* s, DeviceCtx& d, const tinympc_cuda_batch_in& in, const tinympc_cuda_batch_out& out, int lo, int hi,
               double* kernel_ms, int* nchunks_out, long long* marked_out) {
@@ -325,6 +449,14 @@ int run_shard(tinympc_cuda_solver* s, DeviceCtx& d, const tinympc_cuda_batch_in&
     if (out.residuals) CU(s, d.res.reserve(sizeof(float) * 4 * (size_t)n));
     if (out.rho) CU(s, d.rho.reserve(sizeof(float) * (size_t)n));
 
+    // single-launch streamed pipeline: plain (not mixed) solves on a thread-per-problem kernel that honours the watermark
+    if (s->streamed && !(s->mixed_band > 0 && s->precision == 32) && !s->force_wpp && stream_memops().ok) {
+        const KernelEntry* ke = find_kernel(f, s->precision, ppb, in.Xref || in.Uref, s->variant);
+        int nst = s->chunks > 0 ? s->chunks : std::min(64, n / 16384);
+        nst = std::min(nst, kMaxStreamChunks);
+        if (ke && ke->streaming && nst >= 2 && (ppb || f.shared_bounds_ok))
+            return run_shard_streamed(s, d, ke, in, out, lo, hi, nst, kernel_ms, nchunks_out);
+    }
     // chunking: enough chunks to overlap copies with compute, each still many waves of the GPU
     int nch = s->chunks > 0 ? s->chunks : (n >= (1 << 17) ? 8 : (n >= (1 << 15) ? 4 : 1));
     nch = std::min(nch, kMaxChunks);
@@ -422,6 +554,8 @@ int tinympc_cuda_create(tinympc_cuda_solver** out, const int* devices, int n_dev
         if (cudaSetDevice(id) != cudaSuccess) { delete s; return TINYMPC_CUDA_ECUDA; }
         cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, id);
         if (cudaMalloc(&d.counters, sizeof(int) * 3 * kMaxChunks) != cudaSuccess) { delete s; return TINYMPC_CUDA_ECUDA; }
+        if (cudaMalloc(&d.stream_ctl, sizeof(int) * (2 + kMaxStreamChunks)) != cudaSuccess) { delete s; return TINYMPC_CUDA_ECUDA; }
+        cudaEventCreateWithFlags(&d.ev_ctl, cudaEventDisableTiming);
         for (int k = 0; k < kStreams; ++k) cudaStreamCreateWithFlags(&d.streams[k], cudaStreamNonBlocking);
         for (int c = 0; c < kMaxChunks; ++c) { cudaEventCreate(&d.k0[c]); cudaEventCreate(&d.k1[c]); }
         d.events = true;
@@ -443,6 +577,8 @@ int tinympc_cuda_destroy(tinympc_cuda_solver* s) {
         if (d.pack32) cudaFree(d.pack32);
         if (d.pack64) cudaFree(d.pack64);
         if (d.counters) cudaFree(d.counters);
+        if (d.stream_ctl) cudaFree(d.stream_ctl);
+        if (d.ev_ctl) cudaEventDestroy(d.ev_ctl);
         for (DevBuf* b : {&d.x0, &d.Xref, &d.Uref, &d.xmin, &d.xmax, &d.umin, &d.umax, &d.x, &d.u, &d.iter, &d.status, &d.res, &d.rho}) b->release();
         for (auto& b : d.wpp_scratch) b.release();
         for (auto& b : d.ref_scratch) b.release();
@@ -893,6 +1029,8 @@ int tinympc_cuda_set_option(tinympc_cuda_solver* s, const char* name, double val
         s->mixed_band = value;
     } else if (n == "force_wpp") {
         s->force_wpp = (int)value;
+    } else if (n == "streamed") {
+        s->streamed = value != 0;
     } else {
         return fail(s, TINYMPC_CUDA_EINVAL, "unknown option " + n);
     }

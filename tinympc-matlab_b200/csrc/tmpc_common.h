@@ -107,6 +107,13 @@ struct SolveParams {
     float amb_band;            // 0 = off
     const int* index_list;     // NULL, or problem index of work item k (the kernel then runs over *batch_ptr items)
     const int* batch_ptr;      // NULL, or device int holding the number of work items (<= batch)
+    // streamed host pipeline (tmpc_capi.cu run_shard_streamed): ONE persistent launch consumes the batch while the copy engines
+    // are still delivering it.  avail_ptr counts the problems whose inputs have landed (written in stream order behind each
+    // H2D chunk); a lane that claims problem p waits until *avail_ptr > p.  done_counters[p / done_chunk] counts finished
+    // problems per chunk (release, system scope): the D2H stream waits on it (cuStreamWaitValue32) before copying that chunk.
+    const int* avail_ptr;      // NULL = the whole batch is resident
+    int* done_counters;        // NULL = nobody is waiting
+    int done_chunk;            // problems per chunk
 };
 
 constexpr int kAmbiguousBit = 0x100;

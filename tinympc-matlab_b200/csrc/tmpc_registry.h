@@ -22,6 +22,7 @@ struct KernelEntry {
     int affine;          // 1: handles a non-zero affine term (fdyn, APf, BPf); 0: requires f = 0
     int block;           // threads per CTA
     int variant;         // tuning variant (0 = default); selected with the "variant" option
+    int streaming;       // 1: honours SolveParams::avail_ptr / done_counters (the single-launch streamed host pipeline)
     size_t (*smem_bytes)(int pack_elems);
     cudaError_t (*prepare)(size_t smem);                                   // cudaFuncSetAttribute(max dynamic smem)
     cudaError_t (*occupancy)(int* ctas_per_sm, size_t smem);
@@ -52,7 +53,7 @@ const KernelEntry* const* kernel_table(int* count);   // defined in gen/tmpc_tab
         return cudaGetLastError();                                                                                  \
     }                                                                                                               \
     extern const KernelEntry SYM = {#SYM, KF_TPP, CFG::NX, CFG::NU, CFG::NH, FEATV, BITS, CFG::REFMODE,             \
-                                    CFG::PPB ? 1 : 0, CFG::FB ? 1 : 0, 1, CFG::BLOCK, VAR, SYM##_smem, SYM##_prepare, SYM##_occ,     \
+                                    CFG::PPB ? 1 : 0, CFG::FB ? 1 : 0, 1, CFG::BLOCK, VAR, 0, SYM##_smem, SYM##_prepare, SYM##_occ,  \
                                     SYM##_launch};                                                                  \
     }
 
@@ -74,7 +75,7 @@ const KernelEntry* const* kernel_table(int* count);   // defined in gen/tmpc_tab
         return cudaGetLastError();                                                                                  \
     }                                                                                                               \
     extern const KernelEntry SYM = {#SYM, KF_TPP, CFG::NX, CFG::NU, CFG::NH, FEATV, BITS, CFG::REFMODE,             \
-                                    CFG::PPB ? 1 : 0, CFG::FB ? 1 : 0, CFG::AFF ? 1 : 0, CFG::BLOCK, VAR, SYM##_smem, SYM##_prepare, \
+                                    CFG::PPB ? 1 : 0, CFG::FB ? 1 : 0, CFG::AFF ? 1 : 0, CFG::BLOCK, VAR, 1, SYM##_smem, SYM##_prepare, \
                                     SYM##_occ, SYM##_launch};                                                       \
     }
 
@@ -96,6 +97,6 @@ const KernelEntry* const* kernel_table(int* count);   // defined in gen/tmpc_tab
         return cudaGetLastError();                                                                                  \
     }                                                                                                               \
     extern const KernelEntry SYM = {#SYM, KF_TPP, CFG::NX, CFG::NU, CFG::NH, FEATV, BITS, CFG::REFMODE,             \
-                                    CFG::PPB ? 1 : 0, CFG::FB ? 1 : 0, CFG::AFF ? 1 : 0, CFG::BLOCK, VAR, SYM##_smem, SYM##_prepare, \
+                                    CFG::PPB ? 1 : 0, CFG::FB ? 1 : 0, CFG::AFF ? 1 : 0, CFG::BLOCK, VAR, 1, SYM##_smem, SYM##_prepare, \
                                     SYM##_occ, SYM##_launch};                                                       \
     }

@@ -86,6 +86,27 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gme
 }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
+// Streamed host pipeline (SolveParams::avail_ptr / done_counters).  wait_available: block the claiming lane until the copy
+// engine has delivered problem `prob` (the watermark is written in stream order behind the chunk's H2D copies, so an
+// acquire load at system scope orders the lane's later reads of the problem after it).  mark_done: publish a finished
+// problem's stores (release at system scope) and count it for the chunk's D2H copy.
+__device__ __forceinline__ void wait_available(const SolveParams& prm, int prob) {
+    if (prm.avail_ptr == nullptr) return;
+    int seen;
+    unsigned ns = 64;
+    for (;;) {
+        asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(seen) : "l"(prm.avail_ptr) : "memory");
+        if (seen > prob) break;
+        __nanosleep(ns);
+        if (ns < 2048) ns *= 2;
+    }
+}
+__device__ __forceinline__ void mark_done(const SolveParams& prm, int prob) {
+    if (prm.done_counters == nullptr) return;
+    __threadfence_system();
+    atomicAdd(prm.done_counters + prob / prm.done_chunk, 1);
+}
+
 // A warp-uniform value that is always 0 but that the compiler cannot prove to be: bit 31 of the upper clock word
 // (set only after 2^63 cycles).  Added to the constant-bank index of the matrix tables once per time step, it
 // makes their LDCU loads loop-variant.  Without it ptxas hoists ~60 loop-invariant coefficients into the 63
@@ -803,6 +824,7 @@ tpp2_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ typ
                         prob = 0;   // keeps the (unused) per-problem reads of an idle lane in range
                     } else {
                         if (prm.index_list) prob = __ldg(prm.index_list + prob);
+                        wait_available(prm, prob);
                         active = true;
                         k = 0;
                         next_check = check_every;
@@ -1208,6 +1230,7 @@ tpp2_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ typ
                 *reinterpret_cast<float4*>(prm.residuals + 4 * (size_t)prob) = rr;
             }
             if (prm.rho_out) prm.rho_out[prob] = static_cast<float>(rho);
+            mark_done(prm, prob);
             active = false;
         }
         if (!__any_sync(FULL, active)) continue;   // whole warp idle: go refill (or exit) without a backward sweep

@@ -165,6 +165,7 @@ tpp3_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ typ
                         prob = 0;
                     } else {
                         if (prm.index_list) prob = __ldg(prm.index_list + prob);
+                        wait_available(prm, prob);
                         active = mine = true;
                         k = 0;
                         next_check = check_every;
@@ -453,6 +454,7 @@ tpp3_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ typ
             prm.status[prob] = st;
             if (prm.residuals) *reinterpret_cast<float4*>(prm.residuals + 4 * (size_t)prob) = make_float4(res_px, res_dx, res_pu, res_du);
             if (prm.rho_out) prm.rho_out[prob] = rho0;
+            mark_done(prm, prob);
             active = false;
         }
     }
