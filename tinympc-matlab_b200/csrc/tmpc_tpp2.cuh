@@ -86,25 +86,26 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gme
 }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
-// Streamed host pipeline (SolveParams::avail_ptr / done_counters).  wait_available: block the claiming lane until the copy
-// engine has delivered problem `prob` (the watermark is written in stream order behind the chunk's H2D copies, so an
-// acquire load at system scope orders the lane's later reads of the problem after it).  mark_done: publish a finished
-// problem's stores (release at system scope) and count it for the chunk's D2H copy.
-__device__ __forceinline__ void wait_available(const SolveParams& prm, int prob) {
-    if (prm.avail_ptr == nullptr) return;
-    int seen;
-    unsigned ns = 64;
-    for (;;) {
-        asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(seen) : "l"(prm.avail_ptr) : "memory");
-        if (seen > prob) break;
-        __nanosleep(ns);
-        if (ns < 2048) ns *= 2;
-    }
+// Streamed host pipeline (SolveParams::avail_ptr / done_counters).
+// problem_ready: has the copy engine delivered problem `prob`?  The watermark is written in stream order behind the chunk's
+// H2D copies; it is read from L2 (strong load, no L1 involvement) only when the lane's cached copy does not cover `prob`, and
+// the problem's own lines cannot be in this SM's L1 before that (chunk boundaries fall on 128-byte lines, nobody reads ahead
+// of the watermark).  A lane whose claimed problem has not landed stays PENDING and re-checks at its warp's next refill
+// point while the other lanes keep iterating.
+// publish_done: count a finished problem for its chunk's D2H copy.  Called well after the lane stored its solution (half an
+// ADMM iteration later), so the release fence finds those stores already acknowledged by L2 and costs next to nothing; the
+// copy engine and the stream wait both read through L2, hence device scope.
+__device__ __forceinline__ bool problem_ready(const SolveParams& prm, int prob, int& seen) {
+    if (prm.avail_ptr == nullptr || seen > prob) return true;
+    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(prm.avail_ptr) : "memory");
+    return seen > prob;
 }
-__device__ __forceinline__ void mark_done(const SolveParams& prm, int prob) {
-    if (prm.done_counters == nullptr) return;
-    __threadfence_system();
-    atomicAdd(prm.done_counters + prob / prm.done_chunk, 1);
+__device__ __forceinline__ void publish_done(const SolveParams& prm, int& unpub) {
+    if (unpub >= 0) {
+        asm volatile("fence.release.gpu;" ::: "memory");
+        atomicAdd(prm.done_counters + unpub / prm.done_chunk, 1);
+        unpub = -1;
+    }
 }
 
 // A warp-uniform value that is always 0 but that the compiler cannot prove to be: bit 31 of the upper clock word
@@ -759,6 +760,8 @@ tpp2_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ typ
     int prob = 0;           // problem owned by this lane
     bool active = false;    // lane holds an unfinished problem
     bool exhausted = false; // the work counter ran past the batch
+    bool pending = false;   // holds a claimed problem (claim) whose inputs have not landed yet (streamed host pipeline)
+    int claim = 0, seen = 0, unpub = -1;   // seen: cached arrival watermark; unpub: finished problem not yet counted for its chunk
     int k = 0;              // ADMM iterations done on the current problem
     int next_check = check_every;   // next iteration count at which termination is evaluated (iter % check == 0)
     T res_px = 0, res_dx = 0, res_pu = 0, res_du = 0;   // last evaluated residuals (admm.cpp:257-260)
@@ -810,21 +813,33 @@ tpp2_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ typ
     for (;;) {
         // ------------------------------------------------------------------ refill idle lanes
         {
-            const bool want = !active && !exhausted;
-            const unsigned m = __ballot_sync(FULL, want);
-            if (m) {
-                const int leader = __ffs(m) - 1;
+            publish_done(prm, unpub);
+            const bool want = !active && !exhausted && !pending;
+            const unsigned mw = __ballot_sync(FULL, want);
+            if (mw) {   // claim the next problem indices (one atomic per warp)
+                const int leader = __ffs(mw) - 1;
                 int base = 0;
-                if (lane == leader) base = atomicAdd(prm.work_counter, __popc(m));
+                if (lane == leader) base = atomicAdd(prm.work_counter, __popc(mw));
                 base = __shfl_sync(FULL, base, leader);
                 if (want) {
-                    prob = base + __popc(m & ((1u << lane) - 1u));
-                    if (prob >= n_items) {
+                    claim = base + __popc(mw & ((1u << lane) - 1u));
+                    if (claim >= n_items) {
                         exhausted = true;
                         prob = 0;   // keeps the (unused) per-problem reads of an idle lane in range
                     } else {
-                        if (prm.index_list) prob = __ldg(prm.index_list + prob);
-                        wait_available(prm, prob);
+                        if (prm.index_list) claim = __ldg(prm.index_list + claim);
+                        pending = true;
+                    }
+                }
+            }
+            // a claimed problem starts once its inputs have landed (always, unless the host streams the batch in)
+            const bool mine = pending && problem_ready(prm, claim, seen);
+            const unsigned m = __ballot_sync(FULL, mine);
+            if (m) {
+                if (mine) {
+                    {
+                        prob = claim;
+                        pending = false;
                         active = true;
                         k = 0;
                         next_check = check_every;
@@ -928,10 +943,14 @@ tpp2_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ typ
                         }
                     }
                 }
-                TV.reset(want && active);   // warp-collective when TV lives in tensor memory
-                if constexpr (C::CONSTR) { GC.reset(want && active); GL.reset(want && active); }   // SXT is written before it is read
+                TV.reset(mine);   // warp-collective when TV lives in tensor memory
+                if constexpr (C::CONSTR) { GC.reset(mine); GL.reset(mine); }   // SXT is written before it is read
             }
-            if (!__any_sync(FULL, active)) break;
+            if (!__any_sync(FULL, active)) {
+                if (!__any_sync(FULL, pending)) break;
+                __nanosleep(256);   // the whole warp is waiting for the copy engine
+                continue;
+            }
         }
 
         // ------------------------------------------------- forward rollout + slack + dual + residuals
@@ -1230,7 +1249,7 @@ tpp2_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ typ
                 *reinterpret_cast<float4*>(prm.residuals + 4 * (size_t)prob) = rr;
             }
             if (prm.rho_out) prm.rho_out[prob] = static_cast<float>(rho);
-            mark_done(prm, prob);
+            if (prm.done_counters) unpub = prob;
             active = false;
         }
         if (!__any_sync(FULL, active)) continue;   // whole warp idle: go refill (or exit) without a backward sweep

@@ -107,6 +107,8 @@ tpp3_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ typ
     const int n_items = prm.batch_ptr ? min(*prm.batch_ptr, prm.batch) : prm.batch;
     int prob = 0;
     bool active = false, exhausted = false;
+    bool pending = false;   // holds a claimed problem (claim) whose inputs have not landed yet (streamed host pipeline)
+    int claim = 0, seen = 0, unpub = -1;   // seen: cached arrival watermark; unpub: finished problem not yet counted for its chunk
     int k = 0;
     int next_check = check_every;
     T res_px = 0, res_dx = 0, res_pu = 0, res_du = 0;
@@ -150,27 +152,35 @@ tpp3_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ typ
     for (;;) {
         // ------------------------------------------------------------------ refill idle lanes
         {
-            const bool want = !active && !exhausted;
-            const unsigned m = __ballot_sync(FULL, want);
-            if (m) {
-                const int leader = __ffs(m) - 1;
+            const bool want = !active && !exhausted && !pending;
+            const unsigned mw = __ballot_sync(FULL, want);
+            if (mw) {   // claim the next problem indices (one atomic per warp)
+                const int leader = __ffs(mw) - 1;
                 int base = 0;
-                if (lane == leader) base = atomicAdd(prm.work_counter, __popc(m));
+                if (lane == leader) base = atomicAdd(prm.work_counter, __popc(mw));
                 base = __shfl_sync(FULL, base, leader);
-                bool mine = false;
                 if (want) {
-                    prob = base + __popc(m & ((1u << lane) - 1u));
-                    if (prob >= n_items) {
+                    claim = base + __popc(mw & ((1u << lane) - 1u));
+                    if (claim >= n_items) {
                         exhausted = true;
                         prob = 0;
                     } else {
-                        if (prm.index_list) prob = __ldg(prm.index_list + prob);
-                        wait_available(prm, prob);
-                        active = mine = true;
-                        k = 0;
-                        next_check = check_every;
-                        res_px = res_dx = res_pu = res_du = 0;
+                        if (prm.index_list) claim = __ldg(prm.index_list + claim);
+                        pending = true;
                     }
+                }
+            }
+            // a claimed problem starts once its inputs have landed (always, unless the host streams the batch in)
+            const bool mine = pending && problem_ready(prm, claim, seen);
+            const unsigned m = __ballot_sync(FULL, mine);
+            if (m) {
+                if (mine) {
+                    prob = claim;
+                    pending = false;
+                    active = true;
+                    k = 0;
+                    next_check = check_every;
+                    res_px = res_dx = res_pu = res_du = 0;
                 }
                 const bool have_xref = C::REFS && prm.Xref != nullptr, have_uref = C::REFS && prm.Uref != nullptr;
                 if (mine) {
@@ -265,7 +275,12 @@ tpp3_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ typ
                     }
                 }
             }
-            if (!__any_sync(FULL, active)) break;
+            if (!__any_sync(FULL, active)) {
+                publish_done(prm, unpub);
+                if (!__any_sync(FULL, pending)) break;
+                __nanosleep(256);   // the whole warp is waiting for the copy engine
+                continue;
+            }
         }
 
         const size_t pbx = (size_t)prob * SXL, pbu = (size_t)prob * SUL;
@@ -314,6 +329,7 @@ tpp3_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ typ
             }
             X.stores_done();
         }
+        publish_done(prm, unpub);   // the solution stores of the previous finish are half an iteration old by now
         k += 1;   // work->iter += 1 (admm.cpp:328)
 
         // ------------------------------------------------- reverse sweep: slack + dual + residuals fused with the Riccati step
@@ -454,7 +470,7 @@ tpp3_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ typ
             prm.status[prob] = st;
             if (prm.residuals) *reinterpret_cast<float4*>(prm.residuals + 4 * (size_t)prob) = make_float4(res_px, res_dx, res_pu, res_du);
             if (prm.rho_out) prm.rho_out[prob] = rho0;
-            mark_done(prm, prob);
+            if (prm.done_counters) unpub = prob;
             active = false;
         }
     }
