@@ -17,7 +17,7 @@ x0, Xr, Ur = pin(b.x0), pin(b.Xref), pin(b.Uref)
 out = dict(x=torch.empty((B, N, n)).pin_memory().numpy(), u=torch.empty((B, N - 1, m)).pin_memory().numpy(),
            iter=torch.empty(B, dtype=torch.int32).pin_memory().numpy(), status=torch.empty(B, dtype=torch.int32).pin_memory().numpy())
 s = tm.TinyMPC(); s.setup_from_spec(spec, devices=[0]); s.cuda.set_option("variant", variant)
-for streamed, chunks in [(0, 0), (0, 16), (1, 0), (1, 8), (1, 16), (1, 32), (1, 64), (1, 128)]:
+for streamed, chunks in [(0, 0), (1, 0), (1, 8), (1, 16), (1, 24), (1, 32)]:
     s.cuda.set_option("streamed", streamed); s.cuda.set_option("chunks", chunks)
     s.cuda.solve_batch(x0, Xr, Ur, out=out)
     ts = []

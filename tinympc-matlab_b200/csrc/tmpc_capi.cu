@@ -344,10 +344,35 @@ int run_shard_streamed(tinympc_cuda_solver* s, DeviceCtx& d, const KernelEntry* 
     const int n = hi - lo;
     const size_t sx = (size_t)f.nx * f.N, su = (size_t)f.nu * (f.N - 1);
     const bool ppb = in.x_min != nullptr;
-    // chunks of a multiple of 32 problems: every array's chunk boundary then falls on a 128-byte line for any shape, so no
-    // line holds data of two chunks (a lane may read its problem with non-coherent loads as soon as the watermark covers it)
-    int per = (((n + nch - 1) / nch) + 31) & ~31;
-    nch = (n + per - 1) / per;
+    // Granules of a multiple of 32 problems: every array's granule boundary then falls on a 128-byte line for any shape, so
+    // no line holds data of two chunks (a lane reads its problem with non-coherent loads once the watermark covers it).
+    // Chunks are runs of granules.  nch > 0: nch equal chunks.  nch == 0 (auto): 1, 1, 2, 4, 4, ..., 4, 2, 1, 1 sixty-fourths
+    // of the shard -- the kernel starts after 1/64 of the H2D time and the last D2H copy is 1/64 of the results.
+    std::vector<int> bounds;   // chunk c = problems [bounds[c], bounds[c + 1])
+    int gran;
+    {
+        const bool ramp = nch <= 0;
+        const int ng_target = ramp ? kMaxGranules : std::min(nch, kMaxGranules);
+        gran = (((n + ng_target - 1) / ng_target) + 31) & ~31;
+        const int ng = (n + gran - 1) / gran;
+        std::vector<int> runs;
+        if (ramp && ng >= 16) {
+            const int head[3] = {1, 1, 2};
+            int left = ng - 8;
+            for (int h : head) runs.push_back(h);
+            while (left > 0) { runs.push_back(std::min(4, left)); left -= 4; }
+            runs.push_back(2); runs.push_back(1); runs.push_back(1);
+        } else {
+            runs.assign(ng, 1);
+        }
+        int g = 0;
+        bounds.push_back(0);
+        for (size_t c = 0; c < runs.size(); ++c) {
+            g += runs[c];
+            bounds.push_back(std::min(n, g * gran));
+        }
+    }
+    nch = (int)bounds.size() - 1;
     cudaStream_t s_in = d.streams[0], s_k = d.streams[1], s_out = d.streams[2];
     int* ctl = d.stream_ctl;
     CU(s, cudaMemsetAsync(ctl, 0, sizeof(int) * (2 + nch), s_k));
@@ -367,7 +392,9 @@ int run_shard_streamed(tinympc_cuda_solver* s, DeviceCtx& d, const KernelEntry* 
     p.rho_out = out.rho ? (float*)d.rho.p : nullptr;
     p.avail_ptr = ctl + 1;
     p.done_counters = ctl + 2;
-    p.done_chunk = per;
+    p.done_chunk = gran;
+    for (int c = 0; c < nch; ++c)
+        for (int g = bounds[c] / gran; g * gran < bounds[c + 1]; ++g) p.done_map[g] = (unsigned char)c;
     CU(s, cudaEventRecord(d.k0[0], s_k));
     {
         // launch_tpp zeroes the work counter itself (ctl[0], on s_k, before the kernel)
@@ -393,7 +420,7 @@ int run_shard_streamed(tinympc_cuda_solver* s, DeviceCtx& d, const KernelEntry* 
     };
 #define RT(call) do { int rc__ = rt((call), #call); if (rc__) return rc__; } while (0)
     for (int c = 0; c < nch; ++c) {
-        const int c0 = c * per, c1 = std::min(n, c0 + per), cn = c1 - c0;
+        const int c0 = bounds[c], c1 = bounds[c + 1], cn = c1 - c0;
         const size_t g0 = (size_t)lo + c0;
         auto h2d = [&](DevBuf& dst, const float* src, size_t per_problem) -> cudaError_t {
             return cudaMemcpyAsync((float*)dst.p + per_problem * c0, src + per_problem * g0, sizeof(float) * per_problem * cn, cudaMemcpyHostToDevice, s_in);
@@ -406,7 +433,7 @@ int run_shard_streamed(tinympc_cuda_solver* s, DeviceCtx& d, const KernelEntry* 
         if (rc) return rc;
     }
     for (int c = 0; c < nch; ++c) {
-        const int c0 = c * per, c1 = std::min(n, c0 + per), cn = c1 - c0;
+        const int c0 = bounds[c], c1 = bounds[c + 1], cn = c1 - c0;
         const size_t g0 = (size_t)lo + c0;
         int rc = drv(ops.wait(reinterpret_cast<CUstream>(s_out), reinterpret_cast<CUdeviceptr>(ctl + 2 + c), (cuuint32_t)cn, CU_STREAM_WAIT_VALUE_GEQ),
                      "cuStreamWaitValue32");
@@ -452,9 +479,9 @@ int run_shard(tinympc_cuda_solver* s, DeviceCtx& d, const tinympc_cuda_batch_in&
     // single-launch streamed pipeline: plain (not mixed) solves on a thread-per-problem kernel that honours the watermark
     if (s->streamed && !(s->mixed_band > 0 && s->precision == 32) && !s->force_wpp && stream_memops().ok) {
         const KernelEntry* ke = find_kernel(f, s->precision, ppb, in.Xref || in.Uref, s->variant);
-        int nst = s->chunks > 0 ? s->chunks : std::min(64, n / 16384);
-        nst = std::min(nst, kMaxStreamChunks);
-        if (ke && ke->streaming && nst >= 2 && (ppb || f.shared_bounds_ok))
+        // auto (0): the ramped chunk layout for shards of >= 2^16 problems, else equal chunks of >= 2^14 problems
+        int nst = s->chunks > 0 ? std::min(s->chunks, kMaxGranules) : (n >= (1 << 16) ? 0 : n / 16384);
+        if (ke && ke->streaming && (nst == 0 || nst >= 2) && (ppb || f.shared_bounds_ok))
             return run_shard_streamed(s, d, ke, in, out, lo, hi, nst, kernel_ms, nchunks_out);
     }
     // chunking: enough chunks to overlap copies with compute, each still many waves of the GPU

@@ -12,6 +12,7 @@
 namespace tmpc {
 
 constexpr int kMaxCones = 4;     // per family (state cones) and (input cones)
+constexpr int kMaxGranules = 64; // streamed host pipeline: the batch is cut into at most this many equal granules
 
 // Offsets (in elements) of the tables inside the family's master pack (host, double).
 // All small matrices are stored ROW-major: M[r * cols + c].  The "hot" tables are converted into the
@@ -109,11 +110,12 @@ struct SolveParams {
     const int* batch_ptr;      // NULL, or device int holding the number of work items (<= batch)
     // streamed host pipeline (tmpc_capi.cu run_shard_streamed): ONE persistent launch consumes the batch while the copy engines
     // are still delivering it.  avail_ptr counts the problems whose inputs have landed (written in stream order behind each
-    // H2D chunk); a lane that claims problem p waits until *avail_ptr > p.  done_counters[p / done_chunk] counts finished
-    // problems per chunk (release, system scope): the D2H stream waits on it (cuStreamWaitValue32) before copying that chunk.
+    // H2D chunk); a lane that claims problem p starts it once *avail_ptr > p.  done_counters[chunk of p] counts finished
+    // problems per chunk (release): the D2H stream waits on it (cuStreamWaitValue32) before copying that chunk.
     const int* avail_ptr;      // NULL = the whole batch is resident
     int* done_counters;        // NULL = nobody is waiting
-    int done_chunk;            // problems per chunk
+    int done_chunk;            // problems per granule; chunk of problem p = done_map[p / done_chunk]
+    unsigned char done_map[kMaxGranules];   // chunks are runs of granules: short ones first (early start) and last (short tail)
 };
 
 constexpr int kAmbiguousBit = 0x100;

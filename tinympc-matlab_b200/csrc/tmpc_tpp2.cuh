@@ -103,7 +103,7 @@ __device__ __forceinline__ bool problem_ready(const SolveParams& prm, int prob, 
 __device__ __forceinline__ void publish_done(const SolveParams& prm, int& unpub) {
     if (unpub >= 0) {
         asm volatile("fence.release.gpu;" ::: "memory");
-        atomicAdd(prm.done_counters + unpub / prm.done_chunk, 1);
+        atomicAdd(prm.done_counters + prm.done_map[unpub / prm.done_chunk], 1);
         unpub = -1;
     }
 }
