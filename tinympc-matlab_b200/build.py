@@ -45,15 +45,17 @@ def inst(bits, nx, nu, N, feat, refs=REFS_SMEM, ppb=False, variant=0, block=None
     return dict(aff=aff, tm=tm, ntm=ntm, opq=opq, tib=tib, bits=bits, nx=nx, nu=nu, N=N, feat=feat, refs=refs, ppb=ppb, variant=variant, block=block or b, minb=minb or m, fb=fb, gen=gen)
 
 
-def inst3(nx, nu, N, refs=True, ppb=False, fb=False, variant=0, max_warps=24, opq=False, tib=None, aff=None):
-    """incremental-form kernel (tmpc_tpp3.cuh): x and t in tensor memory (2 nx N columns per thread), u, u + y, -dd in shared memory"""
+def inst3(nx, nu, N, refs=True, ppb=False, fb=False, variant=0, max_warps=24, opq=False, tib=None, aff=None, feat=BOX, cones=(0, 0, 0, 0)):
+    """incremental-form kernel (tmpc_tpp3.cuh): x and t in tensor memory (2 nx N columns per thread), u, u + y, -dd in shared memory;
+    with cones / linear rows (feat=CON) two more arrays of each kind (the pre-projection slacks of the two families)"""
     sx, su = nx * N, nu * (N - 1)
-    warps = min(max_warps, 4 * (512 // (2 * sx)), ((226 * 1024 - 1024 - pack_elems(nx, nu, N) * 4) // (3 * su * 4 * 32) // 4) * 4)
+    ntm, nsm = (4, 5) if feat == CON else (2, 3)
+    warps = min(max_warps, 4 * (512 // (ntm * sx)), ((226 * 1024 - 1024 - pack_elems(nx, nu, N) * 4) // (nsm * su * 4 * 32) // 4) * 4)
     assert warps >= 4, "shape does not fit the incremental-form kernel"
     aff = ((nx, nu) == (6, 3)) if aff is None else aff
     tib = (not (nx == 12)) if tib is None else tib
-    return dict(gen=3, bits=32, nx=nx, nu=nu, N=N, feat=BOX, refs=3 if refs else 0, ppb=ppb, fb=fb, variant=variant, block=warps * 32, aff=aff,
-                opq=opq, tib=tib, tm=True, minb=1, ntm=2)
+    return dict(gen=3, bits=32, nx=nx, nu=nu, N=N, feat=feat, refs=3 if refs else 0, ppb=ppb, fb=fb, variant=variant, block=warps * 32, aff=aff,
+                opq=opq, tib=tib, tm=True, minb=1, ntm=ntm, cones=cones)
 
 
 def cols_per_thread(nx, nu, N, feat, refs, ntm=0):
@@ -109,6 +111,10 @@ def default_instances():
             out.append(inst3(nx, nu, N, refs=True, fb=fb))
             out.append(inst3(nx, nu, N, refs=False, fb=fb))
         out.append(inst3(nx, nu, N, refs=True, ppb=True))
+    # box + second-order cones + linear inequalities (rocket landing, rocket_landing_constraints.m:40-55: one cone on the
+    # first three states, one on the three inputs): the same form with two more slack families, cone blocks compiled in
+    for fb in (True, False):
+        out.append(inst3(6, 3, 10, refs=True, fb=fb, feat=CON, cones=(0, 3, 0, 3)))
     for bits in (32, 64):
         for (nx, nu, N) in shapes:
             if bits == 64:            # fp64 parity mode: direct form (admm.cpp order), tmpc_tpp2.cuh
@@ -116,8 +122,9 @@ def default_instances():
                     out.append(inst(bits, nx, nu, N, BOX, refs=REFS_L2, fb=fb, tm=True))
                     out.append(inst(bits, nx, nu, N, BOX, refs=REFS_NONE, fb=fb, tm=True))
                 out.append(inst(bits, nx, nu, N, BOX, refs=REFS_L2, ppb=True, tm=True))
-            out.append(inst(bits, nx, nu, N, CON, refs=REFS_L2, fb=True, tm=True))
-            out.append(inst(bits, nx, nu, N, CON, refs=REFS_L2, tm=True))
+            # fp32: the direct-form cone kernels stay as the A/B baseline (variant 5)
+            out.append(inst(bits, nx, nu, N, CON, refs=REFS_L2, fb=True, tm=True, variant=0 if bits == 64 else 5))
+            out.append(inst(bits, nx, nu, N, CON, refs=REFS_L2, tm=True, variant=0 if bits == 64 else 5))
             if (nx, nu) == (12, 4):
                 out.append(inst(bits, nx, nu, N, ADP, refs=REFS_L2, fb=True, tm=True))
                 out.append(inst(bits, nx, nu, N, ADP, refs=REFS_L2, tm=True))
@@ -142,7 +149,8 @@ def default_instances():
 def name_of(i):
     t = "f32" if i["bits"] == 32 else "f64"
     if i["gen"] == 3:
-        return (f"tpp3_f32_{i['nx']}x{i['nu']}x{i['N']}_box{'' if i['refs'] else '_noref'}{'_ppb' if i['ppb'] else ''}{'_fb' if i['fb'] else ''}"
+        cn = ("_c" + "".join(str(c) for c in i["cones"])) if i["feat"] == CON else ""
+        return (f"tpp3_f32_{i['nx']}x{i['nu']}x{i['N']}_{FEAT_NAME[i['feat']]}{cn}{'' if i['refs'] else '_noref'}{'_ppb' if i['ppb'] else ''}{'_fb' if i['fb'] else ''}"
                 f"{'_aff' if i['aff'] else ''}_v{i['variant']}")
     return (f"tpp{'' if i['gen'] == 1 else '2'}_{t}_{i['nx']}x{i['nu']}x{i['N']}_{FEAT_NAME[i['feat']]}{['_noref', '_refsm', ''][i['refs']]}"
             f"{'_ppb' if i['ppb'] else ''}{'_fb' if i['fb'] else ''}{'_aff' if (i['aff'] and i['gen'] == 2) else ''}{'_tm' if i['tm'] else ''}_v{i['variant']}")
@@ -163,7 +171,7 @@ def gen_sources(instances):
                 "// generated by tinympc-matlab_b200/build.py -- do not edit\n"
                 '#include "../tmpc_tpp3.cuh"\n#include "../tmpc_registry.h"\nusing namespace tmpc;\n'
                 f"using Cfg_{n} = Tpp3Cfg<{i['nx']}, {i['nu']}, {i['N']}, {i['block']}, {b(i['refs'])}, {b(i['ppb'])}, {b(i['fb'])}, {b(i['aff'])}, "
-                f"{b(i['opq'])}, {b(i['tib'])}>;\n"
+                f"{b(i['opq'])}, {b(i['tib'])}, {FEAT_ENUM[i['feat']]}, {', '.join(str(c) for c in i['cones'])}>;\n"
                 f"TMPC_DEFINE_TPP3_ENTRY({n}, Cfg_{n}, {i['feat']}, 32, {i['variant']})\n"
             )
         else:

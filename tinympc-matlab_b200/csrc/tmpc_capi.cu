@@ -140,6 +140,13 @@ const KernelEntry* find_kernel(const Family& f, int bits, bool ppb, bool refs, i
             const KernelEntry* e = tab[i];
             if (e->fastbox && (!f.fastbox || ppb)) continue;      // table order puts the fast-box instances first
             if (f.affine && !e->affine) continue;
+            if (e->cone_fixed) {   // cones compiled into the instance: the family's cone list must be exactly that
+                const SolveParams& b = f.base;
+                const bool fsx = b.en_state_soc && b.n_state_cones > 0, fsu = b.en_input_soc && b.n_input_cones > 0;
+                const bool okx = e->scd > 0 ? (fsx && b.n_state_cones == 1 && b.Acx[0] == e->scs && b.qcx[0] == e->scd) : !fsx;
+                const bool oku = e->ucd > 0 ? (fsu && b.n_input_cones == 1 && b.Acu[0] == e->ucs && b.qcu[0] == e->ucd) : !fsu;
+                if (!okx || !oku) continue;
+            }
             if (e->family == KF_TPP && e->nx == f.nx && e->nu == f.nu && e->N == f.N && e->feat == f.feat && e->dtype_bits == bits &&
                 e->ppb == (ppb ? 1 : 0) && e->variant == variant && ((e->refs != 0) == refs || (pass == 1 && e->refs != 0)))
                 return e;

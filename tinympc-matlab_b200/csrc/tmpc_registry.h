@@ -29,6 +29,10 @@ struct KernelEntry {
     // master_pack: the family's double-precision pack (PackLayout L) on the host; the launcher
     // converts the hot tables into the kernel-parameter constant pack
     cudaError_t (*launch)(const SolveParams& p, int grid, size_t smem, cudaStream_t st, const double* master_pack, const PackLayout& L);
+    // 1: the second-order cones are compiled into the instance -- it serves only families whose cone list is exactly one
+    // state cone on [scs, scs + scd) and one input cone on [ucs, ucs + ucd) (dim 0 = that side has no cone)
+    int cone_fixed;
+    int scs, scd, ucs, ucd;
 };
 
 const KernelEntry* const* kernel_table(int* count);   // defined in gen/tmpc_table.cu
@@ -76,7 +80,7 @@ const KernelEntry* const* kernel_table(int* count);   // defined in gen/tmpc_tab
     }                                                                                                               \
     extern const KernelEntry SYM = {#SYM, KF_TPP, CFG::NX, CFG::NU, CFG::NH, FEATV, BITS, CFG::REFMODE,             \
                                     CFG::PPB ? 1 : 0, CFG::FB ? 1 : 0, CFG::AFF ? 1 : 0, CFG::BLOCK, VAR, 1, SYM##_smem, SYM##_prepare, \
-                                    SYM##_occ, SYM##_launch};                                                       \
+                                    SYM##_occ, SYM##_launch};                                 \
     }
 
 // incremental-form kernel (tmpc_tpp3.cuh)
@@ -98,5 +102,5 @@ const KernelEntry* const* kernel_table(int* count);   // defined in gen/tmpc_tab
     }                                                                                                               \
     extern const KernelEntry SYM = {#SYM, KF_TPP, CFG::NX, CFG::NU, CFG::NH, FEATV, BITS, CFG::REFMODE,             \
                                     CFG::PPB ? 1 : 0, CFG::FB ? 1 : 0, CFG::AFF ? 1 : 0, CFG::BLOCK, VAR, 1, SYM##_smem, SYM##_prepare, \
-                                    SYM##_occ, SYM##_launch};                                                       \
+                                    SYM##_occ, SYM##_launch, CFG::CONSTR ? 1 : 0, CFG::SCS, CFG::SCD, CFG::UCS, CFG::UCD};                                 \
     }

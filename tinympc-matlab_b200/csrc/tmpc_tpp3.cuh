@@ -33,10 +33,18 @@ namespace tmpc {
 
 enum : int { REFS_STATE = 3 };   // registry "refs" code: reference terms parked in the state columns
 
-template <int NX_, int NU_, int NH_, int BLOCK_, bool REFS_, bool PPB_, bool FB_, bool AFF_, bool OPQ_, bool TIB_>
+template <int NX_, int NU_, int NH_, int BLOCK_, bool REFS_, bool PPB_, bool FB_, bool AFF_, bool OPQ_, bool TIB_, int FEAT_ = FEAT_BOX,
+          int SCS_ = 0, int SCD_ = 0, int UCS_ = 0, int UCD_ = 0>
 struct Tpp3Cfg {
     using T = float;
-    static constexpr int NX = NX_, NU = NU_, NH = NH_, FEAT = FEAT_BOX, BLOCK = BLOCK_, MINB = 1;
+    static_assert(FEAT_ == FEAT_BOX || FEAT_ == FEAT_CONSTR, "the incremental form covers box and box + cone + half-space families");
+    static constexpr int NX = NX_, NU = NU_, NH = NH_, FEAT = FEAT_, BLOCK = BLOCK_, MINB = 1;
+    static constexpr bool CONSTR = FEAT_ == FEAT_CONSTR;   // + second-order cones and linear inequalities (admm.cpp:102-173)
+    // The cone blocks are part of the instance: at most one state cone on elements [SCS, SCS + SCD) and one input cone on
+    // [UCS, UCS + UCD) (dim 0 = none), so that the projection is straight-line register code.  Families with any other cone
+    // list run the direct-form kernel (tmpc_tpp2.cuh), whose cones are run-time tables.  The linear rows are run-time.
+    static constexpr int SCS = SCS_, SCD = SCD_, UCS = UCS_, UCD = UCD_;
+    static_assert(SCS_ >= 0 && SCS_ + SCD_ <= NX_ && UCS_ >= 0 && UCS_ + UCD_ <= NU_, "cone block outside the vector");
     static constexpr int REFMODE = REFS_ ? REFS_STATE : REFS_NONE;
     static constexpr bool REFS = REFS_;
     static constexpr bool PPB = PPB_;
@@ -46,13 +54,55 @@ struct Tpp3Cfg {
     static constexpr bool TIB = TIB_ && FB_ && !PPB_ && !OPQ_;
     static constexpr int SX = NX * NH, SU = NU * (NH - 1);
     using CPack = ConstPack2<float, NX_, NU_, NH_, false>;
-    static constexpr int oU = 0, oTZ = SU, oD = 2 * SU, COLS = 3 * SU;
-    static constexpr int TM_COLS_PER_THREAD = 2 * SX;
+    // shared memory: u, u + y_prev, -dd (+ the pre-projection input slacks of the cone and half-space families)
+    static constexpr int oU = 0, oTZ = SU, oD = 2 * SU, oTZC = 3 * SU, oTZL = 4 * SU, COLS = (CONSTR ? 5 : 3) * SU;
+    // tensor memory: x, t (+ the pre-projection state slacks tc = x + gc_prev, tl = x + gl_prev)
+    static constexpr int TM_COLS_PER_THREAD = (CONSTR ? 4 : 2) * SX;
     static_assert(((BLOCK_ / 32 + 3) / 4) * TM_COLS_PER_THREAD <= 512, "the state does not fit the 512 tensor-memory columns");
 };
 
 __device__ __forceinline__ float2 sel0(bool c, float2 a) { return make_float2(c ? 0.f : a.x, c ? 0.f : a.y); }   // c ? 0 : a
 __device__ __forceinline__ float sel0(bool c, float a) { return c ? 0.f : a; }
+
+// Second-order-cone projection (admm.cpp:39-60) of the block [S, S + D) of a register vector, in place; S and D are
+// compile-time, so this is straight-line code on registers.  mu is the reference's float mu; the norm and the two
+// quotients use the approximate SFU forms (sqrt.approx, x * rcp(y): <= 2 ulp) -- the fp32 path is compared to the
+// reference within a tolerance, the fp64 parity kernels keep the IEEE forms.
+template <int S, int D, int N>
+__device__ __forceinline__ void project_soc_fixed(Vec<float, N>& v, float mu, float inv_mu) {
+    if constexpr (D > 0) {
+        float ss = 0.f;
+#pragma unroll
+        for (int e = S; e < S + D - 1; ++e) ss = fmaf(v.get(e), v.get(e), ss);
+        const float lv = v.get(S + D - 1);
+        float a;
+        asm("sqrt.approx.f32 %0, %1;" : "=f"(a) : "f"(ss));
+        const float u0 = lv * mu;
+        const bool zero = a <= -u0, inside = a <= u0;
+        const float fct = fmaf(0.5f, __fdividef(u0, a), 0.5f);
+        const float sc = zero ? 0.f : (inside ? 1.f : fct);
+        const float ln = zero ? 0.f : (inside ? lv : fct * (a * inv_mu));
+#pragma unroll
+        for (int e = S; e < S + D - 1; ++e) v.set(e, sc * v.get(e));
+        v.set(S + D - 1, ln);
+    }
+}
+
+// Half-space projections (admm.cpp:70-73), row after row in place (:148-159 / :162-173).  rows: nrow x N row-major
+// coefficients, then the nrow offsets b, then the nrow squared norms ||a||^2 (the staged cold tables, shared memory).
+template <int N>
+__device__ __forceinline__ void project_rows_reg(Vec<float, N>& v, const float* __restrict__ rows, int nrow) {
+    const float* b = rows + nrow * N;
+    const float* nrm = b + nrow;
+    for (int c = 0; c < nrow; ++c) {
+        float val = 0.f;
+#pragma unroll
+        for (int e = 0; e < N; ++e) val = fmaf(rows[c * N + e], v.get(e), val);
+        const float dist = (val > b[c]) ? __fdividef(val - b[c], nrm[c]) : 0.f;
+#pragma unroll
+        for (int e = 0; e < N; ++e) v.set(e, fmaf(-dist, rows[c * N + e], v.get(e)));
+    }
+}
 
 template <class C>
 __global__ void __launch_bounds__(C::BLOCK, 1)
@@ -95,6 +145,16 @@ tpp3_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ typ
     Traj<T, NU, NH - 1, C::oU, BLOCK> U(cta_cols, tid);      // u(k)
     Traj<T, NU, NH - 1, C::oTZ, BLOCK> TZ(cta_cols, tid);    // u(k) + y(k-1)
     Traj<T, NU, NH - 1, C::oD, BLOCK> ND(cta_cols, tid);     // -dd of the last sweep
+    // cone / half-space families (CONSTR): pre-projection slacks, vc = proj(tc), gc = tc - vc (admm.cpp:103-122,191)
+    const TmemTraj<NX, NH> TC{tm_base + 2 * SXL};            // x(k) + gc(k-1)
+    const TmemTraj<NX, NH> TL{tm_base + 3 * SXL};            // x(k) + gl(k-1)
+    Traj<T, NU, NH - 1, C::oTZC, BLOCK> TZC(cta_cols, tid);  // u(k) + yc(k-1)
+    Traj<T, NU, NH - 1, C::oTZL, BLOCK> TZL(cta_cols, tid);  // u(k) + yl(k-1)
+    const float mu_x = prm.cx[0], mu_u = prm.cu[0], imu_x = 1.f / mu_x, imu_u = 1.f / mu_u;   // the instance's cones (C::SCD, C::UCD)
+    const bool lin_x = C::CONSTR && prm.en_state_linear;     // with zero rows the family still contributes vl - gl = x
+    const bool lin_u = C::CONSTR && prm.en_input_linear;     // to the linear cost (admm.cpp:138-140, 223-225)
+    const T* cAlx = pack + SP::lin;                          // state rows: A (nsl x nx), b, ||a||^2
+    const T* cAlu = cAlx + prm.nsl * (NX + 2);               // input rows
 
     const T* cP = pack + SP::Pinf;
     const T rho0 = static_cast<T>(prm.rho);
@@ -353,6 +413,44 @@ tpp3_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ typ
             const auto dw = twice_minus(e, subv(tnew, told));
             dq = fmas(dw, nrho, ref);
         };
+        // one more constraint family of a column (cone or half-space): traw = stored pre-projection value x(k-1) + dual(k-2)
+        // (garbage of the previous problem on the first sweep, where the cold value is 0 and so is its projection,
+        // tiny_api.cpp:88-100).  Same algebra as the box: vo = proj(t_old), dual = t_old - vo, t_new = x + dual,
+        // vn = proj(t_new), dq -= rho (2 (vn - vo) - (t_new - t_old)).  The projection is recomputed instead of stored:
+        // it is a handful of instructions per column.
+        auto family = [&](auto& tv, const auto& xv, auto& dq, auto&& proj) {
+            using V = std::decay_t<decltype(tv)>;
+            V to, vo, vn;
+#pragma unroll
+            for (int j = 0; j < V::NP; ++j) to.p[j] = sel0(first, tv.p[j]);
+            to.t = V::TAIL ? sel0(first, tv.t) : T(0);
+            vo = to;
+            proj(vo);
+#pragma unroll
+            for (int j = 0; j < V::NP; ++j) { vo.p[j] = sel0(first, vo.p[j]); tv.p[j] = addv(xv.p[j], subv(to.p[j], vo.p[j])); }
+            if constexpr (V::TAIL) { vo.t = sel0(first, vo.t); tv.t = xv.t + (to.t - vo.t); }
+            vn = tv;
+            proj(vn);
+#pragma unroll
+            for (int j = 0; j < V::NP; ++j) dq.p[j] = fmas(twice_minus(subv(vn.p[j], vo.p[j]), subv(tv.p[j], to.p[j])), nrho, dq.p[j]);
+            if constexpr (V::TAIL) dq.t = fmas(twice_minus(vn.t - vo.t, tv.t - to.t), nrho, dq.t);
+        };
+        auto cones_x = [&](VX& v) { project_soc_fixed<C::SCS, C::SCD>(v, mu_x, imu_x); };
+        auto cones_u = [&](VU& v) { project_soc_fixed<C::UCS, C::UCD>(v, mu_u, imu_u); };
+        auto rows_x = [&](VX& v) { project_rows_reg<NX>(v, cAlx, prm.nsl); };
+        auto rows_u = [&](VU& v) { project_rows_reg<NU>(v, cAlu, prm.nil); };
+        auto extra_x = [&](int i, const VX& xv, VX& dq) {
+            if constexpr (C::CONSTR) {
+                if constexpr (C::SCD > 0) { VX tc; TC.load(i, tc); family(tc, xv, dq, cones_x); TC.store(i, tc); }
+                if (lin_x) { VX tl; TL.load(i, tl); family(tl, xv, dq, rows_x); TL.store(i, tl); }
+            }
+        };
+        auto extra_u = [&](int i, const VU& uv, VU& dr) {
+            if constexpr (C::CONSTR) {
+                if constexpr (C::UCD > 0) { VU tc; TZC.load(i, tc); family(tc, uv, dr, cones_u); TZC.store(i, tc); }
+                if (lin_u) { VU tl; TZL.load(i, tl); family(tl, uv, dr, rows_u); TZL.store(i, tl); }
+            }
+        };
         VX dp;
         {   // column N-1: dp_N = -(xref_N' Pinf)' [first sweep] - rho dw_N   (admm.cpp:238-246)
             VX xv, traw, tnew;
@@ -370,6 +468,7 @@ tpp3_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ typ
                 slack(traw.t, xv.t, lo, hi, rpx, rdx, tnew.t, dp.t);
             }
             TT.store(NH - 1, tnew);
+            extra_x(NH - 1, xv, dp);
         }
 #pragma unroll 1
         for (int i = NH - 2; i >= 0; --i) {
@@ -390,6 +489,7 @@ tpp3_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ typ
                 slack(TZ.gett(i), uv.t, lo, hi, rpu, rdu, tn, dr.t);
                 TZ.sett(i, tn);
             }
+            extra_u(i, uv, dr);
             // dd_i = Quu_inv (B' dp + dr)   (admm.cpp:17; BPf cancels in the increment)
             VU t = dr;
             mv_acc<NU, NX>(cp.BT, zb, dp, t);
@@ -419,7 +519,8 @@ tpp3_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ typ
                 slack(traw.t, xv.t, lo, hi, rpx, rdx, tnew.t, dq.t);
             }
             TT.store(i, tnew);
-            if (i > 0) {   // p_0 is never used (admm.cpp:17 reads p_{i+1})
+            if (i > 0) {   // p_0 is never used (admm.cpp:17 reads p_{i+1}), hence neither are q_0 and the cone / half-space slacks of x_0
+                extra_x(i, xv, dq);
                 mv_acc<NX, NX>(cp.AK, zb, dp, dq);
                 mv_acc<NX, NU>(cp.NKT, zb, dr, dq);
                 dp = dq;
