@@ -45,7 +45,7 @@ def inst(bits, nx, nu, N, feat, refs=REFS_SMEM, ppb=False, variant=0, block=None
     return dict(aff=aff, tm=tm, ntm=ntm, opq=opq, tib=tib, bits=bits, nx=nx, nu=nu, N=N, feat=feat, refs=refs, ppb=ppb, variant=variant, block=block or b, minb=minb or m, fb=fb, gen=gen)
 
 
-def inst3(nx, nu, N, refs=True, ppb=False, fb=False, variant=0, max_warps=24, opq=False, tib=None, aff=None, feat=BOX, cones=(0, 0, 0, 0)):
+def inst3(nx, nu, N, refs=True, ppb=False, fb=False, variant=0, max_warps=24, opq=False, tib=None, aff=None, feat=BOX, cones=(0, 0, 0, 0, 0, 0)):
     """incremental-form kernel (tmpc_tpp3.cuh): x and t in tensor memory (2 nx N columns per thread), u, u + y, -dd in shared memory;
     with cones / linear rows (feat=CON) two more arrays of each kind (the pre-projection slacks of the two families)"""
     sx, su = nx * N, nu * (N - 1)
@@ -113,8 +113,10 @@ def default_instances():
         out.append(inst3(nx, nu, N, refs=True, ppb=True))
     # box + second-order cones + linear inequalities (rocket landing, rocket_landing_constraints.m:40-55: one cone on the
     # first three states, one on the three inputs): the same form with two more slack families, cone blocks compiled in
+    # (+ one linear row on each side; the last two numbers are the row counts)
     for fb in (True, False):
-        out.append(inst3(6, 3, 10, refs=True, fb=fb, feat=CON, cones=(0, 3, 0, 3)))
+        out.append(inst3(6, 3, 10, refs=True, fb=fb, feat=CON, cones=(0, 3, 0, 3, 1, 1)))
+        out.append(inst3(6, 3, 10, refs=True, fb=fb, feat=CON, cones=(0, 3, 0, 3, 0, 0)))
     for bits in (32, 64):
         for (nx, nu, N) in shapes:
             if bits == 64:            # fp64 parity mode: direct form (admm.cpp order), tmpc_tpp2.cuh

@@ -145,7 +145,7 @@ const KernelEntry* find_kernel(const Family& f, int bits, bool ppb, bool refs, i
                 const bool fsx = b.en_state_soc && b.n_state_cones > 0, fsu = b.en_input_soc && b.n_input_cones > 0;
                 const bool okx = e->scd > 0 ? (fsx && b.n_state_cones == 1 && b.Acx[0] == e->scs && b.qcx[0] == e->scd) : !fsx;
                 const bool oku = e->ucd > 0 ? (fsu && b.n_input_cones == 1 && b.Acu[0] == e->ucs && b.qcu[0] == e->ucd) : !fsu;
-                if (!okx || !oku) continue;
+                if (!okx || !oku || f.L.nsl != e->nsl || f.L.nil != e->nil) continue;
             }
             if (e->family == KF_TPP && e->nx == f.nx && e->nu == f.nu && e->N == f.N && e->feat == f.feat && e->dtype_bits == bits &&
                 e->ppb == (ppb ? 1 : 0) && e->variant == variant && ((e->refs != 0) == refs || (pass == 1 && e->refs != 0)))

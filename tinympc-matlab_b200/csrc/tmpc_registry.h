@@ -31,8 +31,9 @@ struct KernelEntry {
     cudaError_t (*launch)(const SolveParams& p, int grid, size_t smem, cudaStream_t st, const double* master_pack, const PackLayout& L);
     // 1: the second-order cones are compiled into the instance -- it serves only families whose cone list is exactly one
     // state cone on [scs, scs + scd) and one input cone on [ucs, ucs + ucd) (dim 0 = that side has no cone)
+    // ... and so are the numbers of linear-inequality rows (state, input)
     int cone_fixed;
-    int scs, scd, ucs, ucd;
+    int scs, scd, ucs, ucd, nsl, nil;
 };
 
 const KernelEntry* const* kernel_table(int* count);   // defined in gen/tmpc_table.cu
@@ -96,11 +97,11 @@ const KernelEntry* const* kernel_table(int* count);   // defined in gen/tmpc_tab
     static cudaError_t SYM##_launch(const SolveParams& p, int grid, size_t smem, cudaStream_t st, const double* mp, \
                                     const PackLayout& L) {                                                          \
         typename CFG::CPack cpk;                                                                                    \
-        fill_const_pack2(cpk, mp, L);                                                                               \
+        fill_const_pack3(cpk, mp, L);                                                                               \
         tpp3_kernel<CFG><<<grid, CFG::BLOCK, smem, st>>>(p, cpk);                                                   \
         return cudaGetLastError();                                                                                  \
     }                                                                                                               \
     extern const KernelEntry SYM = {#SYM, KF_TPP, CFG::NX, CFG::NU, CFG::NH, FEATV, BITS, CFG::REFMODE,             \
                                     CFG::PPB ? 1 : 0, CFG::FB ? 1 : 0, CFG::AFF ? 1 : 0, CFG::BLOCK, VAR, 1, SYM##_smem, SYM##_prepare, \
-                                    SYM##_occ, SYM##_launch, CFG::CONSTR ? 1 : 0, CFG::SCS, CFG::SCD, CFG::UCS, CFG::UCD};                                 \
+                                    SYM##_occ, SYM##_launch, CFG::CONSTR ? 1 : 0, CFG::SCS, CFG::SCD, CFG::UCS, CFG::UCD, CFG::NSL, CFG::NIL};                                 \
     }

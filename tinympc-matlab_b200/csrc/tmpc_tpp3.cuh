@@ -33,8 +33,31 @@ namespace tmpc {
 
 enum : int { REFS_STATE = 3 };   // registry "refs" code: reference terms parked in the state columns
 
+// constant-bank pack of the incremental-form instances: the matrices of ConstPack2 + the linear-inequality rows
+// (coefficients row-major, offsets b, 1 / ||a||^2 for project_hyperplane, admm.cpp:70-73)
+template <int NX, int NU, int NH, int NSL, int NIL>
+struct alignas(16) ConstPack3 : ConstPack2<float, NX, NU, NH, false> {
+    float Alx[NSL > 0 ? NSL * NX : 1], blx[NSL > 0 ? NSL : 1], inx[NSL > 0 ? NSL : 1];
+    float Alu[NIL > 0 ? NIL * NU : 1], blu[NIL > 0 ? NIL : 1], inu[NIL > 0 ? NIL : 1];
+};
+template <int NX, int NU, int NH, int NSL, int NIL>
+inline void fill_const_pack3(ConstPack3<NX, NU, NH, NSL, NIL>& c, const double* pk, const PackLayout& L) {
+    fill_const_pack2(static_cast<ConstPack2<float, NX, NU, NH, false>&>(c), pk, L);
+    c.Alx[0] = c.blx[0] = c.inx[0] = c.Alu[0] = c.blu[0] = c.inu[0] = 0.f;
+    for (int k = 0; k < NSL; ++k) {
+        for (int j = 0; j < NX; ++j) c.Alx[k * NX + j] = static_cast<float>(pk[L.Alin_x + k * NX + j]);
+        c.blx[k] = static_cast<float>(pk[L.blin_x + k]);
+        c.inx[k] = static_cast<float>(1.0 / pk[L.nrm_x + k]);
+    }
+    for (int k = 0; k < NIL; ++k) {
+        for (int j = 0; j < NU; ++j) c.Alu[k * NU + j] = static_cast<float>(pk[L.Alin_u + k * NU + j]);
+        c.blu[k] = static_cast<float>(pk[L.blin_u + k]);
+        c.inu[k] = static_cast<float>(1.0 / pk[L.nrm_u + k]);
+    }
+}
+
 template <int NX_, int NU_, int NH_, int BLOCK_, bool REFS_, bool PPB_, bool FB_, bool AFF_, bool OPQ_, bool TIB_, int FEAT_ = FEAT_BOX,
-          int SCS_ = 0, int SCD_ = 0, int UCS_ = 0, int UCD_ = 0>
+          int SCS_ = 0, int SCD_ = 0, int UCS_ = 0, int UCD_ = 0, int NSL_ = 0, int NIL_ = 0>
 struct Tpp3Cfg {
     using T = float;
     static_assert(FEAT_ == FEAT_BOX || FEAT_ == FEAT_CONSTR, "the incremental form covers box and box + cone + half-space families");
@@ -42,8 +65,9 @@ struct Tpp3Cfg {
     static constexpr bool CONSTR = FEAT_ == FEAT_CONSTR;   // + second-order cones and linear inequalities (admm.cpp:102-173)
     // The cone blocks are part of the instance: at most one state cone on elements [SCS, SCS + SCD) and one input cone on
     // [UCS, UCS + UCD) (dim 0 = none), so that the projection is straight-line register code.  Families with any other cone
-    // list run the direct-form kernel (tmpc_tpp2.cuh), whose cones are run-time tables.  The linear rows are run-time.
-    static constexpr int SCS = SCS_, SCD = SCD_, UCS = UCS_, UCD = UCD_;
+    // list run the direct-form kernel (tmpc_tpp2.cuh), whose cones are run-time tables.  So are the numbers of linear rows
+    // (NSL state rows, NIL input rows); their coefficients ride in the constant bank next to the matrices.
+    static constexpr int SCS = SCS_, SCD = SCD_, UCS = UCS_, UCD = UCD_, NSL = NSL_, NIL = NIL_;
     static_assert(SCS_ >= 0 && SCS_ + SCD_ <= NX_ && UCS_ >= 0 && UCS_ + UCD_ <= NU_, "cone block outside the vector");
     static constexpr int REFMODE = REFS_ ? REFS_STATE : REFS_NONE;
     static constexpr bool REFS = REFS_;
@@ -53,7 +77,7 @@ struct Tpp3Cfg {
     static constexpr bool OPQ = OPQ_;
     static constexpr bool TIB = TIB_ && FB_ && !PPB_ && !OPQ_;
     static constexpr int SX = NX * NH, SU = NU * (NH - 1);
-    using CPack = ConstPack2<float, NX_, NU_, NH_, false>;
+    using CPack = ConstPack3<NX_, NU_, NH_, NSL_, NIL_>;
     // shared memory: u, u + y_prev, -dd (+ the pre-projection input slacks of the cone and half-space families)
     static constexpr int oU = 0, oTZ = SU, oD = 2 * SU, oTZC = 3 * SU, oTZL = 4 * SU, COLS = (CONSTR ? 5 : 3) * SU;
     // tensor memory: x, t (+ the pre-projection state slacks tc = x + gc_prev, tl = x + gl_prev)
@@ -88,19 +112,18 @@ __device__ __forceinline__ void project_soc_fixed(Vec<float, N>& v, float mu, fl
     }
 }
 
-// Half-space projections (admm.cpp:70-73), row after row in place (:148-159 / :162-173).  rows: nrow x N row-major
-// coefficients, then the nrow offsets b, then the nrow squared norms ||a||^2 (the staged cold tables, shared memory).
-template <int N>
-__device__ __forceinline__ void project_rows_reg(Vec<float, N>& v, const float* __restrict__ rows, int nrow) {
-    const float* b = rows + nrow * N;
-    const float* nrm = b + nrow;
-    for (int c = 0; c < nrow; ++c) {
+// Half-space projections (admm.cpp:70-73), row after row in place (:148-159 / :162-173); NR rows of N coefficients, their
+// offsets b and 1 / ||a||^2, all in the constant bank: straight-line FFMAs with constant operands.
+template <int NR, int N>
+__device__ __forceinline__ void project_rows_fixed(Vec<float, N>& v, const float* __restrict__ A, const float* __restrict__ b, const float* __restrict__ inv) {
+#pragma unroll
+    for (int c = 0; c < NR; ++c) {
         float val = 0.f;
 #pragma unroll
-        for (int e = 0; e < N; ++e) val = fmaf(rows[c * N + e], v.get(e), val);
-        const float dist = (val > b[c]) ? __fdividef(val - b[c], nrm[c]) : 0.f;
+        for (int e = 0; e < N; ++e) val = fmaf(A[c * N + e], v.get(e), val);
+        const float dist = (val > b[c]) ? (val - b[c]) * inv[c] : 0.f;
 #pragma unroll
-        for (int e = 0; e < N; ++e) v.set(e, fmaf(-dist, rows[c * N + e], v.get(e)));
+        for (int e = 0; e < N; ++e) v.set(e, fmaf(-dist, A[c * N + e], v.get(e)));
     }
 }
 
@@ -153,8 +176,6 @@ tpp3_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ typ
     const float mu_x = prm.cx[0], mu_u = prm.cu[0], imu_x = 1.f / mu_x, imu_u = 1.f / mu_u;   // the instance's cones (C::SCD, C::UCD)
     const bool lin_x = C::CONSTR && prm.en_state_linear;     // with zero rows the family still contributes vl - gl = x
     const bool lin_u = C::CONSTR && prm.en_input_linear;     // to the linear cost (admm.cpp:138-140, 223-225)
-    const T* cAlx = pack + SP::lin;                          // state rows: A (nsl x nx), b, ||a||^2
-    const T* cAlu = cAlx + prm.nsl * (NX + 2);               // input rows
 
     const T* cP = pack + SP::Pinf;
     const T rho0 = static_cast<T>(prm.rho);
@@ -437,8 +458,8 @@ tpp3_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ typ
         };
         auto cones_x = [&](VX& v) { project_soc_fixed<C::SCS, C::SCD>(v, mu_x, imu_x); };
         auto cones_u = [&](VU& v) { project_soc_fixed<C::UCS, C::UCD>(v, mu_u, imu_u); };
-        auto rows_x = [&](VX& v) { project_rows_reg<NX>(v, cAlx, prm.nsl); };
-        auto rows_u = [&](VU& v) { project_rows_reg<NU>(v, cAlu, prm.nil); };
+        auto rows_x = [&](VX& v) { project_rows_fixed<C::NSL>(v, cp.Alx, cp.blx, cp.inx); };
+        auto rows_u = [&](VU& v) { project_rows_fixed<C::NIL>(v, cp.Alu, cp.blu, cp.inu); };
         auto extra_x = [&](int i, const VX& xv, VX& dq) {
             if constexpr (C::CONSTR) {
                 if constexpr (C::SCD > 0) { VX tc; TC.load(i, tc); family(tc, xv, dq, cones_x); TC.store(i, tc); }
