@@ -146,6 +146,7 @@ const KernelEntry* find_kernel(const Family& f, int bits, bool ppb, bool refs, i
                 const bool okx = e->scd > 0 ? (fsx && b.n_state_cones == 1 && b.Acx[0] == e->scs && b.qcx[0] == e->scd) : !fsx;
                 const bool oku = e->ucd > 0 ? (fsu && b.n_input_cones == 1 && b.Acu[0] == e->ucs && b.qcu[0] == e->ucd) : !fsu;
                 if (!okx || !oku || f.L.nsl != e->nsl || f.L.nil != e->nil) continue;
+                if ((e->nsl > 0 && !b.en_state_linear) || (e->nil > 0 && !b.en_input_linear)) continue;   // rows present but switched off
             }
             if (e->family == KF_TPP && e->nx == f.nx && e->nu == f.nu && e->N == f.N && e->feat == f.feat && e->dtype_bits == bits &&
                 e->ppb == (ppb ? 1 : 0) && e->variant == variant && ((e->refs != 0) == refs || (pass == 1 && e->refs != 0)))

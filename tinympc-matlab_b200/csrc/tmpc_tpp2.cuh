@@ -443,6 +443,14 @@ struct TmemTraj {
 #pragma unroll
         for (int e = 0; e < N; ++e) v.set(e, __uint_as_float(r[e]));
     }
+    // split form: issue the load of step i early (no wait), complete it right before the first use -- the tensor-memory
+    // latency then overlaps whatever sits in between.  tcgen05.wait::ld covers every load issued before it.
+    __device__ __forceinline__ void issue(int i, uint32_t (&r)[N]) const { TmemSpan<N>::ld(base + i * N, r); }
+    static __device__ __forceinline__ void complete(uint32_t (&r)[N], Vec<float, N>& v) {
+        TmemSpan<N>::wait(r);
+#pragma unroll
+        for (int e = 0; e < N; ++e) v.set(e, __uint_as_float(r[e]));
+    }
     __device__ __forceinline__ void store(int i, const Vec<float, N>& v) const {
         uint32_t r[N];
 #pragma unroll

@@ -174,8 +174,11 @@ tpp3_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ typ
     Traj<T, NU, NH - 1, C::oTZC, BLOCK> TZC(cta_cols, tid);  // u(k) + yc(k-1)
     Traj<T, NU, NH - 1, C::oTZL, BLOCK> TZL(cta_cols, tid);  // u(k) + yl(k-1)
     const float mu_x = prm.cx[0], mu_u = prm.cu[0], imu_x = 1.f / mu_x, imu_u = 1.f / mu_u;   // the instance's cones (C::SCD, C::UCD)
-    const bool lin_x = C::CONSTR && prm.en_state_linear;     // with zero rows the family still contributes vl - gl = x
-    const bool lin_u = C::CONSTR && prm.en_input_linear;     // to the linear cost (admm.cpp:138-140, 223-225)
+    // An instance with rows serves only families that enable them (tmpc_capi.cu find_kernel), so its row families are
+    // unconditional straight-line code next to the box and the cone of the column.  With zero rows an enabled family still
+    // contributes vl - gl = x to the linear cost (admm.cpp:138-140, 223-225): that rare case is a run-time branch.
+    const bool lin_x = C::CONSTR && prm.en_state_linear;
+    const bool lin_u = C::CONSTR && prm.en_input_linear;
 
     const T* cP = pack + SP::Pinf;
     const T rho0 = static_cast<T>(prm.rho);
@@ -374,16 +377,19 @@ tpp3_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ typ
 #pragma unroll
             for (int j = 0; j < NX / 2; ++j) dx.p[j] = ff ? x0v.p[j] : mk2(T(0), T(0));
             dx.t = ff ? x0v.t : T(0);
+            uint32_t xr[NX];
+            X.issue(0, xr);
 #pragma unroll 1
             for (int i = 0; i < NH; ++i) {
                 const int zf = C::OPQ ? opaque_zero4() : 0;
                 VX xo;
-                X.load(i, xo);
+                TmemTraj<NX, NH>::complete(xr, xo);
 #pragma unroll
                 for (int j = 0; j < NX / 2; ++j) xo.p[j] = addv(sel0(ff, xo.p[j]), dx.p[j]);
                 if constexpr (NX & 1) xo.t = sel0(ff, xo.t) + dx.t;
                 X.store(i, xo);
                 if (i < NH - 1) {
+                    X.issue(i + 1, xr);   // lands behind the mat-vecs of this step
                     // du_i = -Kinf dx_i - dd_i (admm.cpp:29)
                     VU du;
                     ND.load(i, du);
@@ -460,23 +466,32 @@ tpp3_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ typ
         auto cones_u = [&](VU& v) { project_soc_fixed<C::UCS, C::UCD>(v, mu_u, imu_u); };
         auto rows_x = [&](VX& v) { project_rows_fixed<C::NSL>(v, cp.Alx, cp.blx, cp.inx); };
         auto rows_u = [&](VU& v) { project_rows_fixed<C::NIL>(v, cp.Alu, cp.blu, cp.inu); };
+        // the state-sized loads of column i are ISSUED at the top of the column (x, t, tc, tl: tensor memory) and completed
+        // after the input column's work, which hides their latency
+        constexpr bool HAS_TC = C::CONSTR && C::SCD > 0, HAS_TL = C::CONSTR;
+        uint32_t rx[NX], rt[NX], rc[HAS_TC ? NX : 1], rl[HAS_TL ? NX : 1];
+        auto issue_x = [&](int i) {   // every issued load is completed below (column 0 has no cone / half-space work)
+            X.issue(i, rx);
+            TT.issue(i, rt);
+            if constexpr (HAS_TC) { if (i > 0) TC.issue(i, rc); }
+            if constexpr (HAS_TL) { if (i > 0 && (C::NSL > 0 || lin_x)) TL.issue(i, rl); }
+        };
         auto extra_x = [&](int i, const VX& xv, VX& dq) {
-            if constexpr (C::CONSTR) {
-                if constexpr (C::SCD > 0) { VX tc; TC.load(i, tc); family(tc, xv, dq, cones_x); TC.store(i, tc); }
-                if (lin_x) { VX tl; TL.load(i, tl); family(tl, xv, dq, rows_x); TL.store(i, tl); }
-            }
+            if constexpr (HAS_TC) { VX tc; TmemTraj<NX, NH>::complete(rc, tc); family(tc, xv, dq, cones_x); TC.store(i, tc); }
+            if constexpr (HAS_TL) { if (C::NSL > 0 || lin_x) { VX tl; TmemTraj<NX, NH>::complete(rl, tl); family(tl, xv, dq, rows_x); TL.store(i, tl); } }
         };
         auto extra_u = [&](int i, const VU& uv, VU& dr) {
             if constexpr (C::CONSTR) {
                 if constexpr (C::UCD > 0) { VU tc; TZC.load(i, tc); family(tc, uv, dr, cones_u); TZC.store(i, tc); }
-                if (lin_u) { VU tl; TZL.load(i, tl); family(tl, uv, dr, rows_u); TZL.store(i, tl); }
+                if (C::NIL > 0 || lin_u) { VU tl; TZL.load(i, tl); family(tl, uv, dr, rows_u); TZL.store(i, tl); }
             }
         };
         VX dp;
         {   // column N-1: dp_N = -(xref_N' Pinf)' [first sweep] - rho dw_N   (admm.cpp:238-246)
             VX xv, traw, tnew;
-            X.load(NH - 1, xv);
-            TT.load(NH - 1, traw);
+            issue_x(NH - 1);
+            TmemTraj<NX, NH>::complete(rx, xv);
+            TmemTraj<NX, NH>::complete(rt, traw);
 #pragma unroll
             for (int j = 0; j < NX / 2; ++j) {
                 P lo, hi;
@@ -494,6 +509,7 @@ tpp3_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ typ
 #pragma unroll 1
         for (int i = NH - 2; i >= 0; --i) {
             const int zb = C::OPQ ? opaque_zero4() : 0;
+            issue_x(i);
             // ---- input column i: dr_i = -(Uref .* R) [first sweep] - rho dw   (admm.cpp:227-236)
             VU uv, dr;
             U.load(i, uv);
@@ -526,8 +542,8 @@ tpp3_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ typ
             }
             // ---- state column i: dq_i = -(Xref .* Q) [first sweep] - rho dw;  dp_i = dq_i + AmBKt dp - Kinf' dr   (admm.cpp:18)
             VX xv, traw, tnew, dq;
-            X.load(i, xv);
-            TT.load(i, traw);
+            TmemTraj<NX, NH>::complete(rx, xv);
+            TmemTraj<NX, NH>::complete(rt, traw);
 #pragma unroll
             for (int j = 0; j < NX / 2; ++j) {
                 P lo, hi;
