@@ -2,7 +2,7 @@
 """Opcode histogram of an `ncu --page source --csv` export, weighted by executed warp instructions
 and by stall samples.  Usage: sass_hist.py src.csv [warp_iterations]"""
 import csv, sys, collections
-rows = list(csv.reader(open(sys.argv[1])))
+rows = list(csv.reader(open(sys.argv[1], encoding="latin-1")))
 hdr = rows[1]
 ci = {h: i for i, h in enumerate(hdr)}
 ex, smp, cnt = collections.Counter(), collections.Counter(), collections.Counter()

@@ -510,6 +510,19 @@ tpp3_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ typ
         for (int i = NH - 2; i >= 0; --i) {
             const int zb = C::OPQ ? opaque_zero4() : 0;
             issue_x(i);
+            // The two products with dp_{i+1} start from zero and are added to their right-hand sides afterwards: they depend on
+            // nothing of this column, so they run under the latency of the column's tensor-/shared-memory loads and the scheduler
+            // is free to weave the slack updates (ALU pipe) into their FFMA2 stream (FMA pipe).  Measured: rocket +6 %,
+            // quadrotor +1 %; the 4-state shapes lose 1 % to the extra additions and keep the chained form.
+            constexpr bool SPLIT = NX >= 6;
+            VX akp;
+            VU btp;
+            akp.fill(T(0));
+            btp.fill(T(0));
+            if constexpr (SPLIT) {
+                mv_acc<NX, NX>(cp.AK, zb, dp, akp);
+                mv_acc<NU, NX>(cp.BT, zb, dp, btp);
+            }
             // ---- input column i: dr_i = -(Uref .* R) [first sweep] - rho dw   (admm.cpp:227-236)
             VU uv, dr;
             U.load(i, uv);
@@ -529,7 +542,13 @@ tpp3_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ typ
             extra_u(i, uv, dr);
             // dd_i = Quu_inv (B' dp + dr)   (admm.cpp:17; BPf cancels in the increment)
             VU t = dr;
-            mv_acc<NU, NX>(cp.BT, zb, dp, t);
+            if constexpr (SPLIT) {
+#pragma unroll
+                for (int j = 0; j < NU / 2; ++j) t.p[j] = addv(btp.p[j], dr.p[j]);
+                if constexpr (NU & 1) t.t = btp.t + dr.t;
+            } else {
+                mv_acc<NU, NX>(cp.BT, zb, dp, t);
+            }
             VU d;
             d.fill(T(0));
             mv_acc<NU, NU>(cp.Quu, zb, t, d);
@@ -556,12 +575,18 @@ tpp3_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ typ
                 slack(traw.t, xv.t, lo, hi, rpx, rdx, tnew.t, dq.t);
             }
             TT.store(i, tnew);
-            if (i > 0) {   // p_0 is never used (admm.cpp:17 reads p_{i+1}), hence neither are q_0 and the cone / half-space slacks of x_0
-                extra_x(i, xv, dq);
+            // p_0 is never used (admm.cpp:17 reads p_{i+1}), hence neither are q_0 and the cone / half-space slacks of x_0; the
+            // Riccati step of column 0 is computed all the same, which keeps the loop body one basic block.
+            if (C::CONSTR && i > 0) extra_x(i, xv, dq);
+            if constexpr (SPLIT) {
+#pragma unroll
+                for (int j = 0; j < NX / 2; ++j) dq.p[j] = addv(dq.p[j], akp.p[j]);
+                if constexpr (NX & 1) dq.t += akp.t;
+            } else {
                 mv_acc<NX, NX>(cp.AK, zb, dp, dq);
-                mv_acc<NX, NU>(cp.NKT, zb, dr, dq);
-                dp = dq;
             }
+            mv_acc<NX, NU>(cp.NKT, zb, dr, dq);
+            dp = dq;
         }
         TT.stores_done();
 
