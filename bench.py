@@ -98,6 +98,26 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons, "samples": len(sm)}
 
 
+def bind_to_gpu_cpus(local):
+    """Pin this rank (and the pinned host buffers it is about to allocate: first touch) to the CPUs next to its GPU, so that the
+    end-to-end path of every rank crosses its own PCIe root instead of the socket interconnect.  Returns the previous affinity
+    (restored before the CPU baseline, which uses all host threads) and a note for the report."""
+    prev = os.sched_getaffinity(0)
+    try:
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        try:
+            h = pynvml.nvmlDeviceGetHandleByUUID("GPU-" + str(torch.cuda.get_device_properties(local).uuid))
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        now = os.sched_getaffinity(0)
+        return prev, f"gpu-local ({len(now)} of {len(prev)} cpus)"
+    except Exception as ex:
+        return prev, f"unchanged ({type(ex).__name__})"
+
+
 def reference_arm(args, P, spec, batch_np):
     """The reference's own CPU implementation (oracle/_ref = unmodified reference C++ built by
     oracle/Makefile; falls back to the C port) on all host threads, bounded sample per step."""
@@ -190,6 +210,7 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
 
+    prev_affinity, config["cpu_affinity"] = bind_to_gpu_cpus(local) if (world > 1 and not os.environ.get("BENCH_NO_AFFINITY")) else (os.sched_getaffinity(0), "unchanged (single rank)")
     tm = importlib.import_module("tinympc-matlab_b200")
     S = importlib.import_module("tinympc-matlab_b200.sharding")
     B = args.batch
@@ -296,6 +317,7 @@ def main():
             "ns_per_admm_iter": ns_iter, "mean_iters": iters_all / (world * B), "unsolved_frac": unsolved,
             "clocks": clk.summary(), "e2e": e2e, "fp64_resolved": int(marked), "gpu_launches": launches_all, "roofline": roof}
     if not args.no_cpu_baseline:
+        os.sched_setaffinity(0, prev_affinity)
         try:
             cb = reference_arm(args, P, spec, batch_np.slice(0, min(B, 1 << 18)))
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "ns_per_admm_iter")}
