@@ -34,8 +34,23 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 # algorithmic work per ADMM iteration / bytes per solve, SURVEY.md section 8d (box constraints)
-def flops_per_iter(n, m, N):
-    return (N - 1) * (4 * n * n + 8 * n * m + 2 * m * m + 5 * n + 3 * m) + 15 * (n * N + m * (N - 1)) + (2 * n * n + 3 * n)
+def flops_per_iter(n, m, N, spec=None):
+    """box-only count, plus -- when `spec` enables them -- the per-family terms of the same table: 6 flop per trajectory
+    element of every enabled cone / linear family, ~20 per (step, cone), 4 dim + 2 per (step, linear row), and the structured
+    adaptive-rho evaluation every 5th iteration."""
+    F = (N - 1) * (4 * n * n + 8 * n * m + 2 * m * m + 5 * n + 3 * m) + 15 * (n * N + m * (N - 1)) + (2 * n * n + 3 * n)
+    if spec is not None:
+        if spec.en_state_soc and len(spec.qcx):
+            F += 6 * n * N + 20 * N * len(spec.qcx)
+        if spec.en_input_soc and len(spec.qcu):
+            F += 6 * m * (N - 1) + 20 * (N - 1) * len(spec.qcu)
+        if spec.en_state_linear:
+            F += 6 * n * N + (4 * n + 2) * N * len(spec.blin_x)
+        if spec.en_input_linear:
+            F += 6 * m * (N - 1) + (4 * m + 2) * (N - 1) * len(spec.blin_u)
+        if spec.adaptive_rho:
+            F += ((N - 1) * (4 * n * n + 4 * n * m) + 2 * n * n + 12 * (n * N + m * (N - 1))) // 5
+    return F
 
 
 def bytes_per_solve(n, m, N):
@@ -292,7 +307,7 @@ def main():
             dist.destroy_process_group()
         return
 
-    F = flops_per_iter(n, m, N)
+    F = flops_per_iter(n, m, N, spec)
     peak_tf, peak_how = fp32_peak_tflops()
     hbm_pk, hbm_how = hbm_peak_gbs()
     t_launch = ms / args.steps * 1e-3                              # rank-0 kernel launch duration (1 kernel / step)

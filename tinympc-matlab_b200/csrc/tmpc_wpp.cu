@@ -38,16 +38,21 @@ __device__ __forceinline__ T warp_max(T v) {
 }
 
 // out[r] = sum_c M[r*C + c] * x[c]   (row-major M, lanes over rows)
-template <typename T>
+// With compile-time shapes (wpp_kernel<T, NX, NU>) the loops below unroll completely: the 2 C loads of a dot product are then
+// issued back to back ahead of the dependent FMA chain instead of one load-use round trip per term (the run-time-shaped
+// kernel spends ~19 us per ADMM iteration on exactly that).  Same summation order either way.
+template <typename T, int UNR>
 __device__ __forceinline__ T row_dot(const T* __restrict__ M, int r, int C, const T* x) {
     T acc = 0;
+#pragma unroll UNR
     for (int c = 0; c < C; ++c) acc = fma(M[r * C + c], x[c], acc);
     return acc;
 }
 // out[c] = sum_r M[r*C + c] * x[r]   (transposed product, lanes over columns)
-template <typename T>
+template <typename T, int UNR>
 __device__ __forceinline__ T col_dot(const T* __restrict__ M, int c, int R, int C, const T* x) {
     T acc = 0;
+#pragma unroll UNR
     for (int r = 0; r < R; ++r) acc = fma(M[r * C + c], x[r], acc);
     return acc;
 }
@@ -72,13 +77,17 @@ __device__ void project_soc(T* s, int dim, float mu) {
 
 }  // namespace
 
-template <typename T>
+// NXC, NUC > 0: the state / input dimensions are compile-time (instances for the shipped shapes); 0: run-time shapes
+template <typename T, int NXC, int NUC>
 __global__ void __launch_bounds__(128) wpp_kernel(const SolveParams prm, const PackLayout L, const T* __restrict__ pack,
-                                                  const WppLayout W, T* __restrict__ scratch, const int explicit_workspace) {
+                                                  const WppLayout W, T* __restrict__ scratch, const int explicit_workspace,
+                                                  const int ws_in_smem) {
+    extern __shared__ __align__(16) unsigned char wpp_smem[];
     const int lane = threadIdx.x & 31;
     const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int n_warps = (gridDim.x * blockDim.x) >> 5;
-    const int nx = L.nx, nu = L.nu, N = L.N;
+    const int nx = NXC > 0 ? NXC : L.nx, nu = NUC > 0 ? NUC : L.nu, N = L.N;
+    constexpr int UNR = NXC > 0 ? 16 : 1;   // compile-time shapes: every dot product fully unrolled
     const int sx = nx * N, su = nu * (N - 1);
 
     const T* A = pack + L.A;   const T* B = pack + L.B;   const T* AK = pack + L.AmBKt; const T* Quu = pack + L.Quu_inv;
@@ -96,7 +105,14 @@ __global__ void __launch_bounds__(128) wpp_kernel(const SolveParams prm, const P
     for (int prob = warp_global; prob < prm.batch; prob += n_warps) {
         // explicit_workspace 0: one scratch workspace per warp, cold start per problem; 1: ONE live workspace (tiny_solve);
         // 2: a persistent workspace per PROBLEM (a session of warm-started solvers), iterated in place
-        T* ws = scratch + (size_t)(explicit_workspace == 2 ? prob : warp_global) * W.size;
+        // The workspace is iterated in SHARED memory when the launcher says so (ws_in_smem): the lanes of the warp hand the columns
+        // of p, x, u and the scratch vector to each other at every time step.  Live workspaces (sessions) are copied in and out.
+        T* const gws = scratch ? scratch + (size_t)(explicit_workspace == 2 ? prob : warp_global) * W.size : nullptr;
+        T* const ws = ws_in_smem ? reinterpret_cast<T*>(wpp_smem) + (size_t)(threadIdx.x >> 5) * W.size : gws;
+        if (ws_in_smem && explicit_workspace) {
+            for (int e = lane; e < W.size; e += 32) ws[e] = gws[e];
+            __syncwarp();
+        }
         T *x = ws + W.x, *u = ws + W.u, *q = ws + W.q, *r = ws + W.r, *p = ws + W.p, *d = ws + W.d;
         T *v = ws + W.v, *vnew = ws + W.vnew, *z = ws + W.z, *znew = ws + W.znew, *g = ws + W.g, *y = ws + W.y;
         T *vcnew = ws + W.vcnew, *zcnew = ws + W.zcnew, *gc = ws + W.gc, *yc = ws + W.yc;
@@ -142,19 +158,19 @@ __global__ void __launch_bounds__(128) wpp_kernel(const SolveParams prm, const P
             // ---------------- backward_pass_grad, admm.cpp:13-20
             for (int i = N - 2; i >= 0; --i) {
                 const T* pn = p + (i + 1) * nx;
-                for (int a = lane; a < nu; a += 32) tmp[a] = col_dot(B, a, nx, nu, pn) + r[i * nu + a] + BPf[a];
+                for (int a = lane; a < nu; a += 32) tmp[a] = col_dot<T, UNR>(B, a, nx, nu, pn) + r[i * nu + a] + BPf[a];
                 __syncwarp();
-                for (int a = lane; a < nu; a += 32) d[i * nu + a] = row_dot(Quu, a, nu, tmp);
+                for (int a = lane; a < nu; a += 32) d[i * nu + a] = row_dot<T, UNR>(Quu, a, nu, tmp);
                 for (int c = lane; c < nx; c += 32)
-                    p[i * nx + c] = q[i * nx + c] + row_dot(AK, c, nx, pn) - col_dot(K, c, nu, nx, r + i * nu) + APf[c];
+                    p[i * nx + c] = q[i * nx + c] + row_dot<T, UNR>(AK, c, nx, pn) - col_dot<T, UNR>(K, c, nu, nx, r + i * nu) + APf[c];
                 __syncwarp();
             }
             // ---------------- forward_pass, admm.cpp:25-32
             for (int i = 0; i < N - 1; ++i) {
-                for (int a = lane; a < nu; a += 32) u[i * nu + a] = -row_dot(K, a, nx, x + i * nx) - d[i * nu + a];
+                for (int a = lane; a < nu; a += 32) u[i * nu + a] = -row_dot<T, UNR>(K, a, nx, x + i * nx) - d[i * nu + a];
                 __syncwarp();
                 for (int c = lane; c < nx; c += 32)
-                    x[(i + 1) * nx + c] = row_dot(A, c, nx, x + i * nx) + row_dot(B, c, nu, u + i * nu) + f[c];
+                    x[(i + 1) * nx + c] = row_dot<T, UNR>(A, c, nx, x + i * nx) + row_dot<T, UNR>(B, c, nu, u + i * nu) + f[c];
                 __syncwarp();
             }
             // ---------------- update_slack, admm.cpp:81-175
@@ -183,7 +199,7 @@ __global__ void __launch_bounds__(128) wpp_kernel(const SolveParams prm, const P
                 for (int i = lane; i < N; i += 32)
                     for (int c = 0; c < L.nsl; ++c) {          // sequential in place per column, admm.cpp:149-157
                         T* col = vlnew + i * nx;
-                        const T val = row_dot(Alx, c, nx, col);
+                        const T val = row_dot<T, UNR>(Alx, c, nx, col);
                         if (val > blx[c]) {
                             const T dist = (val - blx[c]) / nrx[c];
                             for (int j = 0; j < nx; ++j) col[j] -= dist * Alx[c * nx + j];
@@ -193,7 +209,7 @@ __global__ void __launch_bounds__(128) wpp_kernel(const SolveParams prm, const P
                 for (int i = lane; i < N - 1; i += 32)
                     for (int c = 0; c < L.nil; ++c) {
                         T* col = zlnew + i * nu;
-                        const T val = row_dot(Alu, c, nu, col);
+                        const T val = row_dot<T, UNR>(Alu, c, nu, col);
                         if (val > blu[c]) {
                             const T dist = (val - blu[c]) / nru[c];
                             for (int j = 0; j < nu; ++j) col[j] -= dist * Alu[c * nu + j];
@@ -221,7 +237,7 @@ __global__ void __launch_bounds__(128) wpp_kernel(const SolveParams prm, const P
             {
                 const int o = (N - 1) * nx;
                 for (int c = lane; c < nx; c += 32) {           // p_N = -(xref_N' Pinf)' - rho (...)  admm.cpp:238-246
-                    T pv = -col_dot(P, c, nx, nx, Xref + o);
+                    T pv = -col_dot<T, UNR>(P, c, nx, nx, Xref + o);
                     pv -= rho * (vnew[o + c] - g[o + c]);
                     if (soc_x) pv -= rho * (vcnew[o + c] - gc[o + c]);
                     if (lin_x) pv -= rho * (vlnew[o + c] - gl[o + c]);
@@ -246,7 +262,7 @@ __global__ void __launch_bounds__(128) wpp_kernel(const SolveParams prm, const P
                     const int i = e / nx, c = e % nx;
                     T px, aty = 0;
                     const T qx = Qd[c] * x[e];
-                    if (i < N - 1) { px = qx; aty = col_dot(A, c, nx, nx, g + (i + 1) * nx); } else { px = row_dot(P, c, nx, x + i * nx); }
+                    if (i < N - 1) { px = qx; aty = col_dot<T, UNR>(A, c, nx, nx, g + (i + 1) * nx); } else { px = row_dot<T, UNR>(P, c, nx, x + i * nx); }
                     if (i >= 1) aty -= g[e];
                     dua = tmax(dua, tabs(px + qx + aty));
                     duan = tmax(duan, tmax(tmax(tabs(px), tabs(qx)), tabs(aty)));
@@ -254,7 +270,7 @@ __global__ void __launch_bounds__(128) wpp_kernel(const SolveParams prm, const P
                 for (int e = lane; e < su; e += 32) {             // u blocks
                     const int i = e / nu, a = e % nu;
                     const T ru = Rd[a] * u[e];
-                    const T aty = y[e] + col_dot(B, a, nx, nu, g + (i + 1) * nx);
+                    const T aty = y[e] + col_dot<T, UNR>(B, a, nx, nu, g + (i + 1) * nx);
                     dua = tmax(dua, tabs(ru + ru + aty));
                     duan = tmax(duan, tmax(tabs(ru), tabs(aty)));
                 }
@@ -285,6 +301,10 @@ __global__ void __launch_bounds__(128) wpp_kernel(const SolveParams prm, const P
         }
         // ---------------- results
         if (lane == 0) { sc[0] = rho; sc[1] = static_cast<T>(iter); sc[2] = static_cast<T>(status); sc[3] = r_px; sc[4] = r_dx; sc[5] = r_pu; sc[6] = r_du; sc[7] = static_cast<T>(solved); }
+        if (ws_in_smem && explicit_workspace) {
+            __syncwarp();
+            for (int e = lane; e < W.size; e += 32) gws[e] = ws[e];
+        }
         if (explicit_workspace != 1 && prm.x) {
             for (int e = lane; e < sx; e += 32) prm.x[(size_t)prob * sx + e] = static_cast<float>(vnew[e]);
             for (int e = lane; e < su; e += 32) prm.u[(size_t)prob * su + e] = static_cast<float>(znew[e]);
@@ -324,13 +344,14 @@ template <typename T>
 __global__ void wpp_session_step_kernel(const PackLayout L, const T* __restrict__ pack, const WppLayout W, T* __restrict__ wsp, int batch,
                                         int use_solution) {
     const int nx = L.nx, nu = L.nu;
+    constexpr int UNR = 1;
     const int prob = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (prob >= batch) return;
     T* ws = wsp + (size_t)prob * W.size;
     const T* x0 = ws + W.x;
     const T* u0 = ws + (use_solution ? W.znew : W.u);
     T xn = 0;
-    if (lane < nx) xn = row_dot(pack + L.A, lane, nx, x0) + row_dot(pack + L.B, lane, nu, u0) + pack[L.f + lane];
+    if (lane < nx) xn = row_dot<T, UNR>(pack + L.A, lane, nx, x0) + row_dot<T, UNR>(pack + L.B, lane, nu, u0) + pack[L.f + lane];
     __syncwarp();
     if (lane < nx) ws[W.x + lane] = xn;
 }
@@ -377,9 +398,26 @@ cudaError_t wpp_launch(const SolveParams& p, const PackLayout& L, const void* pa
     const int block = 128;                       // 4 warps per CTA
     int grid = (warps * 32 + block - 1) / block;
     if (grid < 1) grid = 1;
-    wpp_kernel<T><<<grid, warps * 32 < block ? warps * 32 : block, 0, st>>>(p, L, static_cast<const T*>(pack), W, static_cast<T*>(scratch),
-                                                                            explicit_workspace);
-    return cudaGetLastError();
+    const int threads = warps * 32 < block ? warps * 32 : block;
+    const T* pk = static_cast<const T*>(pack);
+    T* sc = static_cast<T*>(scratch);
+    const size_t smem = (size_t)(threads / 32) * W.size * sizeof(T);
+    // fp32 workspaces that fit are iterated in shared memory (measured on 65 536 warm-started quadrotor solvers: 15.0 -> 19.9 M
+    // solves/s); fp64 ones stay in global memory, where the smaller footprint per CTA keeps more warps resident (13.2 M against
+    // 9.2 M solves/s), and so do long horizons that do not fit
+    const int in_smem = (sizeof(T) == 4 && smem <= 200 * 1024) ? 1 : 0;
+    auto go = [&](auto kernel) -> cudaError_t {
+        if (in_smem && smem > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+        }
+        kernel<<<grid, threads, in_smem ? smem : 0, st>>>(p, L, pk, W, sc, explicit_workspace, in_smem);
+        return cudaGetLastError();
+    };
+    if (L.nx == 12 && L.nu == 4) return go(wpp_kernel<T, 12, 4>);
+    if (L.nx == 4 && L.nu == 1) return go(wpp_kernel<T, 4, 1>);
+    if (L.nx == 6 && L.nu == 3) return go(wpp_kernel<T, 6, 3>);
+    return go(wpp_kernel<T, 0, 0>);
 }
 template cudaError_t wpp_launch<float>(const SolveParams&, const PackLayout&, const void*, const WppLayout&, void*, int, int, cudaStream_t);
 template cudaError_t wpp_launch<double>(const SolveParams&, const PackLayout&, const void*, const WppLayout&, void*, int, int, cudaStream_t);
