@@ -161,6 +161,8 @@ int  tinympc_cuda_session_read(tinympc_cuda_session *ss, const char *field, doub
    "mixed" (relative band b in [0,1), 0 = off [default]; with precision 32 and b > 0 the fp32 kernel stops and marks every
    problem whose termination decision (admm.cpp:262-265) has its largest residual/tolerance ratio inside [1-b, 1+b], and an
    fp64 pass re-solves exactly the marked problems: the reference's iteration counts and status codes at close to fp32 speed),
+   "refill_min" (a warp of the thread-per-problem kernel claims new problems once that many of its lanes are free; 0 [default]:
+   chosen by the kernel from the iterations its problems take),
    "streamed" (1 [default]: tinympc_cuda_solve_batch runs each device's shard as ONE persistent launch that consumes the
    problems while the H2D copies are still arriving and returns results chunk by chunk while it is still solving;
    0: one launch per chunk), "ctas_per_sm" (0 = occupancy API), "chunks" (host pipeline depth, 0 = auto),

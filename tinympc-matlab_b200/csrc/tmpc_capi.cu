@@ -87,6 +87,7 @@ struct tinympc_cuda_solver {
     int chunks = 0;                    // 0 = auto
     int variant = 0;
     int force_wpp = 0;                 // option "kernel": 0 auto, 1 always the warp-per-problem kernel
+    int refill_min = 0;                // option "refill_min": free lanes a warp collects before it claims new problems (tmpc_tpp3.cuh); 0 = adaptive
     int streamed = 1;                  // option "streamed": 1 = single-launch streamed host pipeline where it applies, 0 = chunked launches
     double mixed_band = 0;             // option "mixed": > 0 = fp32 pass + fp64 re-solve of the problems whose termination decision
                                        // falls within this relative band of the tolerances (exact iteration counts at ~fp32 speed)
@@ -207,6 +208,7 @@ int launch_tpp(tinympc_cuda_solver* s, DeviceCtx& d, const KernelEntry* ke, Solv
         p.ref_scratch = rb.p;
     }
     p.work_counter = counter;
+    p.refill_min = s->refill_min;
     CU(s, cudaMemsetAsync(counter, 0, sizeof(int), st));
     CU(s, ke->launch(p, grid, smem, st, f.pack.data(), f.L));
     s->launches += 1;
@@ -1066,6 +1068,8 @@ int tinympc_cuda_set_option(tinympc_cuda_solver* s, const char* name, double val
         s->force_wpp = (int)value;
     } else if (n == "streamed") {
         s->streamed = value != 0;
+    } else if (n == "refill_min") {
+        s->refill_min = (int)value;
     } else {
         return fail(s, TINYMPC_CUDA_EINVAL, "unknown option " + n);
     }

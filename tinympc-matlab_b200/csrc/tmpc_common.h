@@ -116,6 +116,10 @@ struct SolveParams {
     int* done_counters;        // NULL = nobody is waiting
     int done_chunk;            // problems per granule; chunk of problem p = done_map[p / done_chunk]
     unsigned char done_map[kMaxGranules];   // chunks are runs of granules: short ones first (early start) and last (short tail)
+    // Batched lane refill (tmpc_tpp3.cuh): a warp claims new problems only once at least refill_min of its lanes are free (or
+    // none is busy).  Claim + input loads + tensor-memory parking are warp-wide code executed for however few lanes need it,
+    // so sharing one pass between several lanes trades a little idle lane time for fewer passes.  1: refill at once; 0: adaptive.
+    int refill_min;
 };
 
 constexpr int kAmbiguousBit = 0x100;

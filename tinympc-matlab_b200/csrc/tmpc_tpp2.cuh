@@ -767,6 +767,7 @@ tpp2_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ typ
     const int n_items = prm.batch_ptr ? min(*prm.batch_ptr, prm.batch) : prm.batch;   // work items (mixed mode: the marked problems)
     int prob = 0;           // problem owned by this lane
     bool active = false;    // lane holds an unfinished problem
+    int last_k = 32;        // iterations of the last problem this lane finished (batched refill)
     bool exhausted = false; // the work counter ran past the batch
     bool pending = false;   // holds a claimed problem (claim) whose inputs have not landed yet (streamed host pipeline)
     int claim = 0, seen = 0, unpub = -1;   // seen: cached arrival watermark; unpub: finished problem not yet counted for its chunk
@@ -823,7 +824,17 @@ tpp2_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ typ
         {
             publish_done(prm, unpub);
             const bool want = !active && !exhausted && !pending;
-            const unsigned mw = __ballot_sync(FULL, want);
+            unsigned mw = __ballot_sync(FULL, want);
+            // batched refill (SolveParams::refill_min; the model behind the adaptive threshold is spelled out in tmpc_tpp3.cuh)
+            if (mw && __any_sync(FULL, active)) {
+                int m = prm.refill_min;
+                if (m <= 0) {
+                    const int sum_k = __reduce_add_sync(FULL, last_k);
+                    m = __float2int_rn(sqrtf(__fdividef(471.f * 32.f, (float)max(sum_k, 32))));
+                    m = min(max(m, 1), 12);
+                }
+                if (__popc(mw) < m) mw = 0;
+            }
             if (mw) {   // claim the next problem indices (one atomic per warp)
                 const int leader = __ffs(mw) - 1;
                 int base = 0;
@@ -1259,6 +1270,7 @@ tpp2_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ typ
             if (prm.rho_out) prm.rho_out[prob] = static_cast<float>(rho);
             if (prm.done_counters) unpub = prob;
             active = false;
+            last_k = k;
         }
         if (!__any_sync(FULL, active)) continue;   // whole warp idle: go refill (or exit) without a backward sweep
 

@@ -192,6 +192,7 @@ tpp3_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ typ
     int prob = 0;
     bool active = false, exhausted = false;
     bool pending = false;   // holds a claimed problem (claim) whose inputs have not landed yet (streamed host pipeline)
+    int last_k = 32;        // iterations of the last problem this lane finished (batched refill)
     int claim = 0, seen = 0, unpub = -1;   // seen: cached arrival watermark; unpub: finished problem not yet counted for its chunk
     int k = 0;
     int next_check = check_every;
@@ -237,7 +238,21 @@ tpp3_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ typ
         // ------------------------------------------------------------------ refill idle lanes
         {
             const bool want = !active && !exhausted && !pending;
-            const unsigned mw = __ballot_sync(FULL, want);
+            unsigned mw = __ballot_sync(FULL, want);
+            // Batched refill: wait until a few lanes are free, unless nothing else keeps the warp busy.  One refill pass costs the
+            // warp R ~ 0.23 iterations whatever the number of lanes it serves; with I iterations per problem 32 / I lanes finish
+            // per iteration, so a threshold m costs 32 R / (I m) in passes and (m - 1) / 64 in idle lanes: m* = sqrt(2048 R / I)
+            // (3 for the hard quadrotor batch, 7 for the easy one; measured optimum 3-4 and >= 8).  I is the warp's mean over
+            // the last problem of each lane.  refill_min > 0 fixes the threshold instead.
+            if (mw && __any_sync(FULL, active)) {
+                int m = prm.refill_min;
+                if (m <= 0) {
+                    const int sum_k = __reduce_add_sync(FULL, last_k);
+                    m = __float2int_rn(sqrtf(__fdividef(471.f * 32.f, (float)max(sum_k, 32))));
+                    m = min(max(m, 1), 12);
+                }
+                if (__popc(mw) < m) mw = 0;
+            }
             if (mw) {   // claim the next problem indices (one atomic per warp)
                 const int leader = __ffs(mw) - 1;
                 int base = 0;
@@ -635,6 +650,7 @@ tpp3_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ typ
             if (prm.rho_out) prm.rho_out[prob] = rho0;
             if (prm.done_counters) unpub = prob;
             active = false;
+            last_k = k;
         }
     }
     tmem_fence_before_sync();
