@@ -440,7 +440,7 @@ tpp3_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ typ
         T rpx = 0, rdx = 0, rpu = 0, rdu = 0;
         // one trajectory element (pair or scalar tail).  traw: stored pre-clamp slack t(k-1) (on the first sweep: the parked
         // reference term, t(0) = 0).  vo = clamp(t_old), g = t_old - vo, t_new = x + g, vn = clamp(t_new)  (admm.cpp:85,92,184);
-        // increment of (slack - dual) = (2 vn - t_new) - (2 vo - t_old) = 2 (vn - vo) - (t_new - t_old); dq = ref - rho dw
+        // increment of (slack - dual) = (2 vn - t_new) - (2 vo - t_old) = 2 (vn - vo) - (t_new - t_old) = (vn - vo) - (x - vn); dq = ref - rho dw
         auto slack = [&](auto traw, auto xv, auto lo, auto hi, T& rp, T& rd, auto& tnew, auto& dq) {
             const auto told = sel0(first, traw);
             const auto ref = subv(traw, told);                 // first ? traw : 0
@@ -449,11 +449,13 @@ tpp3_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ typ
             const auto go = subv(told, vo);
             tnew = addv(xv, go);
             const auto vn = clampv(tnew, lo, hi);
-            rp = amaxv(rp, subv(xv, vn));
-            const auto e = subv(vn, vo);
+            const auto a = subv(xv, vn);                       // primal residual of the element
+            rp = amaxv(rp, a);
+            const auto e = subv(vn, vo);                       // dual residual / rho
             rd = amaxv(rd, e);
-            const auto dw = twice_minus(e, subv(tnew, told));
-            dq = fmas(dw, nrho, ref);
+            // t_new - t_old = x - v_old, hence dw = 2 e - (x - v_old) = e - a: the increment of (slack - dual) is the
+            // difference of the two residuals
+            dq = fmas(subv(e, a), nrho, ref);
         };
         // one more constraint family of a column (cone or half-space): traw = stored pre-projection value x(k-1) + dual(k-2)
         // (garbage of the previous problem on the first sweep, where the cold value is 0 and so is its projection,
