@@ -78,7 +78,7 @@ def test_golden_fp32(name, capi, oracle_mod):
 # measured fp32 iteration-count flip rates (one check interval early/late).  Box-constrained batches run the incremental-form
 # kernel (tmpc_tpp3.cuh): cartpole 0.01 %, quadrotor 0.01-0.04 % (the direct form, variant 5, has 1-2 %); adaptive quadrotor
 # 3 % and rocket 19 % (tol_dua 1e-4 on thrusts of magnitude 100 is at fp32 resolution) still run the direct form.
-FLIP_BOUND = {"cartpole": 0.002, "quadrotor": 0.003, "quadrotor_adaptive": 0.06, "rocket": 0.30}
+FLIP_BOUND = {"cartpole": 0.002, "quadrotor": 0.003, "quadrotor_adaptive": 0.04, "rocket": 0.05}
 FLIP_BOUND_DIRECT = {"cartpole": 0.005, "quadrotor": 0.04}
 
 
@@ -191,3 +191,29 @@ def test_streamed_pipeline_per_problem_bounds(capi, oracle_mod, problems):
     for k in range(0, reps * n, n * 7):
         assert np.array_equal(r["iter"][k:k + n], g["iter"]) and np.array_equal(r["status"][k:k + n], g["status"])
         assert np.abs(r["x"][k:k + n] - g["x"]).max() <= X_TOL_F64 * max(1.0, float(np.abs(g["x"]).max()))
+
+
+@pytest.mark.parametrize("family", ["quadrotor", "cartpole", "rocket"])
+def test_full_size_batch_is_order_independent_and_matches_the_oracle_on_a_sample(family, capi, oracle_mod, problems):
+    """BASELINE size (2^20 problems): properties that do not depend on the size the oracle can afford.
+    (1) Every problem is solved independently of which lane, warp and refill batch picks it up: solving a permuted batch returns
+        the permuted results BIT FOR BIT (this is the check of the lane-refill / batched-refill / work-counter machinery).
+    (2) A strided sample of 2048 problems of the big batch matches the reference on the same inputs."""
+    p = dict(cartpole=problems.cartpole, quadrotor=problems.quadrotor, rocket=problems.rocket)[family]()
+    B = 1 << 20
+    b = problems.make_batch(p, B, 1.0, seed=77)
+    perm = np.random.default_rng(5).permutation(B)
+    take = lambda a: None if a is None else np.ascontiguousarray(a[perm])
+    bp = problems.Batch(take(b.x0), take(b.Xref), take(b.Uref))
+    r = solve_gpu(capi, oracle_mod, p, b, 32)
+    rp = solve_gpu(capi, oracle_mod, p, bp, 32)
+    for k in ("iter", "status", "x", "u"):
+        assert np.array_equal(r[k][perm], rp[k]), f"{family}: field {k} depends on the position of the problem in the batch"
+    idx = np.arange(0, B, B // 2048)
+    sub = problems.Batch(b.x0[idx], None if b.Xref is None else b.Xref[idx], None if b.Uref is None else b.Uref[idx])
+    g = oracle_mod.solve_batch(p, sub, "ref" if oracle_mod.available("ref") else "port")
+    rs = {k: r[k][idx] for k in ("iter", "status", "x", "u")}
+    rs["kernel"] = r["kernel"]
+    flips, dx, du = compare(rs, g, 32, f"{family} 2^20 sample", max_flip_frac=FLIP_BOUND[family])
+    print(f"\n[parity] {family} 2^20 problems: permutation-invariant bit for bit; sample of {len(idx)}: {flips} count flips, "
+          f"max|dx|={dx:.2e} max|du|={du:.2e} kernel={r['kernel']}")

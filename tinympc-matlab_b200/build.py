@@ -45,17 +45,41 @@ def inst(bits, nx, nu, N, feat, refs=REFS_SMEM, ppb=False, variant=0, block=None
     return dict(aff=aff, tm=tm, ntm=ntm, opq=opq, tib=tib, bits=bits, nx=nx, nu=nu, N=N, feat=feat, refs=refs, ppb=ppb, variant=variant, block=block or b, minb=minb or m, fb=fb, gen=gen)
 
 
-def inst3(nx, nu, N, refs=True, ppb=False, fb=False, variant=0, max_warps=24, opq=False, tib=None, aff=None, feat=BOX, cones=(0, 0, 0, 0, 0, 0)):
+def plan_hybrid(nx, nu, N, max_warps=24):
+    """(warps, ttm) of the hybrid layout of tmpc_tpp3.cuh maximising the resident warps: x_1 .. x_{N-2} and t_0 .. t_{ttm-1} in the
+    warp's share of the 512 tensor-memory columns, t_ttm .. t_{N-2} + u, u + y, -dd in shared memory, column N-1 in registers"""
+    su = nu * (N - 1)
+    for warps in range(max_warps, 3, -4):
+        cols = 512 // (warps // 4)
+        ttm = min(N - 1, cols // nx - (N - 2))
+        if ttm < 0:
+            continue
+        smem_cols = 3 * su + (N - 1 - ttm) * nx
+        if smem_cols * warps * 32 * 4 + 1024 + pack_elems(nx, nu, N) * 4 > 226 * 1024:
+            continue
+        if 65536 // (warps * 32) < 64 + 8 * nx:      # registers: ~126 + 2 nx (column N-1) on the quadrotor shape, ~90 with nx = 4
+            continue
+        return warps, ttm
+    return None
+
+
+def inst3(nx, nu, N, refs=True, ppb=False, fb=False, variant=0, max_warps=24, opq=False, tib=None, aff=None, feat=BOX, cones=(0, 0, 0, 0, 0, 0), hyb=False):
     """incremental-form kernel (tmpc_tpp3.cuh): x and t in tensor memory (2 nx N columns per thread), u, u + y, -dd in shared memory;
     with cones / linear rows (feat=CON) two more arrays of each kind (the pre-projection slacks of the two families)"""
     sx, su = nx * N, nu * (N - 1)
     ntm, nsm = (4, 5) if feat == CON else (2, 3)
     warps = min(max_warps, 4 * (512 // (ntm * sx)), ((226 * 1024 - 1024 - pack_elems(nx, nu, N) * 4) // (nsm * su * 4 * 32) // 4) * 4)
+    ttm = -1
+    if hyb:
+        assert feat == BOX
+        warps, ttm = plan_hybrid(nx, nu, N, max_warps)
     assert warps >= 4, "shape does not fit the incremental-form kernel"
     aff = ((nx, nu) == (6, 3)) if aff is None else aff
-    tib = (not (nx == 12)) if tib is None else tib
+    # fast-box bounds read from time row 0 with immediate addresses: with the incremental-form kernel this is a gain on every shape
+    # (quadrotor +3.3 %), unlike the direct form, where the hoisted bounds starved the coefficient stream of the quadrotor instance
+    tib = True if tib is None else tib
     return dict(gen=3, bits=32, nx=nx, nu=nu, N=N, feat=feat, refs=3 if refs else 0, ppb=ppb, fb=fb, variant=variant, block=warps * 32, aff=aff,
-                opq=opq, tib=tib, tm=True, minb=1, ntm=ntm, cones=cones)
+                opq=opq, tib=tib, tm=True, minb=1, ntm=ntm, cones=cones, ttm=ttm)
 
 
 def cols_per_thread(nx, nu, N, feat, refs, ntm=0):
@@ -107,10 +131,12 @@ def default_instances():
     shapes = [(12, 4, 10), (4, 1, 20), (4, 1, 10), (6, 3, 10)]
     # fp32 box-constrained batches: the incremental ("delta") form, tmpc_tpp3.cuh -- the default (variant 0)
     for (nx, nu, N) in shapes:
+        # hybrid state layout where it buys resident warps: the quadrotor shape goes from 8 to 12 warps per SM (+6.7 %)
+        hyb = plan_hybrid(nx, nu, N) is not None and plan_hybrid(nx, nu, N)[0] > inst3(nx, nu, N)["block"] // 32
         for fb in (True, False):      # fb: bounds constant over the horizon and containing 0 (the common case)
-            out.append(inst3(nx, nu, N, refs=True, fb=fb))
-            out.append(inst3(nx, nu, N, refs=False, fb=fb))
-        out.append(inst3(nx, nu, N, refs=True, ppb=True))
+            out.append(inst3(nx, nu, N, refs=True, fb=fb, hyb=hyb))
+            out.append(inst3(nx, nu, N, refs=False, fb=fb, hyb=hyb))
+        out.append(inst3(nx, nu, N, refs=True, ppb=True, hyb=hyb))
     # box + second-order cones + linear inequalities (rocket landing, rocket_landing_constraints.m:40-55: one cone on the
     # first three states, one on the three inputs): the same form with two more slack families, cone blocks compiled in
     # (+ one linear row on each side; the last two numbers are the row counts)
@@ -133,6 +159,10 @@ def default_instances():
     # A/B: the incremental form with opaque (loop-variant) constant offsets, option variant=6
     out.append(inst3(12, 4, 10, refs=True, fb=True, variant=6, opq=True))
     out.append(inst3(4, 1, 20, refs=False, fb=True, variant=6, opq=True))
+    # A/B: the plain state layout (x and t entirely in tensor memory, 8 warps per SM) on the quadrotor shape, option variant=9
+    out.append(inst3(12, 4, 10, refs=True, fb=True, variant=9, hyb=False))
+    # A/B: time-indexed bounds (run-time offsets, LDC.64) on the quadrotor shape, option variant=8
+    out.append(inst3(12, 4, 10, refs=True, fb=True, variant=8, tib=False))
     # A/B: the direct-form fp32 box kernels (16 / 24 warps per SM, tensor-memory TV) on the headline shapes, option variant=5
     out.append(inst(32, 12, 4, 10, BOX, refs=REFS_L2, variant=5, fb=True, tm=True))
     out.append(inst(32, 12, 4, 10, BOX, refs=REFS_L2, variant=5, tm=True))
@@ -173,7 +203,7 @@ def gen_sources(instances):
                 "// generated by tinympc-matlab_b200/build.py -- do not edit\n"
                 '#include "../tmpc_tpp3.cuh"\n#include "../tmpc_registry.h"\nusing namespace tmpc;\n'
                 f"using Cfg_{n} = Tpp3Cfg<{i['nx']}, {i['nu']}, {i['N']}, {i['block']}, {b(i['refs'])}, {b(i['ppb'])}, {b(i['fb'])}, {b(i['aff'])}, "
-                f"{b(i['opq'])}, {b(i['tib'])}, {FEAT_ENUM[i['feat']]}, {', '.join(str(c) for c in i['cones'])}>;\n"
+                f"{b(i['opq'])}, {b(i['tib'])}, {FEAT_ENUM[i['feat']]}, {', '.join(str(c) for c in i['cones'])}, {i['ttm']}>;\n"
                 f"TMPC_DEFINE_TPP3_ENTRY({n}, Cfg_{n}, {i['feat']}, 32, {i['variant']})\n"
             )
         else:

@@ -27,6 +27,8 @@
 // State per problem: X (x), T (t = x + g_prev, pre-clamp slack: v = clamp(t), g = t - v) in tensor memory (2 nx N columns
 // per thread), U, TZ, DD (u, u + y_prev, -dd) in shared memory.
 #pragma once
+#include <type_traits>
+
 #include "tmpc_tpp2.cuh"
 
 namespace tmpc {
@@ -57,7 +59,7 @@ inline void fill_const_pack3(ConstPack3<NX, NU, NH, NSL, NIL>& c, const double* 
 }
 
 template <int NX_, int NU_, int NH_, int BLOCK_, bool REFS_, bool PPB_, bool FB_, bool AFF_, bool OPQ_, bool TIB_, int FEAT_ = FEAT_BOX,
-          int SCS_ = 0, int SCD_ = 0, int UCS_ = 0, int UCD_ = 0, int NSL_ = 0, int NIL_ = 0>
+          int SCS_ = 0, int SCD_ = 0, int UCS_ = 0, int UCD_ = 0, int NSL_ = 0, int NIL_ = 0, int TTM_ = -1>
 struct Tpp3Cfg {
     using T = float;
     static_assert(FEAT_ == FEAT_BOX || FEAT_ == FEAT_CONSTR, "the incremental form covers box and box + cone + half-space families");
@@ -78,10 +80,22 @@ struct Tpp3Cfg {
     static constexpr bool TIB = TIB_ && FB_ && !PPB_ && !OPQ_;
     static constexpr int SX = NX * NH, SU = NU * (NH - 1);
     using CPack = ConstPack3<NX_, NU_, NH_, NSL_, NIL_>;
-    // shared memory: u, u + y_prev, -dd (+ the pre-projection input slacks of the cone and half-space families)
-    static constexpr int oU = 0, oTZ = SU, oD = 2 * SU, oTZC = 3 * SU, oTZL = 4 * SU, COLS = (CONSTR ? 5 : 3) * SU;
-    // tensor memory: x, t (+ the pre-projection state slacks tc = x + gc_prev, tl = x + gl_prev)
-    static constexpr int TM_COLS_PER_THREAD = (CONSTR ? 4 : 2) * SX;
+    // HYBRID state layout (TTM_ >= 0, box instances): the 2 nx N columns of x and t per thread cap the quadrotor shape at 8 warps
+    // per SM (2 per scheduler, 61 % issue utilisation).  Three observations buy a third warp per scheduler:
+    //   * x_0 is the problem's x0, which the lane holds in registers anyway -- column 0 of X is never stored;
+    //   * column N-1 of X and T is produced last by the forward pass / first sweep column and consumed first by the sweep:
+    //     it lives in registers across the iteration (2 nx of the ~40 registers the 12-warp budget leaves free);
+    //   * the columns of T that no longer fit the tensor-memory share of the warp (TTM_ of them do) go to shared memory.
+    static constexpr bool HYB = TTM_ >= 0;
+    static constexpr int TTM = HYB ? TTM_ : NH_;
+    static_assert(!HYB || (FEAT_ == FEAT_BOX && NH_ >= 3 && TTM_ <= NH_ - 1), "hybrid layout: box instances only");
+    // shared memory: u, u + y_prev, -dd (+ the pre-projection input slacks of the cone and half-space families; + the T columns
+    // TTM .. N-2 of the hybrid layout)
+    static constexpr int oU = 0, oTZ = SU, oD = 2 * SU, oTZC = 3 * SU, oTZL = 4 * SU, oTS = 3 * SU;
+    static constexpr int TS_STEPS = HYB ? (NH_ - 1 - TTM) : 0;
+    static constexpr int COLS = (CONSTR ? 5 : 3) * SU + TS_STEPS * NX;
+    // tensor memory: x, t (+ the pre-projection state slacks tc = x + gc_prev, tl = x + gl_prev); hybrid: x_1 .. x_{N-2}, t_0 .. t_{TTM-1}
+    static constexpr int TM_COLS_PER_THREAD = HYB ? ((NH_ - 2) + TTM) * NX : (CONSTR ? 4 : 2) * SX;
     static_assert(((BLOCK_ / 32 + 3) / 4) * TM_COLS_PER_THREAD <= 512, "the state does not fit the 512 tensor-memory columns");
 };
 
@@ -163,8 +177,13 @@ tpp3_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ typ
     const int tid = threadIdx.x;
     const uint32_t w_id = static_cast<uint32_t>(tid) >> 5;
     const uint32_t tm_base = tmem_base_s + ((32u * (w_id & 3u)) << 16) + (w_id >> 2) * C::TM_COLS_PER_THREAD;
-    const TmemTraj<NX, NH> X{tm_base};            // x(k)
-    const TmemTraj<NX, NH> TT{tm_base + SXL};     // t(k) = x(k) + g(k-1)
+    // hybrid layout: X.base is biased by one column block (step i at base + i NX for i = 1 .. N-2), T follows the N-2 blocks of X
+    const TmemTraj<NX, NH> X{C::HYB ? tm_base - NX : tm_base};                       // x(k)
+    const TmemTraj<NX, NH> TT{C::HYB ? tm_base + (NH - 2) * NX : tm_base + SXL};     // t(k) = x(k) + g(k-1)
+    Traj<T, NX, (C::TS_STEPS > 0 ? C::TS_STEPS : 1), C::oTS, BLOCK> TS(cta_cols, tid);   // hybrid: t columns TTM .. N-2
+    VX xlast, tlast;                              // hybrid: column N-1 of x and t
+    xlast.fill(T(0));
+    tlast.fill(T(0));
     Traj<T, NU, NH - 1, C::oU, BLOCK> U(cta_cols, tid);      // u(k)
     Traj<T, NU, NH - 1, C::oTZ, BLOCK> TZ(cta_cols, tid);    // u(k) + y(k-1)
     Traj<T, NU, NH - 1, C::oD, BLOCK> ND(cta_cols, tid);     // -dd of the last sweep
@@ -199,6 +218,37 @@ tpp3_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ typ
     T res_px = 0, res_dx = 0, res_pu = 0, res_du = 0;
     VX x0v;
     x0v.fill(T(0));
+
+    // ---- state accessors (one code path for both layouts; i is warp-uniform, so the hybrid branches are uniform) ----
+    auto bits_of = [](const VX& v, uint32_t (&r)[NX]) {
+#pragma unroll
+        for (int e = 0; e < NX; ++e) r[e] = __float_as_uint(v.get(e));
+    };
+    auto t_issue = [&](int i, uint32_t (&r)[NX]) {
+        if constexpr (!C::HYB) { TT.issue(i, r); }
+        else {
+            if (i < C::TTM) TT.issue(i, r);
+            else if (i == NH - 1) bits_of(tlast, r);
+            else { VX v; TS.load(i - C::TTM, v); bits_of(v, r); }
+        }
+    };
+    // t column c of the lanes with mine := vals, all other lanes keep theirs.  tcgen05.st has no lane mask: tensor-memory columns
+    // are read - select - written warp-wide; shared-memory and register columns are predicated per lane.
+    auto t_park = [&](int c, const VX& vals, bool mine) {
+        if (!C::HYB || c < C::TTM) {
+            uint32_t r[NX];
+            TmemSpan<NX>::ld(TT.base + c * NX, r);
+            TmemSpan<NX>::wait(r);
+#pragma unroll
+            for (int e = 0; e < NX; ++e) r[e] = mine ? __float_as_uint(vals.get(e)) : r[e];
+            TmemSpan<NX>::st(TT.base + c * NX, r);
+        } else if (c == NH - 1) {
+#pragma unroll
+            for (int e = 0; e < NX; ++e) tlast.set(e, mine ? vals.get(e) : tlast.get(e));
+        } else if (mine) {
+            TS.store(c - C::TTM, vals);
+        }
+    };
 
     auto bt = [](int i) { return C::TIB ? 0 : i; };
     auto xb_pair = [&](int i, int j, size_t pb, P& lo, P& hi) {
@@ -313,12 +363,10 @@ tpp3_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ typ
                         for (int r = 0; r < NX; ++r) xr_last[r] = buf[(GX - 1) * NX + r];   // after the last block: xref_N
 #pragma unroll
                         for (int g = 0; g < GX; ++g) {
-                            uint32_t r[NX];
-                            TmemSpan<NX>::ld(TT.base + (b * GX + g) * NX, r);
-                            TmemSpan<NX>::wait(r);
+                            VX vals;
 #pragma unroll
-                            for (int e = 0; e < NX; ++e) r[e] = mine ? __float_as_uint(-(buf[g * NX + e] * cp.Qd[e])) : r[e];
-                            TmemSpan<NX>::st(TT.base + (b * GX + g) * NX, r);
+                            for (int e = 0; e < NX; ++e) vals.set(e, -(buf[g * NX + e] * cp.Qd[e]));
+                            t_park(b * GX + g, vals, mine);
                         }
                     }
                     {   // PT = -(xref_N' Pinf)' as row pairs of Pinf' (Pinf is row-major in the staged pack)
@@ -331,16 +379,19 @@ tpp3_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ typ
                             for (int j = 0; j < NX / 2; ++j) acc.p[j] = fmas(mk2(cP[r * NX + 2 * j], cP[r * NX + 2 * j + 1]), nxr, acc.p[j]);
                             if constexpr (NX & 1) acc.t = fmas(cP[r * NX + NX - 1], nxr, acc.t);
                         }
-                        uint32_t r[NX];
-                        TmemSpan<NX>::ld(TT.base + (NH - 1) * NX, r);
-                        TmemSpan<NX>::wait(r);
-#pragma unroll
-                        for (int e = 0; e < NX; ++e) r[e] = mine ? __float_as_uint(acc.get(e)) : r[e];
-                        TmemSpan<NX>::st(TT.base + (NH - 1) * NX, r);
+                        t_park(NH - 1, acc, mine);
                     }
                     tmem_wait_st();
                 } else {
-                    TT.reset(mine);
+                    if constexpr (!C::HYB) {
+                        TT.reset(mine);
+                    } else {
+                        VX zero;
+                        zero.fill(T(0));
+#pragma unroll 1
+                        for (int c = 0; c < NH; ++c) t_park(c, zero, mine);
+                        tmem_wait_st();
+                    }
                 }
                 if (mine) {
                     // TZ := -(Uref .* R), -dd := -d0 (first backward pass on the zero workspace, tiny_api.cpp:68-105 + admm.cpp:13-20)
@@ -393,18 +444,22 @@ tpp3_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ typ
             for (int j = 0; j < NX / 2; ++j) dx.p[j] = ff ? x0v.p[j] : mk2(T(0), T(0));
             dx.t = ff ? x0v.t : T(0);
             uint32_t xr[NX];
-            X.issue(0, xr);
+            if constexpr (!C::HYB) X.issue(0, xr);
+            // hybrid layout: x_0 = x0 is not stored (its update is the identity), x_{N-1} is a register column updated after the loop
+            constexpr int FEND = C::HYB ? NH - 1 : NH;
 #pragma unroll 1
-            for (int i = 0; i < NH; ++i) {
+            for (int i = 0; i < FEND; ++i) {
                 const int zf = C::OPQ ? opaque_zero4() : 0;
-                VX xo;
-                TmemTraj<NX, NH>::complete(xr, xo);
+                if (!C::HYB || i >= 1) {
+                    VX xo;
+                    TmemTraj<NX, NH>::complete(xr, xo);
 #pragma unroll
-                for (int j = 0; j < NX / 2; ++j) xo.p[j] = addv(sel0(ff, xo.p[j]), dx.p[j]);
-                if constexpr (NX & 1) xo.t = sel0(ff, xo.t) + dx.t;
-                X.store(i, xo);
+                    for (int j = 0; j < NX / 2; ++j) xo.p[j] = addv(sel0(ff, xo.p[j]), dx.p[j]);
+                    if constexpr (NX & 1) xo.t = sel0(ff, xo.t) + dx.t;
+                    X.store(i, xo);
+                }
                 if (i < NH - 1) {
-                    X.issue(i + 1, xr);   // lands behind the mat-vecs of this step
+                    if (!C::HYB || i + 1 <= NH - 2) X.issue(i + 1, xr);   // lands behind the mat-vecs of this step
                     // du_i = -Kinf dx_i - dd_i (admm.cpp:29)
                     VU du;
                     ND.load(i, du);
@@ -428,6 +483,11 @@ tpp3_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ typ
                     mv_acc<NX, NU>(cp.B, zf, du, dxn);
                     dx = dxn;
                 }
+            }
+            if constexpr (C::HYB) {
+#pragma unroll
+                for (int j = 0; j < NX / 2; ++j) xlast.p[j] = addv(sel0(ff, xlast.p[j]), dx.p[j]);
+                if constexpr (NX & 1) xlast.t = sel0(ff, xlast.t) + dx.t;
             }
             X.stores_done();
         }
@@ -487,9 +547,24 @@ tpp3_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ typ
         // after the input column's work, which hides their latency
         constexpr bool HAS_TC = C::CONSTR && C::SCD > 0, HAS_TL = C::CONSTR;
         uint32_t rx[NX], rt[NX], rc[HAS_TC ? NX : 1], rl[HAS_TL ? NX : 1];
-        auto issue_x = [&](int i) {   // every issued load is completed below (column 0 has no cone / half-space work)
-            X.issue(i, rx);
-            TT.issue(i, rt);
+        auto issue_x = [&](int i, auto col0) {   // every issued load is completed below (column 0 has no cone / half-space work)
+            if constexpr (!C::HYB) {
+                X.issue(i, rx);
+                TT.issue(i, rt);
+            } else {   // loop columns N-2 .. 0 only: x_i from tensor memory (x_0 = x0 is taken from registers at the point of use),
+                       // t_i from tensor memory or, beyond the warp's share of it, from shared memory
+                if constexpr (!decltype(col0)::value) X.issue(i, rx);
+                if (i < C::TTM) {
+                    TT.issue(i, rt);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < NX / 2; ++j) {
+                        const P v = TS.getp(i - C::TTM, j);
+                        rt[2 * j] = __float_as_uint(v.x); rt[2 * j + 1] = __float_as_uint(v.y);
+                    }
+                    if constexpr (NX & 1) rt[NX - 1] = __float_as_uint(TS.gett(i - C::TTM));
+                }
+            }
             if constexpr (HAS_TC) { if (i > 0) TC.issue(i, rc); }
             if constexpr (HAS_TL) { if (i > 0 && (C::NSL > 0 || lin_x)) TL.issue(i, rl); }
         };
@@ -506,9 +581,14 @@ tpp3_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ typ
         VX dp;
         {   // column N-1: dp_N = -(xref_N' Pinf)' [first sweep] - rho dw_N   (admm.cpp:238-246)
             VX xv, traw, tnew;
-            issue_x(NH - 1);
-            TmemTraj<NX, NH>::complete(rx, xv);
-            TmemTraj<NX, NH>::complete(rt, traw);
+            if constexpr (C::HYB) {
+                xv = xlast;
+                traw = tlast;
+            } else {
+                issue_x(NH - 1, std::false_type{});
+                TmemTraj<NX, NH>::complete(rx, xv);
+                TmemTraj<NX, NH>::complete(rt, traw);
+            }
 #pragma unroll
             for (int j = 0; j < NX / 2; ++j) {
                 P lo, hi;
@@ -520,13 +600,15 @@ tpp3_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ typ
                 xb_tail(NH - 1, pbx, lo, hi);
                 slack(traw.t, xv.t, lo, hi, rpx, rdx, tnew.t, dp.t);
             }
-            TT.store(NH - 1, tnew);
+            if constexpr (C::HYB) tlast = tnew; else TT.store(NH - 1, tnew);
             extra_x(NH - 1, xv, dp);
         }
-#pragma unroll 1
-        for (int i = NH - 2; i >= 0; --i) {
+        // One column of the sweep.  col0 (compile-time): the peeled column 0 of the hybrid layout -- x_0 = x0 comes from registers,
+        // and the Riccati step is skipped altogether (p_0 and q_0 are never used, admm.cpp:17 reads p_{i+1}).
+        auto sweep_col = [&](int i, auto col0) {
+            constexpr bool COL0 = decltype(col0)::value;
             const int zb = C::OPQ ? opaque_zero4() : 0;
-            issue_x(i);
+            issue_x(i, col0);
             // The two products with dp_{i+1} start from zero and are added to their right-hand sides afterwards: they depend on
             // nothing of this column, so they run under the latency of the column's tensor-/shared-memory loads and the scheduler
             // is free to weave the slack updates (ALU pipe) into their FFMA2 stream (FMA pipe).  Measured: rocket +6 %,
@@ -537,7 +619,7 @@ tpp3_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ typ
             akp.fill(T(0));
             btp.fill(T(0));
             if constexpr (SPLIT) {
-                mv_acc<NX, NX>(cp.AK, zb, dp, akp);
+                if constexpr (!COL0) mv_acc<NX, NX>(cp.AK, zb, dp, akp);
                 mv_acc<NU, NX>(cp.BT, zb, dp, btp);
             }
             // ---- input column i: dr_i = -(Uref .* R) [first sweep] - rho dw   (admm.cpp:227-236)
@@ -578,8 +660,13 @@ tpp3_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ typ
             }
             // ---- state column i: dq_i = -(Xref .* Q) [first sweep] - rho dw;  dp_i = dq_i + AmBKt dp - Kinf' dr   (admm.cpp:18)
             VX xv, traw, tnew, dq;
-            TmemTraj<NX, NH>::complete(rx, xv);
-            TmemTraj<NX, NH>::complete(rt, traw);
+            if constexpr (C::HYB) {
+                TmemTraj<NX, NH>::complete(rt, traw);
+                if constexpr (COL0) xv = x0v; else TmemTraj<NX, NH>::complete(rx, xv);
+            } else {
+                TmemTraj<NX, NH>::complete(rx, xv);
+                TmemTraj<NX, NH>::complete(rt, traw);
+            }
 #pragma unroll
             for (int j = 0; j < NX / 2; ++j) {
                 P lo, hi;
@@ -591,20 +678,29 @@ tpp3_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ typ
                 xb_tail(i, pbx, lo, hi);
                 slack(traw.t, xv.t, lo, hi, rpx, rdx, tnew.t, dq.t);
             }
-            TT.store(i, tnew);
-            // p_0 is never used (admm.cpp:17 reads p_{i+1}), hence neither are q_0 and the cone / half-space slacks of x_0; the
-            // Riccati step of column 0 is computed all the same, which keeps the loop body one basic block.
-            if (C::CONSTR && i > 0) extra_x(i, xv, dq);
-            if constexpr (SPLIT) {
-#pragma unroll
-                for (int j = 0; j < NX / 2; ++j) dq.p[j] = addv(dq.p[j], akp.p[j]);
-                if constexpr (NX & 1) dq.t += akp.t;
+            if constexpr (C::HYB) {
+                if (i < C::TTM) TT.store(i, tnew); else TS.store(i - C::TTM, tnew);
             } else {
-                mv_acc<NX, NX>(cp.AK, zb, dp, dq);
+                TT.store(i, tnew);
             }
-            mv_acc<NX, NU>(cp.NKT, zb, dr, dq);
-            dp = dq;
-        }
+            // p_0 is never used (admm.cpp:17 reads p_{i+1}), hence neither are q_0 and the cone / half-space slacks of x_0; in the
+            // rolled loop the Riccati step of column 0 is computed all the same, which keeps the loop body one basic block.
+            if (C::CONSTR && i > 0) extra_x(i, xv, dq);
+            if constexpr (!COL0) {
+                if constexpr (SPLIT) {
+#pragma unroll
+                    for (int j = 0; j < NX / 2; ++j) dq.p[j] = addv(dq.p[j], akp.p[j]);
+                    if constexpr (NX & 1) dq.t += akp.t;
+                } else {
+                    mv_acc<NX, NX>(cp.AK, zb, dp, dq);
+                }
+                mv_acc<NX, NU>(cp.NKT, zb, dr, dq);
+                dp = dq;
+            }
+        };
+#pragma unroll 1
+        for (int i = NH - 2; i >= (C::HYB ? 1 : 0); --i) sweep_col(i, std::false_type{});
+        if constexpr (C::HYB) sweep_col(0, std::true_type{});
         TT.stores_done();
 
         // ------------------------------------------------- termination (admm.cpp:253-271, 364-388)
@@ -628,7 +724,11 @@ tpp3_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ typ
 #pragma unroll 1
             for (int i = 0; i < NH; ++i) {
                 VX v;
-                TT.load(i, v);
+                {
+                    uint32_t r[NX];
+                    t_issue(i, r);
+                    TmemTraj<NX, NH>::complete(r, v);
+                }
                 if (fin) {
 #pragma unroll
                     for (int j = 0; j < NX / 2; ++j) { P lo, hi; xb_pair(i, j, pbx, lo, hi); v.p[j] = clampv(v.p[j], lo, hi); }
