@@ -159,10 +159,17 @@ def default_instances():
     # A/B: the incremental form with opaque (loop-variant) constant offsets, option variant=6
     out.append(inst3(12, 4, 10, refs=True, fb=True, variant=6, opq=True))
     out.append(inst3(4, 1, 20, refs=False, fb=True, variant=6, opq=True))
-    # A/B: the plain state layout (x and t entirely in tensor memory, 8 warps per SM) on the quadrotor shape, option variant=9
-    out.append(inst3(12, 4, 10, refs=True, fb=True, variant=9, hyb=False))
+    # The plain state layout (x and t entirely in tensor memory, 8 warps per SM) of the shapes whose default is the hybrid one: fewer
+    # instructions per iteration and a 25 % shorter iteration of a lone warp.  The dispatcher picks it for batches that fit one
+    # wave of it (tmpc_capi.cu, kLatencyVariant); option variant=9 forces it.
+    for (nx, nu, N) in shapes:
+        if plan_hybrid(nx, nu, N) is not None and plan_hybrid(nx, nu, N)[0] > inst3(nx, nu, N)["block"] // 32:
+            for fb in (True, False):
+                out.append(inst3(nx, nu, N, refs=True, fb=fb, variant=9))
+                out.append(inst3(nx, nu, N, refs=False, fb=fb, variant=9))
+            out.append(inst3(nx, nu, N, refs=True, ppb=True, variant=9))
     # A/B: time-indexed bounds (run-time offsets, LDC.64) on the quadrotor shape, option variant=8
-    out.append(inst3(12, 4, 10, refs=True, fb=True, variant=8, tib=False))
+    out.append(inst3(12, 4, 10, refs=True, fb=True, variant=8, tib=False, hyb=True))
     # A/B: the direct-form fp32 box kernels (16 / 24 warps per SM, tensor-memory TV) on the headline shapes, option variant=5
     out.append(inst(32, 12, 4, 10, BOX, refs=REFS_L2, variant=5, fb=True, tm=True))
     out.append(inst(32, 12, 4, 10, BOX, refs=REFS_L2, variant=5, tm=True))

@@ -31,6 +31,7 @@ namespace {
 constexpr int kFeatBox = 0, kFeatConstr = 1, kFeatAdapt = 2;
 constexpr int kMaxChunks = 64;
 constexpr int kStreams = 3;
+constexpr int kLatencyVariant = 9;        // registry variant of the plain-layout (latency) instances, see enqueue()
 constexpr int kMaxStreamChunks = 256;    // streamed pipeline: [0] work counter, [1] arrival watermark, [2 + c] finished problems of chunk c
 
 struct DevBuf {
@@ -228,6 +229,12 @@ int enqueue(tinympc_cuda_solver* s, DeviceCtx& d, const tinympc_cuda_batch_in& i
     const bool refs = in.Xref || in.Uref;
     int bits = s->precision;
     const KernelEntry* ke = s->force_wpp ? nullptr : find_kernel(f, bits, ppb, refs, s->variant);
+    // Small batches: where the default instance uses the hybrid state layout (more resident warps, more instructions per
+    // iteration), a batch that fits one wave of the plain-layout instance is latency bound and runs that one.
+    if (ke && s->variant == 0 && bits == 32) {
+        const KernelEntry* kl = find_kernel(f, bits, ppb, refs, kLatencyVariant);
+        if (kl && kl->variant == kLatencyVariant && kl->block < ke->block && in.batch <= d.sm_count * kl->block) ke = kl;
+    }
     // mixed mode needs the specialised kernels in both precisions; any other shape runs entirely in fp64 (exact as well)
     const KernelEntry* ke64 = nullptr;
     const bool mixed = s->mixed_band > 0 && bits == 32;
