@@ -190,6 +190,17 @@ int upload_family(tinympc_cuda_solver* s) {
 }
 
 // Launch one thread-per-problem kernel instance (persistent grid, a multiple of the SM count).
+// find_kernel + the small-batch rule: where the default instance uses the hybrid state layout (more resident warps, more
+// instructions per iteration), a batch that fits one wave of the plain-layout instance is latency bound and runs that one.
+const KernelEntry* pick_kernel(const tinympc_cuda_solver* s, const DeviceCtx& d, const Family& f, int bits, bool ppb, bool refs, int batch) {
+    const KernelEntry* ke = find_kernel(f, bits, ppb, refs, s->variant);
+    if (ke && s->variant == 0 && bits == 32) {
+        const KernelEntry* kl = find_kernel(f, bits, ppb, refs, kLatencyVariant);
+        if (kl && kl->variant == kLatencyVariant && kl->block < ke->block && batch <= d.sm_count * kl->block) ke = kl;
+    }
+    return ke;
+}
+
 int launch_tpp(tinympc_cuda_solver* s, DeviceCtx& d, const KernelEntry* ke, SolveParams& p, DevBuf& rb, int bits, int* counter, cudaStream_t st) {
     const Family& f = s->fam;
     const size_t smem = ke->smem_bytes(f.L.cold_size);
@@ -228,13 +239,7 @@ int enqueue(tinympc_cuda_solver* s, DeviceCtx& d, const tinympc_cuda_batch_in& i
         return fail(s, TINYMPC_CUDA_EINVAL, "bound constraints are enabled but neither the family nor the batch supplies bounds");
     const bool refs = in.Xref || in.Uref;
     int bits = s->precision;
-    const KernelEntry* ke = s->force_wpp ? nullptr : find_kernel(f, bits, ppb, refs, s->variant);
-    // Small batches: where the default instance uses the hybrid state layout (more resident warps, more instructions per
-    // iteration), a batch that fits one wave of the plain-layout instance is latency bound and runs that one.
-    if (ke && s->variant == 0 && bits == 32) {
-        const KernelEntry* kl = find_kernel(f, bits, ppb, refs, kLatencyVariant);
-        if (kl && kl->variant == kLatencyVariant && kl->block < ke->block && in.batch <= d.sm_count * kl->block) ke = kl;
-    }
+    const KernelEntry* ke = s->force_wpp ? nullptr : pick_kernel(s, d, f, bits, ppb, refs, in.batch);
     // mixed mode needs the specialised kernels in both precisions; any other shape runs entirely in fp64 (exact as well)
     const KernelEntry* ke64 = nullptr;
     const bool mixed = s->mixed_band > 0 && bits == 32;
@@ -495,7 +500,7 @@ int run_shard(tinympc_cuda_solver* s, DeviceCtx& d, const tinympc_cuda_batch_in&
 
     // single-launch streamed pipeline: plain (not mixed) solves on a thread-per-problem kernel that honours the watermark
     if (s->streamed && !(s->mixed_band > 0 && s->precision == 32) && !s->force_wpp && stream_memops().ok) {
-        const KernelEntry* ke = find_kernel(f, s->precision, ppb, in.Xref || in.Uref, s->variant);
+        const KernelEntry* ke = pick_kernel(s, d, f, s->precision, ppb, in.Xref || in.Uref, n);
         // auto (0): the ramped chunk layout for shards of >= 2^16 problems, else equal chunks of >= 2^14 problems
         int nst = s->chunks > 0 ? std::min(s->chunks, kMaxGranules) : (n >= (1 << 16) ? 0 : n / 16384);
         if (ke && ke->streaming && (nst == 0 || nst >= 2) && (ppb || f.shared_bounds_ok))
