@@ -31,6 +31,10 @@
 
 #include "tmpc_tpp2.cuh"
 
+#ifndef TMPC_TUNROLL_SMALL
+#define TMPC_TUNROLL_SMALL 10
+#endif
+
 namespace tmpc {
 
 enum : int { REFS_STATE = 3 };   // registry "refs" code: reference terms parked in the state columns
@@ -87,6 +91,11 @@ struct Tpp3Cfg {
     //     it lives in registers across the iteration (2 nx of the ~40 registers the 12-warp budget leaves free);
     //   * the columns of T that no longer fit the tensor-memory share of the warp (TTM_ of them do) go to shared memory.
     static constexpr bool HYB = TTM_ >= 0;
+    // The time loops stay rolled where a step is hundreds of instructions (the body must fit the instruction cache); the small
+    // shapes unroll them partially -- with nx = 4 a step is ~85 instructions and loop control was 28 % of the cartpole kernel
+    // (measured on the N = 20 cartpole batch: rolled 119.9, x4 137.6, x10 148.5, fully unrolled 145.0 M solves/s; the rocket
+    // instance with its ~600-instruction column loses 4 % when unrolled x3 and stays rolled).
+    static constexpr int TUNROLL = (NX_ <= 4 && FEAT_ == FEAT_BOX) ? TMPC_TUNROLL_SMALL : 1;
     static constexpr int TTM = HYB ? TTM_ : NH_;
     static_assert(!HYB || (FEAT_ == FEAT_BOX && NH_ >= 3 && TTM_ <= NH_ - 1), "hybrid layout: box instances only");
     // shared memory: u, u + y_prev, -dd (+ the pre-projection input slacks of the cone and half-space families; + the T columns
@@ -447,7 +456,7 @@ tpp3_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ typ
             if constexpr (!C::HYB) X.issue(0, xr);
             // hybrid layout: x_0 = x0 is not stored (its update is the identity), x_{N-1} is a register column updated after the loop
             constexpr int FEND = C::HYB ? NH - 1 : NH;
-#pragma unroll 1
+#pragma unroll C::TUNROLL
             for (int i = 0; i < FEND; ++i) {
                 const int zf = C::OPQ ? opaque_zero4() : 0;
                 if (!C::HYB || i >= 1) {
@@ -698,7 +707,7 @@ tpp3_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ typ
                 dp = dq;
             }
         };
-#pragma unroll 1
+#pragma unroll C::TUNROLL
         for (int i = NH - 2; i >= (C::HYB ? 1 : 0); --i) sweep_col(i, std::false_type{});
         if constexpr (C::HYB) sweep_col(0, std::true_type{});
         TT.stores_done();
