@@ -114,9 +114,8 @@ class ClockSampler:
             self.stop_flag.wait(0.005)
 
     def _run(self):
-        nv = self._nvml_handle()
-        if nv is not None:
-            return self._run_nvml(*nv)
+        if self.nv is not None:
+            return self._run_nvml(*self.nv)
         while not self.stop_flag.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
@@ -128,6 +127,7 @@ class ClockSampler:
             self.stop_flag.wait(0.02)
 
     def __enter__(self):
+        self.nv = self._nvml_handle()       # NVML initialisation (~0.1 s) happens here, before the timed region
         self.t = threading.Thread(target=self._run, daemon=True)
         self.t.start()
         return self
