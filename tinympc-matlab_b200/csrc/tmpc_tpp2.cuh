@@ -772,6 +772,7 @@ tpp2_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ typ
     bool pending = false;   // holds a claimed problem (claim) whose inputs have not landed yet (streamed host pipeline)
     int claim = 0, seen = 0, unpub = -1;   // seen: cached arrival watermark; unpub: finished problem not yet counted for its chunk
     int k = 0;              // ADMM iterations done on the current problem
+    int wit = 0;            // passes of this warp since it last was idle (warp-uniform): start phase of the adaptive-rho instances
     int next_check = check_every;   // next iteration count at which termination is evaluated (iter % check == 0)
     T res_px = 0, res_dx = 0, res_pu = 0, res_du = 0;   // last evaluated residuals (admm.cpp:257-260)
     // adaptive rho state (cache->rho and the Taylor offset of Kinf/Pinf); *_lc are the values
@@ -825,8 +826,16 @@ tpp2_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ typ
             publish_done(prm, unpub);
             const bool want = !active && !exhausted && !pending;
             unsigned mw = __ballot_sync(FULL, want);
+            // Adaptive rho: problems start only on every 5th pass of the warp.  The adaptation (rho_benchmark.cpp:146-250 in
+            // block form: ~96 extra FFMA2 per time step) is due at the problem's own iterations 5, 10, ... (admm.cpp:339); with
+            // lanes at arbitrary phases some lane is due on practically every pass and the whole warp pays for it every time,
+            // with aligned phases it pays on one pass in five.  A lane waits 2.5 passes on average, about what the batched refill
+            // makes it wait anyway.
+            if (!__any_sync(FULL, active)) wit = 0;     // nobody to stay aligned with
+            const bool phase_ok = !(C::ADAPT && prm.adaptive_rho) || (wit % 5 == 0);
+            if (!phase_ok) mw = 0;
             // batched refill (SolveParams::refill_min; the model behind the adaptive threshold is spelled out in tmpc_tpp3.cuh)
-            if (mw && __any_sync(FULL, active)) {
+            if (mw && __any_sync(FULL, active) && !(C::ADAPT && prm.adaptive_rho)) {
                 int m = prm.refill_min;
                 if (m <= 0) {
                     const int sum_k = __reduce_add_sync(FULL, last_k);
@@ -852,7 +861,7 @@ tpp2_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ typ
                 }
             }
             // a claimed problem starts once its inputs have landed (always, unless the host streams the batch in)
-            const bool mine = pending && problem_ready(prm, claim, seen);
+            const bool mine = phase_ok && pending && problem_ready(prm, claim, seen);
             const unsigned m = __ballot_sync(FULL, mine);
             if (m) {
                 if (mine) {
@@ -1202,6 +1211,7 @@ tpp2_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ typ
         }
         TV.stores_done();
         k += 1;   // work->iter += 1 (admm.cpp:328)
+        wit += 1;
 
         // ------------------------------------------------- adaptive rho (admm.cpp:331-357), i = k-1
         rho_lc = rho; dlt_lc = dlt;   // update_linear_cost of this iteration ran with the pre-adaptation cache
