@@ -94,3 +94,55 @@ def test_setup_validation_and_settings_roundtrip(tm):
     assert d[0] == 1e-3 and i[0] == 77 and i[2] == 1 and i[3] == 1
     with pytest.raises(NotImplementedError):
         s.codegen("out")
+
+
+def test_bench_flop_model_matches_the_survey_table():
+    """bench.py's roofline numerator: SURVEY 8d box-only counts, plus the per-family and adaptive-rho terms of the same table."""
+    import importlib
+    import sys
+    from pathlib import Path
+    sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+    bench = importlib.import_module("bench")
+    P = importlib.import_module("tinympc-matlab_b200.problems")
+    q, c, r, qa = P.quadrotor(), P.cartpole(), P.rocket(), P.quadrotor(adaptive=True)
+    assert bench.flops_per_iter(q.nx, q.nu, q.N) == 12240 and bench.flops_per_iter(q.nx, q.nu, q.N, q) == 12240
+    assert bench.flops_per_iter(c.nx, c.nu, c.N, c) == 3828
+    assert bench.flops_per_iter(r.nx, r.nu, r.N) == 4500
+    # + 6 per element of the 4 enabled families, 20 per (step, cone), 4 dim + 2 per (step, row)
+    assert bench.flops_per_iter(r.nx, r.nu, r.N, r) == 4500 + 2 * 6 * (60 + 27) + 20 * (10 + 9) + 26 * 10 + 14 * 9
+    assert bench.flops_per_iter(qa.nx, qa.nu, qa.N, qa) == 12240 + (9 * (576 + 192) + 288 + 12 * 156) // 5
+    assert bench.bytes_per_solve(12, 4, 10) == 1304 and bench.bytes_per_solve(4, 1, 20) == 816 and bench.bytes_per_solve(6, 3, 10) == 728
+
+
+def test_hybrid_layout_plan_fits_the_sm():
+    """build.py's planner of the hybrid state layout (tmpc_tpp3.cuh): tensor-memory columns, shared memory and registers of the
+    chosen (warps, t columns in tensor memory) fit one SM for every compiled shape."""
+    import importlib.util
+    from pathlib import Path
+    spec = importlib.util.spec_from_file_location("tmpc_build", Path(__file__).resolve().parents[1] / "tinympc-matlab_b200" / "build.py")
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    assert b.plan_hybrid(12, 4, 10) == (12, 6)
+    for nx, nu, N in [(12, 4, 10), (4, 1, 20), (4, 1, 10), (6, 3, 10)]:
+        warps, ttm = b.plan_hybrid(nx, nu, N)
+        assert warps % 4 == 0 and 0 <= ttm <= N - 1
+        assert (warps // 4) * ((N - 2) + ttm) * nx <= 512
+        smem = (3 * nu * (N - 1) + (N - 1 - ttm) * nx) * warps * 32 * 4 + 1024 + b.pack_elems(nx, nu, N) * 4
+        assert smem <= 227 * 1024
+    names = [b.name_of(i) for i in b.default_instances()]
+    assert len(names) == len(set(names)), "two kernel instances with the same name would be one symbol at link time"
+
+
+def test_generated_kernel_instances_are_distinct_template_instantiations():
+    """Every generated translation unit must instantiate a DIFFERENT kernel template: two variants with the same template
+    arguments would be one weak symbol at link time, and the `variant` option would silently run the other one's code."""
+    import re
+    from pathlib import Path
+    gen = Path(__file__).resolve().parents[1] / "tinympc-matlab_b200" / "csrc" / "gen"
+    seen = {}
+    for f in sorted(gen.glob("tpp*.cu")):
+        m = re.search(r"using \w+ = (Tpp\d?Cfg<[^;]*>);", f.read_text())
+        assert m, f.name
+        assert m.group(1) not in seen, f"{f.name} and {seen[m.group(1)]} instantiate the same kernel"
+        seen[m.group(1)] = f.name
+    assert len(seen) > 40
