@@ -136,9 +136,15 @@ def test_hybrid_layout_plan_fits_the_sm():
 def test_generated_kernel_instances_are_distinct_template_instantiations():
     """Every generated translation unit must instantiate a DIFFERENT kernel template: two variants with the same template
     arguments would be one weak symbol at link time, and the `variant` option would silently run the other one's code."""
+    import importlib.util
     import re
     from pathlib import Path
-    gen = Path(__file__).resolve().parents[1] / "tinympc-matlab_b200" / "csrc" / "gen"
+    pkg = Path(__file__).resolve().parents[1] / "tinympc-matlab_b200"
+    spec = importlib.util.spec_from_file_location("tmpc_build", pkg / "build.py")
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    b.gen_sources(b.default_instances())          # idempotent: writes csrc/gen/*.cu only where the text changed
+    gen = pkg / "csrc" / "gen"
     seen = {}
     for f in sorted(gen.glob("tpp*.cu")):
         m = re.search(r"using \w+ = (Tpp\d?Cfg<[^;]*>);", f.read_text())
