@@ -1,4 +1,5 @@
-// tmpc_tpp3.cuh -- batched ADMM throughput kernel for sm_100a, INCREMENTAL ("delta") form, fp32, box constraints.
+// tmpc_tpp3.cuh -- batched ADMM throughput kernel for sm_100a, INCREMENTAL ("delta") form, fp32: box constraints, and box +
+// one second-order cone per side + linear inequalities (the rocket family).
 //
 // Same path and mapping as tmpc_tpp2.cuh (one thread = one problem, packed f32x2 arithmetic, family matrices in the
 // kernel-parameter constant bank, state in tensor memory + shared memory, lane refill); reference: admm.cpp:274-389.
@@ -25,7 +26,11 @@
 // columns are free until the first sweep overwrites them): no scratch buffer, no reference traffic per iteration.
 //
 // State per problem: X (x), T (t = x + g_prev, pre-clamp slack: v = clamp(t), g = t - v) in tensor memory (2 nx N columns
-// per thread), U, TZ, DD (u, u + y_prev, -dd) in shared memory.
+// per thread), U, TZ, DD (u, u + y_prev, -dd) in shared memory; cone / half-space families add their pre-projection slacks
+// (TC, TL in tensor memory, TZC, TZL in shared memory).  The HYBRID layout (Tpp3Cfg::HYB) spreads X and T over registers,
+// tensor memory and shared memory to fit a third warp per scheduler on the quadrotor shape; see the comment there.
+// Throughput devices shared with tmpc_tpp2.cuh: persistent grid, batched lane refill (adaptive threshold), streamed host
+// pipeline hooks (arrival watermark, per-chunk completion counters).
 #pragma once
 #include <type_traits>
 
