@@ -240,3 +240,26 @@ def test_multi_device_split_is_bit_identical(family, streamed, capi, oracle_mod,
     for r in res[1:]:
         for k in ("iter", "status", "x", "u"):
             assert np.array_equal(res[0][k], r[k]), f"{family}: field {k} changes with the device split"
+
+
+@pytest.mark.parametrize("which", ["xref_only", "uref_only", "none"])
+def test_partial_references_on_the_hybrid_layout(which, capi, oracle_mod, problems):
+    """Xref without Uref, Uref without Xref, neither: the reference-parking code of the refill pass has a branch per case
+    (tensor-memory / shared-memory / register columns of the hybrid layout).  60 000 problems, so the hybrid instance runs;
+    a 4 000-problem prefix is compared with the oracle, the rest through the plain-layout instance (bit for bit)."""
+    p = problems.quadrotor()
+    B = 60000
+    b = problems.make_batch(p, B, 1.0, seed=57)
+    Uref = (0.05 * np.random.default_rng(3).standard_normal((B, p.N - 1, p.nu))).astype(np.float32)
+    bb = problems.Batch(b.x0, b.Xref if which == "xref_only" else None, Uref if which == "uref_only" else None)
+    r = solve_gpu(capi, oracle_mod, p, bb, 32)
+    rp = solve_gpu(capi, oracle_mod, p, bb, 32, variant=9)          # plain layout, same arithmetic
+    assert r["kernel"] != rp["kernel"]
+    for k in ("iter", "status", "x", "u"):
+        assert np.array_equal(r[k], rp[k]), f"{which}: hybrid and plain layouts disagree in {k}"
+    n = 4000
+    g = oracle_mod.solve_batch(p, bb.slice(0, n), "ref" if oracle_mod.available("ref") else "port")
+    rs = {k: r[k][:n] for k in ("iter", "status", "x", "u")}
+    rs["kernel"] = r["kernel"]
+    flips, dx, du = compare(rs, g, 32, f"quadrotor {which}", max_flip_frac=FLIP_BOUND["quadrotor"])
+    print(f"\n[parity] quadrotor {which}: hybrid == plain bit for bit; {flips}/{n} count flips, max|dx|={dx:.2e} kernel={r['kernel']}")
