@@ -263,3 +263,41 @@ def test_partial_references_on_the_hybrid_layout(which, capi, oracle_mod, proble
     rs["kernel"] = r["kernel"]
     flips, dx, du = compare(rs, g, 32, f"quadrotor {which}", max_flip_frac=FLIP_BOUND["quadrotor"])
     print(f"\n[parity] quadrotor {which}: hybrid == plain bit for bit; {flips}/{n} count flips, max|dx|={dx:.2e} kernel={r['kernel']}")
+
+
+def test_hybrid_layout_with_per_problem_and_time_varying_bounds(capi, oracle_mod, problems):
+    """The two other hybrid-layout instances of the quadrotor shape at a batch size that selects them (> one wave of the plain
+    layout): per-problem bounds (tiled golden case) and shared bounds that vary over the horizon / do not contain 0 (no fast-box
+    shortcut).  Hybrid == plain layout bit for bit, and both match the reference."""
+    # (a) per-problem bounds
+    p, b0, g = cases.load("batch_quadrotor_perproblem_bounds")
+    reps = 60000 // b0.size + 1
+    tile = lambda a: None if a is None else np.ascontiguousarray(np.concatenate([a] * reps, axis=0))
+    bb = problems.Batch(tile(b0.x0), tile(b0.Xref), tile(b0.Uref), tile(b0.x_min), tile(b0.x_max), tile(b0.u_min), tile(b0.u_max))
+    r = solve_gpu(capi, oracle_mod, p, bb, 32)
+    rp = solve_gpu(capi, oracle_mod, p, bb, 32, variant=9)
+    assert "ppb" in r["kernel"] and r["kernel"] != rp["kernel"]
+    for k in ("iter", "status", "x", "u"):
+        assert np.array_equal(r[k], rp[k]), f"per-problem bounds: hybrid and plain layouts disagree in {k}"
+    n = b0.size
+    same = r["iter"][:n] == g["iter"]
+    assert same.mean() >= 0.95 and np.abs(r["x"][:n][same] - g["x"][same]).max() <= X_TOL_F32 * max(1.0, float(np.abs(g["x"]).max()))
+    assert np.array_equal(r["iter"][:n], r["iter"][7 * n:8 * n]) and np.array_equal(r["x"][:n], r["x"][7 * n:8 * n])
+    # (b) shared bounds varying over the horizon, lower input bound above 0 on the last steps
+    q = problems.quadrotor()
+    u_min, u_max = q.u_min.copy(), q.u_max.copy()
+    u_max[:] = np.linspace(0.5, 0.3, q.N - 1)[:, None]
+    u_min[-3:] = 0.01
+    q2 = q.with_(u_min=u_min, u_max=u_max)
+    b = problems.make_batch(q2, 60000, 1.0, seed=91)
+    r = solve_gpu(capi, oracle_mod, q2, b, 32)
+    rp = solve_gpu(capi, oracle_mod, q2, b, 32, variant=9)
+    assert "_fb" not in r["kernel"] and r["kernel"] != rp["kernel"], r["kernel"]
+    for k in ("iter", "status", "x", "u"):
+        assert np.array_equal(r[k], rp[k]), f"time-varying bounds: hybrid and plain layouts disagree in {k}"
+    n = 3000
+    gg = oracle_mod.solve_batch(q2, b.slice(0, n), "ref" if oracle_mod.available("ref") else "port")
+    rs = {k: r[k][:n] for k in ("iter", "status", "x", "u")}
+    rs["kernel"] = r["kernel"]
+    flips, dx, du = compare(rs, gg, 32, "quadrotor time-varying bounds", max_flip_frac=0.01)
+    print(f"\n[parity] quadrotor hybrid ppb + time-varying bounds: == plain bit for bit; {flips}/{n} count flips, max|dx|={dx:.2e} kernel={r['kernel']}")
