@@ -49,6 +49,19 @@ int main(int argc, char** argv) {
     std::printf("u");
     for (int i = 0; i < 19; ++i) std::printf(" %.10f", mxGetPr(o[1])[i]);
     std::printf("\n");
+    // closed loop on the ONE solver of the gateway (examples/cartpole_example_mpc.m:36-44): x0 <- A x0 + B u_sol(1), solve again
+    double x0n[4];
+    {
+        const double x0[4] = {0.5, 0, 0, 0}, u0 = mxGetPr(o[1])[0];
+        for (int i = 0; i < 4; ++i) {
+            x0n[i] = mxGetPr(B)[i] * u0;
+            for (int j = 0; j < 4; ++j) x0n[i] += mxGetPr(A)[j * 4 + i] * x0[j];
+        }
+        call("set_x0", {M(4, 1, {x0n[0], x0n[1], x0n[2], x0n[3]}), S(0)}, 0);
+        call("solve", {S(0)});
+        auto st2 = call("get_stats", {S(0)}, 4);
+        std::printf("loop_iter2 %g\n", mxGetScalar(st2[0]));
+    }
     // solve_batch: 3 copies of the same x0 (double input) -> every problem must stop at the same iteration
     mxArray* X0 = mxCreateDoubleMatrix(4, 3, mxREAL);
     for (int b = 0; b < 3; ++b) mxGetPr(X0)[4 * b] = 0.5;
@@ -58,6 +71,25 @@ int main(int argc, char** argv) {
     const int* it = static_cast<const int*>(mxGetData(o[2]));
     const float* U = static_cast<const float*>(mxGetData(o[1]));
     std::printf("batch_iter %d %d %d dims %zu u0 %.7f\n", it[0], it[1], it[2], mxGetNumberOfDimensions(o[0]), U[0]);
+    // sessions: 3 warm-started copies of the solver on the GPU, the same closed loop (precision 64 was set above)
+    try { call("session_solve", {}, 0); } catch (const MexError& e) { std::printf("session_error_id %s\n", e.id.c_str()); }
+    call("session_create", {S(3)}, 0);
+    call("session_set_x0", {X0}, 0);
+    call("session_solve", {}, 0);
+    o = call("session_read", {mxCreateString("iter")});
+    std::printf("session_iter %g %g %g\n", mxGetPr(o[0])[0], mxGetPr(o[0])[1], mxGetPr(o[0])[2]);
+    call("session_step", {S(1)}, 0);
+    o = call("session_read", {mxCreateString("x0")});
+    double dmax = 0;
+    for (int b = 0; b < 3; ++b) for (int i = 0; i < 4; ++i) { const double d = mxGetPr(o[0])[4 * b + i] - x0n[i]; dmax = d > dmax ? d : (-d > dmax ? -d : dmax); }
+    std::printf("session_x0_err %.3e\n", dmax);
+    call("session_solve", {}, 0);
+    o = call("session_read", {mxCreateString("iter")});
+    std::printf("session_iter2 %g %g %g\n", mxGetPr(o[0])[0], mxGetPr(o[0])[1], mxGetPr(o[0])[2]);
+    o = call("session_read", {mxCreateString("sol_u")});
+    std::printf("session_dims %zu\n", mxGetNumberOfDimensions(o[0]));
+    try { call("session_read", {mxCreateString("bogus")}); } catch (const MexError& e) { std::printf("session_error_id %s\n", e.id.c_str()); }
+    call("session_destroy", {}, 0);
     call("reset", {S(0)}, 0);
     try { call("solve", {S(0)}); } catch (const MexError& e) { std::printf("error_id %s\n", e.id.c_str()); }
     return 0;

@@ -21,7 +21,7 @@ def driver():
         __graft_entry__.build()
     srcs = [ROOT / "tests" / "stub_mex" / "mex_driver.cpp", PKG / "matlab" / "bindings.cpp"]
     if not EXE.exists() or EXE.stat().st_mtime < max(p.stat().st_mtime for p in srcs + [lib]):
-        subprocess.check_call(["g++", "-std=c++17", "-O1", "-I", str(ROOT / "tests" / "stub_mex"), "-I", str(PKG / "csrc" / "host"),
+        subprocess.check_call(["g++", "-std=c++17", "-O1", "-I", str(ROOT / "tests" / "stub_mex"), "-I", str(PKG / "csrc" / "host"), "-I", str(ROOT / "include"),
                                *map(str, srcs), "-o", str(EXE), f"-L{PKG}", "-ltinympc_b200", f"-Wl,-rpath,{PKG}"])
     return EXE
 
@@ -48,4 +48,11 @@ def test_gateway_cartpole_example_and_solve_batch_on_gpu(driver):
     assert np.abs(u - g["u"][0, :, 0]).max() < 1e-9
     b = next(l for l in lines if l.startswith("batch_iter")).split()
     assert b[1:4] == ["51", "51", "51"] and b[5] == "3" and abs(float(b[7]) - 0.5) < 1e-6
+    # sessions through the gateway: same closed loop as the single solver driven by set_x0 / solve
+    it2 = next(l for l in lines if l.startswith("loop_iter2")).split()[1]
+    assert "session_iter 51 51 51" in lines
+    assert f"session_iter2 {it2} {it2} {it2}" in lines, [l for l in lines if l.startswith("session")]
+    assert float(next(l for l in lines if l.startswith("session_x0_err")).split()[1]) < 1e-12
+    assert "session_dims 3" in lines
+    assert lines.count("session_error_id TinyMPC:NotInitialized") == 1 and "session_error_id TinyMPC:InvalidInput" in lines
     assert lines[-1] == "error_id TinyMPC:NotInitialized"

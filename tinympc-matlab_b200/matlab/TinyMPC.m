@@ -17,6 +17,7 @@ classdef TinyMPC < handle
         settings = struct();
         x_min = []; x_max = []; u_min = []; u_max = [];
         dK = []; dP = []; dC1 = []; dC2 = [];
+        session_size = 0;      % number of warm-started GPU copies of this solver (session_create), 0 = none
     end
 
     methods
@@ -134,9 +135,57 @@ classdef TinyMPC < handle
 
         function set_option(obj, name, value)
             % 'precision' 32 (fast, default for batches) | 64 (iteration counts identical to the CPU reference),
-            % 'chunks', 'ctas_per_sm', 'force_wpp'
+            % 'mixed' (band: fp32 pass + fp64 re-solve of the borderline problems), 'chunks', 'ctas_per_sm', 'force_wpp'
             obj.require_setup();
             tinympc_matlab('set_option', name, value);
+        end
+
+        % ---- sessions: B warm-started copies of this solver on the GPU (closed loops, examples/cartpole_example_mpc.m:36-44,
+        % for B systems at once).  Constraints, settings and options are taken as they are when the session is created.
+        function session_create(obj, B)
+            obj.require_setup();
+            tinympc_matlab('session_create', B);
+            obj.session_size = B;
+        end
+
+        function session_set_x0(obj, X0)
+            % X0: nx x B
+            obj.require_session();
+            tinympc_matlab('session_set_x0', double(X0));
+        end
+
+        function session_set_x_ref(obj, Xref)
+            % Xref: nx x N x B, or nx x N / nx x 1 / scalar (shared by all problems, expanded like set_x_ref)
+            obj.require_session();
+            tinympc_matlab('session_set_x_ref', obj.session_traj(Xref, obj.nx, obj.N));
+        end
+
+        function session_set_u_ref(obj, Uref)
+            obj.require_session();
+            tinympc_matlab('session_set_u_ref', obj.session_traj(Uref, obj.nu, obj.N-1));
+        end
+
+        function session_solve(obj)
+            obj.require_session();
+            tinympc_matlab('session_solve');
+        end
+
+        function session_step(obj, use_solution)
+            % x0 <- A x0 + B u0 + f on the GPU; u0 = work.u(:,1) (default) or the clamped solution u(:,1) (use_solution = true)
+            obj.require_session();
+            if nargin < 2, use_solution = false; end
+            tinympc_matlab('session_step', double(use_solution));
+        end
+
+        function v = session_read(obj, field)
+            % 'x0' | 'x' | 'sol_x' | 'u' | 'sol_u' | 'iter' | 'status' | 'rho' | 'residuals'
+            obj.require_session();
+            v = tinympc_matlab('session_read', field);
+        end
+
+        function session_destroy(obj)
+            tinympc_matlab('session_destroy');
+            obj.session_size = 0;
         end
 
         function codegen(~, varargin)
@@ -221,6 +270,23 @@ classdef TinyMPC < handle
         function require_setup(obj)
             if ~obj.is_setup
                 error('TinyMPC:NotSetup', 'Solver not setup. Call setup() first.');
+            end
+        end
+
+        function require_session(obj)
+            obj.require_setup();
+            if obj.session_size < 1
+                error('TinyMPC:NotSetup', 'No session. Call session_create(B) first.');
+            end
+        end
+
+        function T = session_traj(obj, v, dim, steps)
+            % dim x steps x B stays as it is; anything 2-D is one trajectory shared by all problems
+            if ndims(v) == 3
+                assert(isequal(size(v), [dim, steps, obj.session_size]), 'batched trajectory must be %d x %d x %d', dim, steps, obj.session_size);
+                T = double(v);
+            else
+                T = double(obj.spread(v, dim, steps));
             end
         end
 

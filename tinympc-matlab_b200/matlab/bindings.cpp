@@ -2,7 +2,7 @@
 //
 // Mirrors the command surface of the reference gateway (src/bindings.cpp:641-692: 17 string-dispatched
 // commands, one global solver, real-double inputs, int32-or-double index vectors, auto-enabling of the
-// constraint flags, errors as mexErrMsgIdAndTxt("TinyMPC:<Id>", ...)) and adds 'solve_batch'.  All solves
+// constraint flags, errors as mexErrMsgIdAndTxt("TinyMPC:<Id>", ...)) and adds 'solve_batch', 'set_option' and 'session_*'.  All solves
 // run on the GPU through the host C++ mirror (csrc/host/tiny_api.hpp) -> C ABI (include/tinympc_b200.h).
 // Build inside MATLAB:  mex -I<repo>/tinympc-matlab_b200/csrc/host bindings.cpp -L<repo>/tinympc-matlab_b200 -ltinympc_b200
 // (tests build it against tests/stub_mex/mex.h, since neither MATLAB nor mex.h exist in the build image).
@@ -14,10 +14,13 @@
 
 #include "mex.h"
 #include "tiny_api.hpp"
+#include "tinympc_b200.h"
 
 namespace {
 
 TinySolver* g_solver = nullptr;   // one solver per MEX module, like the reference (src/bindings.cpp:17)
+tinympc_cuda_session* g_session = nullptr;   // NEW: a batch of warm-started copies of that solver, resident on the GPU
+int g_session_batch = 0;
 
 [[noreturn]] void fail(const char* id, const std::string& msg) {
     mexErrMsgIdAndTxt((std::string("TinyMPC:") + id).c_str(), "%s", msg.c_str());
@@ -137,8 +140,14 @@ void cmd_get_stats(int, mxArray* plhs[], int nrhs, const mxArray*[]) {
 void cmd_codegen(int, mxArray*[], int, const mxArray*[]) {
     fail("NotSupported", "codegen targets microcontrollers and is outside the batched GPU hot path of this build");
 }
+void drop_session() {
+    if (g_session) tinympc_cuda_session_destroy(g_session);
+    g_session = nullptr;
+    g_session_batch = 0;
+}
 void cmd_reset(int, mxArray*[], int nrhs, const mxArray*[]) {
     need_args(nrhs, 1, "reset");
+    drop_session();
     tiny_free(g_solver);
     g_solver = nullptr;
 }
@@ -238,6 +247,82 @@ void cmd_set_option(int, mxArray*[], int nrhs, const mxArray* prhs[]) {
     if (rc != 0) fail("SetOptionFailed", tiny_b200_last_error(g_solver));
 }
 
+// NEW.  Sessions: B warm-started copies of the solver on the GPU, the closed loop of examples/cartpole_example_mpc.m:36-44 /
+// quadrotor_hovering.cpp:73-93 for B systems at once (include/tinympc_b200.h, tinympc_cuda_session_*).
+//   tinympc_matlab('session_create', B)            cold workspaces + pristine cache of the current solver (constraints, settings,
+//                                                  options as set so far; 'precision' 64 reproduces the reference's iteration counts)
+//   tinympc_matlab('session_set_x0', X0)           nx x B
+//   tinympc_matlab('session_set_x_ref', Xref)      nx x N (shared) or nx x N x B;   'session_set_u_ref' likewise with nu x (N-1)
+//   tinympc_matlab('session_solve')                tiny_solve on every copy, warm start
+//   tinympc_matlab('session_step', use_solution)   x0 <- A x0 + B u0 + f on the device (u0 = work.u(:,1) or solution.u(:,1))
+//   v = tinympc_matlab('session_read', field)      'x0' nx x B | 'x','sol_x' nx x N x B | 'u','sol_u' nu x (N-1) x B |
+//                                                  'iter','status','rho' B x 1 | 'residuals' 4 x B      (doubles)
+//   tinympc_matlab('session_destroy')
+void need_session() { if (!g_session) fail("NotInitialized", "No session: call session_create first"); }
+void session_check(int rc, const char* what) {
+    if (rc != 0) fail("SessionFailed", std::string(what) + ": " + tinympc_cuda_last_error(static_cast<tinympc_cuda_solver*>(tiny_b200_cuda_handle(g_solver))));
+}
+const double* session_doubles(const mxArray* a, size_t per_problem, int* broadcast) {
+    if (!mxIsDouble(a) || mxIsComplex(a)) fail("InvalidInput", "Input must be a real double array");
+    const size_t n = mxGetNumberOfElements(a);
+    if (n == per_problem * (size_t)g_session_batch) { if (broadcast) *broadcast = 0; }
+    else if (broadcast && n == per_problem) *broadcast = 1;
+    else fail("InvalidInput", "array has " + std::to_string(n) + " elements, expected " + std::to_string(per_problem) + " per problem");
+    return mxGetPr(a);
+}
+void cmd_session_create(int, mxArray*[], int nrhs, const mxArray* prhs[]) {
+    need_args(nrhs, 1, "session_create"); need_solver();
+    const int B = scalar_int(prhs[0]);
+    if (B < 1) fail("InvalidInput", "session_create requires a positive number of problems");
+    drop_session();
+    auto* h = static_cast<tinympc_cuda_solver*>(tiny_b200_cuda_handle(g_solver));   // uploads the family (cache, constraints, settings)
+    if (!h) fail("SessionFailed", std::string("no GPU backend: ") + tiny_b200_last_error(g_solver));
+    const int rc = tinympc_cuda_session_create(h, 0, B, &g_session);
+    if (rc != 0) { g_session = nullptr; fail("SessionFailed", std::string("session_create: ") + tinympc_cuda_last_error(h)); }
+    g_session_batch = B;
+}
+void cmd_session_destroy(int, mxArray*[], int, const mxArray*[]) { drop_session(); }
+void cmd_session_set_x0(int, mxArray*[], int nrhs, const mxArray* prhs[]) {
+    need_args(nrhs, 1, "session_set_x0"); need_solver(); need_session();
+    session_check(tinympc_cuda_session_set_x0(g_session, session_doubles(prhs[0], g_solver->work->nx, nullptr)), "session_set_x0");
+}
+void cmd_session_set_x_ref(int, mxArray*[], int nrhs, const mxArray* prhs[]) {
+    need_args(nrhs, 1, "session_set_x_ref"); need_solver(); need_session();
+    int bc = 0;
+    const double* p = session_doubles(prhs[0], (size_t)g_solver->work->nx * g_solver->work->N, &bc);
+    session_check(tinympc_cuda_session_set_x_ref(g_session, p, bc), "session_set_x_ref");
+}
+void cmd_session_set_u_ref(int, mxArray*[], int nrhs, const mxArray* prhs[]) {
+    need_args(nrhs, 1, "session_set_u_ref"); need_solver(); need_session();
+    int bc = 0;
+    const double* p = session_doubles(prhs[0], (size_t)g_solver->work->nu * (g_solver->work->N - 1), &bc);
+    session_check(tinympc_cuda_session_set_u_ref(g_session, p, bc), "session_set_u_ref");
+}
+void cmd_session_solve(int, mxArray*[], int, const mxArray*[]) {
+    need_solver(); need_session();
+    session_check(tinympc_cuda_session_solve(g_session), "session_solve");
+}
+void cmd_session_step(int, mxArray*[], int nrhs, const mxArray* prhs[]) {
+    need_args(nrhs, 1, "session_step"); need_solver(); need_session();
+    session_check(tinympc_cuda_session_step(g_session, scalar_int(prhs[0]) ? 1 : 0), "session_step");
+}
+void cmd_session_read(int, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
+    need_args(nrhs, 1, "session_read"); need_solver(); need_session();
+    char* raw = mxArrayToString(prhs[0]);
+    const std::string f = raw ? raw : "";
+    mxFree(raw);
+    const mwSize nx = g_solver->work->nx, nu = g_solver->work->nu, N = g_solver->work->N, B = (mwSize)g_session_batch;
+    mxArray* a = nullptr;
+    if (f == "x0") a = mxCreateDoubleMatrix(nx, B, mxREAL);
+    else if (f == "x" || f == "sol_x") { const mwSize d[3] = {nx, N, B}; a = mxCreateNumericArray(3, d, mxDOUBLE_CLASS, mxREAL); }
+    else if (f == "u" || f == "sol_u") { const mwSize d[3] = {nu, N - 1, B}; a = mxCreateNumericArray(3, d, mxDOUBLE_CLASS, mxREAL); }
+    else if (f == "iter" || f == "status" || f == "rho") a = mxCreateDoubleMatrix(B, 1, mxREAL);
+    else if (f == "residuals") a = mxCreateDoubleMatrix(4, B, mxREAL);
+    else fail("InvalidInput", "unknown session field: " + f);
+    plhs[0] = a;
+    session_check(tinympc_cuda_session_read(g_session, f.c_str(), mxGetPr(a)), "session_read");
+}
+
 struct Command { const char* name; void (*fn)(int, mxArray*[], int, const mxArray*[]); };
 const Command kCommands[] = {
     {"setup", cmd_setup}, {"set_x0", cmd_set_x0}, {"set_x_ref", cmd_set_x_ref}, {"set_u_ref", cmd_set_u_ref}, {"solve", cmd_solve},
@@ -246,6 +331,9 @@ const Command kCommands[] = {
     {"set_cache_terms", cmd_set_cache_terms}, {"codegen_with_sensitivity", cmd_codegen}, {"update_settings", cmd_update_settings},
     {"print_problem_data", cmd_print_problem_data}, {"set_linear_constraints", cmd_set_linear_constraints},
     {"set_cone_constraints", cmd_set_cone_constraints}, {"solve_batch", cmd_solve_batch}, {"set_option", cmd_set_option},
+    {"session_create", cmd_session_create}, {"session_destroy", cmd_session_destroy}, {"session_set_x0", cmd_session_set_x0},
+    {"session_set_x_ref", cmd_session_set_x_ref}, {"session_set_u_ref", cmd_session_set_u_ref}, {"session_solve", cmd_session_solve},
+    {"session_step", cmd_session_step}, {"session_read", cmd_session_read},
 };
 
 }  // namespace
