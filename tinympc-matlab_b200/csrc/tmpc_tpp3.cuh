@@ -407,6 +407,33 @@ tpp3_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ typ
                         tmem_wait_st();
                     }
                 }
+                // x := 0, u := 0 for the refilled lanes: the first forward pass then ADDS the full affine map like every later
+                // increment (no per-element select on "first iteration" in the rollout, 2 % of the instructions), and nothing of the
+                // previous problem -- not even a NaN -- survives into the new one.  Tensor-memory columns: read - select - write.
+                if constexpr (C::HYB) {
+#pragma unroll 1
+                    for (int c = 1; c < NH - 1; ++c) {
+                        uint32_t r[NX];
+                        TmemSpan<NX>::ld(X.base + c * NX, r);
+                        TmemSpan<NX>::wait(r);
+#pragma unroll
+                        for (int e = 0; e < NX; ++e) r[e] = mine ? 0u : r[e];
+                        TmemSpan<NX>::st(X.base + c * NX, r);
+                    }
+                    tmem_wait_st();
+#pragma unroll
+                    for (int e = 0; e < NX; ++e) xlast.set(e, mine ? T(0) : xlast.get(e));
+                } else {
+                    X.reset(mine);
+                }
+                if (mine) {
+#pragma unroll 1
+                    for (int i = 0; i < NH - 1; ++i) {
+#pragma unroll
+                        for (int j = 0; j < NU / 2; ++j) U.setp(i, j, mk2(T(0), T(0)));
+                        if constexpr (NU & 1) U.sett(i, T(0));
+                    }
+                }
                 if (mine) {
                     // TZ := -(Uref .* R), -dd := -d0 (first backward pass on the zero workspace, tiny_api.cpp:68-105 + admm.cpp:13-20)
                     if (have_uref) {
@@ -468,8 +495,8 @@ tpp3_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ typ
                     VX xo;
                     TmemTraj<NX, NH>::complete(xr, xo);
 #pragma unroll
-                    for (int j = 0; j < NX / 2; ++j) xo.p[j] = addv(sel0(ff, xo.p[j]), dx.p[j]);
-                    if constexpr (NX & 1) xo.t = sel0(ff, xo.t) + dx.t;
+                    for (int j = 0; j < NX / 2; ++j) xo.p[j] = addv(xo.p[j], dx.p[j]);   // a new problem's columns were zeroed at refill
+                    if constexpr (NX & 1) xo.t = xo.t + dx.t;
                     X.store(i, xo);
                 }
                 if (i < NH - 1) {
@@ -481,8 +508,8 @@ tpp3_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ typ
                     VU un;
                     U.load(i, un);
 #pragma unroll
-                    for (int j = 0; j < NU / 2; ++j) un.p[j] = addv(sel0(ff, un.p[j]), du.p[j]);
-                    if constexpr (NU & 1) un.t = sel0(ff, un.t) + du.t;
+                    for (int j = 0; j < NU / 2; ++j) un.p[j] = addv(un.p[j], du.p[j]);
+                    if constexpr (NU & 1) un.t = un.t + du.t;
                     U.store(i, un);
                     // dx_{i+1} = A dx_i + B du_i (+ f on the first iteration, admm.cpp:30)
                     VX dxn;
@@ -500,8 +527,8 @@ tpp3_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ typ
             }
             if constexpr (C::HYB) {
 #pragma unroll
-                for (int j = 0; j < NX / 2; ++j) xlast.p[j] = addv(sel0(ff, xlast.p[j]), dx.p[j]);
-                if constexpr (NX & 1) xlast.t = sel0(ff, xlast.t) + dx.t;
+                for (int j = 0; j < NX / 2; ++j) xlast.p[j] = addv(xlast.p[j], dx.p[j]);
+                if constexpr (NX & 1) xlast.t = xlast.t + dx.t;
             }
             X.stores_done();
         }
