@@ -207,7 +207,14 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0, help="difficulty of the synthetic batch (SURVEY 8d: 0.3 easy, 1.0 hard)")
     ap.add_argument("--config", default="quadrotor", choices=["quadrotor", "cartpole", "rocket", "quadrotor_adaptive"])
     ap.add_argument("--precision", type=int, default=32)
-    ap.add_argument("--mixed", type=float, default=0.0, help="relative band of the fp32+fp64 exact-count mode (0 = plain fp32)")
+    ap.add_argument("--mixed", type=float, default=-1.0,
+                    help="relative band of the exact-count mode (fp32 pass + fp64 re-solve of the problems whose termination decision is "
+                         "within the band of a tolerance); -1 = the family's measured band (default: the mode that reproduces the "
+                         "reference's iteration counts), 0 = plain fp32")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --batch problems per GPU; strong: --batch problems in total, split by problem index over the GPUs "
+                         "(BASELINE config 3 as worded: 1M problems sharded across 8 B200)")
+    ap.add_argument("--parity-n", dest="parity_n", type=int, default=10000, help="problems of the parity gate (prefix of rank 0's shard)")
     ap.add_argument("--variant", type=int, default=0, help="kernel variant (0 = default; A/B baselines 1, 2, 5)")
     ap.add_argument("--cpu-seconds", dest="cpu_seconds", type=float, default=8.0)
     ap.add_argument("--steps-cpu", dest="steps_cpu", type=int, default=2)
@@ -227,22 +234,29 @@ def main():
     spec = dict(quadrotor=P.quadrotor, cartpole=P.cartpole, rocket=P.rocket,
                 quadrotor_adaptive=lambda: P.quadrotor(adaptive=True))[args.config]()
     n, m, N = spec.nx, spec.nu, spec.N
-    workload = f"{args.config} nx={n} nu={m} N={N}, {args.batch} problems/GPU, per-problem x0+Xref+Uref, box constraints, " \
+    world_cfg = max(world, args.gpus)      # the reference arm runs on rank 0 alone but describes the same job
+    if args.scaling == "strong":
+        assert args.batch % world_cfg == 0, "--scaling strong needs --batch divisible by the number of GPUs"
+        per_gpu = args.batch // world_cfg
+    else:
+        per_gpu = args.batch
+    workload = f"{args.config} nx={n} nu={m} N={N}, {per_gpu} problems/GPU, per-problem x0+Xref+Uref, box constraints, " \
                f"tol {spec.abs_pri_tol:g}, max_iter {spec.max_iter}, difficulty scale {args.scale}"
-    config = {"workload": workload, "batch_per_gpu": args.batch, "scale": args.scale,
-              "l2_policy": "inputs+outputs per step (%.0f MB) exceed the 126 MB L2" % (bytes_per_solve(n, m, N) * args.batch / 1e6),
-              "parallelism": f"problem-index shards x{world}, no collective"}
+    # identical in both arms (the driver compares the dicts); run-specific facts go to the top-level "run" key
+    config = {"workload": workload, "batch_per_gpu": per_gpu, "scale": args.scale,
+              "l2_policy": "inputs+outputs per step (%.0f MB) exceed the 126 MB L2" % (bytes_per_solve(n, m, N) * per_gpu / 1e6),
+              "parallelism": f"problem-index shards x{world_cfg}, no collective"}
 
     # ------------------------------------------------------------------ reference arm (CPU)
     if args.impl == "reference":
         if rank != 0:
             return
-        batch_np = P.make_batch(spec, min(args.batch, 1 << 18), args.scale, seed=1234 + 3)
+        batch_np = P.make_batch(spec, min(per_gpu, 1 << 18), args.scale, seed=1234 + 3)
         args.steps_cpu = max(1, args.steps)
         cb = reference_arm(args, P, spec, batch_np)
         line = {"impl": "reference", "metric": "solves_per_sec", "value": cb["value"], "unit": "solves/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+                "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
                 "ns_per_admm_iter": cb["ns_per_admm_iter"], "mean_iters": cb["mean_iters"],
                 "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 "e2e": {"value": cb["value"], "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -261,11 +275,12 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
 
-    prev_affinity, config["cpu_affinity"] = bind_to_gpu_cpus(local) if (world > 1 and not os.environ.get("BENCH_NO_AFFINITY")) else (os.sched_getaffinity(0), "unchanged (single rank)")
+    run = {}
+    prev_affinity, run["cpu_affinity"] = bind_to_gpu_cpus(local) if (world > 1 and not os.environ.get("BENCH_NO_AFFINITY")) else (os.sched_getaffinity(0), "unchanged (single rank)")
     tm = importlib.import_module("tinympc-matlab_b200")
     S = importlib.import_module("tinympc-matlab_b200.sharding")
-    B = args.batch
-    # weak scaling: the job is world*B problems, rank r owns the contiguous index range [lo, hi) of it
+    B = per_gpu
+    # the job is world*B problems (weak: B = --batch; strong: B = --batch / world), rank r owns the contiguous index range [lo, hi)
     lo, hi = S.shard_range(world * B, rank, world)
     assert hi - lo == B
     batch_np = P.make_batch(spec, B, args.scale, seed=1234 + 3 + 1000 * rank)   # each rank generates its own shard
@@ -273,8 +288,12 @@ def main():
     solver.setup_from_spec(spec, devices=[local])
     solver.cuda.set_option("precision", args.precision)
     solver.cuda.set_option("variant", args.variant)
-    solver.cuda.set_option("mixed", args.mixed)
-    config["mixed_band"] = args.mixed
+    band = P.exact_band(spec) if args.mixed < 0 else args.mixed
+    if args.precision == 64:
+        band = 0.0
+    solver.cuda.set_option("mixed", band)
+    run["mixed_band"] = band
+    run["mode"] = "fp64" if args.precision == 64 else (f"exact-count: fp32 pass + fp64 re-solve of the problems within {band:g} of a tolerance" if band > 0 else "plain fp32")
 
     tdev = lambda a: None if a is None else torch.from_numpy(a).to(dev)
     x0, Xref, Uref = tdev(batch_np.x0), tdev(batch_np.Xref), tdev(batch_np.Uref)
@@ -305,7 +324,7 @@ def main():
         barrier()
     ms = e0.elapsed_time(e1)
     launches = solver.cuda.launch_count - launches0
-    marked = solver.cuda.last_marked if args.mixed > 0 else 0
+    marked = solver.cuda.last_marked if band > 0 else 0
     iters_one = int(it.sum().item())                 # identical every step (same inputs)
     unsolved = float((st == 11).float().mean().item())
     ms_all, (iters_all, launches_all) = S.reduce_report(ms, [iters_one, launches], dist, dev)   # max of times, sum of work
@@ -343,6 +362,29 @@ def main():
             dist.destroy_process_group()
         return
 
+    # ---- parity gate: the first parity_n problems of this very run against the reference C++ on the same inputs
+    parity = None
+    if args.parity_n > 0:
+        try:
+            sys.path.insert(0, str(ROOT / "oracle"))
+            import oracle as O
+            pimpl = "ref" if O.available("ref") else "port"
+            npar = min(B, args.parity_n)
+            g = O.solve_batch(spec, batch_np.slice(0, npar), pimpl, os.cpu_count() or 1)
+            rx, ru = x[:npar].cpu().numpy(), u[:npar].cpu().numpy()
+            ri, rs = it[:npar].cpu().numpy(), st[:npar].cpu().numpy()
+            same = (ri == g["iter"]) & (rs == g["status"])
+            parity = {"n": npar, "oracle": "reference C++ (oracle/_ref)" if pimpl == "ref" else "C port (oracle/tinympc_oracle.c)",
+                      "count_mismatch": int((ri != g["iter"]).sum()), "status_mismatch": int((rs != g["status"]).sum()),
+                      "max_abs_dx": float(np.abs(rx - g["x"]).max()), "max_abs_du": float(np.abs(ru - g["u"]).max()),
+                      "max_abs_dx_matched": float(np.abs(rx[same] - g["x"][same]).max()) if same.any() else None,
+                      "max_abs_du_matched": float(np.abs(ru[same] - g["u"][same]).max()) if same.any() else None,
+                      "tolerance": "identical iter/status; |dx|, |du| <= 1e-4 absolute (north_star)", "mode": run["mode"]}
+            parity["pass"] = bool(parity["count_mismatch"] == 0 and parity["status_mismatch"] == 0 and
+                                  parity["max_abs_dx"] <= 1e-4 and parity["max_abs_du"] <= 1e-4)
+        except Exception as ex:
+            parity = {"n": 0, "error": repr(ex)}
+
     F = flops_per_iter(n, m, N, spec)
     peak_tf, peak_how = fp32_peak_tflops()
     hbm_pk, hbm_how = hbm_peak_gbs()
@@ -355,18 +397,20 @@ def main():
                     "bytes_per_solve": bytes_per_solve(n, m, N)}}
     # DRAM traffic of the same kernel on the same workload from the committed `ncu --set full` capture
     # (profiles/r01/traffic.json: dram__bytes_read.sum + dram__bytes_write.sum per launch)
-    prof = ROOT / "profiles" / "r01" / "traffic.json"
-    if prof.exists():
+    for prof in (ROOT / "profiles" / "r02" / "traffic.json", ROOT / "profiles" / "r01" / "traffic.json"):
+        if not prof.exists() or roof["traffic"] is not None:
+            continue
         for key, t in json.loads(prof.read_text()).items():
             if key.startswith(f"{args.config}_b{B}_s{args.scale:g}") and t.get("kernel") == solver.cuda.last_kernel:
                 roof["traffic"] = t["dram_bytes_per_launch"]
                 roof["traffic_algorithmic"] = bytes_per_solve(n, m, N) * B
 
     line = {"metric": "solves_per_sec", "value": value, "unit": "solves/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_all / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_all / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "f32" if args.precision == 32 else "f64", "data": "synthetic", "config": config,
             "ns_per_admm_iter": ns_iter, "mean_iters": iters_all / (world * B), "unsolved_frac": unsolved,
-            "clocks": clk.summary(), "e2e": e2e, "fp64_resolved": int(marked), "gpu_launches": launches_all, "roofline": roof}
+            "clocks": clk.summary(), "e2e": e2e, "fp64_resolved": int(marked), "gpu_launches": launches_all, "roofline": roof,
+            "parity": parity, "run": run}
     if not args.no_cpu_baseline:
         os.sched_setaffinity(0, prev_affinity)
         try:

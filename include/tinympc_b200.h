@@ -108,7 +108,10 @@ int  tinympc_cuda_set_family(tinympc_cuda_solver *s, const tinympc_cuda_family *
    solvers (tiny_api.cpp:321-323 -> admm.cpp:274-389).  Host buffers; H2D, kernel and D2H inside. */
 int  tinympc_cuda_solve_batch(tinympc_cuda_solver *s, const tinympc_cuda_batch_in *in, const tinympc_cuda_batch_out *out);
 /* same, data already resident on device `dev_index` (index into the create() list); enqueued on
-   `stream` (a cudaStream_t, NULL = default stream) and asynchronous with respect to the host. */
+   `stream` (a cudaStream_t, NULL = default stream) and asynchronous with respect to the host.
+   ONE call in flight per (solver, dev_index): the call uses that device context's work counter and
+   scratch buffers, so issue the next call on the same stream, or after the previous one has
+   completed.  Independent concurrent batches need one solver handle each. */
 int  tinympc_cuda_solve_batch_device(tinympc_cuda_solver *s, int dev_index, const tinympc_cuda_batch_in *in,
                                      const tinympc_cuda_batch_out *out, void *stream);
 

@@ -1,5 +1,5 @@
 #!/usr/bin/env python3
-"""Extract the reference's example problem data into tests/golden/problem_data.json.
+"""Extract the reference's example problem data into tinympc-matlab_b200/problem_data.json.
 
 TEST INFRASTRUCTURE.  Runs only in the build container (needs /root/reference); the JSON it writes
 is committed so that tests / bench.py never read /root/reference at run time.
@@ -15,7 +15,7 @@ import json, re, sys
 from pathlib import Path
 
 REF = Path(sys.argv[1] if len(sys.argv) > 1 else "/root/reference")
-OUT = Path(__file__).resolve().parent.parent / "tests" / "golden" / "problem_data.json"
+OUT = Path(__file__).resolve().parent.parent / "tinympc-matlab_b200" / "problem_data.json"
 
 
 def table(text, name):

@@ -242,6 +242,59 @@ def test_multi_device_split_is_bit_identical(family, streamed, capi, oracle_mod,
             assert np.array_equal(res[0][k], r[k]), f"{family}: field {k} changes with the device split"
 
 
+@pytest.mark.parametrize("streamed", [1, 0])
+def test_multi_device_fanout_stress(streamed, capi, oracle_mod, problems):
+    """Regression for the round-1 abort (GPUTEST_r01: SIGABRT in test_multi_device_split_is_bit_identical): the per-device worker
+    threads of tinympc_cuda_solve_batch wrote the solver's std::string fields concurrently.  50 fan-outs over three contexts,
+    alternating between kernels with names of different length (the reallocation that corrupted the heap), every result compared
+    bit for bit with the single-context run."""
+    q, c = problems.quadrotor(), problems.cartpole()
+    bq, bc = problems.make_batch(q, 6007, 1.0, seed=3), problems.make_batch(c, 6007, 1.0, seed=3)
+    fq, fc = (cases.family_from_spec(p, oracle_mod.get_cache(p, "port")) for p in (q, c))
+    one = capi.CudaSolver(devices=[0])
+    ref = {}
+    for name, fam, b in (("q", fq, bq), ("c", fc, bc)):
+        one.set_family(fam)
+        ref[name] = one.solve_batch(b.x0, b.Xref, b.Uref)
+    one.close()
+    s = capi.CudaSolver(devices=[0, 0, 0])
+    s.set_option("streamed", streamed)
+    s.set_option("chunks", 2)
+    for k in range(50):
+        name, fam, b = (("q", fq, bq), ("c", fc, bc))[k % 2]
+        s.set_family(fam)
+        if k % 10 == 9:
+            s.set_option("precision", 64)      # "tpp2_f64_..." / wpp names in between
+        r = s.solve_batch(b.x0, b.Xref, b.Uref)
+        if k % 10 == 9:
+            s.set_option("precision", 32)
+            continue
+        assert s.last_kernel.startswith("tpp3_"), s.last_kernel
+        for f in ("iter", "status", "x", "u"):
+            assert np.array_equal(ref[name][f], r[f]), f"pass {k}: field {f} differs from the single-context run"
+    assert s.launch_count >= 150
+    s.close()
+
+
+def test_session_outliving_its_solver_fails_cleanly(capi, oracle_mod, problems):
+    """a session kept a raw pointer to its solver.  Destroying the solver now orphans its sessions: later calls
+    return TINYMPC_CUDA_ENOTREADY (5) instead of touching freed memory, and session_destroy still releases the handle."""
+    p = problems.cartpole()
+    s = capi.CudaSolver()
+    s.set_family(cases.family_from_spec(p, oracle_mod.get_cache(p, "port")))
+    ss = s.session(8)
+    ss.set_x0(np.zeros((8, p.nx)))
+    ss.solve()
+    L, h = s.L, ss.h
+    s.close()
+    assert L.tinympc_cuda_session_solve(h) == 5
+    assert L.tinympc_cuda_session_step(h, 0) == 5
+    out = np.zeros(8)
+    assert L.tinympc_cuda_session_read(h, b"iter", out.ctypes.data_as(capi.c_dp)) == 5
+    assert L.tinympc_cuda_session_destroy(h) == 0
+    ss.h = capi.C.c_void_p()
+
+
 @pytest.mark.parametrize("which", ["xref_only", "uref_only", "none"])
 def test_partial_references_on_the_hybrid_layout(which, capi, oracle_mod, problems):
     """Xref without Uref, Uref without Xref, neither: the reference-parking code of the refill pass has a branch per case

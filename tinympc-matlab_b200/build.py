@@ -156,9 +156,6 @@ def default_instances():
             if (nx, nu) == (12, 4):
                 out.append(inst(bits, nx, nu, N, ADP, refs=REFS_L2, fb=True, tm=True))
                 out.append(inst(bits, nx, nu, N, ADP, refs=REFS_L2, tm=True))
-    # A/B: the incremental form with opaque (loop-variant) constant offsets, option variant=6
-    out.append(inst3(12, 4, 10, refs=True, fb=True, variant=6, opq=True))
-    out.append(inst3(4, 1, 20, refs=False, fb=True, variant=6, opq=True))
     # The plain state layout (x and t entirely in tensor memory, 8 warps per SM) of the shapes whose default is the hybrid one: fewer
     # instructions per iteration and a 25 % shorter iteration of a lone warp.  The dispatcher picks it for batches that fit one
     # wave of it (tmpc_capi.cu, kLatencyVariant); option variant=9 forces it.
@@ -168,20 +165,12 @@ def default_instances():
                 out.append(inst3(nx, nu, N, refs=True, fb=fb, variant=9))
                 out.append(inst3(nx, nu, N, refs=False, fb=fb, variant=9))
             out.append(inst3(nx, nu, N, refs=True, ppb=True, variant=9))
-    # A/B: time-indexed bounds (run-time offsets, LDC.64) on the quadrotor shape, option variant=8
-    out.append(inst3(12, 4, 10, refs=True, fb=True, variant=8, tib=False, hyb=True))
     # A/B: the direct-form fp32 box kernels (16 / 24 warps per SM, tensor-memory TV) on the headline shapes, option variant=5
     out.append(inst(32, 12, 4, 10, BOX, refs=REFS_L2, variant=5, fb=True, tm=True))
     out.append(inst(32, 12, 4, 10, BOX, refs=REFS_L2, variant=5, tm=True))
     out.append(inst(32, 12, 4, 10, BOX, refs=REFS_L2, variant=5, ppb=True, tm=True))
     out.append(inst(32, 4, 1, 20, BOX, refs=REFS_NONE, variant=5, fb=True, tm=True))
     out.append(inst(32, 4, 1, 20, BOX, refs=REFS_L2, variant=5, fb=True, tm=True))
-    # A/B baseline: the shared-memory-only (8 warps/SM) direct form of the headline shapes, option variant=2
-    out.append(inst(32, 12, 4, 10, BOX, refs=REFS_L2, variant=2, fb=True))
-    out.append(inst(32, 4, 1, 20, BOX, refs=REFS_NONE, variant=2, fb=True))
-    # A/B baseline: the first-generation (column-pair) kernel on the two headline shapes, option variant=1
-    out.append(inst(32, 12, 4, 10, BOX, refs=REFS_L2, variant=1, fb=True, gen=1))
-    out.append(inst(32, 4, 1, 20, BOX, refs=REFS_NONE, variant=1, fb=True, gen=1))
     return out
 
 
@@ -239,14 +228,36 @@ def gen_sources(instances):
     for stale in GEN.glob("*.cu"):
         if stale.name not in wanted:
             stale.unlink()
+            for ext in (".o", ".d"):
+                (OBJ / (stale.stem + ext)).unlink(missing_ok=True)
     return [GEN / f"{n}.cu" for n in names] + [tpath]
 
 
-def compile_one(src: Path, deps_mtime: float, force: bool, log_dir: Path):
+def up_to_date(obj: Path, dep: Path, src: Path) -> bool:
+    """obj is newer than its source and every header the compiler reported for it (nvcc -MD dependency file)"""
+    if not (obj.exists() and dep.exists()):
+        return False
+    t = obj.stat().st_mtime
+    if src.stat().st_mtime > t:
+        return False
+    toks = dep.read_text().replace("\\\n", " ").split()
+    for f in toks[1:]:
+        if f.startswith(("/usr/", "/opt/")):   # toolchain headers
+            continue
+        try:
+            if os.stat(f).st_mtime > t:
+                return False
+        except OSError:
+            return False
+    return True
+
+
+def compile_one(src: Path, force: bool, log_dir: Path):
     obj = OBJ / (src.stem + ".o")
-    if not force and obj.exists() and obj.stat().st_mtime > max(deps_mtime, src.stat().st_mtime):
+    dep = OBJ / (src.stem + ".d")
+    if not force and up_to_date(obj, dep, src):
         return obj, None
-    cmd = [NVCC, *ARCH, *FLAGS, "-I", str(CSRC), "-I", str(HERE.parent / "include"), "-c", str(src), "-o", str(obj)]
+    cmd = [NVCC, *ARCH, *FLAGS, "-MD", "-MF", str(dep), "-I", str(CSRC), "-I", str(HERE.parent / "include"), "-c", str(src), "-o", str(obj)]
     r = subprocess.run(cmd, capture_output=True, text=True)
     (log_dir / (src.stem + ".log")).write_text(r.stdout + r.stderr)
     if r.returncode != 0:
@@ -260,11 +271,9 @@ def build(jobs: int | None = None, force: bool = False, verbose: bool = True) ->
     log_dir.mkdir(exist_ok=True)
     srcs = gen_sources(default_instances()) + [CSRC / "tmpc_capi.cu"]
     srcs += sorted(CSRC.glob("tmpc_wpp*.cu")) + sorted((CSRC / "host").glob("*.cpp"))
-    headers = list(CSRC.glob("*.h")) + list(CSRC.glob("*.cuh")) + list((CSRC / "host").glob("*.hpp")) + [HERE.parent / "include" / "tinympc_b200.h", Path(__file__)]
-    deps_mtime = max(h.stat().st_mtime for h in headers)
     jobs = jobs or os.cpu_count() or 4
     with ThreadPoolExecutor(max_workers=jobs) as ex:
-        results = list(ex.map(lambda s: compile_one(s, deps_mtime, force, log_dir), srcs))
+        results = list(ex.map(lambda s: compile_one(s, force, log_dir), srcs))
     objs = [str(o) for o, _ in results]
     rebuilt = sum(1 for _, log in results if log is not None)
     if rebuilt or not LIB.exists():

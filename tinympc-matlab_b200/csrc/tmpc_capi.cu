@@ -11,11 +11,14 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -80,6 +83,7 @@ struct Family {
 
 }  // namespace
 
+struct tinympc_cuda_session;
 struct tinympc_cuda_solver {
     std::vector<DeviceCtx> devs;
     Family fam;
@@ -94,9 +98,13 @@ struct tinympc_cuda_solver {
                                        // falls within this relative band of the tolerances (exact iteration counts at ~fp32 speed)
     long long mixed_marked = 0;        // problems re-solved in fp64 by the last mixed solve (host entry: filled by the call)
     int mixed_pending_dev = -1;        // device entry: the count still sits in that device's counter slot
+    // err, last_kernel and launches are written by the per-device worker threads of tinympc_cuda_solve_batch: the strings
+    // only under `mu` (fail(), note_kernel()), the counter atomically.  Everything else a worker touches is its own DeviceCtx.
+    std::mutex mu;
+    std::vector<tinympc_cuda_session*> sessions;   // live sessions; orphaned (their s set to null, buffers freed) by tinympc_cuda_destroy
     std::string err;
     std::string last_kernel;
-    long long launches = 0;
+    std::atomic<long long> launches{0};
     double t_total_ms = 0, t_kernel_ms = 0;
     int t_chunks = 0;
 };
@@ -113,12 +121,24 @@ struct tinympc_cuda_session {
 namespace {
 
 int fail(tinympc_cuda_solver* s, int code, const std::string& msg) {
-    if (s) s->err = msg;
+    if (s) {
+        std::lock_guard<std::mutex> lk(s->mu);
+        s->err = msg;
+    }
     return code;
+}
+void note_kernel(tinympc_cuda_solver* s, const std::string& name) {
+    std::lock_guard<std::mutex> lk(s->mu);
+    if (s->last_kernel != name) s->last_kernel = name;
 }
 int cuda_fail(tinympc_cuda_solver* s, cudaError_t e, const char* what) {
     return fail(s, TINYMPC_CUDA_ECUDA, std::string(what) + ": " + cudaGetErrorString(e));
 }
+struct DeviceGuard {
+    int prev = 0;
+    DeviceGuard() { cudaGetDevice(&prev); }
+    ~DeviceGuard() { cudaSetDevice(prev); }
+};
 #define CU(s, call)                                              \
     do {                                                         \
         cudaError_t e__ = (call);                                \
@@ -265,7 +285,7 @@ int enqueue(tinympc_cuda_solver* s, DeviceCtx& d, const tinympc_cuda_batch_in& i
         const void* full_pack = bits == 64 ? d.pack64 : d.pack32;
         if (bits == 64) CU(s, wpp_launch<double>(p, f.L, full_pack, W, sb.p, warps, 0, st));
         else CU(s, wpp_launch<float>(p, f.L, full_pack, W, sb.p, warps, 0, st));
-        s->last_kernel = bits == 64 ? "wpp_f64_generic" : "wpp_f32_generic";
+        note_kernel(s, bits == 64 ? "wpp_f64_generic" : "wpp_f32_generic");
         s->launches += 1;
         return TINYMPC_CUDA_OK;
     }
@@ -273,7 +293,7 @@ int enqueue(tinympc_cuda_solver* s, DeviceCtx& d, const tinympc_cuda_batch_in& i
     if (!mixed) {
         int rc = launch_tpp(s, d, ke, p, d.ref_scratch[scratch_slot], bits, counter, st);
         if (rc) return rc;
-        s->last_kernel = ke->name;
+        note_kernel(s, ke->name);
         return TINYMPC_CUDA_OK;
     }
     // ---- mixed mode: fp32 pass that marks the ambiguous problems, compaction, fp64 re-solve of the marked ones ----
@@ -295,7 +315,7 @@ int enqueue(tinympc_cuda_solver* s, DeviceCtx& d, const tinympc_cuda_batch_in& i
     p2.batch_ptr = n_marked;
     rc = launch_tpp(s, d, ke64, p2, d.ref_scratch64[scratch_slot], 64, counter2, st);
     if (rc) return rc;
-    s->last_kernel = std::string(ke->name) + "+" + ke64->name;
+    note_kernel(s, std::string(ke->name) + "+" + ke64->name);
     return TINYMPC_CUDA_OK;
 }
 
@@ -417,30 +437,14 @@ int run_shard_streamed(tinympc_cuda_solver* s, DeviceCtx& d, const KernelEntry* 
     p.done_chunk = gran;
     for (int c = 0; c < nch; ++c)
         for (int g = bounds[c] / gran; g * gran < bounds[c + 1]; ++g) p.done_map[g] = (unsigned char)c;
-    CU(s, cudaEventRecord(d.k0[0], s_k));
-    {
-        // launch_tpp zeroes the work counter itself (ctl[0], on s_k, before the kernel)
-        int rc = launch_tpp(s, d, ke, p, d.ref_scratch[0], ke->dtype_bits, ctl, s_k);
-        if (rc) return rc;
-    }
-    CU(s, cudaEventRecord(d.k1[0], s_k));
-    s->last_kernel = ke->name;
-
-    auto drv = [&](CUresult r, const char* what) -> int {
-        if (r == CUDA_SUCCESS) return TINYMPC_CUDA_OK;
-        // the kernel is already waiting for data: release it before reporting (watermark = everything; contents are then
-        // undefined but the call fails anyway)
-        ops.write(reinterpret_cast<CUstream>(s_in), reinterpret_cast<CUdeviceptr>(ctl + 1), (cuuint32_t)n, 0);
-        cudaDeviceSynchronize();
-        return fail(s, TINYMPC_CUDA_ECUDA, std::string(what) + " failed with CUresult " + std::to_string((int)r));
-    };
-    auto rt = [&](cudaError_t e, const char* what) -> int {
-        if (e == cudaSuccess) return TINYMPC_CUDA_OK;
-        ops.write(reinterpret_cast<CUstream>(s_in), reinterpret_cast<CUdeviceptr>(ctl + 1), (cuuint32_t)n, 0);
-        cudaDeviceSynchronize();
-        return cuda_fail(s, e, what);
-    };
-#define RT(call) do { int rc__ = rt((call), #call); if (rc__) return rc__; } while (0)
+    // Order of the enqueues: ALL the input copies and their watermark writes first, then the kernel, then the result copies.
+    // Nothing the kernel waits for is enqueued after its launch, so the pipeline also completes when something serialises
+    // kernel launches on the host (ncu / compute-sanitizer replay, CUDA_LAUNCH_BLOCKING=1): the launch call may block until the
+    // kernel has finished, and the copy engine keeps delivering meanwhile.  The copies are asynchronous (pinned memory), so
+    // the launch is delayed only by the ~100 enqueue calls, less than the arrival time of the first chunk.
+    auto sync_fail = [&](int rc) -> int { cudaDeviceSynchronize(); return rc; };
+#define RT(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return sync_fail(cuda_fail(s, e__, #call)); } while (0)
+#define DRV(call, what) do { CUresult r__ = (call); if (r__ != CUDA_SUCCESS) return sync_fail(fail(s, TINYMPC_CUDA_ECUDA, std::string(what) + " failed with CUresult " + std::to_string((int)r__))); } while (0)
     for (int c = 0; c < nch; ++c) {
         const int c0 = bounds[c], c1 = bounds[c + 1], cn = c1 - c0;
         const size_t g0 = (size_t)lo + c0;
@@ -451,15 +455,20 @@ int run_shard_streamed(tinympc_cuda_solver* s, DeviceCtx& d, const KernelEntry* 
         if (in.Xref) RT(h2d(d.Xref, in.Xref, sx));
         if (in.Uref) RT(h2d(d.Uref, in.Uref, su));
         if (ppb) { RT(h2d(d.xmin, in.x_min, sx)); RT(h2d(d.xmax, in.x_max, sx)); RT(h2d(d.umin, in.u_min, su)); RT(h2d(d.umax, in.u_max, su)); }
-        int rc = drv(ops.write(reinterpret_cast<CUstream>(s_in), reinterpret_cast<CUdeviceptr>(ctl + 1), (cuuint32_t)c1, 0), "cuStreamWriteValue32");
-        if (rc) return rc;
+        DRV(ops.write(reinterpret_cast<CUstream>(s_in), reinterpret_cast<CUdeviceptr>(ctl + 1), (cuuint32_t)c1, 0), "cuStreamWriteValue32");
     }
+    RT(cudaEventRecord(d.k0[0], s_k));
+    {
+        // launch_tpp zeroes the work counter itself (ctl[0], on s_k, before the kernel)
+        int rc = launch_tpp(s, d, ke, p, d.ref_scratch[0], ke->dtype_bits, ctl, s_k);
+        if (rc) return sync_fail(rc);
+    }
+    RT(cudaEventRecord(d.k1[0], s_k));
+    note_kernel(s, ke->name);
     for (int c = 0; c < nch; ++c) {
         const int c0 = bounds[c], c1 = bounds[c + 1], cn = c1 - c0;
         const size_t g0 = (size_t)lo + c0;
-        int rc = drv(ops.wait(reinterpret_cast<CUstream>(s_out), reinterpret_cast<CUdeviceptr>(ctl + 2 + c), (cuuint32_t)cn, CU_STREAM_WAIT_VALUE_GEQ),
-                     "cuStreamWaitValue32");
-        if (rc) return rc;
+        DRV(ops.wait(reinterpret_cast<CUstream>(s_out), reinterpret_cast<CUdeviceptr>(ctl + 2 + c), (cuuint32_t)cn, CU_STREAM_WAIT_VALUE_GEQ), "cuStreamWaitValue32");
         RT(cudaMemcpyAsync(out.x + sx * g0, (float*)d.x.p + sx * c0, sizeof(float) * sx * cn, cudaMemcpyDeviceToHost, s_out));
         RT(cudaMemcpyAsync(out.u + su * g0, (float*)d.u.p + su * c0, sizeof(float) * su * cn, cudaMemcpyDeviceToHost, s_out));
         RT(cudaMemcpyAsync(out.iter + g0, (int*)d.iter.p + c0, sizeof(int) * cn, cudaMemcpyDeviceToHost, s_out));
@@ -467,6 +476,7 @@ int run_shard_streamed(tinympc_cuda_solver* s, DeviceCtx& d, const KernelEntry* 
         if (out.residuals) RT(cudaMemcpyAsync(out.residuals + 4 * g0, (float*)d.res.p + 4 * (size_t)c0, sizeof(float) * 4 * cn, cudaMemcpyDeviceToHost, s_out));
         if (out.rho) RT(cudaMemcpyAsync(out.rho + g0, (float*)d.rho.p + c0, sizeof(float) * cn, cudaMemcpyDeviceToHost, s_out));
     }
+#undef DRV
 #undef RT
     for (int k = 0; k < kStreams; ++k) CU(s, cudaStreamSynchronize(d.streams[k]));
     float ms = 0;
@@ -584,6 +594,9 @@ int tinympc_cuda_create(tinympc_cuda_solver** out, const int* devices, int n_dev
     const int have = tinympc_cuda_device_count();
     if (have <= 0) return TINYMPC_CUDA_ENODEVICE;
     auto* s = new tinympc_cuda_solver();
+    // environment override of the "streamed" option (0 = one launch per chunk), e.g. for tools that cannot follow a kernel
+    // that consumes data while it is still arriving
+    if (const char* e = std::getenv("TINYMPC_B200_STREAMED")) s->streamed = std::atoi(e) != 0;
     std::vector<int> ids;
     if (n_devices <= 0 || !devices) {
         int cur = 0;
@@ -619,6 +632,14 @@ int tinympc_cuda_destroy(tinympc_cuda_solver* s) {
     if (!s) return TINYMPC_CUDA_OK;
     int prev = 0;
     cudaGetDevice(&prev);
+    // a session outliving its solver keeps its handle but loses its device state: every later call on it fails with
+    // TINYMPC_CUDA_ENOTREADY instead of dereferencing the freed solver, and session_destroy still releases the handle
+    for (tinympc_cuda_session* ss : s->sessions) {
+        cudaSetDevice(s->devs[ss->dev].device);
+        for (DevBuf* b : {&ss->ws, &ss->pack, &ss->x, &ss->u, &ss->iter, &ss->status}) b->release();
+        ss->s = nullptr;
+    }
+    s->sessions.clear();
     for (auto& d : s->devs) {
         cudaSetDevice(d.device);
         for (int k = 0; k < kStreams; ++k) if (d.streams[k]) { cudaStreamSynchronize(d.streams[k]); cudaStreamDestroy(d.streams[k]); }
@@ -780,17 +801,16 @@ int tinympc_cuda_solve_batch_device(tinympc_cuda_solver* s, int dev_index, const
     if (rc) return TINYMPC_CUDA_EINVAL;
     DeviceCtx& d = s->devs[dev_index];
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    int prev = 0;
-    cudaGetDevice(&prev);
+    DeviceGuard guard;                 // restores the caller's current device on every return path
     CU(s, cudaSetDevice(d.device));
     if (s->fam.base.max_iter <= 0) {
         rc = zero_iteration_result(s, s->fam, *out, in->batch, st, true);
     } else {
-        // the last counter slot is reserved for the device-resident entry point
+        // The last counter / scratch slot belongs to the device-resident entry point: ONE call in flight per device context
+        // (include/tinympc_b200.h).  A second call on another stream would share the work counter and the scratch buffers.
         rc = enqueue(s, d, *in, *out, kMaxChunks - 1, st, kStreams);
         s->mixed_pending_dev = (s->mixed_band > 0 && s->precision == 32) ? dev_index : -1;
     }
-    cudaSetDevice(prev);
     return rc;
 }
 
@@ -875,7 +895,7 @@ int tinympc_cuda_solve_workspace(tinympc_cuda_solver* s, const tinympc_cuda_work
     CU(s, cudaMemcpyAsync(h.data(), sb.p, sizeof(double) * W.size, cudaMemcpyDeviceToHost, st));
     CU(s, cudaStreamSynchronize(st));
     cudaSetDevice(prev);
-    s->last_kernel = "wpp_f64_workspace";
+    note_kernel(s, "wpp_f64_workspace");
     s->launches += 1;
 
     auto get = [&](double* dst, int at, int n) { if (dst) std::memcpy(dst, h.data() + at, sizeof(double) * n); };
@@ -939,17 +959,22 @@ int tinympc_cuda_session_create(tinympc_cuda_solver* s, int dev_index, int batch
     if (e != cudaSuccess) return bail(e, "session init");
     s->launches += 1;
     cudaSetDevice(prev);
+    s->sessions.push_back(ss);
     *out = ss;
     return TINYMPC_CUDA_OK;
 }
 
 int tinympc_cuda_session_destroy(tinympc_cuda_session* ss) {
     if (!ss) return TINYMPC_CUDA_OK;
-    int prev = 0;
-    cudaGetDevice(&prev);
-    cudaSetDevice(ss->s->devs[ss->dev].device);
-    for (DevBuf* b : {&ss->ws, &ss->pack, &ss->x, &ss->u, &ss->iter, &ss->status}) b->release();
-    cudaSetDevice(prev);
+    if (ss->s) {   // (an orphan's buffers went with its solver)
+        int prev = 0;
+        cudaGetDevice(&prev);
+        cudaSetDevice(ss->s->devs[ss->dev].device);
+        for (DevBuf* b : {&ss->ws, &ss->pack, &ss->x, &ss->u, &ss->iter, &ss->status}) b->release();
+        cudaSetDevice(prev);
+        auto& v = ss->s->sessions;
+        v.erase(std::remove(v.begin(), v.end(), ss), v.end());
+    }
     delete ss;
     return TINYMPC_CUDA_OK;
 }
@@ -958,6 +983,7 @@ namespace {
 // host doubles (rows of `width` elements, `rows_src` of them or ONE broadcast row) -> member `at` of every workspace
 int session_scatter(tinympc_cuda_session* ss, int at, int width, const double* src, bool broadcast) {
     tinympc_cuda_solver* s = ss->s;
+    if (!s) return TINYMPC_CUDA_ENOTREADY;
     const size_t esz = ss->bits == 64 ? sizeof(double) : sizeof(float);
     const size_t n = (size_t)ss->batch * width;
     ss->stage.resize(n * esz);
@@ -976,6 +1002,7 @@ int session_scatter(tinympc_cuda_session* ss, int at, int width, const double* s
 }
 int session_gather(tinympc_cuda_session* ss, int at, int width, double* dst) {
     tinympc_cuda_solver* s = ss->s;
+    if (!s) return TINYMPC_CUDA_ENOTREADY;
     const size_t esz = ss->bits == 64 ? sizeof(double) : sizeof(float);
     const size_t n = (size_t)ss->batch * width;
     ss->stage.resize(n * esz);
@@ -1007,6 +1034,7 @@ int tinympc_cuda_session_set_u_ref(tinympc_cuda_session* ss, const double* Uref,
 int tinympc_cuda_session_solve(tinympc_cuda_session* ss) {
     if (!ss) return TINYMPC_CUDA_EINVAL;
     tinympc_cuda_solver* s = ss->s;
+    if (!s) return TINYMPC_CUDA_ENOTREADY;   // the solver was destroyed under the session
     DeviceCtx& d = s->devs[ss->dev];
     int prev = 0;
     cudaGetDevice(&prev);
@@ -1021,7 +1049,7 @@ int tinympc_cuda_session_solve(tinympc_cuda_session* ss) {
         CU(s, ss->bits == 64 ? wpp_launch<double>(p, ss->fam.L, ss->pack.p, ss->W, ss->ws.p, warps, 2, st)
                              : wpp_launch<float>(p, ss->fam.L, ss->pack.p, ss->W, ss->ws.p, warps, 2, st));
         s->launches += 1;
-        s->last_kernel = ss->bits == 64 ? "wpp_f64_session" : "wpp_f32_session";
+        note_kernel(s, ss->bits == 64 ? "wpp_f64_session" : "wpp_f32_session");
     }
     CU(s, cudaStreamSynchronize(st));
     cudaSetDevice(prev);
@@ -1031,6 +1059,7 @@ int tinympc_cuda_session_solve(tinympc_cuda_session* ss) {
 int tinympc_cuda_session_step(tinympc_cuda_session* ss, int use_solution) {
     if (!ss) return TINYMPC_CUDA_EINVAL;
     tinympc_cuda_solver* s = ss->s;
+    if (!s) return TINYMPC_CUDA_ENOTREADY;   // the solver was destroyed under the session
     DeviceCtx& d = s->devs[ss->dev];
     int prev = 0;
     cudaGetDevice(&prev);
@@ -1046,6 +1075,7 @@ int tinympc_cuda_session_step(tinympc_cuda_session* ss, int use_solution) {
 
 int tinympc_cuda_session_read(tinympc_cuda_session* ss, const char* field, double* host) {
     if (!ss || !field || !host) return TINYMPC_CUDA_EINVAL;
+    if (!ss->s) return TINYMPC_CUDA_ENOTREADY;
     const std::string f(field);
     const WppLayout& W = ss->W;
     const int nx = ss->fam.nx, nu = ss->fam.nu, N = ss->fam.N;
@@ -1090,7 +1120,7 @@ int tinympc_cuda_set_option(tinympc_cuda_solver* s, const char* name, double val
 
 int tinympc_cuda_num_devices(const tinympc_cuda_solver* s) { return s ? (int)s->devs.size() : 0; }
 const char* tinympc_cuda_last_kernel(const tinympc_cuda_solver* s) { return s ? s->last_kernel.c_str() : ""; }
-long long tinympc_cuda_launch_count(const tinympc_cuda_solver* s) { return s ? s->launches : 0; }
+long long tinympc_cuda_launch_count(const tinympc_cuda_solver* s) { return s ? s->launches.load() : 0; }
 int tinympc_cuda_last_timing(const tinympc_cuda_solver* s, double ms[3]) {
     if (!s || !ms) return TINYMPC_CUDA_EINVAL;
     ms[0] = s->t_total_ms; ms[1] = s->t_kernel_ms; ms[2] = (double)s->t_chunks;

@@ -41,27 +41,6 @@ const KernelEntry* const* kernel_table(int* count);   // defined in gen/tmpc_tab
 }  // namespace tmpc
 
 // one of these per generated translation unit
-#define TMPC_DEFINE_TPP_ENTRY(SYM, CFG, FEATV, BITS, VAR)                                                           \
-    namespace tmpc {                                                                                                \
-    static size_t SYM##_smem(int pe) { return tpp_smem_bytes<CFG>(pe); }                                            \
-    static cudaError_t SYM##_prepare(size_t smem) {                                                                 \
-        return cudaFuncSetAttribute(tpp_kernel<CFG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);       \
-    }                                                                                                               \
-    static cudaError_t SYM##_occ(int* n, size_t smem) {                                                             \
-        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(n, tpp_kernel<CFG>, CFG::BLOCK, smem);                 \
-    }                                                                                                               \
-    static cudaError_t SYM##_launch(const SolveParams& p, int grid, size_t smem, cudaStream_t st, const double* mp, \
-                                    const PackLayout& L) {                                                          \
-        typename CFG::CPack cpk;                                                                                    \
-        fill_const_pack(cpk, mp, L);                                                                                \
-        tpp_kernel<CFG><<<grid, CFG::BLOCK, smem, st>>>(p, cpk);                                                    \
-        return cudaGetLastError();                                                                                  \
-    }                                                                                                               \
-    extern const KernelEntry SYM = {#SYM, KF_TPP, CFG::NX, CFG::NU, CFG::NH, FEATV, BITS, CFG::REFMODE,             \
-                                    CFG::PPB ? 1 : 0, CFG::FB ? 1 : 0, 1, CFG::BLOCK, VAR, 0, SYM##_smem, SYM##_prepare, SYM##_occ,  \
-                                    SYM##_launch};                                                                  \
-    }
-
 // packed-pair kernel (tmpc_tpp2.cuh)
 #define TMPC_DEFINE_TPP2_ENTRY(SYM, CFG, FEATV, BITS, VAR)                                                          \
     namespace tmpc {                                                                                                \

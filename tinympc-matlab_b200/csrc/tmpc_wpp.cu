@@ -11,7 +11,7 @@
 //       and downloaded, so a closed-loop MPC written against the reference API behaves identically;
 //   (B) batches whose shape has no specialised thread-per-problem kernel (cold start per problem, one
 //       scratch workspace per resident warp).
-// The throughput path for the BASELINE shapes is tmpc_tpp.cuh.
+// The throughput path for the BASELINE shapes is tmpc_tpp3.cuh / tmpc_tpp2.cuh.
 #include <cuda_runtime.h>
 #include <math_constants.h>
 

@@ -86,6 +86,7 @@ FloatView float_view(const mxArray* a, size_t expect) {
 }
 
 // ------------------------------------------------------------------------------------------ commands
+void drop_session();
 void cmd_setup(int, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
     need_args(nrhs, 10, "setup");   // A, B, fdyn, Q, R, rho, nx, nu, N, verbose
     const double rho = mxGetScalar(prhs[5]);
@@ -95,6 +96,7 @@ void cmd_setup(int, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
     const int status = tiny_setup(&s, to_matrix(prhs[0]), to_matrix(prhs[1]), to_matrix(prhs[2]), to_matrix(prhs[3]), to_matrix(prhs[4]), rho,
                                   nx, nu, N, verbose);
     if (status != 0) { tiny_free(s); fail("SetupFailed", "tiny_setup failed with status " + std::to_string(status)); }
+    drop_session();      // a live session belongs to the solver that is about to go
     tiny_free(g_solver);
     g_solver = s;
     plhs[0] = mxCreateDoubleScalar(0);
@@ -203,6 +205,12 @@ void cmd_set_cone_constraints(int, mxArray*[], int nrhs, const mxArray* prhs[]) 
     // state-first (src/bindings.cpp:465-466 vs tiny_api.cpp:166-168); kept, so MATLAB scripts behave identically.
     VectorXi Acx = to_index_vector(prhs[0]), qcx = to_index_vector(prhs[1]), Acu = to_index_vector(prhs[3]), qcu = to_index_vector(prhs[4]);
     tinyMatrix cx = to_column(prhs[2]), cu = to_column(prhs[5]);
+    // The swap is harmless only when both sides carry cones (the rocket example).  With cones on one side only, the reference
+    // stores them on the OTHER side and then enables the flag of the side that is empty: they are silently not applied.
+    // Reproduced for parity, but said out loud.
+    if ((Acx.size() > 0) != (Acu.size() > 0))
+        mexPrintf("Warning [TinyMPC:ConeSwap]: cones were given on one side only; like the reference gateway (src/bindings.cpp:465-477) "
+                  "this build stores them on the other side and they will NOT be applied. Use the C++ API or solve_batch families for one-sided cones.\n");
     const int status = tiny_set_cone_constraints(g_solver, Acu, qcu, cu, Acx, qcx, cx);
     if (status != 0) fail("SetConeConstraintsFailed", "status " + std::to_string(status));
     if (Acx.size() > 0 && qcx.size() > 0 && cx.size() > 0) g_solver->settings->en_state_soc = 1;   // un-swapped names, :470-477
