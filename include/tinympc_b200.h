@@ -82,6 +82,11 @@ typedef struct {
     const float *Uref;    /* batch*nu*(N-1)  or NULL = zeros replaces tiny_set_u_ref (tiny_api.cpp:399-409) */
     const float *x_min, *x_max;   /* optional per-problem bounds, batch*nx*N     (all four or none) */
     const float *u_min, *u_max;   /*                              batch*nu*(N-1)                    */
+    /* Compact input (instead of Xref): ONE reference state per problem, held over the whole horizon -- what
+       tiny_set_x_ref receives in the closed-loop examples, where every column of Xref is the same set point
+       (tinympc/TinyMPC/examples/quadrotor_hovering.cpp:60-66).  batch*nx; Xref must then be NULL.  The library
+       replicates it on the device: 4 nx bytes cross the bus per problem instead of 4 nx N. */
+    const float *xref_const;
 } tinympc_cuda_batch_in;
 
 typedef struct {
@@ -92,6 +97,10 @@ typedef struct {
     float *residuals;   /* batch*4 or NULL: primal_residual_state, dual_residual_state,
                            primal_residual_input, dual_residual_input (types.hpp:181-184) */
     float *rho;         /* batch or NULL: cache->rho at exit (adaptive rho) */
+    /* Compact output: the first control of every problem, solution->u.col(0) -- all a closed-loop user applies
+       (quadrotor_hovering.cpp:85-88).  batch*nu or NULL.  With u0 given, x and u may be NULL: the trajectories then
+       stay on the device and 4 nu + 8 bytes come back per problem instead of 4 (nx N + nu (N-1)) + 8. */
+    float *u0;
 } tinympc_cuda_batch_out;
 
 /* ---- life cycle ---------------------------------------------------------------------------- */
@@ -132,6 +141,25 @@ typedef struct {
     double *residuals;                   /* out, 4 values or NULL */
 } tinympc_cuda_workspace;
 int  tinympc_cuda_solve_workspace(tinympc_cuda_solver *s, const tinympc_cuda_workspace *w);
+
+/* ---- batched cache precompute + rho-sensitivities on the device ------------------------------------ */
+/* replaces tiny_precompute_and_set_cache (tinympc/TinyMPC/src/tinympc/tiny_api.cpp:244-318) looped over problems that each
+ * bring their OWN dynamics and costs, and TinyMPC.compute_sensitivity_autograd (src/TinyMPC.m:223-241: forward difference in rho,
+ * h = 1e-6, both ends solved to 1e-10) for the derivatives adaptive rho needs.  All arrays are HOST, double, one contiguous
+ * column-major chunk per problem (Eigen's layout); Q and R are the user's diagonals (before "+ rho").  Runs on the current device. */
+typedef struct {
+    int batch, nx, nu;                 /* nx <= 16, nu <= 8 */
+    const double *Adyn, *Bdyn;         /* batch*nx*nx, batch*nx*nu */
+    const double *fdyn;                /* batch*nx or NULL = 0 */
+    const double *Q, *R;               /* batch*nx, batch*nu (diagonals) */
+    const double *rho;                 /* batch */
+} tinympc_cuda_precompute_in;
+typedef struct {
+    double *Kinf, *Pinf, *Quu_inv, *AmBKt, *APf, *BPf;   /* batch*(nu*nx | nx*nx | nu*nu | nx*nx | nx | nu), required */
+    double *dKinf_drho, *dPinf_drho, *dC1_drho, *dC2_drho;   /* optional (give the first two to get any); C1 = Quu_inv, C2 = AmBKt */
+    int *iters;                        /* batch or NULL: Riccati iterations until max|Kinf - Kprev| < 1e-5 (at most 1000) */
+} tinympc_cuda_precompute_out;
+int  tinympc_cuda_precompute_batch(const tinympc_cuda_precompute_in *in, const tinympc_cuda_precompute_out *out);
 
 /* ---- sessions: a batch of warm-started solvers resident on the device ------------------------- */
 /* The closed-loop pattern of the reference (tinympc/TinyMPC/examples/quadrotor_hovering.cpp:73-93,

@@ -28,11 +28,12 @@ def capi():
     return importlib.import_module("tinympc-matlab_b200.capi")
 
 
-def solve_gpu(capi, oracle_mod, p, b, precision, variant=0, mixed=0.0):
+def solve_gpu(capi, oracle_mod, p, b, precision, variant=0, mixed=0.0, fixer_sms=0):
     s = capi.CudaSolver()
     s.set_option("precision", precision)
     s.set_option("variant", variant)
     s.set_option("mixed", mixed)
+    s.set_option("fixer_sms", fixer_sms)
     s.set_family(cases.family_from_spec(p, oracle_mod.get_cache(p, "port")))
     r = s.solve_batch(b.x0, b.Xref, b.Uref, b.x_min, b.x_max, b.u_min, b.u_max)
     r["kernel"] = s.last_kernel
@@ -42,6 +43,11 @@ def solve_gpu(capi, oracle_mod, p, b, precision, variant=0, mixed=0.0):
 
 
 def compare(r, g, precision, name, max_flip_frac=0.0):
+    """north_star: identical status codes and iteration counts; states / controls within 1e-4 ABSOLUTE in fp32.
+    max_flip_frac > 0 only for the plain-fp32 mode (a termination test on rounded values can flip by one check interval,
+    SURVEY H1); the exact-count mode and fp64 are held to 0.  The absolute bar is asserted on every problem that converged with
+    the reference's iteration count; a problem that runs into max_iter never damps its rounding differences (its steps stay
+    large), so those are held to 1e-3 and their maximum is printed."""
     B = len(g["iter"])
     same = (r["iter"] == g["iter"]) & (r["status"] == g["status"])
     flips = int((~same).sum())
@@ -49,11 +55,21 @@ def compare(r, g, precision, name, max_flip_frac=0.0):
     if flips:   # a flipped problem stopped a few iterations early/late: its solution is still the same to ~10 x tol
         scale_f = max(1.0, float(np.abs(g["x"]).max()))
         assert np.abs(r["x"][~same] - g["x"][~same]).max() <= 1e-1 * scale_f, name
-    tol = X_TOL_F64 if precision == 64 else X_TOL_F32
+    if precision == 64:      # fp64 arithmetic behind the float32 batch ABI: output rounding only
+        scale = max(1.0, float(np.abs(g["x"]).max()), float(np.abs(g["u"]).max()))
+        dx = np.abs(r["x"][same] - g["x"][same]).max() if same.any() else 0.0
+        du = np.abs(r["u"][same] - g["u"][same]).max() if same.any() else 0.0
+        assert dx <= X_TOL_F64 * scale and du <= X_TOL_F64 * scale, f"{name}: dx={dx:.3e} du={du:.3e} (kernel {r['kernel']})"
+        return flips, dx, du
+    conv, hard = same & (g["status"] == 1), same & (g["status"] != 1)
+    err = np.maximum(np.abs(r["x"] - g["x"]).reshape(B, -1).max(1), np.abs(r["u"] - g["u"]).reshape(B, -1).max(1))
+    e_conv = float(err[conv].max()) if conv.any() else 0.0
+    e_hard = float(err[hard].max()) if hard.any() else 0.0
     dx = np.abs(r["x"][same] - g["x"][same]).max() if same.any() else 0.0
     du = np.abs(r["u"][same] - g["u"][same]).max() if same.any() else 0.0
-    scale = max(1.0, float(np.abs(g["x"]).max()))
-    assert dx <= tol * scale and du <= tol * scale, f"{name}: dx={dx:.3e} du={du:.3e} (kernel {r['kernel']})"
+    print(f"\n[abs] {name}: max|dxu| converged {e_conv:.2e} ({int(conv.sum())}), at max_iter {e_hard:.2e} ({int(hard.sum())})")
+    assert e_conv <= X_TOL_F32, f"{name}: {e_conv:.3e} > 1e-4 absolute on a converged problem (kernel {r['kernel']})"
+    assert e_hard <= 1e-3, f"{name}: {e_hard:.3e} on a problem stopped at max_iter (kernel {r['kernel']})"
     return flips, dx, du
 
 
@@ -70,15 +86,25 @@ def test_golden_fp64(name, capi, oracle_mod):
 def test_golden_fp32(name, capi, oracle_mod):
     p, b, g = cases.load(name)
     r = solve_gpu(capi, oracle_mod, p, b, 32)
-    # single-problem cases sit exactly on a tolerance by construction (G2: dual residual 9.99986e-5 vs 1e-4)
+    # plain fp32: single-problem cases sit exactly on a tolerance by construction (G2: dual residual 9.99986e-5 vs 1e-4) and may
+    # flip; the exact-count mode below may not
     B = len(g["iter"])
-    compare(r, g, 32, name, max_flip_frac=1.0 if B == 1 else (0.35 if "rocket" in name else 0.08))
+    compare(r, g, 32, name, max_flip_frac=1.0 if B == 1 else 0.08)
+
+
+@pytest.mark.parametrize("name", sorted(cases.CASES))
+def test_golden_exact_mode(name, capi, oracle_mod, problems):
+    """The default mode of the benchmark (option "mixed" = the family's band): every golden case, G2 included, with the
+    reference's iteration count and status, x / u within 1e-4 absolute."""
+    p, b, g = cases.load(name)
+    r = solve_gpu(capi, oracle_mod, p, b, 32, mixed=problems.exact_band(p))
+    compare(r, g, 32, name)
 
 
 # measured fp32 iteration-count flip rates (one check interval early/late).  Box-constrained batches run the incremental-form
 # kernel (tmpc_tpp3.cuh): cartpole 0.01 %, quadrotor 0.01-0.04 % (the direct form, variant 5, has 1-2 %); adaptive quadrotor
 # 3 % and rocket 19 % (tol_dua 1e-4 on thrusts of magnitude 100 is at fp32 resolution) still run the direct form.
-FLIP_BOUND = {"cartpole": 0.002, "quadrotor": 0.003, "quadrotor_adaptive": 0.04, "rocket": 0.05}
+FLIP_BOUND = {"cartpole": 0.001, "quadrotor": 0.0015, "quadrotor_adaptive": 0.04, "rocket": 0.002}
 FLIP_BOUND_DIRECT = {"cartpole": 0.005, "quadrotor": 0.04}
 
 
@@ -110,9 +136,10 @@ def test_direct_form_variant(family, scale, capi, oracle_mod, problems):
     print(f"\n[parity] {family} s={scale} fp32 direct form: {flips}/{B} count flips, max|dx|={dx:.2e} max|du|={du:.2e} kernel={r['kernel']}")
 
 
+@pytest.mark.parametrize("fixer_sms", [0, -1])
 @pytest.mark.parametrize("family,scale,band,max_flips", [("cartpole", 1.0, 0.003, 0), ("cartpole", 0.3, 0.003, 0), ("quadrotor", 0.3, 0.003, 0),
-                                                         ("quadrotor", 1.0, 0.003, 1), ("rocket", 1.0, 0.3, 0), ("quadrotor_adaptive", 1.0, 0.3, 0)])
-def test_mixed_mode_exact_counts(family, scale, band, max_flips, capi, oracle_mod, problems):
+                                                         ("quadrotor", 1.0, 0.003, 1), ("rocket", 1.0, 0.003, 0), ("quadrotor_adaptive", 1.0, 0.3, 0)])
+def test_mixed_mode_exact_counts(family, scale, band, max_flips, fixer_sms, capi, oracle_mod, problems):
     """option "mixed": the fp32 pass stops every problem whose termination decision lies within the relative band of the
     tolerances, an fp64 pass re-solves exactly those -> the reference's iteration counts and status codes.  Measured on 2^18
     problems (profiles/tools/mixed_sweep.py): with the incremental-form kernel a band of 0.3 % leaves 0 (cartpole, easy quadrotor)
@@ -122,8 +149,9 @@ def test_mixed_mode_exact_counts(family, scale, band, max_flips, capi, oracle_mo
     B = 10000
     b = problems.make_batch(p, B, scale, seed=2024)
     g = oracle_mod.solve_batch(p, b, "ref" if oracle_mod.available("ref") else "port")
-    r = solve_gpu(capi, oracle_mod, p, b, 32, mixed=band)
-    assert "+" in r["kernel"] and 0 < r["marked"] < B, (r["kernel"], r["marked"])
+    # fixer_sms 0: the concurrent producer / consumer pair ("fp32|fp64"); -1: the sequential two-pass form ("fp32+fp64")
+    r = solve_gpu(capi, oracle_mod, p, b, 32, mixed=band, fixer_sms=fixer_sms)
+    assert ("|" if fixer_sms >= 0 else "+") in r["kernel"] and 0 < r["marked"] < B, (r["kernel"], r["marked"])
     assert not (r["status"] & 0x100).any(), "a marked problem was not re-solved"
     flips, dx, du = compare(r, g, 32, f"{family}@{scale} mixed", max_flip_frac=max_flips / B)
     print(f"\n[parity] {family} s={scale} mixed band={band}: {flips}/{B} count flips, {r['marked']} re-solved in fp64, max|dx|={dx:.2e} "
@@ -172,6 +200,33 @@ def test_streamed_pipeline_matches_chunked_launches(family, B, chunks, precision
         assert s.last_timing()["chunks"] >= 2, "the streamed path was not taken"
         for k in ("iter", "status", "x", "u", "residuals", "rho"):
             assert np.array_equal(r0[k], r1[k]), f"{family}: streamed pipeline differs in {k}"
+    s.close()
+
+
+@pytest.mark.parametrize("family,B", [("quadrotor", 100003), ("rocket", 50001)])
+def test_streamed_exact_mode_matches_the_two_pass_form(family, B, capi, oracle_mod, problems):
+    """Exact-count mode through the streamed host pipeline: the fp32 producer consumes the batch while it is arriving and queues
+    what it cannot decide, the fp64 consumer runs concurrently on the SMs left free, both count completions per chunk for the
+    D2H stream.  Same iteration counts, statuses and solutions as the sequential form (fp32 pass, compaction, fp64 pass) on one
+    chunk, bit for bit."""
+    p = dict(quadrotor=problems.quadrotor, rocket=problems.rocket)[family]()
+    b = problems.make_batch(p, B, 1.0, seed=13)
+    s = capi.CudaSolver()
+    s.set_family(cases.family_from_spec(p, oracle_mod.get_cache(p, "port")))
+    s.set_option("mixed", problems.exact_band(p))
+    s.set_option("fixer_sms", -1)
+    s.set_option("chunks", 1)
+    r0 = s.solve_batch(b.x0, b.Xref, b.Uref)
+    m0 = s.last_marked
+    assert "+" in s.last_kernel
+    s.set_option("fixer_sms", 0)
+    s.set_option("chunks", 0)
+    for _ in range(2):
+        r1 = s.solve_batch(b.x0, b.Xref, b.Uref)
+        assert "|" in s.last_kernel and s.last_timing()["chunks"] >= 2, (s.last_kernel, s.last_timing())
+        assert s.last_marked == m0 > 0
+        for k in ("iter", "status", "x", "u", "residuals", "rho"):
+            assert np.array_equal(r0[k], r1[k]), f"{family}: streamed exact mode differs in {k}"
     s.close()
 
 
@@ -293,6 +348,44 @@ def test_session_outliving_its_solver_fails_cleanly(capi, oracle_mod, problems):
     assert L.tinympc_cuda_session_read(h, b"iter", out.ctypes.data_as(capi.c_dp)) == 5
     assert L.tinympc_cuda_session_destroy(h) == 0
     ss.h = capi.C.c_void_p()
+
+
+@pytest.mark.parametrize("mixed", [0.0, 0.003])
+@pytest.mark.parametrize("B", [1000, 70001])
+def test_compact_io_matches_full_trajectories(B, mixed, capi, oracle_mod, problems):
+    """tinympc_cuda_batch_in::xref_const (one reference state per problem, replicated over the horizon on the device) and
+    tinympc_cuda_batch_out::u0 (first control only): same iteration counts, statuses and first controls as the full-trajectory
+    call on the replicated reference, through the host entry (chunked pipeline) and the device entry."""
+    import torch
+    p = problems.quadrotor()
+    b = problems.make_batch(p, B, 1.0, seed=21)
+    assert (b.Xref == b.Xref[:, :1]).all() and not b.Uref.any()
+    s = capi.CudaSolver()
+    s.set_option("mixed", mixed)
+    s.set_family(cases.family_from_spec(p, oracle_mod.get_cache(p, "port")))
+    full = s.solve_batch(b.x0, b.Xref, None)
+    xc = np.ascontiguousarray(b.Xref[:, 0, :])
+    c = s.solve_batch(b.x0, xref_const=xc, compact_out=True)
+    assert set(c) == {"u0", "iter", "status"}
+    assert np.array_equal(c["iter"], full["iter"]) and np.array_equal(c["status"], full["status"])
+    assert np.array_equal(c["u0"], full["u"][:, 0, :])
+    # mixed forms: compact input with full output, full input with compact output
+    a = s.solve_batch(b.x0, xref_const=xc)
+    assert np.array_equal(a["x"], full["x"]) and np.array_equal(a["u"], full["u"])
+    d = s.solve_batch(b.x0, b.Xref, None, compact_out=True)
+    assert np.array_equal(d["u0"], full["u"][:, 0, :])
+    # device entry
+    dev = torch.device("cuda", 0)
+    x0, xcd = torch.from_numpy(b.x0).to(dev), torch.from_numpy(xc).to(dev)
+    u0 = torch.empty((B, p.nu), device=dev); it = torch.empty(B, dtype=torch.int32, device=dev); st = torch.empty(B, dtype=torch.int32, device=dev)
+    s.solve_batch_device(B, x0.data_ptr(), None, None, None, None, it.data_ptr(), st.data_ptr(), xref_const=xcd.data_ptr(), u0=u0.data_ptr(),
+                         stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert np.array_equal(it.cpu().numpy(), full["iter"]) and np.array_equal(u0.cpu().numpy(), full["u"][:, 0, :])
+    # argument checks
+    with pytest.raises(capi.TinympcCudaError):
+        s.solve_batch(b.x0, b.Xref, None, xref_const=xc)
+    s.close()
 
 
 @pytest.mark.parametrize("which", ["xref_only", "uref_only", "none"])

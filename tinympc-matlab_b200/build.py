@@ -82,6 +82,21 @@ def inst3(nx, nu, N, refs=True, ppb=False, fb=False, variant=0, max_warps=24, op
                 opq=opq, tib=tib, tm=True, minb=1, ntm=ntm, cones=cones, ttm=ttm)
 
 
+def inst4(nx, nu, N, refs=True, fb=False, variant=0, aff=None, cones=(0, 0, 0, 0, 0, 0)):
+    """mixed-precision kernel of the rocket family (tmpc_tpp4.cuh): fp64 iterates and cone duals, fp32 Riccati increments.
+    Tensor memory per thread: (N-1) [dx | x | cone dual | multiplier] + input multipliers; shared memory: u, input cone dual
+    (double), box duals, -dd."""
+    scs, scd, ucs, ucd, nsl, nil = cones
+    cw = 3 * nx + 2 * scd + 2 * nsl
+    tm = (N - 1) * cw + 2 * nil * (N - 1)
+    sm = 2 * (nu + ucd) * (N - 1) + nx * N + 2 * nu * (N - 1)
+    warps = min(16, 4 * (512 // tm), ((226 * 1024 - 1024 - pack_elems(nx, nu, N) * 4) // (sm * 4 * 32) // 4) * 4)
+    assert warps >= 4, "shape does not fit the mixed-precision kernel"
+    aff = ((nx, nu) == (6, 3)) if aff is None else aff
+    return dict(gen=4, bits=32, nx=nx, nu=nu, N=N, feat=CON, refs=3 if refs else 0, ppb=False, fb=fb, variant=variant, block=warps * 32, aff=aff,
+                opq=False, tib=False, tm=True, minb=1, ntm=0, cones=cones, ttm=-1)
+
+
 def cols_per_thread(nx, nu, N, feat, refs, ntm=0):
     """shared-memory scalar columns per thread; ntm = number of state-sized arrays (TV, GC, GL, SXT) in tensor memory"""
     sx, su = nx * N, nu * (N - 1)
@@ -140,9 +155,13 @@ def default_instances():
     # box + second-order cones + linear inequalities (rocket landing, rocket_landing_constraints.m:40-55: one cone on the
     # first three states, one on the three inputs): the same form with two more slack families, cone blocks compiled in
     # (+ one linear row on each side; the last two numbers are the row counts)
+    # default (variant 0): the mixed-precision kernel, tmpc_tpp4.cuh (fp64 iterates, fp32 increments); the all-fp32 incremental
+    # form of round 1 stays as the A/B baseline, option variant=3
     for fb in (True, False):
-        out.append(inst3(6, 3, 10, refs=True, fb=fb, feat=CON, cones=(0, 3, 0, 3, 1, 1)))
-        out.append(inst3(6, 3, 10, refs=True, fb=fb, feat=CON, cones=(0, 3, 0, 3, 0, 0)))
+        out.append(inst4(6, 3, 10, refs=True, fb=fb, cones=(0, 3, 0, 3, 1, 1)))
+        out.append(inst4(6, 3, 10, refs=True, fb=fb, cones=(0, 3, 0, 3, 0, 0)))
+        out.append(inst3(6, 3, 10, refs=True, fb=fb, feat=CON, cones=(0, 3, 0, 3, 1, 1), variant=3))
+        out.append(inst3(6, 3, 10, refs=True, fb=fb, feat=CON, cones=(0, 3, 0, 3, 0, 0), variant=3))
     for bits in (32, 64):
         for (nx, nu, N) in shapes:
             if bits == 64:            # fp64 parity mode: direct form (admm.cpp order), tmpc_tpp2.cuh
@@ -176,6 +195,9 @@ def default_instances():
 
 def name_of(i):
     t = "f32" if i["bits"] == 32 else "f64"
+    if i["gen"] == 4:
+        cn = "_c" + "".join(str(c) for c in i["cones"])
+        return f"tpp4_mix_{i['nx']}x{i['nu']}x{i['N']}_con{cn}{'' if i['refs'] else '_noref'}{'_fb' if i['fb'] else ''}{'_aff' if i['aff'] else ''}_v{i['variant']}"
     if i["gen"] == 3:
         cn = ("_c" + "".join(str(c) for c in i["cones"])) if i["feat"] == CON else ""
         return (f"tpp3_f32_{i['nx']}x{i['nu']}x{i['N']}_{FEAT_NAME[i['feat']]}{cn}{'' if i['refs'] else '_noref'}{'_ppb' if i['ppb'] else ''}{'_fb' if i['fb'] else ''}"
@@ -194,7 +216,15 @@ def gen_sources(instances):
         T = "float" if i["bits"] == 32 else "double"
         g = "" if i["gen"] == 1 else "2"
         b = lambda v: "true" if v else "false"
-        if i["gen"] == 3:
+        if i["gen"] == 4:
+            src = (
+                "// generated by tinympc-matlab_b200/build.py -- do not edit\n"
+                '#include "../tmpc_tpp4.cuh"\n#include "../tmpc_registry.h"\nusing namespace tmpc;\n'
+                f"using Cfg_{n} = Tpp4Cfg<{i['nx']}, {i['nu']}, {i['N']}, {i['block']}, {b(i['refs'])}, {b(i['fb'])}, {b(i['aff'])}, "
+                f"{', '.join(str(c) for c in i['cones'])}>;\n"
+                f"TMPC_DEFINE_TPP4_ENTRY({n}, Cfg_{n}, {i['feat']}, 32, {i['variant']})\n"
+            )
+        elif i["gen"] == 3:
             src = (
                 "// generated by tinympc-matlab_b200/build.py -- do not edit\n"
                 '#include "../tmpc_tpp3.cuh"\n#include "../tmpc_registry.h"\nusing namespace tmpc;\n'
@@ -242,7 +272,7 @@ def up_to_date(obj: Path, dep: Path, src: Path) -> bool:
         return False
     toks = dep.read_text().replace("\\\n", " ").split()
     for f in toks[1:]:
-        if f.startswith(("/usr/", "/opt/")):   # toolchain headers
+        if f == ":" or f.startswith(("/usr/", "/opt/")):   # separator, toolchain headers
             continue
         try:
             if os.stat(f).st_mtime > t:
@@ -270,7 +300,7 @@ def build(jobs: int | None = None, force: bool = False, verbose: bool = True) ->
     log_dir = OBJ / "logs"
     log_dir.mkdir(exist_ok=True)
     srcs = gen_sources(default_instances()) + [CSRC / "tmpc_capi.cu"]
-    srcs += sorted(CSRC.glob("tmpc_wpp*.cu")) + sorted((CSRC / "host").glob("*.cpp"))
+    srcs += sorted(CSRC.glob("tmpc_wpp*.cu")) + [CSRC / "tmpc_precompute.cu"] + sorted((CSRC / "host").glob("*.cpp"))
     jobs = jobs or os.cpu_count() or 4
     with ThreadPoolExecutor(max_workers=jobs) as ex:
         results = list(ex.map(lambda s: compile_one(s, force, log_dir), srcs))

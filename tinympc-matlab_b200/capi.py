@@ -39,6 +39,7 @@ EXPORTS = [
     "tinympc_cuda_version", "tinympc_cuda_host_alloc", "tinympc_cuda_host_free",
     "tinympc_cuda_session_create", "tinympc_cuda_session_destroy", "tinympc_cuda_session_set_x0", "tinympc_cuda_session_set_x_ref",
     "tinympc_cuda_session_set_u_ref", "tinympc_cuda_session_solve", "tinympc_cuda_session_step", "tinympc_cuda_session_read",
+    "tinympc_cuda_precompute_batch",
 ]
 
 
@@ -71,15 +72,54 @@ class CFamily(C.Structure):
 
 class CBatchIn(C.Structure):
     _fields_ = [("batch", C.c_int), ("x0", C.c_void_p), ("Xref", C.c_void_p), ("Uref", C.c_void_p),
-                ("x_min", C.c_void_p), ("x_max", C.c_void_p), ("u_min", C.c_void_p), ("u_max", C.c_void_p)]
+                ("x_min", C.c_void_p), ("x_max", C.c_void_p), ("u_min", C.c_void_p), ("u_max", C.c_void_p), ("xref_const", C.c_void_p)]
 
 
 class CBatchOut(C.Structure):
     _fields_ = [("x", C.c_void_p), ("u", C.c_void_p), ("iter", C.c_void_p), ("status", C.c_void_p),
-                ("residuals", C.c_void_p), ("rho", C.c_void_p)]
+                ("residuals", C.c_void_p), ("rho", C.c_void_p), ("u0", C.c_void_p)]
+
+
+class CPrecomputeIn(C.Structure):
+    _fields_ = [("batch", C.c_int), ("nx", C.c_int), ("nu", C.c_int), ("Adyn", c_dp), ("Bdyn", c_dp), ("fdyn", c_dp), ("Q", c_dp), ("R", c_dp), ("rho", c_dp)]
+
+
+class CPrecomputeOut(C.Structure):
+    _fields_ = [("Kinf", c_dp), ("Pinf", c_dp), ("Quu_inv", c_dp), ("AmBKt", c_dp), ("APf", c_dp), ("BPf", c_dp),
+                ("dKinf_drho", c_dp), ("dPinf_drho", c_dp), ("dC1_drho", c_dp), ("dC2_drho", c_dp), ("iters", c_ip)]
 
 
 _lib = None
+
+
+def precompute_batch(A, B, Q, R, rho, f=None, sensitivities=False) -> dict:
+    """Batched tiny_precompute_and_set_cache on the GPU (tinympc_cuda_precompute_batch): A (n, nx, nx), B (n, nx, nu), Q (n, nx),
+    R (n, nu) diagonals, rho (n,), optional f (n, nx).  Returns math-shaped arrays Kinf (n, nu, nx), Pinf (n, nx, nx), Quu_inv,
+    AmBKt, APf, BPf, iters (+ dKinf, dPinf, dC1, dC2 with sensitivities=True)."""
+    L = load()
+    A = np.asarray(A, np.float64); Bm = np.asarray(B, np.float64)
+    n, nx, nu = A.shape[0], A.shape[1], Bm.shape[2]
+    cm = lambda a: np.ascontiguousarray(np.swapaxes(a, 1, 2))          # per-problem column-major
+    a_, b_ = cm(A), cm(Bm)
+    q_, r_ = np.ascontiguousarray(Q, np.float64), np.ascontiguousarray(R, np.float64)
+    rho_ = np.ascontiguousarray(np.broadcast_to(np.asarray(rho, np.float64), (n,)))
+    f_ = None if f is None else np.ascontiguousarray(f, np.float64)
+    dp = lambda a: None if a is None else a.ctypes.data_as(c_dp)
+    cin = CPrecomputeIn(n, nx, nu, dp(a_), dp(b_), dp(f_), dp(q_), dp(r_), dp(rho_))
+    o = dict(Kinf=np.empty((n, nx, nu)), Pinf=np.empty((n, nx, nx)), Quu_inv=np.empty((n, nu, nu)), AmBKt=np.empty((n, nx, nx)),
+             APf=np.empty((n, nx)), BPf=np.empty((n, nu)), iters=np.empty(n, np.int32))
+    if sensitivities:
+        o.update(dKinf=np.empty((n, nx, nu)), dPinf=np.empty((n, nx, nx)), dC1=np.empty((n, nu, nu)), dC2=np.empty((n, nx, nx)))
+    co = CPrecomputeOut(dp(o["Kinf"]), dp(o["Pinf"]), dp(o["Quu_inv"]), dp(o["AmBKt"]), dp(o["APf"]), dp(o["BPf"]),
+                        dp(o.get("dKinf")), dp(o.get("dPinf")), dp(o.get("dC1")), dp(o.get("dC2")), o["iters"].ctypes.data_as(c_ip))
+    rc = L.tinympc_cuda_precompute_batch(C.byref(cin), C.byref(co))
+    if rc:
+        raise TinympcCudaError(rc, "tinympc_cuda_precompute_batch failed")
+    # the C ABI returns column-major (rows x cols) chunks: as (cols, rows) C arrays -> transpose to math shape
+    for k in ("Kinf", "Pinf", "Quu_inv", "AmBKt", "dKinf", "dPinf", "dC1", "dC2"):
+        if k in o:
+            o[k] = np.ascontiguousarray(np.swapaxes(o[k], 1, 2))
+    return o
 
 
 def load():
@@ -117,6 +157,7 @@ def load():
         L.tinympc_cuda_session_solve.argtypes = [C.c_void_p]
         L.tinympc_cuda_session_step.argtypes = [C.c_void_p, C.c_int]
         L.tinympc_cuda_session_read.argtypes = [C.c_void_p, C.c_char_p, c_dp]
+        L.tinympc_cuda_precompute_batch.argtypes = [C.POINTER(CPrecomputeIn), C.POINTER(CPrecomputeOut)]
         # plain-C shim over the host C++ API mirror (csrc/host/tiny_capi_shim.cpp)
         dp, ip, vp = c_dp, c_ip, C.c_void_p
         L.tinympc_host_setup.argtypes = [dp, dp, dp, dp, dp, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, ip]
@@ -271,7 +312,9 @@ class CudaSolver:
 
     # ---- host buffers (numpy) ---------------------------------------------------------------
     def solve_batch(self, x0, Xref=None, Uref=None, x_min=None, x_max=None, u_min=None, u_max=None,
-                    want_residuals=True, want_rho=True, out=None) -> dict:
+                    want_residuals=True, want_rho=True, out=None, xref_const=None, compact_out=False) -> dict:
+        """xref_const (B, nx): one reference state per problem held over the horizon (instead of Xref);
+        compact_out: return only u0 (B, nu), iter, status -- the trajectories stay on the device."""
         nx, nu, N = self.dims
         keep = []
 
@@ -287,17 +330,20 @@ class CudaSolver:
         x0 = np.ascontiguousarray(x0, np.float32)
         B = x0.shape[0]
         cin = CBatchIn(B, fptr(x0, (B, nx)), fptr(Xref, (B, N, nx)), fptr(Uref, (B, N - 1, nu)),
-                       fptr(x_min, (B, N, nx)), fptr(x_max, (B, N, nx)), fptr(u_min, (B, N - 1, nu)), fptr(u_max, (B, N - 1, nu)))
+                       fptr(x_min, (B, N, nx)), fptr(x_max, (B, N, nx)), fptr(u_min, (B, N - 1, nu)), fptr(u_max, (B, N - 1, nu)),
+                       fptr(xref_const, (B, nx)))
         if out is None:
-            out = dict(x=np.empty((B, N, nx), np.float32), u=np.empty((B, N - 1, nu), np.float32),
-                       iter=np.empty(B, np.int32), status=np.empty(B, np.int32))
-            if want_residuals:
-                out["residuals"] = np.empty((B, 4), np.float32)
-            if want_rho:
-                out["rho"] = np.empty(B, np.float32)
-        co = CBatchOut(out["x"].ctypes.data, out["u"].ctypes.data, out["iter"].ctypes.data, out["status"].ctypes.data,
-                       out["residuals"].ctypes.data if "residuals" in out else None,
-                       out["rho"].ctypes.data if "rho" in out else None)
+            if compact_out:
+                out = dict(u0=np.empty((B, nu), np.float32), iter=np.empty(B, np.int32), status=np.empty(B, np.int32))
+            else:
+                out = dict(x=np.empty((B, N, nx), np.float32), u=np.empty((B, N - 1, nu), np.float32),
+                           iter=np.empty(B, np.int32), status=np.empty(B, np.int32))
+                if want_residuals:
+                    out["residuals"] = np.empty((B, 4), np.float32)
+                if want_rho:
+                    out["rho"] = np.empty(B, np.float32)
+        opt = lambda k: out[k].ctypes.data if k in out else None
+        co = CBatchOut(opt("x"), opt("u"), out["iter"].ctypes.data, out["status"].ctypes.data, opt("residuals"), opt("rho"), opt("u0"))
         self._check(self.L.tinympc_cuda_solve_batch(self.h, C.byref(cin), C.byref(co)))
         return out
 
@@ -307,9 +353,9 @@ class CudaSolver:
 
     # ---- device buffers (raw pointers, e.g. torch.Tensor.data_ptr()) ---------------------------
     def solve_batch_device(self, batch: int, x0, Xref, Uref, x, u, iters, status, residuals=None, rho=None,
-                           x_min=None, x_max=None, u_min=None, u_max=None, stream=None, dev_index=0):
-        cin = CBatchIn(batch, x0, Xref, Uref, x_min, x_max, u_min, u_max)
-        co = CBatchOut(x, u, iters, status, residuals, rho)
+                           x_min=None, x_max=None, u_min=None, u_max=None, stream=None, dev_index=0, xref_const=None, u0=None):
+        cin = CBatchIn(batch, x0, Xref, Uref, x_min, x_max, u_min, u_max, xref_const)
+        co = CBatchOut(x, u, iters, status, residuals, rho, u0)
         self._check(self.L.tinympc_cuda_solve_batch_device(self.h, dev_index, C.byref(cin), C.byref(co), stream))
 
 

@@ -401,11 +401,11 @@ int tiny_solve_batch(TinySolver* solver, const TinyBatchIn* in, const TinyBatchO
     if (!solver || !in || !out) return TINYMPC_CUDA_EINVAL;
     int rc = sync_family(solver);
     if (rc) return rc;
-    tinympc_cuda_batch_in ci;
+    tinympc_cuda_batch_in ci{};
     ci.batch = in->batch; ci.x0 = in->x0; ci.Xref = in->Xref; ci.Uref = in->Uref;
-    ci.x_min = in->x_min; ci.x_max = in->x_max; ci.u_min = in->u_min; ci.u_max = in->u_max;
-    tinympc_cuda_batch_out co;
-    co.x = out->x; co.u = out->u; co.iter = out->iter; co.status = out->status; co.residuals = out->residuals; co.rho = out->rho;
+    ci.x_min = in->x_min; ci.x_max = in->x_max; ci.u_min = in->u_min; ci.u_max = in->u_max; ci.xref_const = in->xref_const;
+    tinympc_cuda_batch_out co{};
+    co.x = out->x; co.u = out->u; co.iter = out->iter; co.status = out->status; co.residuals = out->residuals; co.rho = out->rho; co.u0 = out->u0;
     rc = tinympc_cuda_solve_batch(solver->backend->cuda, &ci, &co);
     if (rc) solver->backend->err = tinympc_cuda_last_error(solver->backend->cuda);
     return rc;

@@ -97,6 +97,7 @@ struct TinyBatchIn {
     const float* x_max;
     const float* u_min;
     const float* u_max;
+    const float* xref_const = nullptr;   // batch x nx: one reference state per problem, held over the horizon (instead of Xref)
 };
 struct TinyBatchOut {
     float* x;             // batch x (nx*N)
@@ -105,4 +106,5 @@ struct TinyBatchOut {
     int* status;          // batch (1 / 11)
     float* residuals;     // batch x 4 or NULL
     float* rho;           // batch or NULL
+    float* u0 = nullptr;  // batch x nu: first control only; with it x and u may be NULL (the trajectories stay on the device)
 };

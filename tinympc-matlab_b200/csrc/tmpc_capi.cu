@@ -62,11 +62,16 @@ struct DeviceCtx {
     cudaStream_t streams[kStreams] = {nullptr, nullptr, nullptr};
     cudaEvent_t k0[kMaxChunks], k1[kMaxChunks];
     bool events = false;
-    DevBuf x0, Xref, Uref, xmin, xmax, umin, umax, x, u, iter, status, res, rho;
+    DevBuf x0, Xref, Uref, xmin, xmax, umin, umax, x, u, iter, status, res, rho, xrc, u0;
+    DevBuf exp_xref[kStreams + 1], exp_x[kStreams + 1], exp_u[kStreams + 1];   // compact I/O: device-side expansion / full trajectories per slot
     DevBuf ref_scratch[kStreams + 1];   // REFS_L2 kernels: per-slot reference terms
     DevBuf wpp_scratch[kStreams + 1];   // warp-per-problem workspaces (one per pipeline stream + the device/workspace entry)
     DevBuf ref_scratch64[kStreams + 1]; // mixed mode: reference terms of the fp64 re-solve pass
-    DevBuf marked[kStreams + 1];        // mixed mode: indices of the problems the fp32 pass marked ambiguous
+    DevBuf marked[kStreams + 1];        // mixed mode: indices of the problems the fp32 pass marked ambiguous (two-pass form) / the queue
+    // exact-count mode, concurrent form: per slot {q_tail, producer CTAs done, consumer ticket counter, pad}
+    int* qctl = nullptr;                // 4 * kMaxChunks ints, indexed like the work counters (chunk index; the last one = device entry)
+    cudaStream_t fix_stream[kStreams + 1] = {nullptr, nullptr, nullptr, nullptr};   // the fp64 consumer launches
+    cudaEvent_t ev_fork[kStreams + 1] = {nullptr, nullptr, nullptr, nullptr}, ev_join[kStreams + 1] = {nullptr, nullptr, nullptr, nullptr};
 };
 
 struct Family {
@@ -96,6 +101,8 @@ struct tinympc_cuda_solver {
     int streamed = 1;                  // option "streamed": 1 = single-launch streamed host pipeline where it applies, 0 = chunked launches
     double mixed_band = 0;             // option "mixed": > 0 = fp32 pass + fp64 re-solve of the problems whose termination decision
                                        // falls within this relative band of the tolerances (exact iteration counts at ~fp32 speed)
+    int fixer_sms = 0;                 // option "fixer_sms": SMs the fp32 producer leaves to the concurrent fp64 consumer (0 = auto: 13 % of
+                                       // the device; -1 = the sequential two-pass form: fp32 pass, compaction, fp64 pass)
     long long mixed_marked = 0;        // problems re-solved in fp64 by the last mixed solve (host entry: filled by the call)
     int mixed_pending_dev = -1;        // device entry: the count still sits in that device's counter slot
     // err, last_kernel and launches are written by the per-device worker threads of tinympc_cuda_solve_batch: the strings
@@ -192,6 +199,22 @@ __global__ void collect_marked_kernel(const int* __restrict__ status, int n, int
     if (hit) list[base + __popc(m & ((1u << lane) - 1u))] = i;
 }
 
+// compact I/O (tinympc_cuda_batch_in::xref_const, tinympc_cuda_batch_out::u0): the set point replicated over the horizon,
+// the first control picked out of the solution.  One thread per float4 / per element; pure HBM traffic (~0.1 ms per 2^20 problems).
+__global__ void expand_xref_kernel(const float* __restrict__ xc, float* __restrict__ Xref, size_t total, int nx, int sx) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const size_t b = i / sx;
+    const int e = (int)(i - b * sx) % nx;
+    Xref[i] = __ldg(xc + b * nx + e);
+}
+__global__ void gather_u0_kernel(const float* __restrict__ u, float* __restrict__ u0, size_t total, int nu, int su) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const size_t b = i / nu;
+    u0[i] = u[b * su + (i - b * nu)];
+}
+
 int upload_family(tinympc_cuda_solver* s) {
     const Family& f = s->fam;
     std::vector<float> p32(f.pack.size());
@@ -221,7 +244,8 @@ const KernelEntry* pick_kernel(const tinympc_cuda_solver* s, const DeviceCtx& d,
     return ke;
 }
 
-int launch_tpp(tinympc_cuda_solver* s, DeviceCtx& d, const KernelEntry* ke, SolveParams& p, DevBuf& rb, int bits, int* counter, cudaStream_t st) {
+int launch_tpp(tinympc_cuda_solver* s, DeviceCtx& d, const KernelEntry* ke, SolveParams& p, DevBuf& rb, int bits, int* counter, cudaStream_t st,
+               int reserve_sms = 0, int* grid_out = nullptr, int max_sms = 0) {
     const Family& f = s->fam;
     const size_t smem = ke->smem_bytes(f.L.cold_size);
     if (smem > 227u * 1024u) return fail(s, TINYMPC_CUDA_EUNSUPPORTED, std::string("kernel ") + ke->name + " needs more shared memory than an SM has");
@@ -230,7 +254,8 @@ int launch_tpp(tinympc_cuda_solver* s, DeviceCtx& d, const KernelEntry* ke, Solv
     CU(s, ke->occupancy(&occ, smem));
     if (occ < 1) return fail(s, TINYMPC_CUDA_EUNSUPPORTED, std::string("kernel ") + ke->name + " does not fit on an SM");
     if (s->ctas_per_sm > 0 && s->ctas_per_sm < occ) occ = s->ctas_per_sm;
-    int grid = d.sm_count * occ;                       // persistent CTAs: a multiple of the SM count
+    int grid = std::max(1, d.sm_count - reserve_sms) * occ;   // persistent CTAs: a multiple of the SM count (minus the SMs left to a concurrent launch)
+    if (max_sms > 0) grid = std::min(grid, max_sms * occ);
     const int need = (p.batch + ke->block - 1) / ke->block;
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
@@ -244,6 +269,48 @@ int launch_tpp(tinympc_cuda_solver* s, DeviceCtx& d, const KernelEntry* ke, Solv
     CU(s, cudaMemsetAsync(counter, 0, sizeof(int), st));
     CU(s, ke->launch(p, grid, smem, st, f.pack.data(), f.L));
     s->launches += 1;
+    if (grid_out) *grid_out = grid;
+    return TINYMPC_CUDA_OK;
+}
+
+int auto_fixer_sms(const tinympc_cuda_solver* s, const DeviceCtx& d) {
+    if (s->fixer_sms > 0) return std::min(s->fixer_sms, d.sm_count / 2);
+    // The consumer re-solves ~2 % of the problems at ~1/7 of the producer's per-SM rate: ~13 % of the SMs balances the two
+    // launches (measured optimum on the quadrotor batch, profiles/r02/fixer_sweep.jsonl).
+    return std::max(2, (d.sm_count * 13 + 50) / 100);
+}
+
+// Exact-count mode, concurrent form: the fp32 producer on `st` over all but R SMs, the fp64 consumer on the slot's own stream over
+// exactly R.  The two grids together never exceed the device, so whichever of them the hardware starts first leaves room for
+// the other: a consumer that waits on the queue can never keep the producer from running.  p32 / p64 arrive with their in/out
+// pointers (and, for the streamed pipeline, the watermark / completion fields) set.  The producer is launched FIRST: if something
+// serialises the two launches (profilers), the queue is simply complete before the consumer starts.
+int launch_exact_pair(tinympc_cuda_solver* s, DeviceCtx& d, const KernelEntry* ke, const KernelEntry* ke64, SolveParams p32, SolveParams p64, int batch,
+                      int counter_slot, int slot, int* counter, cudaStream_t st) {
+    const Family& f = s->fam;
+    int* q = d.qctl + 4 * counter_slot;
+    DevBuf& list = d.marked[slot];
+    CU(s, list.reserve(sizeof(int) * (size_t)batch));
+    CU(s, cudaMemsetAsync(q, 0, sizeof(int) * 4, st));
+    CU(s, cudaMemsetAsync(list.p, 0xFF, sizeof(int) * (size_t)batch, st));      // every entry -1 = "not written yet"
+    CU(s, cudaEventRecord(d.ev_fork[slot], st));
+    p32.amb_band = static_cast<float>(s->mixed_band);
+    p32.q_tail = q; p32.q_list = static_cast<int*>(list.p); p32.q_prod_done = q + 1; p32.q_consume = 0; p32.q_prod_total = 0;
+    int grid32 = 0;
+    const int R = auto_fixer_sms(s, d);
+    int rc = launch_tpp(s, d, ke, p32, d.ref_scratch[slot], 32, counter, st, R, &grid32);
+    if (rc) return rc;
+    p64.pack = (const void*)((const double*)d.pack64 + f.L.cold);
+    p64.amb_band = 0.f;
+    p64.avail_ptr = nullptr;                 // whatever the producer queued has landed
+    p64.q_tail = q; p64.q_list = static_cast<int*>(list.p); p64.q_prod_done = q + 1; p64.q_consume = 1; p64.q_prod_total = grid32;
+    cudaStream_t fs = d.fix_stream[slot];
+    CU(s, cudaStreamWaitEvent(fs, d.ev_fork[slot], 0));
+    rc = launch_tpp(s, d, ke64, p64, d.ref_scratch64[slot], 64, q + 2, fs, 0, nullptr, R);
+    if (rc) return rc;
+    CU(s, cudaEventRecord(d.ev_join[slot], fs));
+    CU(s, cudaStreamWaitEvent(st, d.ev_join[slot], 0));
+    note_kernel(s, std::string(ke->name) + "|" + ke64->name);
     return TINYMPC_CUDA_OK;
 }
 
@@ -257,6 +324,37 @@ int enqueue(tinympc_cuda_solver* s, DeviceCtx& d, const tinympc_cuda_batch_in& i
         return fail(s, TINYMPC_CUDA_EINVAL, "per-problem bounds need all four of x_min, x_max, u_min, u_max");
     if (!ppb && !f.shared_bounds_ok)
         return fail(s, TINYMPC_CUDA_EINVAL, "bound constraints are enabled but neither the family nor the batch supplies bounds");
+    if (in.xref_const && in.Xref) return fail(s, TINYMPC_CUDA_EINVAL, "give Xref or xref_const, not both");
+    const bool full_out = out.x && out.u;
+    if (!full_out && !out.u0) return fail(s, TINYMPC_CUDA_EINVAL, "x and u are required unless u0 is given");
+    if (in.xref_const || !full_out) {
+        // compact I/O: expand / keep the trajectories in this slot's device scratch, run the ordinary solve on them, pick u0 out
+        const size_t sx = (size_t)f.nx * f.N, su = (size_t)f.nu * (f.N - 1);
+        tinympc_cuda_batch_in in2 = in;
+        tinympc_cuda_batch_out out2 = out;
+        in2.xref_const = nullptr;
+        out2.u0 = nullptr;
+        if (in.xref_const) {
+            DevBuf& xb = d.exp_xref[scratch_slot];
+            CU(s, xb.reserve(sizeof(float) * sx * in.batch));
+            const size_t total = sx * in.batch;
+            expand_xref_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(in.xref_const, static_cast<float*>(xb.p), total, f.nx, (int)sx);
+            CU(s, cudaGetLastError());
+            s->launches += 1;
+            in2.Xref = static_cast<const float*>(xb.p);
+        }
+        if (!out.x) { CU(s, d.exp_x[scratch_slot].reserve(sizeof(float) * sx * in.batch)); out2.x = static_cast<float*>(d.exp_x[scratch_slot].p); }
+        if (!out.u) { CU(s, d.exp_u[scratch_slot].reserve(sizeof(float) * su * in.batch)); out2.u = static_cast<float*>(d.exp_u[scratch_slot].p); }
+        int rc = enqueue(s, d, in2, out2, counter_slot, st, scratch_slot);
+        if (rc) return rc;
+        if (out.u0) {
+            const size_t total = (size_t)f.nu * in.batch;
+            gather_u0_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(out2.u, out.u0, total, f.nu, (int)su);
+            CU(s, cudaGetLastError());
+            s->launches += 1;
+        }
+        return TINYMPC_CUDA_OK;
+    }
     const bool refs = in.Xref || in.Uref;
     int bits = s->precision;
     const KernelEntry* ke = s->force_wpp ? nullptr : pick_kernel(s, d, f, bits, ppb, refs, in.batch);
@@ -296,7 +394,8 @@ int enqueue(tinympc_cuda_solver* s, DeviceCtx& d, const tinympc_cuda_batch_in& i
         note_kernel(s, ke->name);
         return TINYMPC_CUDA_OK;
     }
-    // ---- mixed mode: fp32 pass that marks the ambiguous problems, compaction, fp64 re-solve of the marked ones ----
+    if (s->fixer_sms >= 0) return launch_exact_pair(s, d, ke, ke64, p, p, in.batch, counter_slot, scratch_slot, counter, st);
+    // ---- mixed mode, sequential form: fp32 pass that marks the ambiguous problems, compaction, fp64 re-solve of the marked ones ----
     int* const counter2 = d.counters + kMaxChunks + counter_slot;
     int* const n_marked = d.counters + 2 * kMaxChunks + counter_slot;
     DevBuf& list = d.marked[scratch_slot];
@@ -328,8 +427,9 @@ int check_ptr16(tinympc_cuda_solver* s, const void* p, const char* name) {
 int zero_iteration_result(tinympc_cuda_solver* s, const Family& f, const tinympc_cuda_batch_out& out, int batch, cudaStream_t st, bool device) {
     const size_t sx = (size_t)f.nx * f.N, su = (size_t)f.nu * (f.N - 1);
     if (device) {
-        CU(s, cudaMemsetAsync(out.x, 0, sizeof(float) * sx * batch, st));
-        CU(s, cudaMemsetAsync(out.u, 0, sizeof(float) * su * batch, st));
+        if (out.x) CU(s, cudaMemsetAsync(out.x, 0, sizeof(float) * sx * batch, st));
+        if (out.u) CU(s, cudaMemsetAsync(out.u, 0, sizeof(float) * su * batch, st));
+        if (out.u0) CU(s, cudaMemsetAsync(out.u0, 0, sizeof(float) * f.nu * batch, st));
         CU(s, cudaMemsetAsync(out.iter, 0, sizeof(int) * batch, st));
         std::vector<int> st11(batch, 11);
         CU(s, cudaMemcpyAsync(out.status, st11.data(), sizeof(int) * batch, cudaMemcpyHostToDevice, st));
@@ -341,8 +441,9 @@ int zero_iteration_result(tinympc_cuda_solver* s, const Family& f, const tinympc
             CU(s, cudaStreamSynchronize(st));
         }
     } else {
-        std::memset(out.x, 0, sizeof(float) * sx * batch);
-        std::memset(out.u, 0, sizeof(float) * su * batch);
+        if (out.x) std::memset(out.x, 0, sizeof(float) * sx * batch);
+        if (out.u) std::memset(out.u, 0, sizeof(float) * su * batch);
+        if (out.u0) std::memset(out.u0, 0, sizeof(float) * f.nu * batch);
         for (int b = 0; b < batch; ++b) { out.iter[b] = 0; out.status[b] = 11; }
         if (out.residuals) std::memset(out.residuals, 0, sizeof(float) * 4 * batch);
         if (out.rho) for (int b = 0; b < batch; ++b) out.rho[b] = (float)f.base.rho;
@@ -379,8 +480,8 @@ const StreamMemOps& stream_memops() {
 // kernel, whose lanes wait on the watermark before they read a claimed problem and count every finished problem per chunk;
 // stream 2 waits (cuStreamWaitValue32) for a chunk's count and copies its results back.  No launch boundaries, hence no
 // per-chunk tails of idle lanes, and the three engines (H2D DMA, SMs, D2H DMA) overlap for the whole batch.
-int run_shard_streamed(tinympc_cuda_solver* s, DeviceCtx& d, const KernelEntry* ke, const tinympc_cuda_batch_in& in, const tinympc_cuda_batch_out& out,
-                       int lo, int hi, int nch, double* kernel_ms, int* nchunks_out) {
+int run_shard_streamed(tinympc_cuda_solver* s, DeviceCtx& d, const KernelEntry* ke, const KernelEntry* ke64, const tinympc_cuda_batch_in& in,
+                       const tinympc_cuda_batch_out& out, int lo, int hi, int nch, double* kernel_ms, int* nchunks_out, long long* marked_out) {
     const Family& f = s->fam;
     const StreamMemOps& ops = stream_memops();
     const int n = hi - lo;
@@ -458,13 +559,18 @@ int run_shard_streamed(tinympc_cuda_solver* s, DeviceCtx& d, const KernelEntry* 
         DRV(ops.write(reinterpret_cast<CUstream>(s_in), reinterpret_cast<CUdeviceptr>(ctl + 1), (cuuint32_t)c1, 0), "cuStreamWriteValue32");
     }
     RT(cudaEventRecord(d.k0[0], s_k));
-    {
+    if (ke64) {
+        // exact-count mode: producer (streamed fp32) + concurrent fp64 consumer; a problem counts for its chunk when whichever
+        // of the two finishes it
+        int rc = launch_exact_pair(s, d, ke, ke64, p, p, n, 0, 0, ctl, s_k);
+        if (rc) return sync_fail(rc);
+    } else {
         // launch_tpp zeroes the work counter itself (ctl[0], on s_k, before the kernel)
         int rc = launch_tpp(s, d, ke, p, d.ref_scratch[0], ke->dtype_bits, ctl, s_k);
         if (rc) return sync_fail(rc);
+        note_kernel(s, ke->name);
     }
     RT(cudaEventRecord(d.k1[0], s_k));
-    note_kernel(s, ke->name);
     for (int c = 0; c < nch; ++c) {
         const int c0 = bounds[c], c1 = bounds[c + 1], cn = c1 - c0;
         const size_t g0 = (size_t)lo + c0;
@@ -483,6 +589,11 @@ int run_shard_streamed(tinympc_cuda_solver* s, DeviceCtx& d, const KernelEntry* 
     CU(s, cudaEventElapsedTime(&ms, d.k0[0], d.k1[0]));
     *kernel_ms = ms;
     *nchunks_out = nch;
+    if (ke64) {
+        int q = 0;
+        CU(s, cudaMemcpy(&q, d.qctl, sizeof(int), cudaMemcpyDeviceToHost));
+        *marked_out = q;
+    }
     return TINYMPC_CUDA_OK;
 }
 
@@ -503,18 +614,25 @@ int run_shard(tinympc_cuda_solver* s, DeviceCtx& d, const tinympc_cuda_batch_in&
         CU(s, d.xmin.reserve(sizeof(float) * sx * n)); CU(s, d.xmax.reserve(sizeof(float) * sx * n));
         CU(s, d.umin.reserve(sizeof(float) * su * n)); CU(s, d.umax.reserve(sizeof(float) * su * n));
     }
-    CU(s, d.x.reserve(sizeof(float) * sx * n)); CU(s, d.u.reserve(sizeof(float) * su * n));
+    const bool compact = in.xref_const || !(out.x && out.u);   // compact I/O goes through the chunked pipeline (the bus is no longer the limit)
+    if (in.xref_const) CU(s, d.xrc.reserve(sizeof(float) * f.nx * (size_t)n));
+    if (out.x) CU(s, d.x.reserve(sizeof(float) * sx * n));
+    if (out.u) CU(s, d.u.reserve(sizeof(float) * su * n));
+    if (out.u0) CU(s, d.u0.reserve(sizeof(float) * f.nu * (size_t)n));
     CU(s, d.iter.reserve(sizeof(int) * (size_t)n)); CU(s, d.status.reserve(sizeof(int) * (size_t)n));
     if (out.residuals) CU(s, d.res.reserve(sizeof(float) * 4 * (size_t)n));
     if (out.rho) CU(s, d.rho.reserve(sizeof(float) * (size_t)n));
 
-    // single-launch streamed pipeline: plain (not mixed) solves on a thread-per-problem kernel that honours the watermark
-    if (s->streamed && !(s->mixed_band > 0 && s->precision == 32) && !s->force_wpp && stream_memops().ok) {
+    // single-launch streamed pipeline: a thread-per-problem kernel that honours the watermark; in the exact-count mode the
+    // concurrent producer / consumer pair (both count completions per chunk)
+    const bool mixed = s->mixed_band > 0 && s->precision == 32;
+    if (s->streamed && !compact && !(mixed && s->fixer_sms < 0) && !s->force_wpp && stream_memops().ok) {
         const KernelEntry* ke = pick_kernel(s, d, f, s->precision, ppb, in.Xref || in.Uref, n);
+        const KernelEntry* ke64 = mixed ? find_kernel(f, 64, ppb, in.Xref || in.Uref, 0) : nullptr;
         // auto (0): the ramped chunk layout for shards of >= 2^16 problems, else equal chunks of >= 2^14 problems
         int nst = s->chunks > 0 ? std::min(s->chunks, kMaxGranules) : (n >= (1 << 16) ? 0 : n / 16384);
-        if (ke && ke->streaming && (nst == 0 || nst >= 2) && (ppb || f.shared_bounds_ok))
-            return run_shard_streamed(s, d, ke, in, out, lo, hi, nst, kernel_ms, nchunks_out);
+        if (ke && ke->streaming && (!mixed || (ke64 && ke64->streaming)) && (nst == 0 || nst >= 2) && (ppb || f.shared_bounds_ok))
+            return run_shard_streamed(s, d, ke, ke64, in, out, lo, hi, nst, kernel_ms, nchunks_out, marked_out);
     }
     // chunking: enough chunks to overlap copies with compute, each still many waves of the GPU
     int nch = s->chunks > 0 ? s->chunks : (n >= (1 << 17) ? 8 : (n >= (1 << 15) ? 4 : 1));
@@ -532,19 +650,22 @@ int run_shard(tinympc_cuda_solver* s, DeviceCtx& d, const tinympc_cuda_batch_in&
         };
         CU(s, h2d(d.x0, in.x0, f.nx));
         if (in.Xref) CU(s, h2d(d.Xref, in.Xref, sx));
+        if (in.xref_const) CU(s, h2d(d.xrc, in.xref_const, f.nx));
         if (in.Uref) CU(s, h2d(d.Uref, in.Uref, su));
         if (ppb) { CU(s, h2d(d.xmin, in.x_min, sx)); CU(s, h2d(d.xmax, in.x_max, sx)); CU(s, h2d(d.umin, in.u_min, su)); CU(s, h2d(d.umax, in.u_max, su)); }
         tinympc_cuda_batch_in din{};
         din.batch = cn;
         din.x0 = (float*)d.x0.p + (size_t)f.nx * c0;
         din.Xref = in.Xref ? (float*)d.Xref.p + sx * c0 : nullptr;
+        din.xref_const = in.xref_const ? (float*)d.xrc.p + (size_t)f.nx * c0 : nullptr;
         din.Uref = in.Uref ? (float*)d.Uref.p + su * c0 : nullptr;
         if (ppb) {
             din.x_min = (float*)d.xmin.p + sx * c0; din.x_max = (float*)d.xmax.p + sx * c0;
             din.u_min = (float*)d.umin.p + su * c0; din.u_max = (float*)d.umax.p + su * c0;
         }
         tinympc_cuda_batch_out dout{};
-        dout.x = (float*)d.x.p + sx * c0; dout.u = (float*)d.u.p + su * c0;
+        dout.x = out.x ? (float*)d.x.p + sx * c0 : nullptr; dout.u = out.u ? (float*)d.u.p + su * c0 : nullptr;
+        dout.u0 = out.u0 ? (float*)d.u0.p + (size_t)f.nu * c0 : nullptr;
         dout.iter = (int*)d.iter.p + c0; dout.status = (int*)d.status.p + c0;
         dout.residuals = out.residuals ? (float*)d.res.p + 4 * (size_t)c0 : nullptr;
         dout.rho = out.rho ? (float*)d.rho.p + c0 : nullptr;
@@ -552,8 +673,9 @@ int run_shard(tinympc_cuda_solver* s, DeviceCtx& d, const tinympc_cuda_batch_in&
         int rc = enqueue(s, d, din, dout, c, st, c % kStreams);
         if (rc) return rc;
         CU(s, cudaEventRecord(d.k1[c], st));
-        CU(s, cudaMemcpyAsync(out.x + sx * g0, dout.x, sizeof(float) * sx * cn, cudaMemcpyDeviceToHost, st));
-        CU(s, cudaMemcpyAsync(out.u + su * g0, dout.u, sizeof(float) * su * cn, cudaMemcpyDeviceToHost, st));
+        if (out.x) CU(s, cudaMemcpyAsync(out.x + sx * g0, dout.x, sizeof(float) * sx * cn, cudaMemcpyDeviceToHost, st));
+        if (out.u) CU(s, cudaMemcpyAsync(out.u + su * g0, dout.u, sizeof(float) * su * cn, cudaMemcpyDeviceToHost, st));
+        if (out.u0) CU(s, cudaMemcpyAsync(out.u0 + (size_t)f.nu * g0, dout.u0, sizeof(float) * f.nu * cn, cudaMemcpyDeviceToHost, st));
         CU(s, cudaMemcpyAsync(out.iter + g0, dout.iter, sizeof(int) * cn, cudaMemcpyDeviceToHost, st));
         CU(s, cudaMemcpyAsync(out.status + g0, dout.status, sizeof(int) * cn, cudaMemcpyDeviceToHost, st));
         if (out.residuals) CU(s, cudaMemcpyAsync(out.residuals + 4 * g0, dout.residuals, sizeof(float) * 4 * cn, cudaMemcpyDeviceToHost, st));
@@ -567,10 +689,16 @@ int run_shard(tinympc_cuda_solver* s, DeviceCtx& d, const tinympc_cuda_batch_in&
     }
     *nchunks_out = nch;
     if (s->mixed_band > 0 && s->precision == 32) {
-        int counts[kMaxChunks];
-        CU(s, cudaMemcpy(counts, d.counters + 2 * kMaxChunks, sizeof(int) * nch, cudaMemcpyDeviceToHost));
         long long tot = 0;
-        for (int c = 0; c < nch; ++c) tot += counts[c];
+        if (s->fixer_sms >= 0) {
+            int q[4 * kMaxChunks];
+            CU(s, cudaMemcpy(q, d.qctl, sizeof(int) * 4 * nch, cudaMemcpyDeviceToHost));
+            for (int c = 0; c < nch; ++c) tot += q[4 * c];
+        } else {
+            int counts[kMaxChunks];
+            CU(s, cudaMemcpy(counts, d.counters + 2 * kMaxChunks, sizeof(int) * nch, cudaMemcpyDeviceToHost));
+            for (int c = 0; c < nch; ++c) tot += counts[c];
+        }
         *marked_out = tot;
     }
     return TINYMPC_CUDA_OK;
@@ -617,6 +745,12 @@ int tinympc_cuda_create(tinympc_cuda_solver** out, const int* devices, int n_dev
         cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, id);
         if (cudaMalloc(&d.counters, sizeof(int) * 3 * kMaxChunks) != cudaSuccess) { delete s; return TINYMPC_CUDA_ECUDA; }
         if (cudaMalloc(&d.stream_ctl, sizeof(int) * (2 + kMaxStreamChunks)) != cudaSuccess) { delete s; return TINYMPC_CUDA_ECUDA; }
+        if (cudaMalloc(&d.qctl, sizeof(int) * 4 * kMaxChunks) != cudaSuccess) { delete s; return TINYMPC_CUDA_ECUDA; }
+        for (int k = 0; k <= kStreams; ++k) {
+            cudaStreamCreateWithFlags(&d.fix_stream[k], cudaStreamNonBlocking);
+            cudaEventCreateWithFlags(&d.ev_fork[k], cudaEventDisableTiming);
+            cudaEventCreateWithFlags(&d.ev_join[k], cudaEventDisableTiming);
+        }
         cudaEventCreateWithFlags(&d.ev_ctl, cudaEventDisableTiming);
         for (int k = 0; k < kStreams; ++k) cudaStreamCreateWithFlags(&d.streams[k], cudaStreamNonBlocking);
         for (int c = 0; c < kMaxChunks; ++c) { cudaEventCreate(&d.k0[c]); cudaEventCreate(&d.k1[c]); }
@@ -648,8 +782,17 @@ int tinympc_cuda_destroy(tinympc_cuda_solver* s) {
         if (d.pack64) cudaFree(d.pack64);
         if (d.counters) cudaFree(d.counters);
         if (d.stream_ctl) cudaFree(d.stream_ctl);
+        if (d.qctl) cudaFree(d.qctl);
+        for (int k = 0; k <= kStreams; ++k) {
+            if (d.fix_stream[k]) { cudaStreamSynchronize(d.fix_stream[k]); cudaStreamDestroy(d.fix_stream[k]); }
+            if (d.ev_fork[k]) cudaEventDestroy(d.ev_fork[k]);
+            if (d.ev_join[k]) cudaEventDestroy(d.ev_join[k]);
+        }
         if (d.ev_ctl) cudaEventDestroy(d.ev_ctl);
-        for (DevBuf* b : {&d.x0, &d.Xref, &d.Uref, &d.xmin, &d.xmax, &d.umin, &d.umax, &d.x, &d.u, &d.iter, &d.status, &d.res, &d.rho}) b->release();
+        for (DevBuf* b : {&d.x0, &d.Xref, &d.Uref, &d.xmin, &d.xmax, &d.umin, &d.umax, &d.x, &d.u, &d.iter, &d.status, &d.res, &d.rho, &d.xrc, &d.u0}) b->release();
+        for (auto& b : d.exp_xref) b.release();
+        for (auto& b : d.exp_x) b.release();
+        for (auto& b : d.exp_u) b.release();
         for (auto& b : d.wpp_scratch) b.release();
         for (auto& b : d.ref_scratch) b.release();
         for (auto& b : d.ref_scratch64) b.release();
@@ -792,8 +935,10 @@ int tinympc_cuda_solve_batch_device(tinympc_cuda_solver* s, int dev_index, const
     if (dev_index < 0 || dev_index >= (int)s->devs.size()) return fail(s, TINYMPC_CUDA_EINVAL, "dev_index out of range");
     if (in->batch < 0) return fail(s, TINYMPC_CUDA_EINVAL, "negative batch");
     if (in->batch == 0) return TINYMPC_CUDA_OK;
-    if (!in->x0 || !out->x || !out->u || !out->iter || !out->status) return fail(s, TINYMPC_CUDA_EINVAL, "x0, x, u, iter, status are required");
+    if (!in->x0 || !out->iter || !out->status || !((out->x && out->u) || out->u0))
+        return fail(s, TINYMPC_CUDA_EINVAL, "x0, iter, status and either (x, u) or u0 are required");
     int rc = 0;
+    rc |= check_ptr16(s, in->xref_const, "xref_const"); rc |= check_ptr16(s, out->u0, "u0");
     rc |= check_ptr16(s, in->x0, "x0"); rc |= check_ptr16(s, in->Xref, "Xref"); rc |= check_ptr16(s, in->Uref, "Uref");
     rc |= check_ptr16(s, in->x_min, "x_min"); rc |= check_ptr16(s, in->x_max, "x_max"); rc |= check_ptr16(s, in->u_min, "u_min");
     rc |= check_ptr16(s, in->u_max, "u_max"); rc |= check_ptr16(s, out->x, "x"); rc |= check_ptr16(s, out->u, "u");
@@ -819,7 +964,9 @@ int tinympc_cuda_solve_batch(tinympc_cuda_solver* s, const tinympc_cuda_batch_in
     if (!s->fam.set) return fail(s, TINYMPC_CUDA_ENOTREADY, "tinympc_cuda_set_family has not been called");
     if (in->batch < 0) return fail(s, TINYMPC_CUDA_EINVAL, "negative batch");
     if (in->batch == 0) return TINYMPC_CUDA_OK;
-    if (!in->x0 || !out->x || !out->u || !out->iter || !out->status) return fail(s, TINYMPC_CUDA_EINVAL, "x0, x, u, iter, status are required");
+    if (!in->x0 || !out->iter || !out->status || !((out->x && out->u) || out->u0))
+        return fail(s, TINYMPC_CUDA_EINVAL, "x0, iter, status and either (x, u) or u0 are required");
+    if (in->xref_const && in->Xref) return fail(s, TINYMPC_CUDA_EINVAL, "give Xref or xref_const, not both");
     const bool ppb = in->x_min || in->x_max || in->u_min || in->u_max;
     if (ppb && !(in->x_min && in->x_max && in->u_min && in->u_max))
         return fail(s, TINYMPC_CUDA_EINVAL, "per-problem bounds need all four of x_min, x_max, u_min, u_max");
@@ -1106,6 +1253,8 @@ int tinympc_cuda_set_option(tinympc_cuda_solver* s, const char* name, double val
     } else if (n == "mixed") {
         if (!(value >= 0 && value < 1)) return fail(s, TINYMPC_CUDA_EINVAL, "mixed (relative band) must be in [0, 1)");
         s->mixed_band = value;
+    } else if (n == "fixer_sms") {
+        s->fixer_sms = (int)value;
     } else if (n == "force_wpp") {
         s->force_wpp = (int)value;
     } else if (n == "streamed") {
@@ -1134,7 +1283,7 @@ long long tinympc_cuda_last_marked(tinympc_cuda_solver* s) {
         cudaGetDevice(&prev);
         cudaSetDevice(d.device);
         cudaDeviceSynchronize();
-        cudaMemcpy(&n, d.counters + 3 * kMaxChunks - 1, sizeof(int), cudaMemcpyDeviceToHost);
+        cudaMemcpy(&n, s->fixer_sms >= 0 ? d.qctl + 4 * (kMaxChunks - 1) : d.counters + 3 * kMaxChunks - 1, sizeof(int), cudaMemcpyDeviceToHost);
         cudaSetDevice(prev);
         s->mixed_marked = n;
         s->mixed_pending_dev = -1;

@@ -108,6 +108,18 @@ struct SolveParams {
     float amb_band;            // 0 = off
     const int* index_list;     // NULL, or problem index of work item k (the kernel then runs over *batch_ptr items)
     const int* batch_ptr;      // NULL, or device int holding the number of work items (<= batch)
+    // Exact-count mode as a producer / consumer pair running CONCURRENTLY (tmpc_capi.cu enqueue_exact): the fp32 kernel
+    // (producer, q_consume = 0) pushes every problem it cannot decide onto a device queue instead of finishing it; the fp64
+    // kernel (consumer, q_consume = 1) runs on the SMs the producer's grid leaves free, takes tickets from work_counter, waits
+    // for its ticket to be filled, and exits once every producer CTA has left and the queue is drained.
+    //   q_tail       entries reserved so far (producer: atomicAdd; consumer: how far it may look)
+    //   q_list       problem index per entry, preset to -1, written with release semantics after the reservation
+    //   q_prod_done  producer CTAs that have exited; the queue is complete when it reaches q_prod_total
+    int* q_tail;               // NULL = no queue (plain solve, or the two-pass form with index_list)
+    int* q_list;
+    int* q_prod_done;
+    int q_prod_total;
+    int q_consume;
     // streamed host pipeline (tmpc_capi.cu run_shard_streamed): ONE persistent launch consumes the batch while the copy engines
     // are still delivering it.  avail_ptr counts the problems whose inputs have landed (written in stream order behind each
     // H2D chunk); a lane that claims problem p starts it once *avail_ptr > p.  done_counters[chunk of p] counts finished

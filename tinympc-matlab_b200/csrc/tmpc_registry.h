@@ -84,3 +84,25 @@ const KernelEntry* const* kernel_table(int* count);   // defined in gen/tmpc_tab
                                     CFG::PPB ? 1 : 0, CFG::FB ? 1 : 0, CFG::AFF ? 1 : 0, CFG::BLOCK, VAR, 1, SYM##_smem, SYM##_prepare, \
                                     SYM##_occ, SYM##_launch, CFG::CONSTR ? 1 : 0, CFG::SCS, CFG::SCD, CFG::UCS, CFG::UCD, CFG::NSL, CFG::NIL};                                 \
     }
+
+// mixed-precision rocket-family kernel (tmpc_tpp4.cuh)
+#define TMPC_DEFINE_TPP4_ENTRY(SYM, CFG, FEATV, BITS, VAR)                                                          \
+    namespace tmpc {                                                                                                \
+    static size_t SYM##_smem(int pe) { return tpp4_smem_bytes<CFG>(pe); }                                           \
+    static cudaError_t SYM##_prepare(size_t smem) {                                                                 \
+        return cudaFuncSetAttribute(tpp4_kernel<CFG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
+    }                                                                                                               \
+    static cudaError_t SYM##_occ(int* n, size_t smem) {                                                             \
+        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(n, tpp4_kernel<CFG>, CFG::BLOCK, smem);                \
+    }                                                                                                               \
+    static cudaError_t SYM##_launch(const SolveParams& p, int grid, size_t smem, cudaStream_t st, const double* mp, \
+                                    const PackLayout& L) {                                                          \
+        typename CFG::CPack cpk;                                                                                    \
+        fill_const_pack3(cpk, mp, L);                                                                               \
+        tpp4_kernel<CFG><<<grid, CFG::BLOCK, smem, st>>>(p, cpk);                                                   \
+        return cudaGetLastError();                                                                                  \
+    }                                                                                                               \
+    extern const KernelEntry SYM = {#SYM, KF_TPP, CFG::NX, CFG::NU, CFG::NH, FEATV, BITS, CFG::REFMODE,             \
+                                    0, CFG::FB ? 1 : 0, CFG::AFF ? 1 : 0, CFG::BLOCK, VAR, 1, SYM##_smem, SYM##_prepare, \
+                                    SYM##_occ, SYM##_launch, 1, CFG::SCS, CFG::SCD, CFG::UCS, CFG::UCD, CFG::NSL, CFG::NIL};                                 \
+    }

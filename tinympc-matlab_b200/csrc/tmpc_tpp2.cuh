@@ -97,8 +97,40 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 // copy engine and the stream wait both read through L2, hence device scope.
 __device__ __forceinline__ bool problem_ready(const SolveParams& prm, int prob, int& seen) {
     if (prm.avail_ptr == nullptr || seen > prob) return true;
-    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(prm.avail_ptr) : "memory");
+    // acquire: the problem's inputs (written by the copy engine before the watermark) are read after this load
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(prm.avail_ptr) : "memory");
     return seen > prob;
+}
+
+// ---- exact-count mode queue (SolveParams::q_*) -----------------------------------------------------------------------
+__device__ __forceinline__ int ld_relaxed_gpu(const int* p) { int v; asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) { int v; asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ void st_release_gpu(int* p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+// Producer, warp-collective: the lanes with push == true append their problem (one reservation per warp).
+__device__ __forceinline__ void queue_push(const SolveParams& prm, bool push, int prob, int lane) {
+    const unsigned m = __ballot_sync(0xffffffffu, push);
+    if (!m) return;
+    const int leader = __ffs(m) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(prm.q_tail, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (push) st_release_gpu(prm.q_list + base + __popc(m & ((1u << lane) - 1u)), prob);
+}
+// Consumer: is ticket t filled?  none = the producers are gone and the queue ends before t.
+__device__ __forceinline__ bool queue_take(const SolveParams& prm, int t, int& prob, bool& none) {
+    none = false;
+    if (t < ld_relaxed_gpu(prm.q_tail)) {
+        const int e = ld_acquire_gpu(prm.q_list + t);
+        if (e >= 0) { prob = e; return true; }
+        return false;                                            // reserved, not written yet
+    }
+    if (ld_acquire_gpu(prm.q_prod_done) >= prm.q_prod_total) none = t >= ld_relaxed_gpu(prm.q_tail);
+    return false;
+}
+// Producer CTA exit (after its last push): call from one thread behind a __syncthreads().
+__device__ __forceinline__ void queue_producer_exit(const SolveParams& prm) {
+    __threadfence();
+    atomicAdd(prm.q_prod_done, 1);
 }
 __device__ __forceinline__ void publish_done(const SolveParams& prm, int& unpub) {
     if (unpub >= 0) {
@@ -765,6 +797,8 @@ tpp2_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ typ
 
     const int lane = tid & 31;
     const int n_items = prm.batch_ptr ? min(*prm.batch_ptr, prm.batch) : prm.batch;   // work items (mixed mode: the marked problems)
+    const bool consumer = prm.q_tail != nullptr && prm.q_consume != 0;   // exact-count mode: this launch drains the queue
+    const bool producer = prm.q_tail != nullptr && prm.q_consume == 0;   //                   this launch feeds it
     int prob = 0;           // problem owned by this lane
     bool active = false;    // lane holds an unfinished problem
     int last_k = 32;        // iterations of the last problem this lane finished (batched refill)
@@ -851,7 +885,9 @@ tpp2_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ typ
                 base = __shfl_sync(FULL, base, leader);
                 if (want) {
                     claim = base + __popc(mw & ((1u << lane) - 1u));
-                    if (claim >= n_items) {
+                    if (consumer) {
+                        pending = true;      // claim is a queue ticket: resolved below, once the producer has filled it
+                    } else if (claim >= n_items) {
                         exhausted = true;
                         prob = 0;   // keeps the (unused) per-problem reads of an idle lane in range
                     } else {
@@ -861,7 +897,16 @@ tpp2_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ typ
                 }
             }
             // a claimed problem starts once its inputs have landed (always, unless the host streams the batch in)
-            const bool mine = phase_ok && pending && problem_ready(prm, claim, seen);
+            bool mine;
+            if (consumer) {
+                bool none = false;
+                int qp = 0;
+                mine = pending && queue_take(prm, claim, qp, none) && phase_ok;
+                if (mine) claim = qp;
+                if (pending && none) { pending = false; exhausted = true; prob = 0; }
+            } else {
+                mine = phase_ok && pending && problem_ready(prm, claim, seen);
+            }
             const unsigned m = __ballot_sync(FULL, mine);
             if (m) {
                 if (mine) {
@@ -1247,7 +1292,12 @@ tpp2_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ typ
             }
         }
         if (k >= max_iter) finish = true;
-        const bool fin = active && finish;
+        bool fin = active && finish;
+        if (producer) {   // undecidable problems go to the fp64 consumer: no result, no completion count from this lane
+            const bool amb = fin && (st & kAmbiguousBit);
+            queue_push(prm, amb, prob, lane);
+            if (amb) { fin = false; active = false; last_k = k; }
+        }
         if (__any_sync(FULL, fin)) {
             // solution = (vnew, znew) = clamp of the stored pre-clamp values (the TV read is warp-collective)
 #pragma unroll 1
@@ -1407,6 +1457,10 @@ tpp2_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ typ
             }
             p = pn;
         }
+    }
+    if (producer) {
+        __syncthreads();
+        if (threadIdx.x == 0) queue_producer_exit(prm);
     }
     if constexpr (C::TM) {   // every warp is done with its columns: give the tensor memory back
         tmem_fence_before_sync();

@@ -222,6 +222,7 @@ tpp3_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ typ
 
     const int lane = tid & 31;
     const int n_items = prm.batch_ptr ? min(*prm.batch_ptr, prm.batch) : prm.batch;
+    const bool producer = prm.q_tail != nullptr;   // exact-count mode: undecidable problems are queued for the fp64 consumer launch
     int prob = 0;
     bool active = false, exhausted = false;
     bool pending = false;   // holds a claimed problem (claim) whose inputs have not landed yet (streamed host pipeline)
@@ -759,7 +760,12 @@ tpp3_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ typ
             }
         }
         if (k >= max_iter) finish = true;
-        const bool fin = active && finish;
+        bool fin = active && finish;
+        if (producer) {   // (tmpc_tpp2.cuh, queue_push) no result and no completion count from this lane: the consumer delivers both
+            const bool amb = fin && (st & kAmbiguousBit);
+            queue_push(prm, amb, prob, lane);
+            if (amb) { fin = false; active = false; last_k = k; }
+        }
         if (__any_sync(FULL, fin)) {
             // solution = (vnew, znew) = clamp of the stored pre-clamp values (the T read is warp-collective)
 #pragma unroll 1
@@ -798,6 +804,7 @@ tpp3_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ typ
     }
     tmem_fence_before_sync();
     __syncthreads();
+    if (producer && threadIdx.x == 0) queue_producer_exit(prm);
     if (threadIdx.x < 32) tmem_dealloc(tmem_base_s, 512);
 }
 
