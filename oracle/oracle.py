@@ -174,6 +174,18 @@ def get_cache(p, impl: str = "ref") -> dict:
     return {k: flat[k].reshape(shapes[k], order="F") for k in shapes}
 
 
+def codegen(p, out_dir, impl: str = "ref") -> None:
+    """Run the REFERENCE code generator (tiny_codegen, codegen.cpp:68-80) on the solver this spec sets up (reference build only)."""
+    L = lib(impl)
+    keep = _Keep()
+    cp = c_problem(p, keep)
+    fn = getattr(L, _PREFIX[impl] + "_codegen")
+    fn.restype = C.c_int
+    rc = fn(C.byref(cp), str(out_dir).encode())
+    if rc != 0:
+        raise RuntimeError(f"{impl}_codegen failed rc={rc}")
+
+
 class Session:
     """Warm-started single solver: the closed-loop pattern of quadrotor_hovering.cpp:73-93."""
 

@@ -19,6 +19,7 @@
 #include <vector>
 
 #include "tinympc/tiny_api.hpp"
+#include "tinympc/codegen.hpp"
 
 #include "oracle_abi.h"
 
@@ -241,6 +242,18 @@ int ref_session_solve(void* h, double* x, double* u, int* iter, int* status, dou
     if (iter) *iter = s->solution->iter;
     if (status) *status = w->status;
     if (work_u0) std::memcpy(work_u0, w->u.data(), sizeof(double) * w->nu);  /* work->u.col(0), the control the examples apply */
+    return rc;
+}
+
+/* The reference's own code generator (codegen.cpp:68-80) on the solver this description sets up: writes
+   <dir>/src/tiny_data.cpp, <dir>/tinympc/tiny_data.hpp, <dir>/src/tiny_main.cpp.  Used once, in this container, to produce the
+   golden files tests/test_codegen.py compares the product's generator with (oracle/gen_golden.py). */
+int ref_codegen(const oracle_problem* d, const char* dir) {
+    CoutSilencer quiet;
+    TinySolver* s = make_solver(d);
+    if (!s) return 1;
+    const int rc = tiny_codegen(s, dir, 0);
+    free_solver(s);
     return rc;
 }
 

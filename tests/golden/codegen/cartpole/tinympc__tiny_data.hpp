@@ -1,0 +1,16 @@
+/*
+ */
+
+#pragma once
+
+#include "types.hpp"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+extern TinySolver tiny_solver;
+
+#ifdef __cplusplus
+}
+#endif

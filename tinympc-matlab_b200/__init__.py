@@ -233,12 +233,24 @@ class TinyMPC:
         if rc:
             raise TinympcCudaError(rc, self._L.tinympc_host_last_error(self._h).decode())
 
-    # ------------------------------------------------------------------ codegen: out of scope of the B200 hot path
+    # ------------------------------------------------------------------ codegen (src/TinyMPC.m:159-182)
     def codegen(self, output_dir):
-        raise NotImplementedError("codegen (src/TinyMPC.m:159-168) serialises a solver for microcontrollers; it is outside the "
-                                  "batched-GPU hot path this package replaces")
+        """Generate the standalone project data (tiny_data.cpp / tiny_data.hpp / tiny_main.cpp, as the reference's tiny_codegen
+        writes them) plus tinympc/tiny_b200_family.h, the same solver as a constant family table of the batched C ABI."""
+        self._check_setup()
+        self._push_settings()
+        status = self._L.tinympc_host_codegen(self._h, str(output_dir).encode(), None, None, None, None, 0)
+        if status != 0:
+            raise RuntimeError(f"TinyMPC:CodegenFailed: Code generation failed with status: {status}")
 
-    codegen_with_sensitivity = codegen
+    def codegen_with_sensitivity(self, output_dir, dK, dP, dC1, dC2):
+        self._check_setup()
+        self.set_sensitivity_matrices(dK, dP, dC1, dC2)
+        self._push_settings()
+        arrs = [_cm(dK, self.nu, self.nx), _cm(dP, self.nx, self.nx), _cm(dC1, self.nu, self.nu), _cm(dC2, self.nx, self.nx)]
+        status = self._L.tinympc_host_codegen(self._h, str(output_dir).encode(), *[_dp(a) for a in arrs], 0)
+        if status != 0:
+            raise RuntimeError(f"TinyMPC:CodegenWithSensitivityFailed: Code generation with sensitivity failed with status: {status}")
 
     # ------------------------------------------------------------------ sensitivities / cache helpers (src/TinyMPC.m:184-241)
     def set_sensitivity_matrices(self, dK, dP, dC1, dC2):

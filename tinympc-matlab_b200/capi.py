@@ -25,7 +25,8 @@ HOST_EXPORTS = [
     "tinympc_host_set_linear_constraints", "tinympc_host_update_settings", "tinympc_host_set_x0", "tinympc_host_set_x_ref",
     "tinympc_host_set_u_ref", "tinympc_host_solve", "tinympc_host_get_solution", "tinympc_host_get_stats", "tinympc_host_get_cache",
     "tinympc_host_set_cache_terms", "tinympc_host_init_sensitivity", "tinympc_host_set_sensitivity", "tinympc_host_reset_workspace",
-    "tinympc_host_solve_batch", "tinympc_host_set_devices", "tinympc_host_set_option", "tinympc_host_cuda_handle",
+    "tinympc_host_solve_batch", "tinympc_host_set_devices", "tinympc_host_set_option", "tinympc_host_cuda_handle", "tinympc_host_codegen",
+    "tiny_codegen", "tiny_codegen_with_sensitivity",
     # the C++ API mirror itself (extern "C" names of the reference, tiny_api.hpp:10-50)
     "tiny_setup", "tiny_set_bound_constraints", "tiny_set_cone_constraints", "tiny_set_linear_constraints",
     "tiny_precompute_and_set_cache", "tiny_solve", "tiny_update_settings", "tiny_set_default_settings", "tiny_set_x0",
@@ -163,6 +164,7 @@ def load():
         L.tinympc_host_setup.argtypes = [dp, dp, dp, dp, dp, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, ip]
         L.tinympc_host_setup.restype = vp
         L.tinympc_host_free.argtypes = [vp]
+        L.tinympc_host_codegen.argtypes = [vp, C.c_char_p, dp, dp, dp, dp, C.c_int]
         L.tinympc_host_set_bound_constraints.argtypes = [vp, dp, dp, dp, dp]
         L.tinympc_host_set_cone_constraints.argtypes = [vp, C.c_int, ip, ip, dp, C.c_int, ip, ip, dp]
         L.tinympc_host_set_linear_constraints.argtypes = [vp, C.c_int, dp, dp, C.c_int, dp, dp]

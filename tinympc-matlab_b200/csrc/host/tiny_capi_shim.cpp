@@ -5,6 +5,7 @@
 
 #include "../../../include/tinympc_b200.h"
 #include "tiny_api.hpp"
+#include "codegen.hpp"
 
 namespace {
 tinyMatrix mat(const double* p, int r, int c) {
@@ -31,6 +32,13 @@ void* tinympc_host_setup(const double* A, const double* B, const double* f, cons
     return s;
 }
 void tinympc_host_free(void* h) { tiny_free(S(h)); }
+/* tiny_codegen / tiny_codegen_with_sensitivity (codegen.hpp); sensitivities column-major or all NULL */
+int tinympc_host_codegen(void* h, const char* output_dir, const double* dK, const double* dP, const double* dC1, const double* dC2, int verbose) {
+    const TinyWorkspace* w = S(h)->work;
+    if (!dK || !dP || !dC1 || !dC2) return tiny_codegen(S(h), output_dir, verbose);
+    tinyMatrix a = mat(dK, w->nu, w->nx), b = mat(dP, w->nx, w->nx), c = mat(dC1, w->nu, w->nu), d = mat(dC2, w->nx, w->nx);
+    return tiny_codegen_with_sensitivity(S(h), output_dir, &a, &b, &c, &d, verbose);
+}
 
 int tinympc_host_set_bound_constraints(void* h, const double* xmin, const double* xmax, const double* umin, const double* umax) {
     const TinyWorkspace* w = S(h)->work;

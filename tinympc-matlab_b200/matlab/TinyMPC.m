@@ -7,7 +7,6 @@ classdef TinyMPC < handle
     % set_sensitivity_matrices, compute_cache_terms, compute_sensitivity_autograd, reset) so that
     % existing scripts run unchanged; every solve executes on the GPU through the MEX gateway
     % tinympc_matlab (matlab/bindings.cpp).  New: solve_batch, set_option, get_stats.
-    % codegen / codegen_with_sensitivity target microcontrollers and are not part of this build.
 
     properties
         nx = 0; nu = 0; N = 0;
@@ -188,12 +187,24 @@ classdef TinyMPC < handle
             obj.session_size = 0;
         end
 
-        function codegen(~, varargin)
-            error('TinyMPC:NotSupported', 'codegen targets microcontrollers and is not part of the B200 build');
+        function codegen(obj, output_dir)
+            % Generate the standalone project data (tiny_data.cpp/.hpp, tiny_main.cpp) + the B200 family table
+            obj.require_setup();
+            status = tinympc_matlab('codegen', output_dir, false);
+            if status ~= 0
+                error('TinyMPC:CodegenFailed', 'Code generation failed with status: %d', status);
+            end
+            fprintf('Code generation completed successfully in: %s\n', output_dir);
         end
 
-        function codegen_with_sensitivity(obj, varargin)
-            obj.codegen();
+        function codegen_with_sensitivity(obj, output_dir, dK, dP, dC1, dC2)
+            obj.require_setup();
+            obj.set_sensitivity_matrices(dK, dP, dC1, dC2);
+            status = tinympc_matlab('codegen_with_sensitivity', output_dir, dK, dP, dC1, dC2, false);
+            if status ~= 0
+                error('TinyMPC:CodegenWithSensitivityFailed', 'Code generation with sensitivity failed with status: %d', status);
+            end
+            fprintf('Code generation with sensitivity matrices completed successfully in: %s\n', output_dir);
         end
 
         function set_sensitivity_matrices(obj, dK, dP, dC1, dC2)

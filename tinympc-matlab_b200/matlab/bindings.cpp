@@ -14,6 +14,7 @@
 
 #include "mex.h"
 #include "tiny_api.hpp"
+#include "codegen.hpp"
 #include "tinympc_b200.h"
 
 namespace {
@@ -139,8 +140,24 @@ void cmd_get_stats(int, mxArray* plhs[], int nrhs, const mxArray*[]) {
     plhs[2] = mxCreateDoubleScalar(g_solver->work->primal_residual_state);
     plhs[3] = mxCreateDoubleScalar(g_solver->work->primal_residual_input);
 }
-void cmd_codegen(int, mxArray*[], int, const mxArray*[]) {
-    fail("NotSupported", "codegen targets microcontrollers and is outside the batched GPU hot path of this build");
+// status = tinympc_matlab('codegen', output_dir, verbose)                                  (src/bindings.cpp:288-309)
+void cmd_codegen(int, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
+    need_args(nrhs, 2, "codegen"); need_solver();
+    char* dir = mxArrayToString(prhs[0]);
+    if (!dir) fail("InvalidInput", "output_dir must be a string");
+    const int status = tiny_codegen(g_solver, dir, scalar_int(prhs[1]));
+    mxFree(dir);
+    plhs[0] = mxCreateDoubleScalar(status);
+}
+// status = tinympc_matlab('codegen_with_sensitivity', output_dir, dK, dP, dC1, dC2, verbose)   (src/bindings.cpp:481-520)
+void cmd_codegen_with_sensitivity(int, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
+    need_args(nrhs, 6, "codegen_with_sensitivity"); need_solver();
+    char* dir = mxArrayToString(prhs[0]);
+    if (!dir) fail("InvalidInput", "output_dir must be a string");
+    tinyMatrix dK = to_matrix(prhs[1]), dP = to_matrix(prhs[2]), dC1 = to_matrix(prhs[3]), dC2 = to_matrix(prhs[4]);
+    const int status = tiny_codegen_with_sensitivity(g_solver, dir, &dK, &dP, &dC1, &dC2, scalar_int(prhs[5]));
+    mxFree(dir);
+    plhs[0] = mxCreateDoubleScalar(status);
 }
 void drop_session() {
     if (g_session) tinympc_cuda_session_destroy(g_session);
@@ -336,7 +353,7 @@ const Command kCommands[] = {
     {"setup", cmd_setup}, {"set_x0", cmd_set_x0}, {"set_x_ref", cmd_set_x_ref}, {"set_u_ref", cmd_set_u_ref}, {"solve", cmd_solve},
     {"get_solution", cmd_get_solution}, {"get_stats", cmd_get_stats}, {"codegen", cmd_codegen}, {"reset", cmd_reset},
     {"set_bound_constraints", cmd_set_bound_constraints}, {"set_sensitivity_matrices", cmd_set_sensitivity_matrices},
-    {"set_cache_terms", cmd_set_cache_terms}, {"codegen_with_sensitivity", cmd_codegen}, {"update_settings", cmd_update_settings},
+    {"set_cache_terms", cmd_set_cache_terms}, {"codegen_with_sensitivity", cmd_codegen_with_sensitivity}, {"update_settings", cmd_update_settings},
     {"print_problem_data", cmd_print_problem_data}, {"set_linear_constraints", cmd_set_linear_constraints},
     {"set_cone_constraints", cmd_set_cone_constraints}, {"solve_batch", cmd_solve_batch}, {"set_option", cmd_set_option},
     {"session_create", cmd_session_create}, {"session_destroy", cmd_session_destroy}, {"session_set_x0", cmd_session_set_x0},
