@@ -92,8 +92,11 @@ def test_setup_validation_and_settings_roundtrip(tm):
     s._L.tinympc_host_get_settings.argtypes = [ctypes.c_void_p, tm.capi.c_dp, ctypes.POINTER(ctypes.c_int * 11)]
     s._L.tinympc_host_get_settings(s._h, d.ctypes.data_as(tm.capi.c_dp), ctypes.byref(i))
     assert d[0] == 1e-3 and i[0] == 77 and i[2] == 1 and i[3] == 1
-    with pytest.raises(NotImplementedError):
-        s.codegen("out")
+    import tempfile
+    from pathlib import Path
+    with tempfile.TemporaryDirectory() as td:       # codegen is part of the surface now (tests/test_codegen.py checks the contents)
+        s.codegen(Path(td) / "out")
+        assert (Path(td) / "out" / "src" / "tiny_data.cpp").exists() and (Path(td) / "out" / "tinympc" / "tiny_b200_family.h").exists()
 
 
 def test_bench_flop_model_matches_the_survey_table():
