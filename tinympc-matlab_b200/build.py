@@ -63,7 +63,7 @@ def plan_hybrid(nx, nu, N, max_warps=24):
     return None
 
 
-def inst3(nx, nu, N, refs=True, ppb=False, fb=False, variant=0, max_warps=24, opq=False, tib=None, aff=None, feat=BOX, cones=(0, 0, 0, 0, 0, 0), hyb=False):
+def inst3(nx, nu, N, refs=True, ppb=False, fb=False, variant=0, max_warps=24, opq=False, tib=None, aff=None, feat=BOX, cones=(0, 0, 0, 0, 0, 0), hyb=False, conv=-1):
     """incremental-form kernel (tmpc_tpp3.cuh): x and t in tensor memory (2 nx N columns per thread), u, u + y, -dd in shared memory;
     with cones / linear rows (feat=CON) two more arrays of each kind (the pre-projection slacks of the two families)"""
     sx, su = nx * N, nu * (N - 1)
@@ -79,7 +79,7 @@ def inst3(nx, nu, N, refs=True, ppb=False, fb=False, variant=0, max_warps=24, op
     # (quadrotor +3.3 %), unlike the direct form, where the hoisted bounds starved the coefficient stream of the quadrotor instance
     tib = True if tib is None else tib
     return dict(gen=3, bits=32, nx=nx, nu=nu, N=N, feat=feat, refs=3 if refs else 0, ppb=ppb, fb=fb, variant=variant, block=warps * 32, aff=aff,
-                opq=opq, tib=tib, tm=True, minb=1, ntm=ntm, cones=cones, ttm=ttm)
+                opq=opq, tib=tib, tm=True, minb=1, ntm=ntm, cones=cones, ttm=ttm, conv=conv)
 
 
 def inst4(nx, nu, N, refs=True, fb=False, variant=0, aff=None, cones=(0, 0, 0, 0, 0, 0)):
@@ -184,6 +184,8 @@ def default_instances():
                 out.append(inst3(nx, nu, N, refs=True, fb=fb, variant=9))
                 out.append(inst3(nx, nu, N, refs=False, fb=fb, variant=9))
             out.append(inst3(nx, nu, N, refs=True, ppb=True, variant=9))
+    # A/B: the costate recursion instead of the impulse-response form of the backward pass (tmpc_tpp3.cuh, Tpp3Cfg::CONV), option variant=7
+    out.append(inst3(12, 4, 10, refs=True, fb=True, hyb=True, variant=7, conv=0))
     # A/B: the direct-form fp32 box kernels (16 / 24 warps per SM, tensor-memory TV) on the headline shapes, option variant=5
     out.append(inst(32, 12, 4, 10, BOX, refs=REFS_L2, variant=5, fb=True, tm=True))
     out.append(inst(32, 12, 4, 10, BOX, refs=REFS_L2, variant=5, tm=True))
@@ -229,7 +231,7 @@ def gen_sources(instances):
                 "// generated by tinympc-matlab_b200/build.py -- do not edit\n"
                 '#include "../tmpc_tpp3.cuh"\n#include "../tmpc_registry.h"\nusing namespace tmpc;\n'
                 f"using Cfg_{n} = Tpp3Cfg<{i['nx']}, {i['nu']}, {i['N']}, {i['block']}, {b(i['refs'])}, {b(i['ppb'])}, {b(i['fb'])}, {b(i['aff'])}, "
-                f"{b(i['opq'])}, {b(i['tib'])}, {FEAT_ENUM[i['feat']]}, {', '.join(str(c) for c in i['cones'])}, {i['ttm']}>;\n"
+                f"{b(i['opq'])}, {b(i['tib'])}, {FEAT_ENUM[i['feat']]}, {', '.join(str(c) for c in i['cones'])}, {i['ttm']}, {i['conv']}>;\n"
                 f"TMPC_DEFINE_TPP3_ENTRY({n}, Cfg_{n}, {i['feat']}, 32, {i['variant']})\n"
             )
         else:

@@ -46,15 +46,40 @@ enum : int { REFS_STATE = 3 };   // registry "refs" code: reference terms parked
 
 // constant-bank pack of the incremental-form instances: the matrices of ConstPack2 + the linear-inequality rows
 // (coefficients row-major, offsets b, 1 / ||a||^2 for project_hyperplane, admm.cpp:70-73)
-template <int NX, int NU, int NH, int NSL, int NIL>
+// CONV: + the impulse-response tables of the backward pass (Tpp3Cfg::CONV): NG[k] = -Quu_inv B' AmBKt^k (k = 0 .. N-2, each NU x NX,
+// column-major like every other table) and NQ = -Quu_inv.
+template <int NX, int NU, int NH, int NSL, int NIL, bool CONV = false>
 struct alignas(16) ConstPack3 : ConstPack2<float, NX, NU, NH, false> {
     float Alx[NSL > 0 ? NSL * NX : 1], blx[NSL > 0 ? NSL : 1], inx[NSL > 0 ? NSL : 1];
     float Alu[NIL > 0 ? NIL * NU : 1], blu[NIL > 0 ? NIL : 1], inu[NIL > 0 ? NIL : 1];
+    float NG[CONV ? (NH - 1) * NX * pad2(NU) : 2], NQ[CONV ? NU * pad2(NU) : 2];
 };
-template <int NX, int NU, int NH, int NSL, int NIL>
-inline void fill_const_pack3(ConstPack3<NX, NU, NH, NSL, NIL>& c, const double* pk, const PackLayout& L) {
+template <int NX, int NU, int NH, int NSL, int NIL, bool CONV>
+inline void fill_const_pack3(ConstPack3<NX, NU, NH, NSL, NIL, CONV>& c, const double* pk, const PackLayout& L) {
     fill_const_pack2(static_cast<ConstPack2<float, NX, NU, NH, false>&>(c), pk, L);
     c.Alx[0] = c.blx[0] = c.inx[0] = c.Alu[0] = c.blu[0] = c.inu[0] = 0.f;
+    c.NG[0] = c.NG[1] = c.NQ[0] = c.NQ[1] = 0.f;
+    if constexpr (CONV) {
+        constexpr int NUP = pad2(NU);
+        double G[NU * NX], Gn[NU * NX];                 // row-major NU x NX, double
+        for (int a = 0; a < NU; ++a)
+            for (int cc = 0; cc < NX; ++cc) {           // G_0 = Quu_inv B'
+                double acc = 0.0;
+                for (int b = 0; b < NU; ++b) acc += pk[L.Quu_inv + a * NU + b] * pk[L.B + cc * NU + b];
+                G[a * NX + cc] = acc;
+            }
+        for (int k = 0; k < NH - 1; ++k) {
+            for (int a = 0; a < NU; ++a) for (int cc = 0; cc < NX; ++cc) c.NG[k * NX * NUP + cc * NUP + a] = static_cast<float>(-G[a * NX + cc]);
+            for (int a = 0; a < NU; ++a)                // G_{k+1} = G_k AmBKt
+                for (int cc = 0; cc < NX; ++cc) {
+                    double acc = 0.0;
+                    for (int r = 0; r < NX; ++r) acc += G[a * NX + r] * pk[L.AmBKt + r * NX + cc];
+                    Gn[a * NX + cc] = acc;
+                }
+            for (int e = 0; e < NU * NX; ++e) G[e] = Gn[e];
+        }
+        for (int a = 0; a < NU; ++a) for (int b = 0; b < NU; ++b) c.NQ[b * NUP + a] = static_cast<float>(-pk[L.Quu_inv + a * NU + b]);
+    }
     for (int k = 0; k < NSL; ++k) {
         for (int j = 0; j < NX; ++j) c.Alx[k * NX + j] = static_cast<float>(pk[L.Alin_x + k * NX + j]);
         c.blx[k] = static_cast<float>(pk[L.blin_x + k]);
@@ -68,7 +93,7 @@ inline void fill_const_pack3(ConstPack3<NX, NU, NH, NSL, NIL>& c, const double* 
 }
 
 template <int NX_, int NU_, int NH_, int BLOCK_, bool REFS_, bool PPB_, bool FB_, bool AFF_, bool OPQ_, bool TIB_, int FEAT_ = FEAT_BOX,
-          int SCS_ = 0, int SCD_ = 0, int UCS_ = 0, int UCD_ = 0, int NSL_ = 0, int NIL_ = 0, int TTM_ = -1>
+          int SCS_ = 0, int SCD_ = 0, int UCS_ = 0, int UCD_ = 0, int NSL_ = 0, int NIL_ = 0, int TTM_ = -1, int CONV_ = -1>
 struct Tpp3Cfg {
     using T = float;
     static_assert(FEAT_ == FEAT_BOX || FEAT_ == FEAT_CONSTR, "the incremental form covers box and box + cone + half-space families");
@@ -88,7 +113,18 @@ struct Tpp3Cfg {
     static constexpr bool OPQ = OPQ_;
     static constexpr bool TIB = TIB_ && FB_ && !PPB_ && !OPQ_;
     static constexpr int SX = NX * NH, SU = NU * (NH - 1);
-    using CPack = ConstPack3<NX_, NU_, NH_, NSL_, NIL_>;
+    // IMPULSE-RESPONSE form of the backward pass (CONV).  The costate recursion p_i = q_i + AmBKt p_{i+1} - Kinf' r_i followed by
+    // d_i = Quu_inv (B' p_{i+1} + r_i) (admm.cpp:13-20) is the ill-conditioned step of the iteration in float32: on the quadrotor
+    // the costates are ~13x their right-hand sides and B' p cancels to ~1 % of its terms, so d carries 2.6e-6 of relative rounding
+    // error per sweep -- the drift of ~6e-5 the fp32 iterates pick up over a solve.  Unrolling the recursion,
+    //     d_i = Quu_inv r_i + sum_{j > i} G_{j-i-1} s_j,    s_j = q_j - Kinf' r_j (j <= N-2),  s_{N-1} = p_N,    G_k = Quu_inv B' AmBKt^k,
+    // with the small matrices G_k (|G_k| <= 9e-3 on the quadrotor) formed once on the host in double: no large intermediate, no
+    // cancellation -- 1.6e-7 relative error in d, 16x better, for N (N-1) / 2 products of nu x nx instead of N-1 steps of
+    // (nx x nx + 2 nu x nx + nu x nu), i.e. 2 160 against 2 304 multiply-adds on the quadrotor shape.  Column j of the sweep
+    // scatters -G_k s_j into the -dd slots of the steps before it.  The cost grows with N^2 nu nx against N nx^2, so the form is
+    // the default where it matters and is cheap (nx >= 6); the nx = 4 shapes keep the recursion, which is well conditioned there.
+    static constexpr bool CONV = CONV_ < 0 ? (NX_ >= 12 && FEAT_ == FEAT_BOX) : (CONV_ != 0);
+    using CPack = ConstPack3<NX_, NU_, NH_, NSL_, NIL_, CONV>;
     // HYBRID state layout (TTM_ >= 0, box instances): the 2 nx N columns of x and t per thread cap the quadrotor shape at 8 warps
     // per SM (2 per scheduler, 61 % issue utilisation).  Three observations buy a third warp per scheduler:
     //   * x_0 is the problem's x0, which the lane holds in registers anyway -- column 0 of X is never stored;
@@ -505,6 +541,11 @@ tpp3_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ typ
                     // du_i = -Kinf dx_i - dd_i (admm.cpp:29)
                     VU du;
                     ND.load(i, du);
+                    if constexpr (C::CONV) {   // the sweep accumulates the next -dd in this slot
+#pragma unroll
+                        for (int j = 0; j < NU / 2; ++j) ND.setp(i, j, mk2(T(0), T(0)));
+                        if constexpr (NU & 1) ND.sett(i, T(0));
+                    }
                     if (i > 0 || anyff) mv_acc<NU, NX>(cp.NK, zf, dx, du);     // dx_0 = 0 unless this is a first iteration
                     VU un;
                     U.load(i, un);
@@ -620,6 +661,43 @@ tpp3_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ typ
                 if (C::NIL > 0 || lin_u) { VU tl; TZL.load(i, tl); family(tl, uv, dr, rows_u); TZL.store(i, tl); }
             }
         };
+        // impulse-response form (C::CONV): -dd_t += -G_k s_j for the steps t = j-1-k before column j.  The slots were zeroed by the
+        // forward pass when it consumed them.  Two accumulator chains per product (columns split in halves); the blocks of one
+        // call are independent.  Called at the top of column j-1, so that the products run under the latency of that column's
+        // state loads, and so that the terminal column needs no copy of this code (the hot loop must fit the 32 KB instruction cache).
+        auto scatter = [&](int j, const VX& sv) {
+            constexpr int NG1 = NX * NUP, H = NX / 2;
+#pragma unroll
+            for (int kk = NH - 2; kk >= 0; --kk) {
+                if (kk < j) {
+                    const int t = j - 1 - kk;
+                    VU a, b;
+                    ND.load(t, a);
+                    b.fill(T(0));
+                    const T* __restrict__ M = cp.NG + kk * NG1;
+#pragma unroll
+                    for (int c = 0; c < H; ++c) {
+                        const T x0c = sv.get(c), x1c = sv.get(c + H);
+#pragma unroll
+                        for (int jj = 0; jj < NU / 2; ++jj) {
+                            a.p[jj] = fmas(mk2(M[c * NUP + 2 * jj], M[c * NUP + 2 * jj + 1]), x0c, a.p[jj]);
+                            b.p[jj] = fmas(mk2(M[(c + H) * NUP + 2 * jj], M[(c + H) * NUP + 2 * jj + 1]), x1c, b.p[jj]);
+                        }
+                        if constexpr (NU & 1) { a.t = fmas(M[c * NUP + NU - 1], x0c, a.t); b.t = fmas(M[(c + H) * NUP + NU - 1], x1c, b.t); }
+                    }
+                    if constexpr (NX & 1) {
+                        const T xc = sv.get(NX - 1);
+#pragma unroll
+                        for (int jj = 0; jj < NU / 2; ++jj) a.p[jj] = fmas(mk2(M[(NX - 1) * NUP + 2 * jj], M[(NX - 1) * NUP + 2 * jj + 1]), xc, a.p[jj]);
+                        if constexpr (NU & 1) a.t = fmas(M[(NX - 1) * NUP + NU - 1], xc, a.t);
+                    }
+#pragma unroll
+                    for (int jj = 0; jj < NU / 2; ++jj) a.p[jj] = addv(a.p[jj], b.p[jj]);
+                    if constexpr (NU & 1) a.t = a.t + b.t;
+                    ND.store(t, a);
+                }
+            }
+        };
         VX dp;
         {   // column N-1: dp_N = -(xref_N' Pinf)' [first sweep] - rho dw_N   (admm.cpp:238-246)
             VX xv, traw, tnew;
@@ -651,11 +729,12 @@ tpp3_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ typ
             constexpr bool COL0 = decltype(col0)::value;
             const int zb = C::OPQ ? opaque_zero4() : 0;
             issue_x(i, col0);
+            if constexpr (C::CONV) scatter(COL0 ? 1 : i + 1, dp);   // s_{i+1} -> the -dd slots of the steps 0 .. i
             // The two products with dp_{i+1} start from zero and are added to their right-hand sides afterwards: they depend on
             // nothing of this column, so they run under the latency of the column's tensor-/shared-memory loads and the scheduler
             // is free to weave the slack updates (ALU pipe) into their FFMA2 stream (FMA pipe).  Measured: rocket +6 %,
             // quadrotor +1 %; the 4-state shapes lose 1 % to the extra additions and keep the chained form.
-            constexpr bool SPLIT = NX >= 6;
+            constexpr bool SPLIT = NX >= 6 && !C::CONV;
             VX akp;
             VU btp;
             akp.fill(T(0));
@@ -682,6 +761,12 @@ tpp3_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ typ
             }
             extra_u(i, uv, dr);
             // dd_i = Quu_inv (B' dp + dr)   (admm.cpp:17; BPf cancels in the increment)
+            if constexpr (C::CONV) {   // the products with the later columns are already in the slot: -dd_i = slot - Quu_inv dr_i
+                VU a;
+                ND.load(i, a);
+                mv_acc<NU, NU>(cp.NQ, zb, dr, a);
+                ND.store(i, a);
+            } else {
             VU t = dr;
             if constexpr (SPLIT) {
 #pragma unroll
@@ -699,6 +784,7 @@ tpp3_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ typ
                 for (int j = 0; j < NU / 2; ++j) nd.p[j] = negv(d.p[j]);
                 if constexpr (NU & 1) nd.t = -d.t;
                 ND.store(i, nd);
+            }
             }
             // ---- state column i: dq_i = -(Xref .* Q) [first sweep] - rho dw;  dp_i = dq_i + AmBKt dp - Kinf' dr   (admm.cpp:18)
             VX xv, traw, tnew, dq;
@@ -729,6 +815,11 @@ tpp3_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ typ
             // rolled loop the Riccati step of column 0 is computed all the same, which keeps the loop body one basic block.
             if (C::CONSTR && i > 0) extra_x(i, xv, dq);
             if constexpr (!COL0) {
+                if constexpr (C::CONV) {
+                    // s_i = dq_i - Kinf' dr_i, scattered to the steps before i at the top of the next column
+                    mv_acc<NX, NU>(cp.NKT, zb, dr, dq);
+                    dp = dq;
+                } else {
                 if constexpr (SPLIT) {
 #pragma unroll
                     for (int j = 0; j < NX / 2; ++j) dq.p[j] = addv(dq.p[j], akp.p[j]);
@@ -738,6 +829,7 @@ tpp3_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ typ
                 }
                 mv_acc<NX, NU>(cp.NKT, zb, dr, dq);
                 dp = dq;
+                }
             }
         };
 #pragma unroll C::TUNROLL
