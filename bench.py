@@ -211,8 +211,9 @@ def main():
                     help="relative band of the exact-count mode (fp32 pass + fp64 re-solve of the problems whose termination decision is "
                          "within the band of a tolerance); -1 = the family's measured band (default: the mode that reproduces the "
                          "reference's iteration counts), 0 = plain fp32")
-    ap.add_argument("--fixer-sms", dest="fixer_sms", type=int, default=0,
-                    help="exact-count mode: SMs left to the concurrent fp64 consumer (0 = auto, -1 = sequential two-pass form)")
+    ap.add_argument("--fixer-sms", dest="fixer_sms", type=int, default=-2,
+                    help="exact-count mode: SMs left to the concurrent fp64 consumer (0 = 13 %% of the device, -1 = always the sequential two-pass "
+                         "form, -2 = library default: two-pass form on the device, concurrent pair inside the streamed host pipeline)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: --batch problems per GPU; strong: --batch problems in total, split by problem index over the GPUs "
                          "(BASELINE config 3 as worded: 1M problems sharded across 8 B200)")

@@ -197,7 +197,11 @@ int  tinympc_cuda_session_read(tinympc_cuda_session *ss, const char *field, doub
    "streamed" (1 [default]: tinympc_cuda_solve_batch runs each device's shard as ONE persistent launch that consumes the
    problems while the H2D copies are still arriving and returns results chunk by chunk while it is still solving;
    0: one launch per chunk), "ctas_per_sm" (0 = occupancy API), "chunks" (host pipeline depth, 0 = auto),
-   "variant" (kernel tuning variant, 0 = default) */
+   "fixer_sms" (how the exact-count mode schedules its fp64 pass: -2 [default] the sequential two-pass form for device-resident and
+   chunked batches, the concurrent producer / consumer pair inside the streamed host pipeline; -1 always sequential; 0 always the
+   pair with 13 % of the SMs left to the consumer; n > 0 the pair with n SMs),
+   "variant" (kernel tuning variant, 0 = default; 7 = costate recursion instead of the impulse-response backward pass of the
+   fp32 quadrotor kernels, 5 = direct-form fp32 kernels, 6 = thread-per-problem fp64 kernels, 9 = plain state layout) */
 int  tinympc_cuda_set_option(tinympc_cuda_solver *s, const char *name, double value);
 int  tinympc_cuda_device_count(void);
 int  tinympc_cuda_num_devices(const tinympc_cuda_solver *s);

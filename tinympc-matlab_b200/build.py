@@ -97,6 +97,13 @@ def inst4(nx, nu, N, refs=True, fb=False, variant=0, aff=None, cones=(0, 0, 0, 0
                 opq=False, tib=False, tm=True, minb=1, ntm=0, cones=cones, ttm=-1)
 
 
+def instg(nx, nu, N, variant=0):
+    """lane-group-per-problem fp64 kernel (tmpc_gpp.cuh): one lane per state row and per input row, groups of 8 / 16 / 32 lanes"""
+    gs = 8 if nx + nu <= 8 else (16 if nx + nu <= 16 else 32)
+    assert nx + nu <= 32
+    return dict(gen=5, bits=64, nx=nx, nu=nu, N=N, feat=BOX, refs=2, ppb=False, fb=False, variant=variant, block=128, aff=True, gs=gs)
+
+
 def cols_per_thread(nx, nu, N, feat, refs, ntm=0):
     """shared-memory scalar columns per thread; ntm = number of state-sized arrays (TV, GC, GL, SXT) in tensor memory"""
     sx, su = nx * N, nu * (N - 1)
@@ -162,12 +169,16 @@ def default_instances():
         out.append(inst4(6, 3, 10, refs=True, fb=fb, cones=(0, 3, 0, 3, 0, 0)))
         out.append(inst3(6, 3, 10, refs=True, fb=fb, feat=CON, cones=(0, 3, 0, 3, 1, 1), variant=3))
         out.append(inst3(6, 3, 10, refs=True, fb=fb, feat=CON, cones=(0, 3, 0, 3, 0, 0), variant=3))
+    # fp64 box families with shared bounds: the lane-group-per-problem kernel (tmpc_gpp.cuh) -- 20x shorter iteration, which is what
+    # the second pass of the exact-count mode and small fp64 batches need, and a higher fp64 throughput as well
+    for (nx, nu, N) in shapes:
+        out.append(instg(nx, nu, N))
     for bits in (32, 64):
         for (nx, nu, N) in shapes:
-            if bits == 64:            # fp64 parity mode: direct form (admm.cpp order), tmpc_tpp2.cuh
+            if bits == 64:            # fp64 thread-per-problem direct form (admm.cpp order), tmpc_tpp2.cuh: per-problem bounds; A/B (variant 6) otherwise
                 for fb in (True, False):
-                    out.append(inst(bits, nx, nu, N, BOX, refs=REFS_L2, fb=fb, tm=True))
-                    out.append(inst(bits, nx, nu, N, BOX, refs=REFS_NONE, fb=fb, tm=True))
+                    out.append(inst(bits, nx, nu, N, BOX, refs=REFS_L2, fb=fb, tm=True, variant=6))
+                    out.append(inst(bits, nx, nu, N, BOX, refs=REFS_NONE, fb=fb, tm=True, variant=6))
                 out.append(inst(bits, nx, nu, N, BOX, refs=REFS_L2, ppb=True, tm=True))
             # fp32: the direct-form cone kernels stay as the A/B baseline (variant 5)
             out.append(inst(bits, nx, nu, N, CON, refs=REFS_L2, fb=True, tm=True, variant=0 if bits == 64 else 5))
@@ -197,6 +208,8 @@ def default_instances():
 
 def name_of(i):
     t = "f32" if i["bits"] == 32 else "f64"
+    if i["gen"] == 5:
+        return f"gpp_f64_{i['nx']}x{i['nu']}x{i['N']}_box_g{i['gs']}_v{i['variant']}"
     if i["gen"] == 4:
         cn = "_c" + "".join(str(c) for c in i["cones"])
         return f"tpp4_mix_{i['nx']}x{i['nu']}x{i['N']}_con{cn}{'' if i['refs'] else '_noref'}{'_fb' if i['fb'] else ''}{'_aff' if i['aff'] else ''}_v{i['variant']}"
@@ -218,7 +231,14 @@ def gen_sources(instances):
         T = "float" if i["bits"] == 32 else "double"
         g = "" if i["gen"] == 1 else "2"
         b = lambda v: "true" if v else "false"
-        if i["gen"] == 4:
+        if i["gen"] == 5:
+            src = (
+                "// generated by tinympc-matlab_b200/build.py -- do not edit\n"
+                '#include "../tmpc_gpp.cuh"\n#include "../tmpc_registry.h"\nusing namespace tmpc;\n'
+                f"using Cfg_{n} = GppCfg<{i['nx']}, {i['nu']}, {i['N']}, {i['gs']}, {i['block']}>;\n"
+                f"TMPC_DEFINE_GPP_ENTRY({n}, Cfg_{n}, {i['variant']})\n"
+            )
+        elif i["gen"] == 4:
             src = (
                 "// generated by tinympc-matlab_b200/build.py -- do not edit\n"
                 '#include "../tmpc_tpp4.cuh"\n#include "../tmpc_registry.h"\nusing namespace tmpc;\n'

@@ -101,8 +101,10 @@ struct tinympc_cuda_solver {
     int streamed = 1;                  // option "streamed": 1 = single-launch streamed host pipeline where it applies, 0 = chunked launches
     double mixed_band = 0;             // option "mixed": > 0 = fp32 pass + fp64 re-solve of the problems whose termination decision
                                        // falls within this relative band of the tolerances (exact iteration counts at ~fp32 speed)
-    int fixer_sms = 0;                 // option "fixer_sms": SMs the fp32 producer leaves to the concurrent fp64 consumer (0 = auto: 13 % of
-                                       // the device; -1 = the sequential two-pass form: fp32 pass, compaction, fp64 pass)
+    int fixer_sms = -2;                // option "fixer_sms", exact-count mode: > 0 SMs the fp32 producer leaves to the concurrent fp64 consumer, 0 =
+                                       // 13 % of the device; -1 = always the sequential two-pass form (fp32 pass, compaction, fp64 pass);
+                                       // -2 (default) = the two-pass form for device-resident and chunked batches (its fp64 pass is the
+                                       // lane-group kernel, ~1 ms per 2^20 problems), the concurrent pair inside the streamed host pipeline
     long long mixed_marked = 0;        // problems re-solved in fp64 by the last mixed solve (host entry: filled by the call)
     int mixed_pending_dev = -1;        // device entry: the count still sits in that device's counter slot
     // err, last_kernel and launches are written by the per-device worker threads of tinympc_cuda_solve_batch: the strings
@@ -256,7 +258,8 @@ int launch_tpp(tinympc_cuda_solver* s, DeviceCtx& d, const KernelEntry* ke, Solv
     if (s->ctas_per_sm > 0 && s->ctas_per_sm < occ) occ = s->ctas_per_sm;
     int grid = std::max(1, d.sm_count - reserve_sms) * occ;   // persistent CTAs: a multiple of the SM count (minus the SMs left to a concurrent launch)
     if (max_sms > 0) grid = std::min(grid, max_sms * occ);
-    const int need = (p.batch + ke->block - 1) / ke->block;
+    const int per_cta = ke->lanes_per_problem > 1 ? ke->block / ke->lanes_per_problem : ke->block;   // problems a CTA holds at a time
+    const int need = (p.batch + per_cta - 1) / per_cta;
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
     if (ke->refs == 2) {   // reference terms live in a lane-interleaved global scratch that stays L2 resident
@@ -626,7 +629,7 @@ int run_shard(tinympc_cuda_solver* s, DeviceCtx& d, const tinympc_cuda_batch_in&
     // single-launch streamed pipeline: a thread-per-problem kernel that honours the watermark; in the exact-count mode the
     // concurrent producer / consumer pair (both count completions per chunk)
     const bool mixed = s->mixed_band > 0 && s->precision == 32;
-    if (s->streamed && !compact && !(mixed && s->fixer_sms < 0) && !s->force_wpp && stream_memops().ok) {
+    if (s->streamed && !compact && !(mixed && s->fixer_sms == -1) && !s->force_wpp && stream_memops().ok) {
         const KernelEntry* ke = pick_kernel(s, d, f, s->precision, ppb, in.Xref || in.Uref, n);
         const KernelEntry* ke64 = mixed ? find_kernel(f, 64, ppb, in.Xref || in.Uref, 0) : nullptr;
         // auto (0): the ramped chunk layout for shards of >= 2^16 problems, else equal chunks of >= 2^14 problems
@@ -634,14 +637,25 @@ int run_shard(tinympc_cuda_solver* s, DeviceCtx& d, const tinympc_cuda_batch_in&
         if (ke && ke->streaming && (!mixed || (ke64 && ke64->streaming)) && (nst == 0 || nst >= 2) && (ppb || f.shared_bounds_ok))
             return run_shard_streamed(s, d, ke, ke64, in, out, lo, hi, nst, kernel_ms, nchunks_out, marked_out);
     }
-    // chunking: enough chunks to overlap copies with compute, each still many waves of the GPU
-    int nch = s->chunks > 0 ? s->chunks : (n >= (1 << 17) ? 8 : (n >= (1 << 15) ? 4 : 1));
-    nch = std::min(nch, kMaxChunks);
-    int per = (n + nch - 1) / nch;
-    per = (per + 3) & ~3;                     // keeps every chunk's arrays 16 B aligned for all shapes
-    nch = (n + per - 1) / per;
+    // chunking: enough chunks to overlap copies with compute, each still many waves of the GPU.  Compact I/O moves ~120 bytes per
+    // problem, so there is next to nothing to overlap and every extra chunk costs a partial last wave of the persistent kernel plus
+    // the latency-bound end of its fp64 pass: two chunks, a short first one (its upload is all that precedes the first launch).
+    std::vector<int> cuts;   // chunk c = [cuts[c], cuts[c + 1])
+    if (s->chunks <= 0 && compact) {
+        cuts.push_back(0);
+        if (n >= (1 << 17)) cuts.push_back((n / 8 + 3) & ~3);
+        cuts.push_back(n);
+    } else {
+        int nch0 = s->chunks > 0 ? s->chunks : (n >= (1 << 17) ? 8 : (n >= (1 << 15) ? 4 : 1));
+        nch0 = std::min(nch0, kMaxChunks);
+        int per = (n + nch0 - 1) / nch0;
+        per = (per + 3) & ~3;                     // keeps every chunk's arrays 16 B aligned for all shapes
+        for (int c0 = 0; c0 < n; c0 += per) cuts.push_back(c0);
+        cuts.push_back(n);
+    }
+    const int nch = (int)cuts.size() - 1;
     for (int c = 0; c < nch; ++c) {
-        const int c0 = c * per, c1 = std::min(n, c0 + per), cn = c1 - c0;
+        const int c0 = cuts[c], c1 = cuts[c + 1], cn = c1 - c0;
         cudaStream_t st = d.streams[c % kStreams];
         const size_t g0 = (size_t)lo + c0;    // global problem index of the chunk start
         auto h2d = [&](DevBuf& dst, const float* src, size_t per_problem) -> cudaError_t {

@@ -34,6 +34,7 @@ struct KernelEntry {
     // ... and so are the numbers of linear-inequality rows (state, input)
     int cone_fixed;
     int scs, scd, ucs, ucd, nsl, nil;
+    int lanes_per_problem;   // 0 / 1: thread per problem; GS: a problem is spread over GS lanes (tmpc_gpp.cuh), a CTA holds block / GS problems
 };
 
 const KernelEntry* const* kernel_table(int* count);   // defined in gen/tmpc_table.cu
@@ -105,4 +106,26 @@ const KernelEntry* const* kernel_table(int* count);   // defined in gen/tmpc_tab
     extern const KernelEntry SYM = {#SYM, KF_TPP, CFG::NX, CFG::NU, CFG::NH, FEATV, BITS, CFG::REFMODE,             \
                                     0, CFG::FB ? 1 : 0, CFG::AFF ? 1 : 0, CFG::BLOCK, VAR, 1, SYM##_smem, SYM##_prepare, \
                                     SYM##_occ, SYM##_launch, 1, CFG::SCS, CFG::SCD, CFG::UCS, CFG::UCD, CFG::NSL, CFG::NIL};                                 \
+    }
+
+// lane-group-per-problem fp64 kernel (tmpc_gpp.cuh)
+#define TMPC_DEFINE_GPP_ENTRY(SYM, CFG, VAR)                                                                        \
+    namespace tmpc {                                                                                                \
+    static size_t SYM##_smem(int pe) { return gpp_smem_bytes<CFG>(pe); }                                            \
+    static cudaError_t SYM##_prepare(size_t smem) {                                                                 \
+        return cudaFuncSetAttribute(gpp_kernel<CFG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);       \
+    }                                                                                                               \
+    static cudaError_t SYM##_occ(int* n, size_t smem) {                                                             \
+        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(n, gpp_kernel<CFG>, CFG::BLOCK, smem);                 \
+    }                                                                                                               \
+    static cudaError_t SYM##_launch(const SolveParams& p, int grid, size_t smem, cudaStream_t st, const double* mp, \
+                                    const PackLayout& L) {                                                          \
+        GppTab<CFG::NX, CFG::NU, CFG::NH, CFG::GS> tab;                                                             \
+        fill_gpp_tab(tab, mp, L, p);                                                                                \
+        gpp_kernel<CFG><<<grid, CFG::BLOCK, smem, st>>>(p, tab);                                                    \
+        return cudaGetLastError();                                                                                  \
+    }                                                                                                               \
+    extern const KernelEntry SYM = {#SYM, KF_TPP, CFG::NX, CFG::NU, CFG::NH, 0 /* FEAT_BOX */, 64, 1 /* serves batches with and without references */, \
+                                    0, 0, 1, CFG::BLOCK, VAR, 1, SYM##_smem, SYM##_prepare,                        \
+                                    SYM##_occ, SYM##_launch, 0, 0, 0, 0, 0, 0, 0, CFG::GS};                         \
     }
