@@ -206,7 +206,7 @@ def main():
     ap.add_argument("--batch", type=int, default=1 << 20, help="problems per GPU")
     ap.add_argument("--scale", type=float, default=1.0, help="difficulty of the synthetic batch (SURVEY 8d: 0.3 easy, 1.0 hard)")
     ap.add_argument("--config", default="quadrotor", choices=["quadrotor", "cartpole", "rocket", "quadrotor_adaptive"])
-    ap.add_argument("--precision", type=int, default=32)
+    ap.add_argument("--precision", type=int, default=0, help="32 / 64; 0 = the family's parity-exact default (fp32 exact-count mode; fp64 under adaptive rho)")
     ap.add_argument("--mixed", type=float, default=-1.0,
                     help="relative band of the exact-count mode (fp32 pass + fp64 re-solve of the problems whose termination decision is "
                          "within the band of a tolerance); -1 = the family's measured band (default: the mode that reproduces the "
@@ -239,6 +239,8 @@ def main():
     spec = dict(quadrotor=P.quadrotor, cartpole=P.cartpole, rocket=P.rocket,
                 quadrotor_adaptive=lambda: P.quadrotor(adaptive=True))[args.config]()
     n, m, N = spec.nx, spec.nu, spec.N
+    if args.precision == 0:
+        args.precision = P.exact_precision(spec) if args.mixed < 0 else 32
     world_cfg = max(world, args.gpus)      # the reference arm runs on rank 0 alone but describes the same job
     if args.scaling == "strong":
         assert args.batch % world_cfg == 0, "--scaling strong needs --batch divisible by the number of GPUs"

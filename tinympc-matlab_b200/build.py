@@ -97,11 +97,11 @@ def inst4(nx, nu, N, refs=True, fb=False, variant=0, aff=None, cones=(0, 0, 0, 0
                 opq=False, tib=False, tm=True, minb=1, ntm=0, cones=cones, ttm=-1)
 
 
-def instg(nx, nu, N, variant=0):
+def instg(nx, nu, N, variant=0, adapt=False):
     """lane-group-per-problem fp64 kernel (tmpc_gpp.cuh): one lane per state row and per input row, groups of 8 / 16 / 32 lanes"""
     gs = 8 if nx + nu <= 8 else (16 if nx + nu <= 16 else 32)
     assert nx + nu <= 32
-    return dict(gen=5, bits=64, nx=nx, nu=nu, N=N, feat=BOX, refs=2, ppb=False, fb=False, variant=variant, block=128, aff=True, gs=gs)
+    return dict(gen=5, bits=64, nx=nx, nu=nu, N=N, feat=ADP if adapt else BOX, refs=2, ppb=False, fb=False, variant=variant, block=128, aff=True, gs=gs)
 
 
 def cols_per_thread(nx, nu, N, feat, refs, ntm=0):
@@ -173,6 +173,7 @@ def default_instances():
     # the second pass of the exact-count mode and small fp64 batches need, and a higher fp64 throughput as well
     for (nx, nu, N) in shapes:
         out.append(instg(nx, nu, N))
+    out.append(instg(12, 4, 10, adapt=True))     # adaptive rho: the fp64 path of BASELINE config 5
     for bits in (32, 64):
         for (nx, nu, N) in shapes:
             if bits == 64:            # fp64 thread-per-problem direct form (admm.cpp order), tmpc_tpp2.cuh: per-problem bounds; A/B (variant 6) otherwise
@@ -183,9 +184,9 @@ def default_instances():
             # fp32: the direct-form cone kernels stay as the A/B baseline (variant 5)
             out.append(inst(bits, nx, nu, N, CON, refs=REFS_L2, fb=True, tm=True, variant=0 if bits == 64 else 5))
             out.append(inst(bits, nx, nu, N, CON, refs=REFS_L2, tm=True, variant=0 if bits == 64 else 5))
-            if (nx, nu) == (12, 4):
-                out.append(inst(bits, nx, nu, N, ADP, refs=REFS_L2, fb=True, tm=True))
-                out.append(inst(bits, nx, nu, N, ADP, refs=REFS_L2, tm=True))
+            if (nx, nu) == (12, 4):   # adaptive rho, thread per problem: the fp32 kernels; fp64 is A/B (variant 6) next to tmpc_gpp.cuh
+                out.append(inst(bits, nx, nu, N, ADP, refs=REFS_L2, fb=True, tm=True, variant=0 if bits == 32 else 6))
+                out.append(inst(bits, nx, nu, N, ADP, refs=REFS_L2, tm=True, variant=0 if bits == 32 else 6))
     # The plain state layout (x and t entirely in tensor memory, 8 warps per SM) of the shapes whose default is the hybrid one: fewer
     # instructions per iteration and a 25 % shorter iteration of a lone warp.  The dispatcher picks it for batches that fit one
     # wave of it (tmpc_capi.cu, kLatencyVariant); option variant=9 forces it.
@@ -209,7 +210,7 @@ def default_instances():
 def name_of(i):
     t = "f32" if i["bits"] == 32 else "f64"
     if i["gen"] == 5:
-        return f"gpp_f64_{i['nx']}x{i['nu']}x{i['N']}_box_g{i['gs']}_v{i['variant']}"
+        return f"gpp_f64_{i['nx']}x{i['nu']}x{i['N']}_{FEAT_NAME[i['feat']]}_g{i['gs']}_v{i['variant']}"
     if i["gen"] == 4:
         cn = "_c" + "".join(str(c) for c in i["cones"])
         return f"tpp4_mix_{i['nx']}x{i['nu']}x{i['N']}_con{cn}{'' if i['refs'] else '_noref'}{'_fb' if i['fb'] else ''}{'_aff' if i['aff'] else ''}_v{i['variant']}"
@@ -235,7 +236,7 @@ def gen_sources(instances):
             src = (
                 "// generated by tinympc-matlab_b200/build.py -- do not edit\n"
                 '#include "../tmpc_gpp.cuh"\n#include "../tmpc_registry.h"\nusing namespace tmpc;\n'
-                f"using Cfg_{n} = GppCfg<{i['nx']}, {i['nu']}, {i['N']}, {i['gs']}, {i['block']}>;\n"
+                f"using Cfg_{n} = GppCfg<{i['nx']}, {i['nu']}, {i['N']}, {i['gs']}, {i['block']}, {b(i['feat'] == ADP)}>;\n"
                 f"TMPC_DEFINE_GPP_ENTRY({n}, Cfg_{n}, {i['variant']})\n"
             )
         elif i["gen"] == 4:

@@ -33,13 +33,15 @@
 
 namespace tmpc {
 
-template <int NX_, int NU_, int NH_, int GS_, int BLOCK_ = 128>
+template <int NX_, int NU_, int NH_, int GS_, int BLOCK_ = 128, bool ADAPT_ = false>
 struct GppCfg {
     using T = double;
     static constexpr int NX = NX_, NU = NU_, NH = NH_, GS = GS_, BLOCK = BLOCK_;
+    static constexpr bool ADAPT = ADAPT_;   // adaptive rho (rho_benchmark.cpp:44-250 in closed block form)
     static_assert(GS_ == 8 || GS_ == 16 || GS_ == 32, "group size: 8, 16 or 32 lanes");
     static_assert(NX_ + NU_ <= GS_, "one lane per state row and input row");
     static_assert(NX_ % 2 == 0 || true, "");
+    static constexpr int MINB = NH_ > 12 ? 2 : 3;        // CTAs per SM the register allocation aims at (the per-lane state grows with N)
     static constexpr int GPW = 32 / GS_;                 // problems per warp
     static constexpr int GPB = BLOCK_ / GS_;             // problems per CTA
     static constexpr int NV = NX_ + NU_;
@@ -50,17 +52,20 @@ struct GppCfg {
 };
 
 // Per-lane tables, built on the host in double from the family's master pack and passed in the kernel-parameter space.
-template <int NX, int NU, int NH, int GS>
+template <int NX, int NU, int NH, int GS, bool ADAPT = false>
 struct alignas(16) GppTab {
     double CF1[GS][NX], CF2[GS][NU], cf0[GS];     // forward : acc = cf0 + CF1 . x_i + CF2 . d_i
     double CB1[GS][NX], CB2[GS][NU], cb0[GS];     // backward: acc = cb0 + CB1 . p_{i+1} + CB2 . r_i (+ q_i on state lanes)
     double wref[GS];                               // Qd_r / Rd_a: weight of the lane's reference term (work->Q, work->R)
     double lo[NH][GS], hi[NH][GS];                 // box of the element the lane handles in forward slot s (state: column s + 1; input: step s); row NH-1: column 0
     double Pinf[NX][NX];                           // row-major: terminal term -(xref_N' Pinf)'
+    // adaptive rho: d/drho of the rows that contain Kinf (Kinf, Pinf move with rho; Quu_inv and AmBKt do not: the reference updates
+    // its copies C1, C2, which the sweeps never read), the rows of A' / B' for the dual residual, dPinf/drho
+    double dCF1[ADAPT ? GS : 1][NX], dCB2[ADAPT ? GS : 1][NU], AT[ADAPT ? GS : 1][NX], dPinf[ADAPT ? NX : 1][NX];
 };
 
-template <int NX, int NU, int NH, int GS>
-inline void fill_gpp_tab(GppTab<NX, NU, NH, GS>& t, const double* pk, const PackLayout& L, const SolveParams& prm) {
+template <int NX, int NU, int NH, int GS, bool ADAPT>
+inline void fill_gpp_tab(GppTab<NX, NU, NH, GS, ADAPT>& t, const double* pk, const PackLayout& L, const SolveParams& prm) {
     std::memset(&t, 0, sizeof(t));
     const double* A = pk + L.A; const double* B = pk + L.B; const double* K = pk + L.Kinf; const double* AK = pk + L.AmBKt;
     const double* Qi = pk + L.Quu_inv;
@@ -100,11 +105,40 @@ inline void fill_gpp_tab(GppTab<NX, NU, NH, GS>& t, const double* pk, const Pack
             for (int s = 0; s < NH - 1; ++s) { t.lo[s][l] = pk[L.umin + s * NU + a]; t.hi[s][l] = pk[L.umax + s * NU + a]; }
     }
     for (int r = 0; r < NX; ++r) for (int c = 0; c < NX; ++c) t.Pinf[r][c] = pk[L.Pinf + r * NX + c];
+    if constexpr (ADAPT) {
+        const double* dK = pk + L.dKinf;
+        for (int r = 0; r < NX; ++r) {
+            for (int c = 0; c < NX; ++c) {
+                double acc = 0.0;
+                for (int a = 0; a < NU; ++a) acc -= B[r * NU + a] * dK[a * NX + c];      // d/drho (A - B Kinf)[r][c]
+                t.dCF1[r][c] = acc;
+                t.AT[r][c] = A[c * NX + r];                                               // (A' g)_r = sum_c A[c][r] g_c
+                t.dPinf[r][c] = pk[L.dPinf + r * NX + c];
+            }
+            for (int a = 0; a < NU; ++a) t.dCB2[r][a] = -dK[a * NX + r];
+        }
+        for (int a = 0; a < NU; ++a) {
+            const int l = NX + a;
+            for (int c = 0; c < NX; ++c) { t.dCF1[l][c] = -dK[a * NX + c]; t.AT[l][c] = B[c * NU + a]; }   // (B' g)_a = sum_c B[c][a] g_c
+        }
+    }
 }
 
+// max / min / clamp of finite-or-infinite doubles as one compare + select: the library fmax / fmin carry NaN handling that costs
+// ~8 instructions per call in fp64, and this kernel takes ~6 of them per element and step (no NaN can arise: bounds may be infinite,
+// iterates are finite).
+__device__ __forceinline__ double gmax(double a, double b) { return a > b ? a : b; }
+__device__ __forceinline__ double gmin(double a, double b) { return a < b ? a : b; }
+// max(r, |a|) for r >= 0 without touching the FP64 pipe for the absolute value (the sign bit is cleared on the selected word)
+__device__ __forceinline__ double gabsmax(double r, double a) {
+    const bool keep = r > fabs(a);
+    return __hiloint2double(keep ? __double2hiint(r) : (__double2hiint(a) & 0x7fffffff), keep ? __double2loint(r) : __double2loint(a));
+}
+__device__ __forceinline__ double gclamp(double t, double lo, double hi) { return gmin(hi, gmax(lo, t)); }   // admm.cpp:91-98 order
+
 template <class C>
-__global__ void __launch_bounds__(C::BLOCK)
-gpp_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ GppTab<C::NX, C::NU, C::NH, C::GS> tab) {
+__global__ void __launch_bounds__(C::BLOCK, C::MINB)
+gpp_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ GppTab<C::NX, C::NU, C::NH, C::GS, C::ADAPT> tab) {
     using T = double;
     constexpr int NX = C::NX, NU = C::NU, NH = C::NH, GS = C::GS, NXP = C::NXP, NUP = C::NUP, SXL = C::SX, SUL = C::SU;
     constexpr unsigned FULL = 0xffffffffu;
@@ -120,7 +154,22 @@ gpp_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ GppT
     const int row = is_x ? l : (is_u ? l - NX : 0);
     const int lc = (is_x || is_u) ? l : 0;         // idle lanes compute lane 0's (discarded) values
 
+    // adaptive rho: the rows read with a lane-dependent index at every adaptation live in shared memory (a divergent read of the
+    // kernel-parameter bank is serialised address by address)
+    T* const at_t = hi_t + NH * GS;                  // [GS][NX]  rows of A' / B'
+    T* const dcf1_t = at_t + GS * NX;                // [GS][NX]
+    T* const dcb2_t = dcf1_t + GS * NX;              // [GS][NU]
+    T* const pinf_t = dcb2_t + GS * NU;              // [NX][NX]
+    T* const dpinf_t = pinf_t + NX * NX;             // [NX][NX]
+    // parking area of an adaptation pass: this lane's iterate and dual of every slot, [group][slot][lane of the group]
+    T* const sval = dpinf_t + NX * NX + (size_t)(threadIdx.x / GS) * 2 * (NH - 1) * GS + l;
+    T* const sdual = sval + (NH - 1) * GS;
     for (int e = threadIdx.x; e < NH * GS; e += C::BLOCK) { lo_t[e] = tab.lo[e / GS][e % GS]; hi_t[e] = tab.hi[e / GS][e % GS]; }
+    if constexpr (C::ADAPT) {
+        for (int e = threadIdx.x; e < GS * NX; e += C::BLOCK) { at_t[(e % NX) * GS + e / NX] = tab.AT[e / NX][e % NX]; dcf1_t[(e % NX) * GS + e / NX] = tab.dCF1[e / NX][e % NX]; }   // [c][lane]: conflict free
+        for (int e = threadIdx.x; e < GS * NU; e += C::BLOCK) dcb2_t[(e % NU) * GS + e / NU] = tab.dCB2[e / NU][e % NU];
+        for (int e = threadIdx.x; e < NX * NX; e += C::BLOCK) { pinf_t[(e % NX) * NX + e / NX] = tab.Pinf[e / NX][e % NX]; dpinf_t[(e % NX) * NX + e / NX] = tab.dPinf[e / NX][e % NX]; }   // [c][row]
+    }
     __syncthreads();
 
     // ---- this lane's rows of the matrices
@@ -130,7 +179,8 @@ gpp_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ GppT
 #pragma unroll
     for (int a = 0; a < NU; ++a) { cf2[a] = tab.CF2[lc][a]; cb2[a] = tab.CB2[lc][a]; }
     const T cf0 = tab.cf0[lc], cb0 = tab.cb0[lc], wref = tab.wref[lc];
-    const T rho = prm.rho, tol_pri = prm.abs_pri_tol, tol_dua = prm.abs_dua_tol;
+    const T rho0 = prm.rho, tol_pri = prm.abs_pri_tol, tol_dua = prm.abs_dua_tol;
+    const bool adaptive = C::ADAPT && prm.adaptive_rho != 0;
     const int max_iter = prm.max_iter, check_every = prm.check_termination;
     const int n_items = prm.batch_ptr ? min(*prm.batch_ptr, prm.batch) : prm.batch;
     const bool consumer = prm.q_tail != nullptr && prm.q_consume != 0;
@@ -139,6 +189,10 @@ gpp_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ GppT
     T G[NH], V[NH];          // dual (g / y) and slack (v / z) of the lane's row
     float RF[NH];            // reference term before weighting: Xref / Uref of the row (slot N-2 of a state lane is replaced by PT below)
     T PT = 0;                // state lanes: -(xref_N' Pinf)'_r
+    T PT1 = 0;               // adaptive rho: its derivative, -(xref_N' dPinf)'_r
+    // cache->rho and the accumulated rho' - rho0 of this problem; *_lc: the values update_linear_cost saw (it runs BEFORE the
+    // adaptation inside an iteration, admm.cpp:326-357)
+    T rho = rho0, rho_lc = rho0, dlt = 0, dlt_lc = 0;
     T x0r = 0;               // state lanes: x0_r
 #pragma unroll
     for (int s = 0; s < NH; ++s) { G[s] = 0; V[s] = 0; RF[s] = 0.f; }
@@ -196,9 +250,18 @@ gpp_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ GppT
                 pending = false; active = true;
                 k = 0; next_check = check_every; m0 = 0;
                 res_px = res_dx = res_pu = res_du = 0;
+                if constexpr (C::ADAPT) {   // pristine cache for every problem
+                    if (dlt != T(0)) {
+#pragma unroll
+                        for (int c = 0; c < NX; ++c) cf1[c] = tab.CF1[lc][c];
+#pragma unroll
+                        for (int a = 0; a < NU; ++a) cb2[a] = tab.CB2[lc][a];
+                    }
+                    rho = rho_lc = rho0; dlt = dlt_lc = 0;
+                }
 #pragma unroll
                 for (int s = 0; s < NH; ++s) { G[s] = 0; V[s] = 0; RF[s] = 0.f; }
-                PT = 0;
+                PT = 0; PT1 = 0;
                 if (is_x) {
                     x0r = static_cast<T>(__ldg(prm.x0 + (size_t)prob * NX + row));
                     if (prm.Xref) {
@@ -219,10 +282,13 @@ gpp_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ GppT
                 if (mine && is_x) xb[row] = static_cast<T>(RF[NH - 2]);
                 __syncwarp();
                 if (mine && is_x) {
-                    T acc = 0;
+                    T acc = 0, acc1 = 0;
 #pragma unroll
-                    for (int c = 0; c < NX; ++c) acc = fma(xb[c], tab.Pinf[c][row], acc);
-                    PT = -acc;
+                    for (int c = 0; c < NX; ++c) {
+                        acc = fma(xb[c], tab.Pinf[c][row], acc);
+                        if constexpr (C::ADAPT) acc1 = fma(xb[c], tab.dPinf[c][row], acc1);
+                    }
+                    PT = -acc; PT1 = -acc1;
                 }
                 __syncwarp();
             }
@@ -235,9 +301,12 @@ gpp_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ GppT
         }
 
         // weighted reference term of slot s: -(Xref .* Q) / -(Uref .* R); the terminal slot of a state lane holds PT instead
-        auto refterm = [&](int s) -> T { return (s == NH - 2 && is_x) ? PT : -(static_cast<T>(RF[s]) * wref); };
+        auto refterm = [&](int s) -> T {
+            if (s == NH - 2 && is_x) return C::ADAPT ? fma(dlt_lc, PT1, PT) : PT;
+            return -(static_cast<T>(RF[s]) * wref);
+        };
         // w_s = q / r of slot s as update_linear_cost left it (admm.cpp:218-246): ref - rho (v - g); 0 on the cold workspace
-        auto lincost = [&](int s) -> T { return m0 * fma(-rho, V[s] - G[s], refterm(s)); };
+        auto lincost = [&](int s) -> T { return m0 * fma(-rho_lc, V[s] - G[s], refterm(s)); };
 
         // ------------------------------------------------------------------ backward_pass_grad (admm.cpp:13-20)
         {
@@ -278,13 +347,18 @@ gpp_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ GppT
 
         // ------------------------------------------------------------------ forward_pass + update_slack + update_dual + residuals
         T rp = 0, rd = 0;
+        // adaptive rho: is the adaptation due at the end of this iteration (loop index i = k > 0, i % 5 == 0, admm.cpp:339)?  The
+        // groups of a warp may be at different phases; the extra hand-offs are executed by the whole warp when any group is due.
+        const bool due = adaptive && k > 0 && k % 5 == 0;
+        const bool anydue = C::ADAPT && __any_sync(FULL, due);
+        T a_pri = 0, a_prin = 0, a_dua = 0, a_duan = 0;
         auto element = [&](int s, T val) {   // the lane's element of slot s: vnew = clamp(x + g), g += x - vnew (admm.cpp:85-98, 184-187)
             const T lo = lo_t[s * GS + lc], hi = hi_t[s * GS + lc];
             const T t = val + G[s];
-            const T vn = fmin(hi, fmax(lo, t));
+            const T vn = gclamp(t, lo, hi);
             G[s] = t - vn;
-            rp = fmax(rp, fabs(val - vn));
-            rd = fmax(rd, fabs(V[s] - vn));
+            rp = gabsmax(rp, val - vn);
+            rd = gabsmax(rd, V[s] - vn);
             V[s] = vn;
         };
         {
@@ -311,7 +385,78 @@ gpp_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ GppT
                 const T val = (a0 + a1) + (a2 + a3);      // x_{s+1,r} or u_{s,a}
                 if (is_x && s < NH - 2) xb[((s + 1) & 1) * NXP + row] = val;
                 element(s, val);
+                if constexpr (C::ADAPT) {
+                    // Park this step's iterate and updated dual for the block pass of an adaptation, and take the primal rows -- inputs:
+                    // u - znew (= rp); states: (A x + B u - x_next) - vnew_next = -f - vnew_next.  Unconditional: a branch on "due" here
+                    // makes the compiler keep two copies of the unrolled sweep, which no longer fit the instruction cache.
+                    sval[s * GS] = val;
+                    sdual[s * GS] = G[s];
+                    const T pa = is_x ? cf0 + V[s] : T(0), pb2 = is_x ? cf0 : val;
+                    a_pri = gabsmax(a_pri, pa);
+                    a_prin = gabsmax(gabsmax(a_prin, V[s]), pb2);
+                }
                 if (s < NH - 2) __syncwarp();
+            }
+            if constexpr (C::ADAPT) {
+                if (anydue) {
+                    // Closed block form of the dual residual of rho_benchmark.cpp:146-173, one ROLLED pass over the parked
+                    // columns (the unrolled sweeps above already fill most of the 32 KB instruction cache).  Column s: x-block
+                    // A' g_{s+1} - g_s [s >= 1], u-block y_s + B' g_{s+1}, with Px = qv = Q .* x_s (R .* u_s).
+                    __syncwarp();
+                    const T* gsv = sdual - l;          // the group's row of slot s starts at gsv + s * GS (state lanes 0 .. NX-1)
+                    const T* xsv = sval - l;
+#pragma unroll 1
+                    for (int s = 0; s < NH - 1; ++s) {
+                        T at0 = 0, at1 = 0;
+#pragma unroll
+                        for (int c = 0; c < NX; ++c) { if (c & 1) at1 = fma(at_t[c * GS + lc], gsv[s * GS + c], at1); else at0 = fma(at_t[c * GS + lc], gsv[s * GS + c], at0); }
+                        const T at = at0 + at1;
+                        const T own = is_x ? (s >= 1 ? sval[(s - 1) * GS] : x0r) : sval[s * GS];           // x_s / u_s
+                        const T aty = is_x ? (s >= 1 ? at - sdual[(s - 1) * GS] : at) : at + sdual[s * GS];   // - g_s / + y_s
+                        const T qx = wref * own;
+                        a_dua = gabsmax(a_dua, qx + qx + aty);
+                        a_duan = gabsmax(gabsmax(a_duan, qx), aty);
+                    }
+                    {   // last state block: Px = Pinf x_N (the cache's current Pinf), qv = Q .* x_N, A'y = -g_N
+                        T px0 = 0, px1 = 0;
+#pragma unroll
+                        for (int c = 0; c < NX; ++c) {
+                            const T pc = fma(dlt, dpinf_t[c * NX + row], pinf_t[c * NX + row]);
+                            if (c & 1) px1 = fma(pc, xsv[(NH - 2) * GS + c], px1); else px0 = fma(pc, xsv[(NH - 2) * GS + c], px0);
+                        }
+                        if (is_x) {
+                            const T px = px0 + px1, qx = wref * sval[(NH - 2) * GS], aty = -G[NH - 2];
+                            a_dua = gabsmax(a_dua, px + qx + aty);
+                            a_duan = gabsmax(gabsmax(gabsmax(a_duan, px), qx), aty);
+                        }
+                    }
+                    if (is_u) a_pri = gmax(a_pri, rp);      // input rows: u - znew
+                    if (!(is_x || is_u)) { a_pri = a_prin = a_dua = a_duan = 0; }
+#pragma unroll
+                    for (int o = GS / 2; o > 0; o >>= 1) {
+                        a_pri = gmax(a_pri, __shfl_xor_sync(FULL, a_pri, o));
+                        a_prin = gmax(a_prin, __shfl_xor_sync(FULL, a_prin, o));
+                        a_dua = gmax(a_dua, __shfl_xor_sync(FULL, a_dua, o));
+                        a_duan = gmax(a_duan, __shfl_xor_sync(FULL, a_duan, o));
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+        rho_lc = rho; dlt_lc = dlt;   // update_linear_cost of this iteration ran with the pre-adaptation cache
+        if constexpr (C::ADAPT) {
+            if (due) {   // predict_rho + update_matrices_with_derivatives (rho_benchmark.cpp:175-212)
+                const T eps = 1e-10;
+                const T npri = a_pri / (a_prin + eps), ndua = a_dua / (a_duan + eps);
+                T nr = rho * sqrt(npri / (ndua + eps));
+                if (prm.rho_clip) nr = gmin(gmax(nr, prm.rho_min), prm.rho_max);
+                const T step = nr - rho;
+#pragma unroll
+                for (int c = 0; c < NX; ++c) cf1[c] = fma(step, dcf1_t[c * GS + lc], cf1[c]);
+#pragma unroll
+                for (int a = 0; a < NU; ++a) cb2[a] = fma(step, dcb2_t[a * GS + lc], cb2[a]);
+                dlt += step;
+                rho = nr;
             }
         }
         m0 = 1;
@@ -325,10 +470,10 @@ gpp_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ GppT
             T px = is_x ? rp : T(0), dx = is_x ? rd : T(0), pu = is_u ? rp : T(0), du = is_u ? rd : T(0);
 #pragma unroll
             for (int o = GS / 2; o > 0; o >>= 1) {
-                px = fmax(px, __shfl_xor_sync(FULL, px, o));
-                dx = fmax(dx, __shfl_xor_sync(FULL, dx, o));
-                pu = fmax(pu, __shfl_xor_sync(FULL, pu, o));
-                du = fmax(du, __shfl_xor_sync(FULL, du, o));
+                px = gmax(px, __shfl_xor_sync(FULL, px, o));
+                dx = gmax(dx, __shfl_xor_sync(FULL, dx, o));
+                pu = gmax(pu, __shfl_xor_sync(FULL, pu, o));
+                du = gmax(du, __shfl_xor_sync(FULL, du, o));
             }
             if (chk) {
                 next_check += check_every;
@@ -364,7 +509,8 @@ gpp_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ GppT
 
 template <class C>
 inline size_t gpp_smem_bytes(int) {
-    return ((size_t)C::GPB * C::GWORDS + 2 * (size_t)C::NH * C::GS) * sizeof(double);
+    return ((size_t)C::GPB * C::GWORDS + 2 * (size_t)C::NH * C::GS +
+            (C::ADAPT ? 2 * (size_t)C::GS * C::NX + (size_t)C::GS * C::NU + 2 * (size_t)C::NX * C::NX + 2 * (size_t)(C::NH - 1) * C::BLOCK : 0)) * sizeof(double);
 }
 
 }  // namespace tmpc

@@ -120,12 +120,12 @@ const KernelEntry* const* kernel_table(int* count);   // defined in gen/tmpc_tab
     }                                                                                                               \
     static cudaError_t SYM##_launch(const SolveParams& p, int grid, size_t smem, cudaStream_t st, const double* mp, \
                                     const PackLayout& L) {                                                          \
-        GppTab<CFG::NX, CFG::NU, CFG::NH, CFG::GS> tab;                                                             \
+        GppTab<CFG::NX, CFG::NU, CFG::NH, CFG::GS, CFG::ADAPT> tab;                                                           \
         fill_gpp_tab(tab, mp, L, p);                                                                                \
         gpp_kernel<CFG><<<grid, CFG::BLOCK, smem, st>>>(p, tab);                                                    \
         return cudaGetLastError();                                                                                  \
     }                                                                                                               \
-    extern const KernelEntry SYM = {#SYM, KF_TPP, CFG::NX, CFG::NU, CFG::NH, 0 /* FEAT_BOX */, 64, 1 /* serves batches with and without references */, \
+    extern const KernelEntry SYM = {#SYM, KF_TPP, CFG::NX, CFG::NU, CFG::NH, CFG::ADAPT ? 2 : 0 /* FEAT_ADAPT : FEAT_BOX */, 64, 1 /* serves batches with and without references */, \
                                     0, 0, 1, CFG::BLOCK, VAR, 1, SYM##_smem, SYM##_prepare,                        \
                                     SYM##_occ, SYM##_launch, 0, 0, 0, 0, 0, 0, 0, CFG::GS};                         \
     }

@@ -154,6 +154,16 @@ def exact_band(p: "ProblemSpec") -> float:
     return EXACT_BAND.get(p.name, 0.3)
 
 
+# Families whose parity-exact mode is plain fp64: under adaptive rho the fp32 direct-form kernel needs a 30 % band (two thirds of the
+# batch re-solved) and its un-marked problems still drift 5e-4 away at max_iter, so the lane-group fp64 kernel (tmpc_gpp.cuh) solves
+# the whole batch -- faster than the mixed mode, and exact.
+EXACT_PRECISION = {"quadrotor_adaptive": 64}
+
+
+def exact_precision(p: "ProblemSpec") -> int:
+    return EXACT_PRECISION.get(p.name, 32)
+
+
 ROCKET_XINIT = np.array([4.0, 2.0, 20.0, -3.0, 2.0, -4.5])
 
 
