@@ -42,12 +42,14 @@ def solve_gpu(capi, oracle_mod, p, b, precision, variant=0, mixed=0.0, fixer_sms
     return r
 
 
-def compare(r, g, precision, name, max_flip_frac=0.0):
+def compare(r, g, precision, name, max_flip_frac=0.0, hard_tol=X_TOL_F32):
     """north_star: identical status codes and iteration counts; states / controls within 1e-4 ABSOLUTE in fp32.
     max_flip_frac > 0 only for the plain-fp32 mode (a termination test on rounded values can flip by one check interval,
     SURVEY H1); the exact-count mode and fp64 are held to 0.  The absolute bar is asserted on every problem that converged with
-    the reference's iteration count; a problem that runs into max_iter never damps its rounding differences (its steps stay
-    large), so those are held to 1e-3 and their maximum is printed."""
+    the reference's iteration count, and -- since the backward pass of the fp32 kernels runs in impulse-response form -- on the
+    problems that run into max_iter as well (hard_tol = 1e-4).  Only the direct-form fp32 kernels kept as A/B variants and the fp32
+    adaptive-rho kernel (neither is a default of the benchmark) pass hard_tol = 1e-3 for the problems stopped at max_iter, whose
+    steps stay large and never damp a rounding difference."""
     B = len(g["iter"])
     same = (r["iter"] == g["iter"]) & (r["status"] == g["status"])
     flips = int((~same).sum())
@@ -69,7 +71,7 @@ def compare(r, g, precision, name, max_flip_frac=0.0):
     du = np.abs(r["u"][same] - g["u"][same]).max() if same.any() else 0.0
     print(f"\n[abs] {name}: max|dxu| converged {e_conv:.2e} ({int(conv.sum())}), at max_iter {e_hard:.2e} ({int(hard.sum())})")
     assert e_conv <= X_TOL_F32, f"{name}: {e_conv:.3e} > 1e-4 absolute on a converged problem (kernel {r['kernel']})"
-    assert e_hard <= 1e-3, f"{name}: {e_hard:.3e} on a problem stopped at max_iter (kernel {r['kernel']})"
+    assert e_hard <= hard_tol, f"{name}: {e_hard:.3e} on a problem stopped at max_iter (kernel {r['kernel']})"
     return flips, dx, du
 
 
@@ -89,7 +91,7 @@ def test_golden_fp32(name, capi, oracle_mod):
     # plain fp32: single-problem cases sit exactly on a tolerance by construction (G2: dual residual 9.99986e-5 vs 1e-4) and may
     # flip; the exact-count mode below may not
     B = len(g["iter"])
-    compare(r, g, 32, name, max_flip_frac=1.0 if B == 1 else 0.08)
+    compare(r, g, 32, name, max_flip_frac=1.0 if B == 1 else 0.08, hard_tol=1e-3 if p.adaptive_rho else X_TOL_F32)
 
 
 @pytest.mark.parametrize("name", sorted(cases.CASES))
@@ -97,8 +99,9 @@ def test_golden_exact_mode(name, capi, oracle_mod, problems):
     """The default mode of the benchmark (option "mixed" = the family's band): every golden case, G2 included, with the
     reference's iteration count and status, x / u within 1e-4 absolute."""
     p, b, g = cases.load(name)
-    r = solve_gpu(capi, oracle_mod, p, b, 32, mixed=problems.exact_band(p))
-    compare(r, g, 32, name)
+    prec = problems.exact_precision(p)     # adaptive rho: the parity-exact mode is plain fp64 (tmpc_gpp.cuh)
+    r = solve_gpu(capi, oracle_mod, p, b, prec, mixed=problems.exact_band(p) if prec == 32 else 0.0)
+    compare(r, g, prec, name)
 
 
 # measured fp32 iteration-count flip rates (one check interval early/late).  Box-constrained batches run the incremental-form
@@ -119,7 +122,8 @@ def test_random_batch_vs_oracle(family, scale, precision, capi, oracle_mod, prob
     impl = "ref" if oracle_mod.available("ref") else "port"
     g = oracle_mod.solve_batch(p, b, impl)
     r = solve_gpu(capi, oracle_mod, p, b, precision)
-    flips, dx, du = compare(r, g, precision, f"{family}@{scale}", max_flip_frac=0.0 if precision == 64 else FLIP_BOUND[family])
+    flips, dx, du = compare(r, g, precision, f"{family}@{scale}", max_flip_frac=0.0 if precision == 64 else FLIP_BOUND[family],
+                            hard_tol=1e-3 if family == "quadrotor_adaptive" else X_TOL_F32)
     print(f"\n[parity] {family} s={scale} fp{precision}: {flips}/{B} count flips, max|dx|={dx:.2e} max|du|={du:.2e} kernel={r['kernel']}")
 
 
@@ -132,13 +136,13 @@ def test_direct_form_variant(family, scale, capi, oracle_mod, problems):
     g = oracle_mod.solve_batch(p, b, "ref" if oracle_mod.available("ref") else "port")
     r = solve_gpu(capi, oracle_mod, p, b, 32, variant=5)
     assert r["kernel"].startswith("tpp2_f32"), r["kernel"]
-    flips, dx, du = compare(r, g, 32, f"{family}@{scale} direct", max_flip_frac=FLIP_BOUND_DIRECT[family])
+    flips, dx, du = compare(r, g, 32, f"{family}@{scale} direct", max_flip_frac=FLIP_BOUND_DIRECT[family], hard_tol=1e-3)
     print(f"\n[parity] {family} s={scale} fp32 direct form: {flips}/{B} count flips, max|dx|={dx:.2e} max|du|={du:.2e} kernel={r['kernel']}")
 
 
 @pytest.mark.parametrize("fixer_sms", [0, -1])
-@pytest.mark.parametrize("family,scale,band,max_flips", [("cartpole", 1.0, 0.003, 0), ("cartpole", 0.3, 0.003, 0), ("quadrotor", 0.3, 0.003, 0),
-                                                         ("quadrotor", 1.0, 0.003, 1), ("rocket", 1.0, 0.003, 0), ("quadrotor_adaptive", 1.0, 0.3, 0)])
+@pytest.mark.parametrize("family,scale,band,max_flips", [("cartpole", 1.0, 0.003, 0), ("cartpole", 0.3, 0.003, 0), ("quadrotor", 0.3, 0.002, 0),
+                                                         ("quadrotor", 1.0, 0.002, 0), ("rocket", 1.0, 0.003, 0), ("quadrotor_adaptive", 1.0, 0.3, 0)])
 def test_mixed_mode_exact_counts(family, scale, band, max_flips, fixer_sms, capi, oracle_mod, problems):
     """option "mixed": the fp32 pass stops every problem whose termination decision lies within the relative band of the
     tolerances, an fp64 pass re-solves exactly those -> the reference's iteration counts and status codes.  Measured on 2^18
@@ -153,7 +157,7 @@ def test_mixed_mode_exact_counts(family, scale, band, max_flips, fixer_sms, capi
     r = solve_gpu(capi, oracle_mod, p, b, 32, mixed=band, fixer_sms=fixer_sms)
     assert ("|" if fixer_sms >= 0 else "+") in r["kernel"] and 0 < r["marked"] < B, (r["kernel"], r["marked"])
     assert not (r["status"] & 0x100).any(), "a marked problem was not re-solved"
-    flips, dx, du = compare(r, g, 32, f"{family}@{scale} mixed", max_flip_frac=max_flips / B)
+    flips, dx, du = compare(r, g, 32, f"{family}@{scale} mixed", max_flip_frac=max_flips / B, hard_tol=1e-3 if family == "quadrotor_adaptive" else X_TOL_F32)
     print(f"\n[parity] {family} s={scale} mixed band={band}: {flips}/{B} count flips, {r['marked']} re-solved in fp64, max|dx|={dx:.2e} "
           f"max|du|={du:.2e} kernel={r['kernel']}")
 
@@ -447,3 +451,74 @@ def test_hybrid_layout_with_per_problem_and_time_varying_bounds(capi, oracle_mod
     rs["kernel"] = r["kernel"]
     flips, dx, du = compare(rs, gg, 32, "quadrotor time-varying bounds", max_flip_frac=0.01)
     print(f"\n[parity] quadrotor hybrid ppb + time-varying bounds: == plain bit for bit; {flips}/{n} count flips, max|dx|={dx:.2e} kernel={r['kernel']}")
+
+
+# ---- lane-group-per-problem fp64 kernel (tmpc_gpp.cuh) ---------------------------------------------------------------------------
+def _gpp_family(problems, name):
+    """box families of the three compiled shapes; the rocket without its cones and rows (a box family with the gravity term f)"""
+    if name == "rocket_box":
+        p = problems.rocket(linear=False)
+        p.en_state_soc = p.en_input_soc = 0
+        p.Acx = p.qcx = p.Acu = p.qcu = np.zeros(0, np.int32)
+        p.cx = p.cu = np.zeros(0)
+        p.name = "rocket_box"
+        return p
+    return dict(cartpole=problems.cartpole, quadrotor=problems.quadrotor)[name]()
+
+
+@pytest.mark.parametrize("tweak", ["plain", "norefs", "moving_bounds", "no_bounds", "check3", "x0_outside", "few_iters"])
+@pytest.mark.parametrize("family", ["quadrotor", "cartpole", "rocket_box"])
+def test_lane_group_kernel_matches_the_reference(family, tweak, capi, oracle_mod, problems):
+    """fp64 batches of the compiled box shapes run the lane-group kernel: the reference's iteration counts and statuses on every
+    problem, x / u to float32 output rounding -- with and without references, bounds that move along the horizon (not the
+    fast-box case), bounds switched off, check_termination = 3, x0 outside its box (the column-0 slack never converges), a
+    max_iter that cuts every solve short -- and the thread-per-problem fp64 kernel (variant 6) returns the same counts."""
+    p = _gpp_family(problems, family)
+    B = 3000
+    b = problems.make_batch(p, B, 1.0, seed=77)
+    if tweak == "norefs":
+        b.Xref = None; b.Uref = None
+    elif tweak == "moving_bounds":
+        ramp = np.linspace(1.0, 0.6, p.N)[:, None]
+        p.x_min, p.x_max = p.x_min * ramp, p.x_max * ramp
+        p.u_min, p.u_max = p.u_min * ramp[:-1], p.u_max * ramp[:-1]
+    elif tweak == "no_bounds":
+        p.en_state_bound = p.en_input_bound = 0
+    elif tweak == "check3":
+        p.check_termination = 3
+    elif tweak == "x0_outside":
+        b.x0 = (b.x0 + np.float32(1.2) * np.asarray(p.x_max[0], np.float32) * (np.arange(B)[:, None] % 3 == 0)).astype(np.float32)
+    elif tweak == "few_iters":
+        p.max_iter = 7
+    g = oracle_mod.solve_batch(p, b, "ref" if oracle_mod.available("ref") else "port")
+    r = solve_gpu(capi, oracle_mod, p, b, 64)
+    assert r["kernel"].startswith("gpp_f64"), r["kernel"]
+    compare(r, g, 64, f"{family}/{tweak}")
+    r6 = solve_gpu(capi, oracle_mod, p, b, 64, variant=6)
+    assert r6["kernel"].startswith("tpp2_f64"), r6["kernel"]
+    assert np.array_equal(r["iter"], r6["iter"]) and np.array_equal(r["status"], r6["status"])
+    assert np.abs(r["x"] - r6["x"]).max() <= 1e-6 * max(1.0, float(np.abs(g["x"]).max()))
+
+
+def test_lane_group_kernel_adaptive_rho_matches_the_reference(capi, oracle_mod, problems):
+    """adaptive rho on the lane-group kernel: counts, statuses, solutions AND the final rho of every problem (rho_benchmark.cpp:175-212)"""
+    p = problems.quadrotor(adaptive=True)
+    B = 4000
+    b = problems.make_batch(p, B, 1.0, seed=78)
+    g = oracle_mod.solve_batch(p, b, "ref" if oracle_mod.available("ref") else "port")
+    r = solve_gpu(capi, oracle_mod, p, b, 64)
+    assert r["kernel"].startswith("gpp_f64") and "_adp_" in r["kernel"], r["kernel"]
+    compare(r, g, 64, "quadrotor_adaptive/gpp")
+    assert np.abs(r["rho"] - g["rho"]).max() < 1e-5 * max(1.0, float(np.abs(g["rho"]).max()))
+    assert len(np.unique(np.round(g["rho"], 3))) > 10      # the batch really adapts
+
+
+@pytest.mark.parametrize("B", [1, 2, 17, 4097])
+def test_lane_group_kernel_ragged_batches(B, capi, oracle_mod, problems):
+    """batches that do not fill a warp / a CTA / a wave: idle groups must neither write nor stall the others"""
+    p = problems.quadrotor()
+    b = problems.make_batch(p, B, 1.0, seed=79)
+    g = oracle_mod.solve_batch(p, b, "ref" if oracle_mod.available("ref") else "port")
+    r = solve_gpu(capi, oracle_mod, p, b, 64)
+    assert r["kernel"].startswith("gpp_f64"), r["kernel"]
+    compare(r, g, 64, f"ragged {B}")
