@@ -1052,11 +1052,32 @@ int tinympc_cuda_solve_workspace(tinympc_cuda_solver* s, const tinympc_cuda_work
     SolveParams p = f.base;
     p.batch = 1;
     if (w->rho) p.rho = *w->rho;
-    CU(s, wpp_launch<double>(p, f.L, d.pack64, W, sb.p, 1, 1, st));
+    // A box family of a compiled shape whose live cache is the family's own (no adaptive rho, no set_cache_terms override) runs the
+    // lane-group kernel in session mode on this one workspace: ~2.5 us per ADMM iteration instead of ~10 (tmpc_gpp.cuh); every member
+    // of the workspace comes back as the reference would leave it.
+    auto same = [&](const double* a, int at, int rows, int cols) {   // a: column-major (Eigen) vs the row-major pack
+        if (!a) return true;
+        for (int r = 0; r < rows; ++r) for (int c = 0; c < cols; ++c) if (a[(size_t)c * rows + r] != f.pack[at + r * cols + c]) return false;
+        return true;
+    };
+    const KernelEntry* kg = (!s->force_wpp && f.feat == kFeatBox && f.shared_bounds_ok && p.max_iter > 0 && p.rho == f.base.rho &&
+                             same(w->Kinf, f.L.Kinf, nu, nx) && same(w->Pinf, f.L.Pinf, nx, nx)) ? find_kernel(f, 64, false, true, 0) : nullptr;
+    if (kg && kg->session_launch) {
+        const size_t smem = kg->smem_bytes(f.L.cold_size);
+        p.work_counter = d.counters + kMaxChunks - 1;
+        p.x = nullptr; p.u = nullptr;
+        CU(s, cudaMemsetAsync(p.work_counter, 0, sizeof(int), st));
+        CU(s, d.iter.reserve(sizeof(int) * 4));
+        p.iter = static_cast<int*>(d.iter.p); p.status = p.iter + 1;
+        CU(s, kg->session_launch(p, 1, smem, st, f.pack.data(), f.L, static_cast<double*>(sb.p), W, 1));
+        note_kernel(s, std::string(kg->name) + "_workspace");
+    } else {
+        CU(s, wpp_launch<double>(p, f.L, d.pack64, W, sb.p, 1, 1, st));
+        note_kernel(s, "wpp_f64_workspace");
+    }
     CU(s, cudaMemcpyAsync(h.data(), sb.p, sizeof(double) * W.size, cudaMemcpyDeviceToHost, st));
     CU(s, cudaStreamSynchronize(st));
     cudaSetDevice(prev);
-    note_kernel(s, "wpp_f64_workspace");
     s->launches += 1;
 
     auto get = [&](double* dst, int at, int n) { if (dst) std::memcpy(dst, h.data() + at, sizeof(double) * n); };
@@ -1206,7 +1227,23 @@ int tinympc_cuda_session_solve(tinympc_cuda_session* ss) {
     p.iter = static_cast<int*>(ss->iter.p); p.status = static_cast<int*>(ss->status.p);
     const int warps = std::max(1, std::min(ss->batch, d.sm_count * 16));
     cudaStream_t st = d.streams[0];
-    if (ss->fam.base.max_iter > 0) {
+    // fp64 sessions of a box family with a compiled shape run the lane-group kernel on the same workspaces (tmpc_gpp.cuh, session
+    // mode): the reference's warm-start semantics at ~4x the rate of the warp-per-problem kernel; option "kernel" = 1 keeps the latter
+    const KernelEntry* kg = (ss->bits == 64 && !s->force_wpp && ss->fam.feat == kFeatBox && ss->fam.shared_bounds_ok) ? find_kernel(ss->fam, 64, false, true, 0) : nullptr;
+    if (kg && !kg->session_launch) kg = nullptr;
+    if (ss->fam.base.max_iter > 0 && kg) {
+        const size_t smem = kg->smem_bytes(ss->fam.L.cold_size);
+        int occ = 1;
+        CU(s, kg->prepare(smem));
+        CU(s, kg->occupancy(&occ, smem));
+        const int per_cta = kg->block / std::max(1, kg->lanes_per_problem);
+        const int grid = std::max(1, std::min(d.sm_count * std::max(1, occ), (ss->batch + per_cta - 1) / per_cta));
+        p.work_counter = d.counters + kMaxChunks - 1;
+        CU(s, cudaMemsetAsync(p.work_counter, 0, sizeof(int), st));
+        CU(s, kg->session_launch(p, grid, smem, st, ss->fam.pack.data(), ss->fam.L, static_cast<double*>(ss->ws.p), ss->W, 0));
+        s->launches += 1;
+        note_kernel(s, std::string(kg->name) + "_session");
+    } else if (ss->fam.base.max_iter > 0) {
         CU(s, ss->bits == 64 ? wpp_launch<double>(p, ss->fam.L, ss->pack.p, ss->W, ss->ws.p, warps, 2, st)
                              : wpp_launch<float>(p, ss->fam.L, ss->pack.p, ss->W, ss->ws.p, warps, 2, st));
         s->launches += 1;

@@ -30,6 +30,7 @@
 // same SolveParams protocol as tmpc_tpp2.cuh) and small batches of the compiled shapes.
 #pragma once
 #include "tmpc_tpp2.cuh"
+#include "tmpc_wpp.h"
 
 namespace tmpc {
 
@@ -124,6 +125,18 @@ inline void fill_gpp_tab(GppTab<NX, NU, NH, GS, ADAPT>& t, const double* pk, con
     }
 }
 
+// Session mode (tinympc_cuda_session_*): `batch` persistent solver workspaces in the layout of the warp-per-problem
+// kernel (WppLayout, the members of TinyWorkspace in double) are iterated IN PLACE with the reference's warm-start semantics
+// (admm.cpp:291-292, 379-380): the first backward pass runs on the q, r, p_N the previous solve left behind, the first dual residual
+// compares against the stored work->v / work->z, and on exit x, u, vnew, znew, v, z, g, y, q, r, p_N, iter, status and the residuals go
+// back (d and the inner columns of p are recomputed by every solve before they are read and are not written).
+struct GppSession {
+    double* ws;        // batch * W.size doubles, or NULL (batch mode)
+    WppLayout W;
+    int full;          // 1: also write d, every column of p and the unused columns 0 and N-1 of q (tiny_solve on ONE live workspace, whose
+                       // owner may look at any member of TinyWorkspace afterwards); 0: only what the next warm start reads
+};
+
 // max / min / clamp of finite-or-infinite doubles as one compare + select: the library fmax / fmin carry NaN handling that costs
 // ~8 instructions per call in fp64, and this kernel takes ~6 of them per element and step (no NaN can arise: bounds may be infinite,
 // iterates are finite).
@@ -136,9 +149,11 @@ __device__ __forceinline__ double gabsmax(double r, double a) {
 }
 __device__ __forceinline__ double gclamp(double t, double lo, double hi) { return gmin(hi, gmax(lo, t)); }   // admm.cpp:91-98 order
 
-template <class C>
+template <class C, bool SESSION = false>
 __global__ void __launch_bounds__(C::BLOCK, C::MINB)
-gpp_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ GppTab<C::NX, C::NU, C::NH, C::GS, C::ADAPT> tab) {
+gpp_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ GppTab<C::NX, C::NU, C::NH, C::GS, C::ADAPT> tab,
+           const __grid_constant__ GppSession ses) {
+    static_assert(!(SESSION && C::ADAPT), "adaptive-rho sessions keep a cache per problem: they stay on the warp-per-problem kernel");
     using T = double;
     constexpr int NX = C::NX, NU = C::NU, NH = C::NH, GS = C::GS, NXP = C::NXP, NUP = C::NUP, SXL = C::SX, SUL = C::SU;
     constexpr unsigned FULL = 0xffffffffu;
@@ -161,9 +176,11 @@ gpp_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ GppT
     T* const dcb2_t = dcf1_t + GS * NX;              // [GS][NU]
     T* const pinf_t = dcb2_t + GS * NU;              // [NX][NX]
     T* const dpinf_t = pinf_t + NX * NX;             // [NX][NX]
-    // parking area of an adaptation pass: this lane's iterate and dual of every slot, [group][slot][lane of the group]
-    T* const sval = dpinf_t + NX * NX + (size_t)(threadIdx.x / GS) * 2 * (NH - 1) * GS + l;
-    T* const sdual = sval + (NH - 1) * GS;
+    // parking area: this lane's iterate and (adaptive rho) updated dual / (sessions) previous slack of every slot,
+    // [group][array][slot][lane of the group]
+    T* const sval = (C::ADAPT ? dpinf_t + NX * NX : hi_t + NH * GS) + (size_t)(threadIdx.x / GS) * 2 * NH * GS + l;
+    T* const sdual = sval + NH * GS;
+    T* const sold = sdual;      // sessions: work->v / work->z as the last iteration found it (adaptive rho and sessions never combine)
     for (int e = threadIdx.x; e < NH * GS; e += C::BLOCK) { lo_t[e] = tab.lo[e / GS][e % GS]; hi_t[e] = tab.hi[e / GS][e % GS]; }
     if constexpr (C::ADAPT) {
         for (int e = threadIdx.x; e < GS * NX; e += C::BLOCK) { at_t[(e % NX) * GS + e / NX] = tab.AT[e / NX][e % NX]; dcf1_t[(e % NX) * GS + e / NX] = tab.dCF1[e / NX][e % NX]; }   // [c][lane]: conflict free
@@ -202,6 +219,7 @@ gpp_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ GppT
     T m0 = 0;                // 0 on a problem's first iteration (q = r = p = 0 on the cold workspace, tiny_api.cpp:68-105), then 1
     T res_px = 0, res_dx = 0, res_pu = 0, res_du = 0;
 
+    T* wsp = ses.ws;                 // sessions: this problem's workspace
     T* const xb = gbase + C::oXB;    // [2][NXP]
     T* const pb = gbase + C::oPB;    // [2][NXP + NUP]
     T* const dt = gbase + C::oDT;    // [NH-1][NUP]
@@ -262,6 +280,16 @@ gpp_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ GppT
 #pragma unroll
                 for (int s = 0; s < NH; ++s) { G[s] = 0; V[s] = 0; RF[s] = 0.f; }
                 PT = 0; PT1 = 0;
+                if constexpr (SESSION) {
+                    wsp = ses.ws + (size_t)prob * ses.W.size;
+                    m0 = 1;                                   // the stored q, r, p_N open the first backward pass (zeros on a cold workspace)
+                    const int og = is_x ? ses.W.g + NX : ses.W.y, ov = is_x ? ses.W.v + NX : ses.W.z, st_ = is_x ? NX : NU;
+                    if (is_x || is_u) {
+#pragma unroll
+                        for (int s = 0; s < NH - 1; ++s) { G[s] = wsp[og + s * st_ + row]; V[s] = wsp[ov + s * st_ + row]; }
+                    }
+                    if (is_x) { x0r = wsp[ses.W.x + row]; G[NH - 1] = wsp[ses.W.g + row]; V[NH - 1] = wsp[ses.W.v + row]; }
+                } else
                 if (is_x) {
                     x0r = static_cast<T>(__ldg(prm.x0 + (size_t)prob * NX + row));
                     if (prm.Xref) {
@@ -279,7 +307,7 @@ gpp_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ GppT
             }
             if (__any_sync(FULL, mine)) {
                 // terminal term: PT_r = -(xref_N' Pinf)_r = -sum_c xref_N[c] Pinf[c][r]   (admm.cpp:238-240)
-                if (mine && is_x) xb[row] = static_cast<T>(RF[NH - 2]);
+                if (mine && is_x) xb[row] = SESSION ? wsp[ses.W.Xref + (NH - 1) * NX + row] : static_cast<T>(RF[NH - 2]);
                 __syncwarp();
                 if (mine && is_x) {
                     T acc = 0, acc1 = 0;
@@ -303,10 +331,19 @@ gpp_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ GppT
         // weighted reference term of slot s: -(Xref .* Q) / -(Uref .* R); the terminal slot of a state lane holds PT instead
         auto refterm = [&](int s) -> T {
             if (s == NH - 2 && is_x) return C::ADAPT ? fma(dlt_lc, PT1, PT) : PT;
-            return -(static_cast<T>(RF[s]) * wref);
+            if constexpr (SESSION) return -(wsp[(is_x ? ses.W.Xref + (s + 1) * NX : ses.W.Uref + s * NU) + row] * wref);
+            else return -(static_cast<T>(RF[s]) * wref);
         };
-        // w_s = q / r of slot s as update_linear_cost left it (admm.cpp:218-246): ref - rho (v - g); 0 on the cold workspace
-        auto lincost = [&](int s) -> T { return m0 * fma(-rho_lc, V[s] - G[s], refterm(s)); };
+        // w_s = q / r of slot s as update_linear_cost left it (admm.cpp:218-246): ref - rho (v - g); 0 on the cold workspace.
+        // Sessions: the first backward pass of a solve reads what the PREVIOUS solve stored (its references may have changed since).
+        auto lincost_now = [&](int s) -> T { return m0 * fma(-rho_lc, V[s] - G[s], refterm(s)); };
+        auto lincost = [&](int s) -> T {
+            if constexpr (SESSION) {
+                if (s == NH - 1) return k == 0 ? wsp[ses.W.q + row] : fma(-rho_lc, V[NH - 1] - G[NH - 1], -(wsp[ses.W.Xref + row] * wref));   // q_0, full mode only
+                if (k == 0) return wsp[(is_x ? (s == NH - 2 ? ses.W.p + (NH - 1) * NX : ses.W.q + (s + 1) * NX) : ses.W.r + s * NU) + row];
+            }
+            return lincost_now(s);
+        };
 
         // ------------------------------------------------------------------ backward_pass_grad (admm.cpp:13-20)
         {
@@ -339,6 +376,9 @@ gpp_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ GppT
                     const T w1 = lincost(i - 1);          // state lane: q_i (column i = slot i-1); input lane: r_{i-1}
                     T* dst = pb + (i & 1) * (NXP + NUP);
                     if (is_x) dst[row] = acc + w1; else if (is_u) dst[NXP + row] = w1;
+                    if constexpr (SESSION) { if (ses.full && is_x) wsp[ses.W.p + i * NX + row] = acc + w1; }
+                } else {
+                    if constexpr (SESSION) { if (ses.full && is_x) wsp[ses.W.p + row] = acc + lincost(NH - 1); }   // p_0 = q_0 + ... (never read)
                 }
                 if (is_u) dt[i * NUP + row] = acc;         // d_i
                 __syncwarp();
@@ -356,6 +396,7 @@ gpp_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ GppT
             const T lo = lo_t[s * GS + lc], hi = hi_t[s * GS + lc];
             const T t = val + G[s];
             const T vn = gclamp(t, lo, hi);
+            if constexpr (SESSION) { sold[s * GS] = V[s]; sval[s * GS] = val; }
             G[s] = t - vn;
             rp = gabsmax(rp, val - vn);
             rd = gabsmax(rd, V[s] - vn);
@@ -484,6 +525,7 @@ gpp_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ GppT
         if (k >= max_iter) finish = true;
         if (active && finish) {
             // solution = (vnew, znew) (admm.cpp:364-376, 384-388)
+            if (!SESSION || prm.x != nullptr) {
             if (is_x) {
                 float* dst = prm.x + (size_t)prob * SXL + row;
                 dst[0] = static_cast<float>(V[NH - 1]);
@@ -493,6 +535,46 @@ gpp_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ GppT
                 float* dst = prm.u + (size_t)prob * SUL + row;
 #pragma unroll
                 for (int s = 0; s < NH - 1; ++s) dst[s * NU] = static_cast<float>(V[s]);
+            }
+            }
+            if constexpr (SESSION) {
+                const bool conv = st == 1;     // converged: the reference returns BEFORE v <- vnew (admm.cpp:364-380)
+                if (is_x || is_u) {
+                    const int st_ = is_x ? NX : NU;
+                    T* wx = wsp + (is_x ? ses.W.x + NX : ses.W.u) + row;
+                    T* wvn = wsp + (is_x ? ses.W.vnew + NX : ses.W.znew) + row;
+                    T* wv = wsp + (is_x ? ses.W.v + NX : ses.W.z) + row;
+                    T* wg = wsp + (is_x ? ses.W.g + NX : ses.W.y) + row;
+                    T* wq = wsp + (is_x ? ses.W.q + NX : ses.W.r) + row;
+#pragma unroll
+                    for (int s = 0; s < NH - 1; ++s) {
+                        wx[s * st_] = sval[s * GS];
+                        wvn[s * st_] = V[s];
+                        wv[s * st_] = conv ? sold[s * GS] : V[s];
+                        wg[s * st_] = G[s];
+                        if (is_x && s == NH - 2) wsp[ses.W.p + (NH - 1) * NX + row] = lincost_now(s);
+                        else wq[s * st_] = lincost_now(s);
+                    }
+                    if (ses.full) {
+                        if (is_u) {
+#pragma unroll
+                            for (int s = 0; s < NH - 1; ++s) wsp[ses.W.d + s * NU + row] = dt[s * NUP + row];
+                        } else {   // q of the columns the backward pass never reads (admm.cpp:218-225 computes them all the same)
+                            wsp[ses.W.q + row] = fma(-rho_lc, V[NH - 1] - G[NH - 1], -(wsp[ses.W.Xref + row] * wref));
+                            wsp[ses.W.q + (NH - 1) * NX + row] = fma(-rho_lc, V[NH - 2] - G[NH - 2], -(wsp[ses.W.Xref + (NH - 1) * NX + row] * wref));
+                        }
+                    }
+                    if (is_x) {
+                        wsp[ses.W.vnew + row] = V[NH - 1];
+                        wsp[ses.W.v + row] = conv ? sold[(NH - 1) * GS] : V[NH - 1];
+                        wsp[ses.W.g + row] = G[NH - 1];
+                    }
+                }
+                if (l == 0) {
+                    T* sc = wsp + ses.W.scalars;
+                    sc[0] = rho; sc[1] = static_cast<T>(k); sc[2] = static_cast<T>(st); sc[3] = res_px; sc[4] = res_dx; sc[5] = res_pu; sc[6] = res_du;
+                    sc[7] = conv ? T(1) : T(0);
+                }
             }
             if (l == 0) {
                 prm.iter[prob] = k;
@@ -510,7 +592,7 @@ gpp_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ GppT
 template <class C>
 inline size_t gpp_smem_bytes(int) {
     return ((size_t)C::GPB * C::GWORDS + 2 * (size_t)C::NH * C::GS +
-            (C::ADAPT ? 2 * (size_t)C::GS * C::NX + (size_t)C::GS * C::NU + 2 * (size_t)C::NX * C::NX + 2 * (size_t)(C::NH - 1) * C::BLOCK : 0)) * sizeof(double);
+            (C::ADAPT ? 2 * (size_t)C::GS * C::NX + (size_t)C::GS * C::NU + 2 * (size_t)C::NX * C::NX : 0) + 2 * (size_t)C::NH * C::BLOCK) * sizeof(double);
 }
 
 }  // namespace tmpc

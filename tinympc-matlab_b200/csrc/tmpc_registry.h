@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include "tmpc_common.h"
+#include "tmpc_wpp.h"
 
 namespace tmpc {
 
@@ -35,6 +36,10 @@ struct KernelEntry {
     int cone_fixed;
     int scs, scd, ucs, ucd, nsl, nil;
     int lanes_per_problem;   // 0 / 1: thread per problem; GS: a problem is spread over GS lanes (tmpc_gpp.cuh), a CTA holds block / GS problems
+    // sessions (tinympc_cuda_session_solve): iterate p.batch persistent double-precision workspaces of layout W in place; NULL = the
+    // instance has no session form (the warp-per-problem kernel serves the session)
+    cudaError_t (*session_launch)(const SolveParams& p, int grid, size_t smem, cudaStream_t st, const double* master_pack, const PackLayout& L,
+                                  double* ws, const WppLayout& W, int full);
 };
 
 const KernelEntry* const* kernel_table(int* count);   // defined in gen/tmpc_table.cu
@@ -122,10 +127,20 @@ const KernelEntry* const* kernel_table(int* count);   // defined in gen/tmpc_tab
                                     const PackLayout& L) {                                                          \
         GppTab<CFG::NX, CFG::NU, CFG::NH, CFG::GS, CFG::ADAPT> tab;                                                           \
         fill_gpp_tab(tab, mp, L, p);                                                                                \
-        gpp_kernel<CFG><<<grid, CFG::BLOCK, smem, st>>>(p, tab);                                                    \
+        gpp_kernel<CFG><<<grid, CFG::BLOCK, smem, st>>>(p, tab, GppSession{});                                      \
         return cudaGetLastError();                                                                                  \
+    }                                                                                                               \
+    static cudaError_t SYM##_session(const SolveParams& p, int grid, size_t smem, cudaStream_t st, const double* mp,\
+                                     const PackLayout& L, double* ws, const WppLayout& W, int full) {               \
+        if constexpr (CFG::ADAPT) { return cudaErrorNotSupported; } else {                                          \
+        GppTab<CFG::NX, CFG::NU, CFG::NH, CFG::GS, CFG::ADAPT> tab;                                                 \
+        fill_gpp_tab(tab, mp, L, p);                                                                                \
+        cudaError_t e = cudaFuncSetAttribute(gpp_kernel<CFG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        if (e != cudaSuccess) return e;                                                                             \
+        gpp_kernel<CFG, true><<<grid, CFG::BLOCK, smem, st>>>(p, tab, GppSession{ws, W, full});                     \
+        return cudaGetLastError(); }                                                                                \
     }                                                                                                               \
     extern const KernelEntry SYM = {#SYM, KF_TPP, CFG::NX, CFG::NU, CFG::NH, CFG::ADAPT ? 2 : 0 /* FEAT_ADAPT : FEAT_BOX */, 64, 1 /* serves batches with and without references */, \
                                     0, 0, 1, CFG::BLOCK, VAR, 1, SYM##_smem, SYM##_prepare,                        \
-                                    SYM##_occ, SYM##_launch, 0, 0, 0, 0, 0, 0, 0, CFG::GS};                         \
+                                    SYM##_occ, SYM##_launch, 0, 0, 0, 0, 0, 0, 0, CFG::GS, CFG::ADAPT ? nullptr : SYM##_session};                         \
     }
