@@ -211,6 +211,10 @@ long long tinympc_cuda_launch_count(const tinympc_cuda_solver *s);
 /* last tinympc_cuda_solve_batch(): ms[0] host wall time of the call, ms[1] summed device time of its kernels
    (CUDA events, max over devices), ms[2] number of pipeline chunks */
 int  tinympc_cuda_last_timing(const tinympc_cuda_solver *s, double ms[3]);
+/* option "pass_timing" = 1: a device-resident exact-count solve (sequential form) records CUDA events around its two passes on the
+   caller's stream; ms[0] = fp32 pass, ms[1] = compaction + fp64 pass of the LAST such solve (synchronises on its end).
+   TINYMPC_CUDA_ENOTREADY if none was timed. */
+int  tinympc_cuda_last_pass_ms(tinympc_cuda_solver *s, double ms[2]);
 /* number of problems the last "mixed" solve re-solved in fp64 (after a device-resident solve this synchronises the device) */
 long long tinympc_cuda_last_marked(tinympc_cuda_solver *s);
 const char *tinympc_cuda_last_error(const tinympc_cuda_solver *s);

@@ -36,7 +36,7 @@ HOST_EXPORTS = [
 EXPORTS = [
     "tinympc_cuda_create", "tinympc_cuda_destroy", "tinympc_cuda_set_family", "tinympc_cuda_solve_batch",
     "tinympc_cuda_solve_batch_device", "tinympc_cuda_solve_workspace", "tinympc_cuda_set_option", "tinympc_cuda_device_count", "tinympc_cuda_num_devices",
-    "tinympc_cuda_last_kernel", "tinympc_cuda_launch_count", "tinympc_cuda_last_timing", "tinympc_cuda_last_marked", "tinympc_cuda_last_error",
+    "tinympc_cuda_last_kernel", "tinympc_cuda_launch_count", "tinympc_cuda_last_timing", "tinympc_cuda_last_pass_ms", "tinympc_cuda_last_marked", "tinympc_cuda_last_error",
     "tinympc_cuda_version", "tinympc_cuda_host_alloc", "tinympc_cuda_host_free",
     "tinympc_cuda_session_create", "tinympc_cuda_session_destroy", "tinympc_cuda_session_set_x0", "tinympc_cuda_session_set_x_ref",
     "tinympc_cuda_session_set_u_ref", "tinympc_cuda_session_solve", "tinympc_cuda_session_step", "tinympc_cuda_session_read",
@@ -142,6 +142,8 @@ def load():
         L.tinympc_cuda_launch_count.argtypes = [C.c_void_p]
         L.tinympc_cuda_launch_count.restype = C.c_longlong
         L.tinympc_cuda_last_timing.argtypes = [C.c_void_p, c_dp]
+        L.tinympc_cuda_last_pass_ms.argtypes = [C.c_void_p, c_dp]
+        L.tinympc_cuda_last_pass_ms.restype = C.c_int
         L.tinympc_cuda_last_marked.argtypes = [C.c_void_p]
         L.tinympc_cuda_last_marked.restype = C.c_longlong
         L.tinympc_cuda_last_error.argtypes = [C.c_void_p]
@@ -311,6 +313,11 @@ class CudaSolver:
         ms = (C.c_double * 3)()
         self.L.tinympc_cuda_last_timing(self.h, ms)
         return dict(total_ms=ms[0], kernel_ms=ms[1], chunks=int(ms[2]))
+
+    def last_pass_ms(self):
+        """(fp32 pass, compaction + fp64 pass) of the last device-resident exact-count solve; None unless option pass_timing = 1"""
+        ms = (C.c_double * 2)()
+        return None if self.L.tinympc_cuda_last_pass_ms(self.h, ms) else (ms[0], ms[1])
 
     # ---- host buffers (numpy) ---------------------------------------------------------------
     def solve_batch(self, x0, Xref=None, Uref=None, x_min=None, x_max=None, u_min=None, u_max=None,

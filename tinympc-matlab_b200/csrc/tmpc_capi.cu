@@ -72,6 +72,8 @@ struct DeviceCtx {
     int* qctl = nullptr;                // 4 * kMaxChunks ints, indexed like the work counters (chunk index; the last one = device entry)
     cudaStream_t fix_stream[kStreams + 1] = {nullptr, nullptr, nullptr, nullptr};   // the fp64 consumer launches
     cudaEvent_t ev_fork[kStreams + 1] = {nullptr, nullptr, nullptr, nullptr}, ev_join[kStreams + 1] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_p0 = nullptr, ev_p1 = nullptr, ev_p2 = nullptr;   // option "pass_timing": around the fp32 pass and the fp64 pass of a device-resident exact-count solve
+    bool pass_timed = false;
 };
 
 struct Family {
@@ -101,6 +103,7 @@ struct tinympc_cuda_solver {
     int streamed = 1;                  // option "streamed": 1 = single-launch streamed host pipeline where it applies, 0 = chunked launches
     double mixed_band = 0;             // option "mixed": > 0 = fp32 pass + fp64 re-solve of the problems whose termination decision
                                        // falls within this relative band of the tolerances (exact iteration counts at ~fp32 speed)
+    int pass_timing = 0;               // option "pass_timing": 1 = record CUDA events around the two passes of the sequential exact-count form
     int fixer_sms = -2;                // option "fixer_sms", exact-count mode: > 0 SMs the fp32 producer leaves to the concurrent fp64 consumer, 0 =
                                        // 13 % of the device; -1 = always the sequential two-pass form (fp32 pass, compaction, fp64 pass);
                                        // -2 (default) = the two-pass form for device-resident and chunked batches (its fp64 pass is the
@@ -404,8 +407,11 @@ int enqueue(tinympc_cuda_solver* s, DeviceCtx& d, const tinympc_cuda_batch_in& i
     DevBuf& list = d.marked[scratch_slot];
     CU(s, list.reserve(sizeof(int) * (size_t)in.batch));
     p.amb_band = static_cast<float>(s->mixed_band);
+    const bool timed = s->pass_timing != 0 && scratch_slot == kStreams;     // the device-resident entry point only
+    if (timed) CU(s, cudaEventRecord(d.ev_p0, st));
     int rc = launch_tpp(s, d, ke, p, d.ref_scratch[scratch_slot], 32, counter, st);
     if (rc) return rc;
+    if (timed) CU(s, cudaEventRecord(d.ev_p1, st));
     CU(s, cudaMemsetAsync(n_marked, 0, sizeof(int), st));
     collect_marked_kernel<<<(in.batch + 255) / 256, 256, 0, st>>>(out.status, in.batch, static_cast<int*>(list.p), n_marked);
     CU(s, cudaGetLastError());
@@ -417,6 +423,7 @@ int enqueue(tinympc_cuda_solver* s, DeviceCtx& d, const tinympc_cuda_batch_in& i
     p2.batch_ptr = n_marked;
     rc = launch_tpp(s, d, ke64, p2, d.ref_scratch64[scratch_slot], 64, counter2, st);
     if (rc) return rc;
+    if (timed) { CU(s, cudaEventRecord(d.ev_p2, st)); d.pass_timed = true; }
     note_kernel(s, std::string(ke->name) + "+" + ke64->name);
     return TINYMPC_CUDA_OK;
 }
@@ -766,6 +773,7 @@ int tinympc_cuda_create(tinympc_cuda_solver** out, const int* devices, int n_dev
             cudaEventCreateWithFlags(&d.ev_join[k], cudaEventDisableTiming);
         }
         cudaEventCreateWithFlags(&d.ev_ctl, cudaEventDisableTiming);
+        cudaEventCreate(&d.ev_p0); cudaEventCreate(&d.ev_p1); cudaEventCreate(&d.ev_p2);
         for (int k = 0; k < kStreams; ++k) cudaStreamCreateWithFlags(&d.streams[k], cudaStreamNonBlocking);
         for (int c = 0; c < kMaxChunks; ++c) { cudaEventCreate(&d.k0[c]); cudaEventCreate(&d.k1[c]); }
         d.events = true;
@@ -1304,6 +1312,8 @@ int tinympc_cuda_set_option(tinympc_cuda_solver* s, const char* name, double val
     } else if (n == "mixed") {
         if (!(value >= 0 && value < 1)) return fail(s, TINYMPC_CUDA_EINVAL, "mixed (relative band) must be in [0, 1)");
         s->mixed_band = value;
+    } else if (n == "pass_timing") {
+        s->pass_timing = (int)value;
     } else if (n == "fixer_sms") {
         s->fixer_sms = (int)value;
     } else if (n == "force_wpp") {
@@ -1324,6 +1334,23 @@ long long tinympc_cuda_launch_count(const tinympc_cuda_solver* s) { return s ? s
 int tinympc_cuda_last_timing(const tinympc_cuda_solver* s, double ms[3]) {
     if (!s || !ms) return TINYMPC_CUDA_EINVAL;
     ms[0] = s->t_total_ms; ms[1] = s->t_kernel_ms; ms[2] = (double)s->t_chunks;
+    return TINYMPC_CUDA_OK;
+}
+int tinympc_cuda_last_pass_ms(tinympc_cuda_solver* s, double ms[2]) {
+    if (!s || !ms) return TINYMPC_CUDA_EINVAL;
+    ms[0] = ms[1] = 0.0;
+    DeviceCtx& d = s->devs[0];
+    if (!d.pass_timed) return TINYMPC_CUDA_ENOTREADY;
+    int prev = 0;
+    cudaGetDevice(&prev);
+    cudaSetDevice(d.device);
+    float a = 0.f, b = 0.f;
+    cudaError_t e = cudaEventSynchronize(d.ev_p2);
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&a, d.ev_p0, d.ev_p1);
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&b, d.ev_p1, d.ev_p2);
+    cudaSetDevice(prev);
+    if (e != cudaSuccess) return cuda_fail(s, e, "pass timing");
+    ms[0] = a; ms[1] = b;
     return TINYMPC_CUDA_OK;
 }
 long long tinympc_cuda_last_marked(tinympc_cuda_solver* s) {
