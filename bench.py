@@ -229,8 +229,11 @@ def main():
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3   # timing rule: at least 3 warm-up steps
 
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-        os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION", "WARN"):
+        # rank 0 prints exactly one JSON line: NCCL writes its version banner to stdout at every level from VERSION up (WARN included),
+        # so unless somebody asked for INFO / TRACE output, its log goes to the null device
+        os.environ["NCCL_DEBUG"] = "WARN"
+        os.environ.setdefault("NCCL_DEBUG_FILE", os.devnull)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))

@@ -18,6 +18,8 @@ ap.add_argument("--step-log2", type=int, default=2)
 ap.add_argument("--scale", type=float, default=1.0)
 ap.add_argument("--precision", type=int, default=32)
 a = ap.parse_args()
+if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION", "WARN"):
+    os.environ.setdefault("NCCL_DEBUG_FILE", os.devnull)     # keep NCCL's version banner out of the JSON lines
 rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", "0"), ("WORLD_SIZE", "1"), ("LOCAL_RANK", "0")))
 torch.cuda.set_device(local); dev = torch.device("cuda", local)
 dist = None
