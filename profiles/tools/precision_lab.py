@@ -12,6 +12,9 @@ held and how the dual residual is formed:
            before and after (no representation noise of the stored values in the test)
   comp   : x, u, t held to double-float accuracy (emulated with float64 storage); increments still float32
   comp+ince
+  +conv  : the backward pass in impulse-response form, d_i = Quu_inv r_i + sum_{j>i} G_{j-i-1} s_j (what tmpc_tpp3.cuh ships for the
+           quadrotor shapes), instead of the costate recursion; +p64 / +p64q: the recursion (and Quu_inv B' p) carried in float64;
+           +f64w: the rollout in float64; <variant>:K : the first K iterations' sweeps entirely in float64
 
 For every variant: iteration-count mismatches against the fp64 run of the same model, and -- the quantity that sizes the band --
 for every problem the largest relative disagreement |r32 - r64| / tol of a termination residual over the iterations both runs
@@ -35,6 +38,11 @@ f32 = np.float32
 
 def admm(p, cache, b, dt, variant="base", kmax=None):
     """dt: arithmetic type of the increments (float32 / float64).  Returns it, st, residual trace (K, B, 4), x, u."""
+    KF = int(variant.split(":")[1]) if ":" in variant else 0
+    variant = variant.split(":")[0]
+    P64 = 2 if "p64q" in variant else (1 if "p64" in variant else 0)
+    F64 = "f64w" in variant
+    CONV = "conv" in variant
     comp = "comp" in variant
     ince = "ince" in variant
     xdf = variant.startswith("xdf")            # x, u double-float; per-family DUALS stored in float32 (not the pre-projection t)
@@ -57,13 +65,64 @@ def admm(p, cache, b, dt, variant="base", kmax=None):
     kmax = kmax or p.max_iter
     trace = np.full((kmax, Bn, 4), np.nan)
 
+    D_ = np.float64
+    B64, Qi64, AK64, K64 = (np.asarray(a, D_) for a in (np.asarray(p.B).reshape(n, m), cache["Quu_inv"], cache["AmBKt"], cache["Kinf"]))
+    APf64, BPf64 = np.asarray(cache["APf"], D_).ravel(), np.asarray(cache["BPf"], D_).ravel()
+    A64 = np.asarray(p.A, D_); fd64 = np.asarray(p.f, D_).ravel()
+    G64 = [Qi64 @ B64.T]
+    for _k in range(N - 2): G64.append(G64[-1] @ AK64)
+    G32 = [np.asarray(g_, dt) for g_ in G64]
     def sweeps(q, r, pN, x_init, affine):
         d = np.zeros((Bn, N - 1, m), dt)
+        if CONV:
+            # impulse-response form of the backward pass, float32: dd_i = Quu_inv r_i + sum_{j>i} G_{j-i-1} s_j, s_j = q_j - K' r_j, s_{N-1} = p_N
+            s_ = np.zeros((Bn, N, n), dt)
+            for j in range(N - 1): s_[:, j] = q[:, j] - r[:, j] @ K
+            s_[:, N - 1] = pN
+            acc = np.zeros((Bn, N - 1, m), dt)
+            for j in range(N - 1, 0, -1):
+                for k in range(j):
+                    acc[:, j - 1 - k] = acc[:, j - 1 - k] + s_[:, j] @ G32[k].T
+            for i in range(N - 1):
+                d[:, i] = acc[:, i] + (r[:, i] + (BPf if affine else 0)) @ Qi.T
+            if affine and np.abs(APf64).max() > 0: raise SystemExit('conv: affine APf not modelled')
+        elif P64:
+            pv = pN.astype(D_)
+            for i in range(N - 2, -1, -1):
+                r64 = r[:, i].astype(D_)
+                bp = pv @ B64                                  # B' p in double
+                if P64 == 1:
+                    d[:, i] = ((bp + r64 + (BPf64 if affine else 0)).astype(dt)) @ Qi.T       # Quu_inv product in float32
+                else:
+                    d[:, i] = ((bp + r64 + (BPf64 if affine else 0)) @ Qi64.T).astype(dt)
+                pv = q[:, i].astype(D_) + pv @ AK64.T - r64 @ K64 + (APf64 if affine else 0)
+        else:
+          pv = pN.copy()
+          for i in range(N - 2, -1, -1):
+            d[:, i] = (pv @ Bm + r[:, i] + (BPf if affine else 0)) @ Qi.T
+            pv = q[:, i] + pv @ AK.T - r[:, i] @ K + (APf if affine else 0)
+        if F64:
+            xs = np.zeros((Bn, N, n), D_); us = np.zeros((Bn, N - 1, m), D_)
+            xs[:, 0] = x_init
+            for i in range(N - 1):
+                us[:, i] = -(xs[:, i] @ K64.T) - d[:, i]
+                xs[:, i + 1] = xs[:, i] @ A64.T + us[:, i] @ B64.T + (fd64 if affine else 0)
+            return xs.astype(dt), us.astype(dt)
+        xs = np.zeros((Bn, N, n), dt); us = np.zeros((Bn, N - 1, m), dt)
+        xs[:, 0] = x_init
+        for i in range(N - 1):
+            us[:, i] = -(xs[:, i] @ K.T) - d[:, i]
+            xs[:, i + 1] = xs[:, i] @ A.T + us[:, i] @ Bm.T + (fd if affine else 0)
+        return xs, us
+
+    def sweeps64(q, r, pN, x_init, affine):
+        D=np.float64
+        d = np.zeros((Bn, N - 1, m), D)
         pv = pN.copy()
         for i in range(N - 2, -1, -1):
             d[:, i] = (pv @ Bm + r[:, i] + (BPf if affine else 0)) @ Qi.T
             pv = q[:, i] + pv @ AK.T - r[:, i] @ K + (APf if affine else 0)
-        xs = np.zeros((Bn, N, n), dt); us = np.zeros((Bn, N - 1, m), dt)
+        xs = np.zeros((Bn, N, n), D); us = np.zeros((Bn, N - 1, m), D)
         xs[:, 0] = x_init
         for i in range(N - 1):
             us[:, i] = -(xs[:, i] @ K.T) - d[:, i]
@@ -89,7 +148,20 @@ def admm(p, cache, b, dt, variant="base", kmax=None):
     q = np.zeros((Bn, N, n), dt); r = np.zeros((Bn, N - 1, m), dt); pN = np.zeros((Bn, n), dt)
     x = np.zeros((Bn, N, n), sdt); u = np.zeros((Bn, N - 1, m), sdt)
     for k in range(kmax):
-        if k == 0:
+        if k < KF:
+            A_, Bm_, K_, Qi_, AK_, APf_, BPf_, fd_ = A, Bm, K, Qi, AK, APf, BPf, fd
+            g=lambda a: np.asarray(a, np.float64)
+            A, Bm, K, Pinf, Qi, AK = g(p.A), g(np.asarray(p.B).reshape(n, m)), g(cache["Kinf"]), g(cache["Pinf"]), g(cache["Quu_inv"]), g(cache["AmBKt"])
+            APf, BPf, fd = g(cache["APf"]).ravel(), g(cache["BPf"]).ravel(), g(p.f).ravel()
+            dt_save=dt
+            if k == 0:
+                dxs, dus = sweeps64(g(q), g(r), g(pN), g(x0), True)
+            else:
+                dxs, dus = sweeps64(g(dq), g(dr), g(dpN), np.zeros((Bn, n)), False)
+            dxs=dxs.astype(dt); dus=dus.astype(dt)
+            A, Bm, K, Qi, AK, APf, BPf, fd = A_, Bm_, K_, Qi_, AK_, APf_, BPf_, fd_
+            Pinf=f(cache["Pinf"])
+        elif k == 0:
             dxs, dus = sweeps(q, r, pN, x0, True)
         else:
             dxs, dus = sweeps(dq, dr, dpN, np.zeros((Bn, n), dt), False)
