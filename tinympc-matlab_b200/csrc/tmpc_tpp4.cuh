@@ -531,75 +531,68 @@ tpp4_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ typ
             for (int a = 0; a < NU; ++a) dr.set(a, fmaf(static_cast<float>(dw[a]), nrho, ref[a]));
         };
 
+        // ONE rolled loop over the columns N-1 .. 0 with warp-uniform branches for the two special columns, so that state_col and
+        // input_col are instantiated once each: with a peeled terminal column and a peeled column 0 the hot loop was 45 KB, past the
+        // 32 KB instruction cache (stall_no_instruction 1.05 per issue, profiles/r02/ncu_full_rocket_tpp4.json).
+        //   i = N-1 : state column only; dp_N = -(xref_N' Pinf)' [first sweep] - rho dw_N            (admm.cpp:238-246)
+        //   i = 0   : input column and dd_0; of x_0 = x0 only the box slack (p_0, q_0 and its cone / half-space slacks are never used)
         VX dp;
-        state_col(NH - 1, dp);   // dp_N = -(xref_N' Pinf)' [first sweep] - rho dw_N   (admm.cpp:238-246)
+        dp.fill(T(0));
 #pragma unroll 1
-        for (int i = NH - 2; i >= 1; --i) {
-            // the two products with dp_{i+1} depend on nothing of this column: they run under its loads and its FP64 work
+        for (int i = NH - 1; i >= 0; --i) {
+            const bool inner = i < NH - 1;
             VX akp;
-            VU btp;
+            VU btp, dr;
             akp.fill(T(0));
             btp.fill(T(0));
-            mv_acc<NX, NX>(cp.AK, 0, dp, akp);
-            mv_acc<NU, NX>(cp.BT, 0, dp, btp);
-            VU dr;
-            input_col(i, dr);
-            // dd_i = Quu_inv (B' dp + dr)   (admm.cpp:17; BPf cancels in the increment)
-            VU t;
+            dr.fill(T(0));
+            if (inner) {
+                // the two products with dp_{i+1} depend on nothing of this column: they run under its loads and its FP64 work
+                if (i >= 1) mv_acc<NX, NX>(cp.AK, 0, dp, akp);
+                mv_acc<NU, NX>(cp.BT, 0, dp, btp);
+                input_col(i, dr);
+                // dd_i = Quu_inv (B' dp + dr)   (admm.cpp:17; BPf cancels in the increment)
+                VU t;
 #pragma unroll
-            for (int j = 0; j < NU / 2; ++j) t.p[j] = addv(btp.p[j], dr.p[j]);
-            if constexpr (NU & 1) t.t = btp.t + dr.t;
-            VU d;
-            d.fill(T(0));
-            mv_acc<NU, NU>(cp.Quu, 0, t, d);
-            {
+                for (int j = 0; j < NU / 2; ++j) t.p[j] = addv(btp.p[j], dr.p[j]);
+                if constexpr (NU & 1) t.t = btp.t + dr.t;
+                VU d;
+                d.fill(T(0));
+                mv_acc<NU, NU>(cp.Quu, 0, t, d);
                 VU nd;
 #pragma unroll
                 for (int j = 0; j < NU / 2; ++j) nd.p[j] = negv(d.p[j]);
                 if constexpr (NU & 1) nd.t = -d.t;
                 ND.store(i, nd);
             }
-            // dp_i = dq_i + AmBKt dp - Kinf' dr   (admm.cpp:18)
-            VX dq;
-            state_col(i, dq);
+            if (i >= 1) {
+                // dp_i = dq_i + AmBKt dp - Kinf' dr   (admm.cpp:18)
+                VX dq;
+                state_col(i, dq);
+                if (inner) {
 #pragma unroll
-            for (int j = 0; j < NX / 2; ++j) dq.p[j] = addv(dq.p[j], akp.p[j]);
-            if constexpr (NX & 1) dq.t += akp.t;
-            mv_acc<NX, NU>(cp.NKT, 0, dr, dq);
-            dp = dq;
-        }
-        {   // column 0: dd_0, and the box slack of x_0 = x0 (p_0, q_0 and the cone / half-space slacks of x_0 are never used)
-            VU btp, dr;
-            btp.fill(T(0));
-            mv_acc<NU, NX>(cp.BT, 0, dp, btp);
-            input_col(0, dr);
-            VU t;
+                    for (int j = 0; j < NX / 2; ++j) dq.p[j] = addv(dq.p[j], akp.p[j]);
+                    if constexpr (NX & 1) dq.t += akp.t;
+                    mv_acc<NX, NU>(cp.NKT, 0, dr, dq);
+                }
+                dp = dq;
+            } else {
 #pragma unroll
-            for (int j = 0; j < NU / 2; ++j) t.p[j] = addv(btp.p[j], dr.p[j]);
-            if constexpr (NU & 1) t.t = btp.t + dr.t;
-            VU d;
-            d.fill(T(0));
-            mv_acc<NU, NU>(cp.Quu, 0, t, d);
-            VU nd;
-#pragma unroll
-            for (int j = 0; j < NU / 2; ++j) nd.p[j] = negv(d.p[j]);
-            if constexpr (NU & 1) nd.t = -d.t;
-            ND.store(0, nd);
-#pragma unroll
-            for (int e = 0; e < NX; ++e) {
-                const double x0d = static_cast<double>(x0v.get(e));
-                const T sbv = SB_at(0, e);
-                const double s = static_cast<double>(first ? T(0) : sbv);
-                const double lo = xlo(0, e), hi = xhi(0, e);
-                const double to = x0d + s;
-                const double go = first ? 0.0 : box_dual(to, lo, hi);
-                const double vo = first ? 0.0 : (to - go);           // v(0) = 0, g(0) = 0 on the cold workspace, while x_0 = x0 from the start
-                const float gf = static_cast<float>(go);
-                const double tn = x0d + static_cast<double>(gf);
-                const double vn = tn - box_dual(tn, lo, hi);
-                amax_w(rpx_h, rpx_l, x0d - vn);
-                amax_w(rdx_h, rdx_l, vn - vo);
-                SB_at(0, e) = gf;
+                for (int e = 0; e < NX; ++e) {
+                    const double x0d = static_cast<double>(x0v.get(e));
+                    const T sbv = SB_at(0, e);
+                    const double s = static_cast<double>(first ? T(0) : sbv);
+                    const double lo = xlo(0, e), hi = xhi(0, e);
+                    const double to = x0d + s;
+                    const double go = first ? 0.0 : box_dual(to, lo, hi);
+                    const double vo = first ? 0.0 : (to - go);           // v(0) = 0, g(0) = 0 on the cold workspace, while x_0 = x0 from the start
+                    const float gf = static_cast<float>(go);
+                    const double tn = x0d + static_cast<double>(gf);
+                    const double vn = tn - box_dual(tn, lo, hi);
+                    amax_w(rpx_h, rpx_l, x0d - vn);
+                    amax_w(rdx_h, rdx_l, vn - vo);
+                    SB_at(0, e) = gf;
+                }
             }
         }
         tmem_wait_st();
