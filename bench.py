@@ -167,13 +167,14 @@ def bind_to_gpu_cpus(local):
         return prev, f"unchanged ({type(ex).__name__})"
 
 
-def reference_arm(args, P, spec, batch_np):
+def reference_arm(args, P, spec, batch_np, build="ref"):
     """The reference's own CPU implementation (oracle/_ref = unmodified reference C++ built by
-    oracle/Makefile; falls back to the C port) on all host threads, bounded sample per step."""
+    oracle/Makefile; falls back to the C port) on all host threads, bounded sample per step.  build: "ref" (-O3 -DNDEBUG, the
+    reference's Release flags) or "ref_O2" (-O2, asserts on: the second row BASELINE.md section 3 asks for)."""
     sys.path.insert(0, str(ROOT / "oracle"))
     import oracle as O
-    kind = "reference" if O.available("ref") else "port"
-    impl = "ref" if kind == "reference" else "port"
+    kind = "reference" if O.available(build) else "port"
+    impl = build if kind == "reference" else "port"
     if kind == "port" and not O.available("port"):
         subprocess.check_call(["make", "-C", str(ROOT / "oracle"), "liboracle_port.so"])
     cores = os.cpu_count() or 1
@@ -476,6 +477,12 @@ def main():
         try:
             cb = reference_arm(args, P, spec, batch_np.slice(0, min(B, 1 << 18)))
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "ns_per_admm_iter")}
+            line["cpu_baseline"]["flags"] = "-O3 -DNDEBUG (the reference's Release build)"
+            import oracle as O
+            if O.available("ref_O2"):      # the same sources at -O2
+                half = argparse.Namespace(**{**vars(args), "cpu_seconds": args.cpu_seconds / 2, "steps_cpu": 1, "warmup": 0})
+                cb2 = reference_arm(half, P, spec, batch_np.slice(0, min(B, 1 << 17)), build="ref_O2")
+                line["cpu_baseline_O2"] = {**{k: cb2[k] for k in ("value", "unit", "cores", "kind", "sample", "ns_per_admm_iter")}, "flags": "-O2"}
         except Exception as ex:  # the checker is optional for the GPU number, never the other way round
             line["cpu_baseline"] = {"value": None, "unit": "solves/s", "cores": os.cpu_count(), "kind": "unavailable", "sample": repr(ex)}
     print(json.dumps(line))

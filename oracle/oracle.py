@@ -19,9 +19,9 @@ from pathlib import Path
 import numpy as np
 
 HERE = Path(__file__).resolve().parent
-_LIBS = {"ref": HERE / "_ref" / "libtinympc_ref.so", "port": HERE / "liboracle_port.so",
+_LIBS = {"ref": HERE / "_ref" / "libtinympc_ref.so", "ref_O2": HERE / "_ref" / "libtinympc_ref_O2.so", "port": HERE / "liboracle_port.so",
          "refhost_b200": HERE / "_ref" / "libtinympc_refhost_b200.so"}
-_PREFIX = {"ref": "ref", "port": "port", "refhost_b200": "ref"}
+_PREFIX = {"ref": "ref", "ref_O2": "ref", "port": "port", "refhost_b200": "ref"}
 _loaded = {}
 
 c_dp = C.POINTER(C.c_double)
