@@ -149,9 +149,38 @@ def test_generated_kernel_instances_are_distinct_template_instantiations():
     b.gen_sources(b.default_instances())          # idempotent: writes csrc/gen/*.cu only where the text changed
     gen = pkg / "csrc" / "gen"
     seen = {}
-    for f in sorted(gen.glob("tpp*.cu")):
-        m = re.search(r"using \w+ = (Tpp\d?Cfg<[^;]*>);", f.read_text())
+    for f in sorted(list(gen.glob("tpp*.cu")) + list(gen.glob("gpp*.cu"))):
+        m = re.search(r"using \w+ = ((?:Tpp\d?|Gpp)Cfg<[^;]*>);", f.read_text())
         assert m, f.name
         assert m.group(1) not in seen, f"{f.name} and {seen[m.group(1)]} instantiate the same kernel"
         seen[m.group(1)] = f.name
     assert len(seen) > 40
+
+
+def test_instance_list_covers_the_dispatch_rules():
+    """build.py's instance list is what tmpc_capi.cu::find_kernel dispatches over: every BASELINE shape must have (a) an fp32
+    incremental-form box instance as variant 0, the quadrotor ones with the impulse-response backward pass (CONV = auto) and the
+    costate recursion kept as variant 7, (b) a lane-group fp64 instance (box; adaptive rho for the quadrotor) ahead of the
+    thread-per-problem fp64 instances, which move to variant 6 except for per-problem bounds and the cone family."""
+    import importlib.util
+    from pathlib import Path
+    pkg = Path(__file__).resolve().parents[1] / "tinympc-matlab_b200"
+    spec = importlib.util.spec_from_file_location("tmpc_build", pkg / "build.py")
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    inst = b.default_instances()
+    names = [b.name_of(i) for i in inst]
+    shapes = [(12, 4, 10), (4, 1, 20), (4, 1, 10), (6, 3, 10)]
+    for (nx, nu, N) in shapes:
+        assert any(i["gen"] == 3 and (i["nx"], i["nu"], i["N"]) == (nx, nu, N) and i["feat"] == b.BOX and i["variant"] == 0 for i in inst)
+        g = [k for k, i in enumerate(inst) if i["gen"] == 5 and (i["nx"], i["nu"], i["N"]) == (nx, nu, N) and i["feat"] == b.BOX]
+        t = [k for k, i in enumerate(inst) if i["gen"] == 2 and i["bits"] == 64 and (i["nx"], i["nu"], i["N"]) == (nx, nu, N)
+             and i["feat"] == b.BOX and not i["ppb"]]
+        assert len(g) == 1 and inst[g[0]]["variant"] == 0 and inst[g[0]]["gs"] >= nx + nu
+        assert t and all(inst[k]["variant"] == 6 for k in t), "shared-bounds fp64 box batches belong to the lane-group kernel"
+        assert any(i["gen"] == 2 and i["bits"] == 64 and i["ppb"] and i["variant"] == 0 and (i["nx"], i["nu"], i["N"]) == (nx, nu, N) for i in inst)
+    assert any(i["gen"] == 5 and i["feat"] == b.ADP and (i["nx"], i["nu"]) == (12, 4) and i["variant"] == 0 for i in inst)
+    assert all(i["variant"] == 6 for i in inst if i["gen"] == 2 and i["bits"] == 64 and i["feat"] == b.ADP)
+    q = [i for i in inst if i["gen"] == 3 and (i["nx"], i["nu"]) == (12, 4) and i["feat"] == b.BOX]
+    assert all(i["conv"] == -1 for i in q if i["variant"] in (0, 9)) and any(i["conv"] == 0 and i["variant"] == 7 for i in q)
+    assert len(names) == len(set(names))
