@@ -522,3 +522,20 @@ def test_lane_group_kernel_ragged_batches(B, capi, oracle_mod, problems):
     r = solve_gpu(capi, oracle_mod, p, b, 64)
     assert r["kernel"].startswith("gpp_f64"), r["kernel"]
     compare(r, g, 64, f"ragged {B}")
+
+
+@pytest.mark.parametrize("linear", [True, False])
+def test_lane_group_kernel_cone_family_matches_the_reference(linear, capi, oracle_mod, problems):
+    """rocket family (box + one second-order cone per side, with and without the two linear rows) in fp64 on the lane-group kernel
+    (rolled loops, per-slot state in shared memory, cone / half-space projections by the owning lanes): the reference's counts on
+    every problem; and as the second pass of the exact-count mode behind the mixed-precision kernel."""
+    p = problems.rocket(linear=linear)
+    B = 6000
+    b = problems.make_batch(p, B, 1.0, seed=81)
+    g = oracle_mod.solve_batch(p, b, "ref" if oracle_mod.available("ref") else "port")
+    r = solve_gpu(capi, oracle_mod, p, b, 64)
+    assert r["kernel"].startswith("gpp_f64") and "_con_" in r["kernel"], r["kernel"]
+    compare(r, g, 64, f"rocket linear={linear} gpp")
+    rx = solve_gpu(capi, oracle_mod, p, b, 32, mixed=problems.exact_band(p), fixer_sms=-1)
+    assert "tpp4" in rx["kernel"] and "+gpp_f64" in rx["kernel"] and 0 < rx["marked"] < B, (rx["kernel"], rx["marked"])
+    compare(rx, g, 32, f"rocket linear={linear} exact-count")

@@ -34,21 +34,36 @@
 
 namespace tmpc {
 
-template <int NX_, int NU_, int NH_, int GS_, int BLOCK_ = 128, bool ADAPT_ = false>
+template <int NX_, int NU_, int NH_, int GS_, int BLOCK_ = 128, bool ADAPT_ = false,
+          int SCS_ = 0, int SCD_ = 0, int UCS_ = 0, int UCD_ = 0, int NSL_ = 0, int NIL_ = 0, bool CONSTR_ = false>
 struct GppCfg {
     using T = double;
     static constexpr int NX = NX_, NU = NU_, NH = NH_, GS = GS_, BLOCK = BLOCK_;
     static constexpr bool ADAPT = ADAPT_;   // adaptive rho (rho_benchmark.cpp:44-250 in closed block form)
+    // cone / half-space families (admm.cpp:100-175): at most one second-order cone per side on the elements [SCS, SCS + SCD) /
+    // [UCS, UCS + UCD) (dim 0 = none) and at most one linear row per side, compiled into the instance like in tmpc_tpp3/4.cuh
+    static constexpr bool CONSTR = CONSTR_;
+    static constexpr int SCS = SCS_, SCD = SCD_, UCS = UCS_, UCD = UCD_, NSL = NSL_, NIL = NIL_;
+    static_assert(CONSTR_ || (SCD_ == 0 && UCD_ == 0 && NSL_ == 0 && NIL_ == 0), "cones / rows need CONSTR");
+    static_assert(!(CONSTR_ && ADAPT_), "adaptive rho with cones / rows stays on the warp-per-problem kernel");
+    static_assert(NSL_ <= 1 && NIL_ <= 1 && SCS_ + SCD_ <= NX_ && UCS_ + UCD_ <= NU_, "one row per side; cone block inside the vector");
     static_assert(GS_ == 8 || GS_ == 16 || GS_ == 32, "group size: 8, 16 or 32 lanes");
     static_assert(NX_ + NU_ <= GS_, "one lane per state row and input row");
     static_assert(NX_ % 2 == 0 || true, "");
+    // ROLLED: the per-slot state of the lane (dual, slack, reference, family duals) lives in shared memory instead of registers and
+    // the two time loops stay rolled.  The cone / half-space families add ~150 instructions per step: unrolled, the loop of the rocket
+    // instance was 47 KB -- past the 32 KB instruction cache -- and ran at a third of the box kernel's rate.
+    static constexpr bool ROLLED = CONSTR_;
+    static constexpr int TUNROLL = ROLLED ? 1 : 64;
+    static constexpr int NSTATE = ROLLED ? 6 : 0;        // shared-memory state arrays per lane: G, V, GC, GL, EC, RF
     static constexpr int MINB = NH_ > 12 ? 2 : 3;        // CTAs per SM the register allocation aims at (the per-lane state grows with N)
     static constexpr int GPW = 32 / GS_;                 // problems per warp
     static constexpr int GPB = BLOCK_ / GS_;             // problems per CTA
     static constexpr int NV = NX_ + NU_;
     static constexpr int NXP = (NX_ + 1) & ~1, NUP = (NU_ + 1) & ~1;   // exchange slots padded to 16 bytes
     // shared memory per group (doubles): forward slot x (2 buffers), backward slot [p | r] (2 buffers), table of d (N-1 steps)
-    static constexpr int oXB = 0, oPB = 2 * NXP, oDT = oPB + 2 * (NXP + NUP), GWORDS = oDT + (NH_ - 1) * NUP;
+    static constexpr int oXB = 0, oPB = 2 * NXP, oDT = oPB + 2 * (NXP + NUP), oTC = oDT + (NH_ - 1) * NUP;   // oTC: [2 buffers][2][GS] pre-projection slacks (CONSTR)
+    static constexpr int GWORDS = oTC + (CONSTR_ ? 4 * GS_ : 0);
     static constexpr int SX = NX_ * NH_, SU = NU_ * (NH_ - 1);
 };
 
@@ -60,6 +75,8 @@ struct alignas(16) GppTab {
     double wref[GS];                               // Qd_r / Rd_a: weight of the lane's reference term (work->Q, work->R)
     double lo[NH][GS], hi[NH][GS];                 // box of the element the lane handles in forward slot s (state: column s + 1; input: step s); row NH-1: column 0
     double Pinf[NX][NX];                           // row-major: terminal term -(xref_N' Pinf)'
+    // cone / half-space families: the one linear row of each side (coefficients, offset, ||a||^2)
+    double ax[NX], au[NU], bx, bu, nrx, nru;     // nrx, nru = 1 / ||a||^2
     // adaptive rho: d/drho of the rows that contain Kinf (Kinf, Pinf move with rho; Quu_inv and AmBKt do not: the reference updates
     // its copies C1, C2, which the sweeps never read), the rows of A' / B' for the dual residual, dPinf/drho
     double dCF1[ADAPT ? GS : 1][NX], dCB2[ADAPT ? GS : 1][NU], AT[ADAPT ? GS : 1][NX], dPinf[ADAPT ? NX : 1][NX];
@@ -106,6 +123,9 @@ inline void fill_gpp_tab(GppTab<NX, NU, NH, GS, ADAPT>& t, const double* pk, con
             for (int s = 0; s < NH - 1; ++s) { t.lo[s][l] = pk[L.umin + s * NU + a]; t.hi[s][l] = pk[L.umax + s * NU + a]; }
     }
     for (int r = 0; r < NX; ++r) for (int c = 0; c < NX; ++c) t.Pinf[r][c] = pk[L.Pinf + r * NX + c];
+    t.nrx = t.nru = 1.0;
+    if (L.nsl > 0) { for (int e = 0; e < NX; ++e) t.ax[e] = pk[L.Alin_x + e]; t.bx = pk[L.blin_x]; t.nrx = 1.0 / pk[L.nrm_x]; }
+    if (L.nil > 0) { for (int e = 0; e < NU; ++e) t.au[e] = pk[L.Alin_u + e]; t.bu = pk[L.blin_u]; t.nru = 1.0 / pk[L.nrm_u]; }
     if constexpr (ADAPT) {
         const double* dK = pk + L.dKinf;
         for (int r = 0; r < NX; ++r) {
@@ -135,6 +155,17 @@ struct GppSession {
     WppLayout W;
     int full;          // 1: also write d, every column of p and the unused columns 0 and N-1 of q (tiny_solve on ONE live workspace, whose
                        // owner may look at any member of TinyWorkspace afterwards); 0: only what the next warm start reads
+};
+
+// per-slot state of a lane: registers (statically indexed, unrolled time loops) or a shared-memory column [slot][thread]
+template <typename E, int N> struct RegArr {
+    E a[N];
+    __device__ __forceinline__ E& operator[](int i) { return a[i]; }
+    __device__ __forceinline__ const E& operator[](int i) const { return a[i]; }
+};
+template <typename E, int STRIDE> struct SmemArr {
+    E* p;
+    __device__ __forceinline__ E& operator[](int i) const { return p[i * STRIDE]; }
 };
 
 // max / min / clamp of finite-or-infinite doubles as one compare + select: the library fmax / fmin carry NaN handling that costs
@@ -178,7 +209,7 @@ gpp_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ GppT
     T* const dpinf_t = pinf_t + NX * NX;             // [NX][NX]
     // parking area: this lane's iterate and (adaptive rho) updated dual / (sessions) previous slack of every slot,
     // [group][array][slot][lane of the group]
-    T* const sval = (C::ADAPT ? dpinf_t + NX * NX : hi_t + NH * GS) + (size_t)(threadIdx.x / GS) * 2 * NH * GS + l;
+    T* const sval = (C::ADAPT ? dpinf_t + NX * NX : hi_t + NH * GS + (size_t)C::NSTATE * NH * C::BLOCK) + (size_t)(threadIdx.x / GS) * 2 * NH * GS + l;
     T* const sdual = sval + NH * GS;
     T* const sold = sdual;      // sessions: work->v / work->z as the last iteration found it (adaptive rho and sessions never combine)
     for (int e = threadIdx.x; e < NH * GS; e += C::BLOCK) { lo_t[e] = tab.lo[e / GS][e % GS]; hi_t[e] = tab.hi[e / GS][e % GS]; }
@@ -203,8 +234,19 @@ gpp_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ GppT
     const bool consumer = prm.q_tail != nullptr && prm.q_consume != 0;
 
     // ---- per-problem state of this lane: slot s = state column s + 1 / input step s; slot N-1 (state lanes) = column 0
-    T G[NH], V[NH];          // dual (g / y) and slack (v / z) of the lane's row
-    float RF[NH];            // reference term before weighting: Xref / Uref of the row (slot N-2 of a state lane is replaced by PT below)
+    // dual (g / y) and slack (v / z) of the lane's row; cone / half-space duals and (vc - gc) + (vl - gl); reference term before
+    // weighting: Xref / Uref of the row (slot N-2 of a state lane is replaced by PT below)
+    T* const sst = reinterpret_cast<T*>(gpp_smem) + (size_t)C::GPB * C::GWORDS + 2 * NH * GS + threadIdx.x;   // ROLLED: [array][slot][thread]
+    using ArrT = std::conditional_t<C::ROLLED, SmemArr<T, C::BLOCK>, RegArr<T, NH>>;
+    using ArrC = std::conditional_t<C::ROLLED, SmemArr<T, C::BLOCK>, RegArr<T, 1>>;
+    using ArrF = std::conditional_t<C::ROLLED, SmemArr<T, C::BLOCK>, RegArr<float, NH>>;
+    ArrT G, V;
+    ArrC GC, GL, EC;
+    ArrF RF;
+    if constexpr (C::ROLLED) {
+        G.p = sst; V.p = sst + NH * C::BLOCK; GC.p = sst + 2 * NH * C::BLOCK; GL.p = sst + 3 * NH * C::BLOCK;
+        EC.p = sst + 4 * NH * C::BLOCK; RF.p = sst + 5 * NH * C::BLOCK;
+    }
     T PT = 0;                // state lanes: -(xref_N' Pinf)'_r
     T PT1 = 0;               // adaptive rho: its derivative, -(xref_N' dPinf)'_r
     // cache->rho and the accumulated rho' - rho0 of this problem; *_lc: the values update_linear_cost saw (it runs BEFORE the
@@ -219,6 +261,10 @@ gpp_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ GppT
     T m0 = 0;                // 0 on a problem's first iteration (q = r = p = 0 on the cold workspace, tiny_api.cpp:68-105), then 1
     T res_px = 0, res_dx = 0, res_pu = 0, res_du = 0;
 
+    T* const tcb0 = gbase + C::oTC;  // [2 buffers][2][GS]: x + gc and x + gl of every lane of the group
+    const bool lin_on = C::CONSTR && (is_x ? prm.en_state_linear != 0 : prm.en_input_linear != 0);   // with zero rows the family still adds x to the cost
+    const bool soc_on = C::CONSTR && (is_x ? C::SCD > 0 : C::UCD > 0);
+    const T arow = !C::CONSTR ? T(0) : (is_x ? (C::NSL > 0 ? tab.ax[row] : T(0)) : (C::NIL > 0 && is_u ? tab.au[row] : T(0)));
     T* wsp = ses.ws;                 // sessions: this problem's workspace
     T* const xb = gbase + C::oXB;    // [2][NXP]
     T* const pb = gbase + C::oPB;    // [2][NXP + NUP]
@@ -279,6 +325,10 @@ gpp_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ GppT
                 }
 #pragma unroll
                 for (int s = 0; s < NH; ++s) { G[s] = 0; V[s] = 0; RF[s] = 0.f; }
+                if constexpr (C::CONSTR) {
+#pragma unroll
+                    for (int s = 0; s < NH; ++s) { GC[s] = 0; GL[s] = 0; EC[s] = 0; }
+                }
                 PT = 0; PT1 = 0;
                 if constexpr (SESSION) {
                     wsp = ses.ws + (size_t)prob * ses.W.size;
@@ -336,7 +386,10 @@ gpp_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ GppT
         };
         // w_s = q / r of slot s as update_linear_cost left it (admm.cpp:218-246): ref - rho (v - g); 0 on the cold workspace.
         // Sessions: the first backward pass of a solve reads what the PREVIOUS solve stored (its references may have changed since).
-        auto lincost_now = [&](int s) -> T { return m0 * fma(-rho_lc, V[s] - G[s], refterm(s)); };
+        auto lincost_now = [&](int s) -> T {
+            if constexpr (C::CONSTR) return m0 * fma(-rho_lc, (V[s] - G[s]) + EC[s], refterm(s));   // + (vc - gc) + (vl - gl), admm.cpp:219-246
+            else return m0 * fma(-rho_lc, V[s] - G[s], refterm(s));
+        };
         auto lincost = [&](int s) -> T {
             if constexpr (SESSION) {
                 if (s == NH - 1) return k == 0 ? wsp[ses.W.q + row] : fma(-rho_lc, V[NH - 1] - G[NH - 1], -(wsp[ses.W.Xref + row] * wref));   // q_0, full mode only
@@ -352,7 +405,7 @@ gpp_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ GppT
             T* buf = pb + ((NH - 1) & 1) * (NXP + NUP);
             if (is_x) buf[row] = w; else if (is_u) buf[NXP + row] = w;
             __syncwarp();
-#pragma unroll
+#pragma unroll C::TUNROLL
             for (int i = NH - 2; i >= 0; --i) {
                 const T* src = pb + ((i + 1) & 1) * (NXP + NUP);
                 T pv[NXP], rv[NUP];
@@ -405,7 +458,7 @@ gpp_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ GppT
         {
             if (is_x) { xb[row] = x0r; element(NH - 1, x0r); }   // column 0: x_0 = x0 (never rewritten, admm.cpp:25-32)
             __syncwarp();
-#pragma unroll
+#pragma unroll C::TUNROLL
             for (int s = 0; s < NH - 1; ++s) {
                 const T* src = xb + (s & 1) * NXP;
                 T xv[NXP], dv[NUP];
@@ -425,7 +478,66 @@ gpp_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ GppT
                 for (int a = 0; a < NU; ++a) a3 = fma(cf2[a], dv[a], a3);
                 const T val = (a0 + a1) + (a2 + a3);      // x_{s+1,r} or u_{s,a}
                 if (is_x && s < NH - 2) xb[((s + 1) & 1) * NXP + row] = val;
-                element(s, val);
+                if constexpr (!C::CONSTR) element(s, val);
+                if constexpr (C::CONSTR) {
+                    // cone and half-space families of the column (admm.cpp:100-175, 189-207): the pre-projection slacks x + gc, x + gl of
+                    // the whole group go round together with x_{s+1} -- ONE hand-off per step -- and the projections (recomputed by every
+                    // lane that owns a component) and the box work sit BEHIND the barrier, in one basic block with the loads and the
+                    // product of the next step, which do not depend on them
+                    const T tc = val + GC[s], tl = val + GL[s];
+                    T* const tcb = tcb0 + (s & 1) * 2 * GS;
+                    tcb[l] = tc;
+                    tcb[GS + l] = tl;
+                    __syncwarp();
+                    element(s, val);
+                    T vc = tc, vl = tl;
+                    auto cone = [&](int base, auto dim, float mu, int me) {   // admm.cpp:39-60 with its float norm and float a / mu
+                        constexpr int D = decltype(dim)::value;
+                        if constexpr (D > 0) {
+                            T w[D], ss = 0;
+#pragma unroll
+                            for (int e = 0; e < D; ++e) w[e] = tcb[base + e];
+#pragma unroll
+                            for (int e = 0; e < D - 1; ++e) ss = fma(w[e], w[e], ss);
+                            const T u0 = w[D - 1] * static_cast<T>(mu);
+                            // float(sqrt(ss)) and 1 / a without the library's fp64 sqrt / division (~70 instructions each, on every lane and
+                            // step): float estimates + one Newton step in double, 1e-14 relative (the form tmpc_tpp4.cuh uses)
+                            float y0f, r0f;
+                            asm("sqrt.approx.f32 %0, %1;" : "=f"(y0f) : "f"(static_cast<float>(ss)));
+                            asm("rcp.approx.f32 %0, %1;" : "=f"(r0f) : "f"(y0f));
+                            const T y0 = static_cast<T>(y0f);
+                            const T y1 = ss > 1e-30 ? fma(fma(-y0, y0, ss), static_cast<T>(0.5f * r0f), y0) : T(0);
+                            const float a = static_cast<float>(y1);
+                            const T ad = static_cast<T>(a), r0 = static_cast<T>(r0f);
+                            const T ra = r0 * fma(-ad, r0, T(2));
+                            const T fct = T(0.5) * fma(u0, ra, T(1));
+                            const bool zero = ad <= -u0, inside = ad <= u0, mine = me >= 0 && me < D;
+                            const T outv = me == D - 1 ? fct * static_cast<T>(a / mu) : fct * tc;   // the lane's own component is tc itself
+                            vc = !mine ? tc : (zero ? T(0) : (inside ? tc : outv));
+                        }
+                    };
+                    if (is_x) cone(C::SCS, std::integral_constant<int, C::SCD>{}, prm.cx[0], row - C::SCS);
+                    else if (is_u) cone(NX + C::UCS, std::integral_constant<int, C::UCD>{}, prm.cu[0], row - C::UCS);
+                    if constexpr (C::NSL > 0) {
+                        if (is_x) {   // admm.cpp:70-73, 148-159: v <- v - (a.v - b) / ||a||^2 a  where a.v > b
+                            T dv2 = 0;
+#pragma unroll
+                            for (int e = 0; e < NX; ++e) dv2 = fma(tab.ax[e], tcb[GS + e], dv2);
+                            vl = dv2 > tab.bx ? tl - ((dv2 - tab.bx) * tab.nrx) * arow : tl;
+                        }
+                    }
+                    if constexpr (C::NIL > 0) {
+                        if (is_u) {
+                            T dv2 = 0;
+#pragma unroll
+                            for (int e = 0; e < NU; ++e) dv2 = fma(tab.au[e], tcb[GS + NX + e], dv2);
+                            vl = dv2 > tab.bu ? tl - ((dv2 - tab.bu) * tab.nru) * arow : tl;
+                        }
+                    }
+                    GC[s] = tc - vc;
+                    GL[s] = tl - vl;
+                    EC[s] = (soc_on ? vc - GC[s] : T(0)) + (lin_on ? vl - GL[s] : T(0));
+                }
                 if constexpr (C::ADAPT) {
                     // Park this step's iterate and updated dual for the block pass of an adaptation, and take the primal rows -- inputs:
                     // u - znew (= rp); states: (A x + B u - x_next) - vnew_next = -f - vnew_next.  Unconditional: a branch on "due" here
@@ -436,7 +548,7 @@ gpp_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ GppT
                     a_pri = gabsmax(a_pri, pa);
                     a_prin = gabsmax(gabsmax(a_prin, V[s]), pb2);
                 }
-                if (s < NH - 2) __syncwarp();
+                if constexpr (!C::CONSTR) { if (s < NH - 2) __syncwarp(); }
             }
             if constexpr (C::ADAPT) {
                 if (anydue) {
@@ -592,7 +704,8 @@ gpp_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ GppT
 template <class C>
 inline size_t gpp_smem_bytes(int) {
     return ((size_t)C::GPB * C::GWORDS + 2 * (size_t)C::NH * C::GS +
-            (C::ADAPT ? 2 * (size_t)C::GS * C::NX + (size_t)C::GS * C::NU + 2 * (size_t)C::NX * C::NX : 0) + 2 * (size_t)C::NH * C::BLOCK) * sizeof(double);
+            (C::ADAPT ? 2 * (size_t)C::GS * C::NX + (size_t)C::GS * C::NU + 2 * (size_t)C::NX * C::NX : 0) +
+            (size_t)C::NSTATE * C::NH * C::BLOCK + (C::CONSTR ? 0 : 2 * (size_t)C::NH * C::BLOCK)) * sizeof(double);
 }
 
 }  // namespace tmpc

@@ -132,7 +132,7 @@ const KernelEntry* const* kernel_table(int* count);   // defined in gen/tmpc_tab
     }                                                                                                               \
     static cudaError_t SYM##_session(const SolveParams& p, int grid, size_t smem, cudaStream_t st, const double* mp,\
                                      const PackLayout& L, double* ws, const WppLayout& W, int full) {               \
-        if constexpr (CFG::ADAPT) { return cudaErrorNotSupported; } else {                                          \
+        if constexpr (CFG::ADAPT || CFG::CONSTR) { return cudaErrorNotSupported; } else {                                          \
         GppTab<CFG::NX, CFG::NU, CFG::NH, CFG::GS, CFG::ADAPT> tab;                                                 \
         fill_gpp_tab(tab, mp, L, p);                                                                                \
         cudaError_t e = cudaFuncSetAttribute(gpp_kernel<CFG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
@@ -140,7 +140,8 @@ const KernelEntry* const* kernel_table(int* count);   // defined in gen/tmpc_tab
         gpp_kernel<CFG, true><<<grid, CFG::BLOCK, smem, st>>>(p, tab, GppSession{ws, W, full});                     \
         return cudaGetLastError(); }                                                                                \
     }                                                                                                               \
-    extern const KernelEntry SYM = {#SYM, KF_TPP, CFG::NX, CFG::NU, CFG::NH, CFG::ADAPT ? 2 : 0 /* FEAT_ADAPT : FEAT_BOX */, 64, 1 /* serves batches with and without references */, \
+    extern const KernelEntry SYM = {#SYM, KF_TPP, CFG::NX, CFG::NU, CFG::NH, CFG::CONSTR ? 1 : (CFG::ADAPT ? 2 : 0) /* FEAT_CONSTR : FEAT_ADAPT : FEAT_BOX */, 64, 1 /* serves batches with and without references */, \
                                     0, 0, 1, CFG::BLOCK, VAR, 1, SYM##_smem, SYM##_prepare,                        \
-                                    SYM##_occ, SYM##_launch, 0, 0, 0, 0, 0, 0, 0, CFG::GS, CFG::ADAPT ? nullptr : SYM##_session};                         \
+                                    SYM##_occ, SYM##_launch, CFG::CONSTR ? 1 : 0, CFG::SCS, CFG::SCD, CFG::UCS, CFG::UCD, CFG::NSL, CFG::NIL, CFG::GS,     \
+                                    (CFG::ADAPT || CFG::CONSTR) ? nullptr : SYM##_session};                         \
     }
