@@ -97,12 +97,12 @@ def inst4(nx, nu, N, refs=True, fb=False, variant=0, aff=None, cones=(0, 0, 0, 0
                 opq=False, tib=False, tm=True, minb=1, ntm=0, cones=cones, ttm=-1)
 
 
-def instg(nx, nu, N, variant=0, adapt=False, cones=None):
+def instg(nx, nu, N, variant=0, adapt=False, cones=None, rolled=False):
     """lane-group-per-problem fp64 kernel (tmpc_gpp.cuh): one lane per state row and per input row, groups of 8 / 16 / 32 lanes"""
     gs = 8 if nx + nu <= 8 else (16 if nx + nu <= 16 else 32)
     assert nx + nu <= 32
     return dict(gen=5, bits=64, nx=nx, nu=nu, N=N, feat=CON if cones else (ADP if adapt else BOX), refs=2, ppb=False, fb=False, variant=variant, block=128,
-                aff=True, gs=gs, cones=cones)
+                aff=True, gs=gs, cones=cones, rolled=rolled)
 
 
 def cols_per_thread(nx, nu, N, feat, refs, ntm=0):
@@ -242,7 +242,7 @@ def gen_sources(instances):
                 "// generated by tinympc-matlab_b200/build.py -- do not edit\n"
                 '#include "../tmpc_gpp.cuh"\n#include "../tmpc_registry.h"\nusing namespace tmpc;\n'
                 f"using Cfg_{n} = GppCfg<{i['nx']}, {i['nu']}, {i['N']}, {i['gs']}, {i['block']}, {b(i['feat'] == ADP)}"
-                + (f", {', '.join(str(c) for c in i['cones'])}, true" if i.get("cones") else "") + ">;\n"
+                + (f", {', '.join(str(c) for c in i['cones'])}, true" if i.get("cones") else (", 0, 0, 0, 0, 0, 0, false, true" if i.get("rolled") else "")) + ">;\n"
                 f"TMPC_DEFINE_GPP_ENTRY({n}, Cfg_{n}, {i['variant']})\n"
             )
         elif i["gen"] == 4:

@@ -35,7 +35,7 @@
 namespace tmpc {
 
 template <int NX_, int NU_, int NH_, int GS_, int BLOCK_ = 128, bool ADAPT_ = false,
-          int SCS_ = 0, int SCD_ = 0, int UCS_ = 0, int UCD_ = 0, int NSL_ = 0, int NIL_ = 0, bool CONSTR_ = false>
+          int SCS_ = 0, int SCD_ = 0, int UCS_ = 0, int UCD_ = 0, int NSL_ = 0, int NIL_ = 0, bool CONSTR_ = false, bool ROLLED_ = CONSTR_>
 struct GppCfg {
     using T = double;
     static constexpr int NX = NX_, NU = NU_, NH = NH_, GS = GS_, BLOCK = BLOCK_;
@@ -53,9 +53,9 @@ struct GppCfg {
     // ROLLED: the per-slot state of the lane (dual, slack, reference, family duals) lives in shared memory instead of registers and
     // the two time loops stay rolled.  The cone / half-space families add ~150 instructions per step: unrolled, the loop of the rocket
     // instance was 47 KB -- past the 32 KB instruction cache -- and ran at a third of the box kernel's rate.
-    static constexpr bool ROLLED = CONSTR_;
+    static constexpr bool ROLLED = ROLLED_;
     static constexpr int TUNROLL = ROLLED ? 1 : 64;
-    static constexpr int NSTATE = ROLLED ? 6 : 0;        // shared-memory state arrays per lane: G, V, GC, GL, EC, RF
+    static constexpr int NSTATE = ROLLED ? (CONSTR_ ? 6 : 3) : 0;   // shared-memory state arrays per lane: G, V, RF (+ GC, GL, EC)
     static constexpr int MINB = NH_ > 12 ? 2 : 3;        // CTAs per SM the register allocation aims at (the per-lane state grows with N)
     static constexpr int GPW = 32 / GS_;                 // problems per warp
     static constexpr int GPB = BLOCK_ / GS_;             // problems per CTA
@@ -244,8 +244,8 @@ gpp_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ GppT
     ArrC GC, GL, EC;
     ArrF RF;
     if constexpr (C::ROLLED) {
-        G.p = sst; V.p = sst + NH * C::BLOCK; GC.p = sst + 2 * NH * C::BLOCK; GL.p = sst + 3 * NH * C::BLOCK;
-        EC.p = sst + 4 * NH * C::BLOCK; RF.p = sst + 5 * NH * C::BLOCK;
+        G.p = sst; V.p = sst + NH * C::BLOCK; RF.p = sst + 2 * NH * C::BLOCK;
+        GC.p = sst + 3 * NH * C::BLOCK; GL.p = sst + 4 * NH * C::BLOCK; EC.p = sst + 5 * NH * C::BLOCK;     // CONSTR only
     }
     T PT = 0;                // state lanes: -(xref_N' Pinf)'_r
     T PT1 = 0;               // adaptive rho: its derivative, -(xref_N' dPinf)'_r
