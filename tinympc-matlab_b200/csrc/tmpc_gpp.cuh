@@ -153,8 +153,8 @@ inline void fill_gpp_tab(GppTab<NX, NU, NH, GS, ADAPT>& t, const double* pk, con
 struct GppSession {
     double* ws;        // batch * W.size doubles, or NULL (batch mode)
     WppLayout W;
-    int full;          // 1: also write d, every column of p and the unused columns 0 and N-1 of q (tiny_solve on ONE live workspace, whose
-                       // owner may look at any member of TinyWorkspace afterwards); 0: only what the next warm start reads
+    int full;          // informational: the launcher instantiates MODE 2 (also write d, every column of p and the unused columns 0 and N-1
+                       // of q: tiny_solve on ONE live workspace, whose owner may look at any member of TinyWorkspace afterwards) or MODE 1
 };
 
 // per-slot state of a lane: registers (statically indexed, unrolled time loops) or a shared-memory column [slot][thread]
@@ -180,10 +180,11 @@ __device__ __forceinline__ double gabsmax(double r, double a) {
 }
 __device__ __forceinline__ double gclamp(double t, double lo, double hi) { return gmin(hi, gmax(lo, t)); }   // admm.cpp:91-98 order
 
-template <class C, bool SESSION = false>
+template <class C, int MODE = 0>   // 0: batch; 1: sessions (what the next warm start reads is written back); 2: tiny_solve on one live workspace (every member)
 __global__ void __launch_bounds__(C::BLOCK, C::MINB)
 gpp_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ GppTab<C::NX, C::NU, C::NH, C::GS, C::ADAPT> tab,
            const __grid_constant__ GppSession ses) {
+    constexpr bool SESSION = MODE != 0, FULLWS = MODE == 2;
     static_assert(!(SESSION && C::ADAPT), "adaptive-rho sessions keep a cache per problem: they stay on the warp-per-problem kernel");
     using T = double;
     constexpr int NX = C::NX, NU = C::NU, NH = C::NH, GS = C::GS, NXP = C::NXP, NUP = C::NUP, SXL = C::SX, SUL = C::SU;
@@ -429,9 +430,9 @@ gpp_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ GppT
                     const T w1 = lincost(i - 1);          // state lane: q_i (column i = slot i-1); input lane: r_{i-1}
                     T* dst = pb + (i & 1) * (NXP + NUP);
                     if (is_x) dst[row] = acc + w1; else if (is_u) dst[NXP + row] = w1;
-                    if constexpr (SESSION) { if (ses.full && is_x) wsp[ses.W.p + i * NX + row] = acc + w1; }
+                    if constexpr (FULLWS) { if (is_x) wsp[ses.W.p + i * NX + row] = acc + w1; }
                 } else {
-                    if constexpr (SESSION) { if (ses.full && is_x) wsp[ses.W.p + row] = acc + lincost(NH - 1); }   // p_0 = q_0 + ... (never read)
+                    if constexpr (FULLWS) { if (is_x) wsp[ses.W.p + row] = acc + lincost(NH - 1); }   // p_0 = q_0 + ... (never read)
                 }
                 if (is_u) dt[i * NUP + row] = acc;         // d_i
                 __syncwarp();
@@ -667,7 +668,7 @@ gpp_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ GppT
                         if (is_x && s == NH - 2) wsp[ses.W.p + (NH - 1) * NX + row] = lincost_now(s);
                         else wq[s * st_] = lincost_now(s);
                     }
-                    if (ses.full) {
+                    if constexpr (FULLWS) {
                         if (is_u) {
 #pragma unroll
                             for (int s = 0; s < NH - 1; ++s) wsp[ses.W.d + s * NU + row] = dt[s * NUP + row];

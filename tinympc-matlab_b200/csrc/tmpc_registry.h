@@ -135,10 +135,13 @@ const KernelEntry* const* kernel_table(int* count);   // defined in gen/tmpc_tab
         if constexpr (CFG::ADAPT || CFG::CONSTR) { return cudaErrorNotSupported; } else {                                          \
         GppTab<CFG::NX, CFG::NU, CFG::NH, CFG::GS, CFG::ADAPT> tab;                                                 \
         fill_gpp_tab(tab, mp, L, p);                                                                                \
-        cudaError_t e = cudaFuncSetAttribute(gpp_kernel<CFG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-        if (e != cudaSuccess) return e;                                                                             \
-        gpp_kernel<CFG, true><<<grid, CFG::BLOCK, smem, st>>>(p, tab, GppSession{ws, W, full});                     \
-        return cudaGetLastError(); }                                                                                \
+        auto go = [&](auto kernel) -> cudaError_t {                                                                 \
+            cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
+            if (e != cudaSuccess) return e;                                                                         \
+            kernel<<<grid, CFG::BLOCK, smem, st>>>(p, tab, GppSession{ws, W, full});                                \
+            return cudaGetLastError();                                                                              \
+        };                                                                                                          \
+        return full ? go(gpp_kernel<CFG, 2>) : go(gpp_kernel<CFG, 1>); }                                            \
     }                                                                                                               \
     extern const KernelEntry SYM = {#SYM, KF_TPP, CFG::NX, CFG::NU, CFG::NH, CFG::CONSTR ? 1 : (CFG::ADAPT ? 2 : 0) /* FEAT_CONSTR : FEAT_ADAPT : FEAT_BOX */, 64, 1 /* serves batches with and without references */, \
                                     0, 0, 1, CFG::BLOCK, VAR, 1, SYM##_smem, SYM##_prepare,                        \
