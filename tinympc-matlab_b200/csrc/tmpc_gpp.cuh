@@ -56,7 +56,10 @@ struct GppCfg {
     static constexpr bool ROLLED = ROLLED_;
     static constexpr int TUNROLL = ROLLED ? 1 : 64;
     static constexpr int NSTATE = ROLLED ? (CONSTR_ ? 6 : 3) : 0;   // shared-memory state arrays per lane: G, V, RF (+ GC, GL, EC)
-    static constexpr int MINB = NH_ > 12 ? 2 : 3;        // CTAs per SM the register allocation aims at (the per-lane state grows with N)
+    // Register budget: the full 255 (two CTAs of 128 threads per SM).  Aiming at three CTAs (168 registers) made ptxas spill a few words
+    // and re-read launch parameters inside the dependent chain of every step: 37 % slower in bulk (16.7 against 23.0 M fp64 quadrotor
+    // solves/s) in spite of the 50 % more resident warps -- the kernel is bound by the latency of one group's step, not by issue.
+    static constexpr int MINB = 2;        // CTAs per SM the register allocation aims at (the per-lane state grows with N)
     static constexpr int GPW = 32 / GS_;                 // problems per warp
     static constexpr int GPB = BLOCK_ / GS_;             // problems per CTA
     static constexpr int NV = NX_ + NU_;
