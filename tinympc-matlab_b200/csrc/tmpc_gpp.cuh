@@ -24,10 +24,16 @@
 //     slot: one 8-byte store per lane, __syncwarp, NX/2 + NU/2 broadcast 16-byte loads;
 //   * slack, dual, linear-cost and residual terms are element-wise on the owning lane; the four infinity norms are shuffle
 //     max-reductions over the group (admm.cpp:257-260).
-// One ADMM iteration of the quadrotor shape is 18 such steps of ~45 instructions: ~2 us, 20x shorter than the thread-per-problem
-// fp64 iteration, and -- because the FP64 pipe sees four chains per lane and two problems per warp -- a higher fp64 throughput
-// as well.  It serves fp64 batches (precision = 64), the second pass of the exact-count mode (index list or device queue,
-// same SolveParams protocol as tmpc_tpp2.cuh) and small batches of the compiled shapes.
+// One ADMM iteration of the quadrotor shape is 18 such steps of ~45 instructions: 2.0 us on a lone warp, 18x shorter than the
+// thread-per-problem fp64 iteration, and -- because the FP64 pipe sees four chains per lane and two problems per warp -- twice the
+// fp64 throughput as well (23 against 11 M quadrotor solves/s).  Modes and variants of the one kernel:
+//   batch (MODE 0)      fp64 batches (precision = 64), the second pass of the exact-count mode (index list or device queue, same
+//                       SolveParams protocol as tmpc_tpp2.cuh), small batches of the compiled shapes
+//   ADAPT               adaptive rho in the closed block form of rho_benchmark.cpp:146-212 (a rolled pass over parked columns)
+//   CONSTR / ROLLED     the rocket family: one second-order cone per side and 0/1 linear rows; per-slot state in shared memory and
+//                       rolled time loops, because the unrolled form no longer fits the 32 KB instruction cache
+//   session (MODE 1)    persistent TinyWorkspace images iterated in place with the reference's warm-start semantics
+//   workspace (MODE 2)  the same for ONE live workspace, every member written back: tiny_solve
 #pragma once
 #include "tmpc_tpp2.cuh"
 #include "tmpc_wpp.h"
