@@ -84,8 +84,9 @@ typedef struct {
     const float *u_min, *u_max;   /*                              batch*nu*(N-1)                    */
     /* Compact input (instead of Xref): ONE reference state per problem, held over the whole horizon -- what
        tiny_set_x_ref receives in the closed-loop examples, where every column of Xref is the same set point
-       (tinympc/TinyMPC/examples/quadrotor_hovering.cpp:60-66).  batch*nx; Xref must then be NULL.  The library
-       replicates it on the device: 4 nx bytes cross the bus per problem instead of 4 nx N. */
+       (tinympc/TinyMPC/examples/quadrotor_hovering.cpp:60-66).  batch*nx; Xref must then be NULL.  4 nx bytes cross the
+       bus per problem instead of 4 nx N; the incremental fp32 kernels and the lane-group fp64 kernels read the state in
+       place of every column, for any other kernel the library replicates it over the horizon on the device first. */
     const float *xref_const;
 } tinympc_cuda_batch_in;
 
@@ -196,7 +197,12 @@ int  tinympc_cuda_session_read(tinympc_cuda_session *ss, const char *field, doub
    chosen by the kernel from the iterations its problems take),
    "streamed" (1 [default]: tinympc_cuda_solve_batch runs each device's shard as ONE persistent launch that consumes the
    problems while the H2D copies are still arriving and returns results chunk by chunk while it is still solving;
-   0: one launch per chunk), "ctas_per_sm" (0 = occupancy API), "chunks" (host pipeline depth, 0 = auto),
+   0: one launch per chunk),
+   "compact_streamed" (1 [default]: a host batch with compact I/O -- xref_const in and / or u0 out -- of >= 2^16 problems per
+   device runs as one launch chain over the whole shard while its inputs are still arriving in a few chunks of doubling size
+   behind an arrival watermark; 0: the chunked pipeline), "compact_in_kernel" (1 [default]: kernels read xref_const in place
+   where they can; 0: always replicate it on the device first),
+   "ctas_per_sm" (0 = occupancy API), "chunks" (host pipeline depth, 0 = auto),
    "fixer_sms" (how the exact-count mode schedules its fp64 pass: -2 [default] the sequential two-pass form for device-resident and
    chunked batches, the concurrent producer / consumer pair inside the streamed host pipeline; -1 always sequential; 0 always the
    pair with 13 % of the SMs left to the consumer; n > 0 the pair with n SMs),

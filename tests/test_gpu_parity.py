@@ -354,23 +354,36 @@ def test_session_outliving_its_solver_fails_cleanly(capi, oracle_mod, problems):
     ss.h = capi.C.c_void_p()
 
 
+@pytest.mark.parametrize("pipeline", ["streamed", "chunked"])
 @pytest.mark.parametrize("mixed", [0.0, 0.003])
 @pytest.mark.parametrize("B", [1000, 70001])
-def test_compact_io_matches_full_trajectories(B, mixed, capi, oracle_mod, problems):
-    """tinympc_cuda_batch_in::xref_const (one reference state per problem, replicated over the horizon on the device) and
+def test_compact_io_matches_full_trajectories(B, mixed, pipeline, capi, oracle_mod, problems):
+    """tinympc_cuda_batch_in::xref_const (one reference state per problem, standing for every column of the horizon) and
     tinympc_cuda_batch_out::u0 (first control only): same iteration counts, statuses and first controls as the full-trajectory
-    call on the replicated reference, through the host entry (chunked pipeline) and the device entry."""
+    call on the replicated reference, through the host entry and the device entry.  "streamed" (default): the kernels read the
+    compact reference in place and a shard of >= 2^16 problems goes through one launch chain behind an arrival watermark
+    (run_shard_compact_streamed); "chunked": the reference is replicated on the device first, one launch per chunk."""
     import torch
     p = problems.quadrotor()
     b = problems.make_batch(p, B, 1.0, seed=21)
     assert (b.Xref == b.Xref[:, :1]).all() and not b.Uref.any()
     s = capi.CudaSolver()
     s.set_option("mixed", mixed)
+    s.set_option("compact_streamed", 1 if pipeline == "streamed" else 0)
+    s.set_option("compact_in_kernel", 1 if pipeline == "streamed" else 0)
     s.set_family(cases.family_from_spec(p, oracle_mod.get_cache(p, "port")))
     full = s.solve_batch(b.x0, b.Xref, None)
     xc = np.ascontiguousarray(b.Xref[:, 0, :])
-    c = s.solve_batch(b.x0, xref_const=xc, compact_out=True)
-    assert set(c) == {"u0", "iter", "status"}
+    for early in (1, 0, 1):   # (the control words are reused from call to call)
+        # exact-count mode of the streamed form: result copies under the fp64 pass + its packed result list, or all copies at the end
+        s.set_option("compact_early_d2h", early)
+        c = s.solve_batch(b.x0, xref_const=xc, compact_out=True)
+        assert (s.last_timing()["chunks"] >= 2) == (pipeline == "streamed" and B >= 65536), s.last_timing()
+        if mixed > 0:
+            assert s.last_marked > 0 and "+" in s.last_kernel, (s.last_marked, s.last_kernel)
+        assert set(c) == {"u0", "iter", "status"}
+        assert np.array_equal(c["iter"], full["iter"]) and np.array_equal(c["status"], full["status"]), f"early={early}"
+        assert np.array_equal(c["u0"], full["u"][:, 0, :]), f"early={early}"
     assert np.array_equal(c["iter"], full["iter"]) and np.array_equal(c["status"], full["status"])
     assert np.array_equal(c["u0"], full["u"][:, 0, :])
     # mixed forms: compact input with full output, full input with compact output
@@ -389,6 +402,58 @@ def test_compact_io_matches_full_trajectories(B, mixed, capi, oracle_mod, proble
     # argument checks
     with pytest.raises(capi.TinympcCudaError):
         s.solve_batch(b.x0, b.Xref, None, xref_const=xc)
+    s.close()
+
+
+def test_compact_streamed_wide_band(capi, oracle_mod, problems):
+    """A band so wide that the fp64 pass re-solves more problems than the first fetch of its packed result list holds
+    (run_shard_compact_streamed: the rest of the list is fetched separately)."""
+    p = problems.quadrotor()
+    B = 70001
+    b = problems.make_batch(p, B, 1.0, seed=23)
+    xc = np.ascontiguousarray(b.Xref[:, 0, :])
+    s = capi.CudaSolver()
+    s.set_option("mixed", 0.25)
+    s.set_family(cases.family_from_spec(p, oracle_mod.get_cache(p, "port")))
+    s.set_option("chunks", 1)
+    s.set_option("fixer_sms", -1)
+    full = s.solve_batch(b.x0, b.Xref, None)
+    s.set_option("chunks", 0)
+    c = s.solve_batch(b.x0, xref_const=xc, compact_out=True)
+    assert s.last_timing()["chunks"] >= 2 and s.last_marked > max(1024, B // 16), (s.last_timing(), s.last_marked)
+    s.close()
+    assert np.array_equal(c["iter"], full["iter"]) and np.array_equal(c["status"], full["status"])
+    assert np.array_equal(c["u0"], full["u"][:, 0, :])
+
+
+@pytest.mark.parametrize("family,precision,B", [("cartpole", 32, 3000), ("cartpole", 64, 3000), ("quadrotor", 64, 3000), ("quadrotor", 32, 60000),
+                                                ("rocket", 32, 3000), ("quadrotor_adaptive", 64, 3000), ("cartpole", 32, 140000)])
+def test_compact_reference_read_in_place(family, precision, B, capi, oracle_mod, problems):
+    """SolveParams::xref_const: the incremental fp32 kernel and the lane-group fp64 kernel read ONE reference state per problem in
+    place of every column of the horizon; every other kernel (here: the rocket's mixed-precision kernel) gets the reference
+    replicated on the device first.  Either way the result is, bit for bit, that of the full-trajectory call."""
+    p = dict(cartpole=problems.cartpole, quadrotor=problems.quadrotor, rocket=problems.rocket,
+             quadrotor_adaptive=lambda: problems.quadrotor(adaptive=True))[family]()
+    b = problems.make_batch(p, B, 1.0, seed=41)
+    xc = (0.1 * np.random.default_rng(9).standard_normal((B, p.nx))).astype(np.float32)
+    Xref = np.ascontiguousarray(np.repeat(xc[:, None, :], p.N, axis=1))
+    s = capi.CudaSolver()
+    s.set_option("precision", precision)
+    if precision == 32:
+        s.set_option("mixed", problems.exact_band(p))
+    s.set_family(cases.family_from_spec(p, oracle_mod.get_cache(p, "port")))
+    s.set_option("chunks", 1)
+    full = s.solve_batch(b.x0, Xref, None)
+    s.set_option("chunks", 0)
+    for in_kernel in (1, 0):
+        s.set_option("compact_in_kernel", in_kernel)
+        c = s.solve_batch(b.x0, xref_const=xc)
+        for k in ("iter", "status", "x", "u"):
+            assert np.array_equal(full[k], c[k]), f"{family} fp{precision} in_kernel={in_kernel}: compact reference changes {k} ({s.last_kernel})"
+        # ... and SolveParams::u0: the first control as the only solution output (no trajectory scratch, no gather)
+        c = s.solve_batch(b.x0, xref_const=xc, compact_out=True)
+        assert np.array_equal(full["iter"], c["iter"]) and np.array_equal(full["status"], c["status"])
+        assert np.array_equal(full["u"][:, 0, :], c["u0"]), f"{family} fp{precision} in_kernel={in_kernel}: compact output differs ({s.last_kernel})"
     s.close()
 
 

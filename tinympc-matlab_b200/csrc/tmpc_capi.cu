@@ -68,6 +68,10 @@ struct DeviceCtx {
     DevBuf wpp_scratch[kStreams + 1];   // warp-per-problem workspaces (one per pipeline stream + the device/workspace entry)
     DevBuf ref_scratch64[kStreams + 1]; // mixed mode: reference terms of the fp64 re-solve pass
     DevBuf marked[kStreams + 1];        // mixed mode: indices of the problems the fp32 pass marked ambiguous (two-pass form) / the queue
+    DevBuf fix;                         // compact streamed pipeline: results of the fp64 pass as a packed list (run_shard_compact_streamed)
+    int* hfix = nullptr;                // ... and its pinned host copy
+    size_t hfix_cap = 0;
+    cudaEvent_t ev_pass = nullptr;      // ... end of the first pass: the early result copies wait for it
     // exact-count mode, concurrent form: per slot {q_tail, producer CTAs done, consumer ticket counter, pad}
     int* qctl = nullptr;                // 4 * kMaxChunks ints, indexed like the work counters (chunk index; the last one = device entry)
     cudaStream_t fix_stream[kStreams + 1] = {nullptr, nullptr, nullptr, nullptr};   // the fp64 consumer launches
@@ -101,6 +105,12 @@ struct tinympc_cuda_solver {
     int force_wpp = 0;                 // option "kernel": 0 auto, 1 always the warp-per-problem kernel
     int refill_min = 0;                // option "refill_min": free lanes a warp collects before it claims new problems (tmpc_tpp3.cuh); 0 = adaptive
     int streamed = 1;                  // option "streamed": 1 = single-launch streamed host pipeline where it applies, 0 = chunked launches
+    int compact_streamed = 1;          // option "compact_streamed": compact host I/O through one launch chain behind an arrival watermark
+                                       // (run_shard_compact_streamed); 0 = the chunked pipeline
+    int compact_early_d2h = 1;         // option "compact_early_d2h": exact-count mode of that pipeline -- the results of the first pass go
+                                       // back while the fp64 pass runs, which returns a packed list the host scatters over them
+    int compact_in_kernel = 1;         // option "compact_in_kernel": kernels read tinympc_cuda_batch_in::xref_const in place where they can;
+                                       // 0 = always replicate it over the horizon on the device first
     double mixed_band = 0;             // option "mixed": > 0 = fp32 pass + fp64 re-solve of the problems whose termination decision
                                        // falls within this relative band of the tolerances (exact iteration counts at ~fp32 speed)
     int pass_timing = 0;               // option "pass_timing": 1 = record CUDA events around the two passes of the sequential exact-count form
@@ -220,6 +230,20 @@ __global__ void gather_u0_kernel(const float* __restrict__ u, float* __restrict_
     u0[i] = u[b * su + (i - b * nu)];
 }
 
+// compact streamed pipeline: what the fp64 pass produced, as a packed list the host scatters over the early result copies.
+// fix[0] = number of entries; entry k at fix + 4 + k * (3 + nu): problem index, iter, status, u0[nu].
+__global__ void pack_fix_kernel(const int* __restrict__ list, const int* __restrict__ count, const int* __restrict__ iter,
+                                const int* __restrict__ status, const float* __restrict__ u0, int nu, int* __restrict__ fix) {
+    const int n = *count;
+    if (blockIdx.x == 0 && threadIdx.x == 0) fix[0] = n;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const int i = list[k];
+        int* e = fix + 4 + (size_t)k * (3 + nu);
+        e[0] = i; e[1] = iter[i]; e[2] = status[i];
+        for (int a = 0; a < nu; ++a) e[3 + a] = __float_as_int(u0[(size_t)i * nu + a]);
+    }
+}
+
 int upload_family(tinympc_cuda_solver* s) {
     const Family& f = s->fam;
     std::vector<float> p32(f.pack.size());
@@ -320,10 +344,28 @@ int launch_exact_pair(tinympc_cuda_solver* s, DeviceCtx& d, const KernelEntry* k
     return TINYMPC_CUDA_OK;
 }
 
+// Do the kernels that will serve the batch do compact I/O themselves (SolveParams::xref_const / u0, KernelEntry::compact_ok)?
+// Mirrors the kernel choice of enqueue(): the first-pass kernel and, in the exact-count mode, the fp64 kernel of the second pass.
+bool compact_in_kernel(const tinympc_cuda_solver* s, const DeviceCtx& d, bool ppb, bool refs, int batch, const KernelEntry** ke_out = nullptr,
+                       const KernelEntry** ke64_out = nullptr) {
+    const Family& f = s->fam;
+    if (ke_out) *ke_out = nullptr;
+    if (ke64_out) *ke64_out = nullptr;
+    if (s->force_wpp) return false;
+    const KernelEntry* ke = pick_kernel(s, d, f, s->precision, ppb, refs, batch);
+    const bool mixed = s->mixed_band > 0 && s->precision == 32;
+    const KernelEntry* ke64 = mixed ? find_kernel(f, 64, ppb, refs, 0) : nullptr;
+    if (ke_out) *ke_out = ke;
+    if (ke64_out) *ke64_out = ke64;
+    return s->compact_in_kernel && ke && ke->compact_ok && (!mixed || (ke64 && ke64->compact_ok));
+}
+
+constexpr int kDirectXref = 1, kDirectU0 = 2;   // enqueue(): compact I/O handed to the kernels as it is
+
 // Enqueue the solve of `in`/`out` (device pointers) on `st`.  slot selects the work counters and scratch buffers
 // (one set per pipeline stream + one for the device-resident entry point).
 int enqueue(tinympc_cuda_solver* s, DeviceCtx& d, const tinympc_cuda_batch_in& in, const tinympc_cuda_batch_out& out, int counter_slot,
-            cudaStream_t st, int scratch_slot) {
+            cudaStream_t st, int scratch_slot, int direct = 0) {
     const Family& f = s->fam;
     const bool ppb = in.x_min || in.x_max || in.u_min || in.u_max;
     if (ppb && !(in.x_min && in.x_max && in.u_min && in.u_max))
@@ -333,27 +375,42 @@ int enqueue(tinympc_cuda_solver* s, DeviceCtx& d, const tinympc_cuda_batch_in& i
     if (in.xref_const && in.Xref) return fail(s, TINYMPC_CUDA_EINVAL, "give Xref or xref_const, not both");
     const bool full_out = out.x && out.u;
     if (!full_out && !out.u0) return fail(s, TINYMPC_CUDA_EINVAL, "x and u are required unless u0 is given");
-    if (in.xref_const || !full_out) {
-        // compact I/O: expand / keep the trajectories in this slot's device scratch, run the ordinary solve on them, pick u0 out
+    if (!direct && (in.xref_const || !full_out)) {
+        // compact I/O.  Kernels with KernelEntry::compact_ok read the one reference state per problem in place of every column and
+        // write the first control alone; for any other kernel the reference is replicated over the horizon first and the
+        // trajectories go to this slot's device scratch, from which u0 is gathered.
         const size_t sx = (size_t)f.nx * f.N, su = (size_t)f.nu * (f.N - 1);
+        const bool in_kernel = compact_in_kernel(s, d, ppb, in.xref_const || in.Xref || in.Uref, in.batch);
         tinympc_cuda_batch_in in2 = in;
         tinympc_cuda_batch_out out2 = out;
         in2.xref_const = nullptr;
-        out2.u0 = nullptr;
+        int dir = 0;
         if (in.xref_const) {
-            DevBuf& xb = d.exp_xref[scratch_slot];
-            CU(s, xb.reserve(sizeof(float) * sx * in.batch));
-            const size_t total = sx * in.batch;
-            expand_xref_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(in.xref_const, static_cast<float*>(xb.p), total, f.nx, (int)sx);
-            CU(s, cudaGetLastError());
-            s->launches += 1;
-            in2.Xref = static_cast<const float*>(xb.p);
+            if (in_kernel) {
+                in2.Xref = in.xref_const;
+                dir |= kDirectXref;
+            } else {
+                DevBuf& xb = d.exp_xref[scratch_slot];
+                CU(s, xb.reserve(sizeof(float) * sx * in.batch));
+                const size_t total = sx * in.batch;
+                expand_xref_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(in.xref_const, static_cast<float*>(xb.p), total, f.nx, (int)sx);
+                CU(s, cudaGetLastError());
+                s->launches += 1;
+                in2.Xref = static_cast<const float*>(xb.p);
+            }
         }
-        if (!out.x) { CU(s, d.exp_x[scratch_slot].reserve(sizeof(float) * sx * in.batch)); out2.x = static_cast<float*>(d.exp_x[scratch_slot].p); }
-        if (!out.u) { CU(s, d.exp_u[scratch_slot].reserve(sizeof(float) * su * in.batch)); out2.u = static_cast<float*>(d.exp_u[scratch_slot].p); }
-        int rc = enqueue(s, d, in2, out2, counter_slot, st, scratch_slot);
+        const bool u0_direct = in_kernel && out.u0 && !out.x && !out.u;
+        if (u0_direct) {
+            dir |= kDirectU0;
+        } else {
+            out2.u0 = nullptr;
+            if (!out.x) { CU(s, d.exp_x[scratch_slot].reserve(sizeof(float) * sx * in.batch)); out2.x = static_cast<float*>(d.exp_x[scratch_slot].p); }
+            if (!out.u) { CU(s, d.exp_u[scratch_slot].reserve(sizeof(float) * su * in.batch)); out2.u = static_cast<float*>(d.exp_u[scratch_slot].p); }
+        }
+        if (dir == 0) dir = -1;   // plain trajectories from here on: do not come back into this branch
+        int rc = enqueue(s, d, in2, out2, counter_slot, st, scratch_slot, dir);
         if (rc) return rc;
-        if (out.u0) {
+        if (out.u0 && !u0_direct) {
             const size_t total = (size_t)f.nu * in.batch;
             gather_u0_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(out2.u, out.u0, total, f.nu, (int)su);
             CU(s, cudaGetLastError());
@@ -361,6 +418,7 @@ int enqueue(tinympc_cuda_solver* s, DeviceCtx& d, const tinympc_cuda_batch_in& i
         }
         return TINYMPC_CUDA_OK;
     }
+    if (direct < 0) direct = 0;
     const bool refs = in.Xref || in.Uref;
     int bits = s->precision;
     const KernelEntry* ke = s->force_wpp ? nullptr : pick_kernel(s, d, f, bits, ppb, refs, in.batch);
@@ -376,9 +434,13 @@ int enqueue(tinympc_cuda_solver* s, DeviceCtx& d, const tinympc_cuda_batch_in& i
     p.pack_elems = f.L.cold_size;
     p.batch = in.batch;
     p.x0 = in.x0; p.Xref = in.Xref; p.Uref = in.Uref;
+    p.xref_const = (direct & kDirectXref) ? 1 : 0;
     p.x_min = in.x_min; p.x_max = in.x_max; p.u_min = in.u_min; p.u_max = in.u_max;
     p.x = out.x; p.u = out.u; p.iter = out.iter; p.status = out.status; p.residuals = out.residuals; p.rho_out = out.rho;
+    p.u0 = (direct & kDirectU0) ? out.u0 : nullptr;
 
+    if (direct && !(ke && ke->compact_ok && (!mixed || ke64->compact_ok)))
+        return fail(s, TINYMPC_CUDA_EUNSUPPORTED, "internal: compact I/O handed to a kernel that does not do it");
     if (!ke) {
         // no specialised thread-per-problem kernel for this shape / feature mix: general warp-per-problem kernel
         const WppLayout W = WppLayout::make(f.nx, f.nu, f.N);
@@ -607,6 +669,190 @@ int run_shard_streamed(tinympc_cuda_solver* s, DeviceCtx& d, const KernelEntry* 
     return TINYMPC_CUDA_OK;
 }
 
+// Compact host I/O (x0 + one reference state per problem in, u0 + iter + status out: ~120 bytes per problem) as ONE launch chain.
+// The chunked pipeline pays for every chunk a partial last wave of the persistent kernel and the latency-bound end of its fp64
+// pass, and its first launch waits for the first chunk's upload; here stream 0 uploads the inputs in a few chunks of doubling
+// size, each followed by a write of the arrival watermark, and stream 1 runs the solve over the WHOLE shard -- first kernel
+// (lanes start a claimed problem once the watermark covers it; the kernels read the compact reference in place, so no
+// expansion kernel has to find room next to a persistent launch), then, in the exact-count mode, compaction + fp64 pass,
+// then the u0 gather and the result copies.  The link delivers ~50 GB/s, the kernel consumes ~7: after the first chunk
+// (1/64 of the shard) the upload is entirely hidden.  Enqueue order as in run_shard_streamed: every copy the kernel waits
+// for is enqueued before its launch.
+int run_shard_compact_streamed(tinympc_cuda_solver* s, DeviceCtx& d, const KernelEntry* ke, const KernelEntry* ke64, const tinympc_cuda_batch_in& in,
+                               const tinympc_cuda_batch_out& out, int lo, int hi, double* kernel_ms, int* nchunks_out, long long* marked_out) {
+    const Family& f = s->fam;
+    const StreamMemOps& ops = stream_memops();
+    const int n = hi - lo;
+    const size_t sx = (size_t)f.nx * f.N, su = (size_t)f.nu * (f.N - 1);
+    const bool ppb = in.x_min != nullptr;
+    const bool mixed = ke64 != nullptr;
+    // chunks = runs of granules of a multiple of 32 problems (no 128-byte line holds inputs of two chunks, see run_shard_streamed);
+    // auto: 1, 1, 2, 4, 8, ... sixty-fourths of the shard; chunks = k > 1: k equal chunks
+    std::vector<int> bounds;
+    {
+        const bool ramp = s->chunks <= 0;
+        const int ng_target = ramp ? kMaxGranules : std::min(s->chunks, kMaxGranules);
+        const int gran = (((n + ng_target - 1) / ng_target) + 31) & ~31;
+        const int ng = (n + gran - 1) / gran;
+        bounds.push_back(0);
+        int g = 0, run = 1;
+        while (g < ng) {
+            g = std::min(ng, g + run);
+            bounds.push_back(std::min(n, g * gran));
+            if (ramp && bounds.size() > 2) run *= 2;
+        }
+    }
+    const int nch = (int)bounds.size() - 1;
+    cudaStream_t s_in = d.streams[0], s_k = d.streams[1];
+    int* ctl = d.stream_ctl;   // [0] work counter of the first kernel, [1] arrival watermark
+    CU(s, cudaMemsetAsync(ctl, 0, sizeof(int) * 2, s_k));
+    CU(s, cudaEventRecord(d.ev_ctl, s_k));
+    CU(s, cudaStreamWaitEvent(s_in, d.ev_ctl, 0));
+    // kernels that write the first control alone (KernelEntry::compact_ok) need no trajectory scratch and no gather
+    const bool u0_direct = s->compact_in_kernel && out.u0 && !out.x && !out.u && ke->compact_ok && (!mixed || ke64->compact_ok);
+    if (!u0_direct) {
+        if (!out.x) CU(s, d.exp_x[0].reserve(sizeof(float) * sx * n));
+        if (!out.u) CU(s, d.exp_u[0].reserve(sizeof(float) * su * n));
+    }
+    DevBuf& list = d.marked[0];
+    if (mixed) CU(s, list.reserve(sizeof(int) * (size_t)n));
+    // Exact-count mode with compact output: everything but the ~1 % of marked problems is final after the first pass, so the
+    // result copies (u0, iter, status: the whole D2H volume) start then, on the third stream, under the fp64 pass.  That pass
+    // returns its results as a packed list {index, iter, status, u0} which the host scatters over the copied arrays.  (The copies
+    // may see a marked problem's entries before or after the fp64 pass rewrites them; either way the list overrides them.)
+    const bool early = mixed && u0_direct && s->compact_early_d2h && !out.residuals && !out.rho;
+    const size_t fix_entry = 3 + (size_t)f.nu, fix_words = 4 + fix_entry * (size_t)n;
+    const int fix_first = std::max(1024, n / 16);          // entries fetched with the header; more only if the band is wide
+    if (early) {
+        CU(s, d.fix.reserve(sizeof(int) * fix_words));
+        if (d.hfix_cap < fix_words) {
+            if (d.hfix) cudaFreeHost(d.hfix);
+            d.hfix = nullptr; d.hfix_cap = 0;
+            CU(s, cudaMallocHost(reinterpret_cast<void**>(&d.hfix), sizeof(int) * fix_words));
+            d.hfix_cap = fix_words;
+        }
+    }
+
+    const int bits = ke->dtype_bits;
+    SolveParams p = f.base;
+    p.pack = bits == 64 ? (const void*)((const double*)d.pack64 + f.L.cold) : (const void*)((const float*)d.pack32 + f.L.cold);
+    p.pack_elems = f.L.cold_size;
+    p.batch = n;
+    p.x0 = (const float*)d.x0.p;
+    p.Xref = in.xref_const ? (const float*)d.xrc.p : (in.Xref ? (const float*)d.Xref.p : nullptr);
+    p.xref_const = in.xref_const ? 1 : 0;
+    p.Uref = in.Uref ? (const float*)d.Uref.p : nullptr;
+    if (ppb) { p.x_min = (const float*)d.xmin.p; p.x_max = (const float*)d.xmax.p; p.u_min = (const float*)d.umin.p; p.u_max = (const float*)d.umax.p; }
+    if (u0_direct) {
+        p.x = nullptr; p.u = nullptr; p.u0 = (float*)d.u0.p;
+    } else {
+        p.x = out.x ? (float*)d.x.p : (float*)d.exp_x[0].p;
+        p.u = out.u ? (float*)d.u.p : (float*)d.exp_u[0].p;
+    }
+    p.iter = (int*)d.iter.p; p.status = (int*)d.status.p;
+    p.residuals = out.residuals ? (float*)d.res.p : nullptr;
+    p.rho_out = out.rho ? (float*)d.rho.p : nullptr;
+    p.avail_ptr = ctl + 1;
+
+    auto sync_fail = [&](int rc) -> int { cudaDeviceSynchronize(); return rc; };
+#define RT(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return sync_fail(cuda_fail(s, e__, #call)); } while (0)
+    for (int c = 0; c < nch; ++c) {
+        const int c0 = bounds[c], c1 = bounds[c + 1], cn = c1 - c0;
+        const size_t g0 = (size_t)lo + c0;
+        auto h2d = [&](DevBuf& dst, const float* src, size_t per_problem) -> cudaError_t {
+            return cudaMemcpyAsync((float*)dst.p + per_problem * c0, src + per_problem * g0, sizeof(float) * per_problem * cn, cudaMemcpyHostToDevice, s_in);
+        };
+        RT(h2d(d.x0, in.x0, f.nx));
+        if (in.xref_const) RT(h2d(d.xrc, in.xref_const, f.nx));
+        if (in.Xref) RT(h2d(d.Xref, in.Xref, sx));
+        if (in.Uref) RT(h2d(d.Uref, in.Uref, su));
+        if (ppb) { RT(h2d(d.xmin, in.x_min, sx)); RT(h2d(d.xmax, in.x_max, sx)); RT(h2d(d.umin, in.u_min, su)); RT(h2d(d.umax, in.u_max, su)); }
+        CUresult r = ops.write(reinterpret_cast<CUstream>(s_in), reinterpret_cast<CUdeviceptr>(ctl + 1), (cuuint32_t)c1, 0);
+        if (r != CUDA_SUCCESS) return sync_fail(fail(s, TINYMPC_CUDA_ECUDA, "cuStreamWriteValue32 failed with CUresult " + std::to_string((int)r)));
+    }
+    RT(cudaEventRecord(d.k0[0], s_k));
+    int* const n_marked = d.counters + 2 * kMaxChunks;
+    if (!mixed) {
+        int rc = launch_tpp(s, d, ke, p, d.ref_scratch[0], bits, ctl, s_k);
+        if (rc) return sync_fail(rc);
+        note_kernel(s, ke->name);
+    } else {   // sequential exact-count form (enqueue()): fp32 pass that marks, compaction, fp64 re-solve of the marked problems
+        p.amb_band = static_cast<float>(s->mixed_band);
+        int rc = launch_tpp(s, d, ke, p, d.ref_scratch[0], 32, ctl, s_k);
+        if (rc) return sync_fail(rc);
+        if (early) {
+            cudaStream_t s_out = d.streams[2];
+            RT(cudaEventRecord(d.ev_pass, s_k));
+            RT(cudaStreamWaitEvent(s_out, d.ev_pass, 0));
+            RT(cudaMemcpyAsync(out.u0 + (size_t)f.nu * lo, d.u0.p, sizeof(float) * f.nu * n, cudaMemcpyDeviceToHost, s_out));
+            RT(cudaMemcpyAsync(out.iter + lo, d.iter.p, sizeof(int) * n, cudaMemcpyDeviceToHost, s_out));
+            RT(cudaMemcpyAsync(out.status + lo, d.status.p, sizeof(int) * n, cudaMemcpyDeviceToHost, s_out));
+        }
+        RT(cudaMemsetAsync(n_marked, 0, sizeof(int), s_k));
+        collect_marked_kernel<<<(n + 255) / 256, 256, 0, s_k>>>(p.status, n, static_cast<int*>(list.p), n_marked);
+        RT(cudaGetLastError());
+        s->launches += 1;
+        SolveParams p2 = p;
+        p2.pack = (const void*)((const double*)d.pack64 + f.L.cold);
+        p2.amb_band = 0.f;
+        p2.avail_ptr = nullptr;            // the first pass has seen every problem
+        p2.index_list = static_cast<const int*>(list.p);
+        p2.batch_ptr = n_marked;
+        rc = launch_tpp(s, d, ke64, p2, d.ref_scratch64[0], 64, d.counters + kMaxChunks, s_k);
+        if (rc) return sync_fail(rc);
+        note_kernel(s, std::string(ke->name) + "+" + ke64->name);
+    }
+    if (out.u0 && !u0_direct) {
+        const size_t total = (size_t)f.nu * n;
+        gather_u0_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s_k>>>(p.u, (float*)d.u0.p, total, f.nu, (int)su);
+        RT(cudaGetLastError());
+        s->launches += 1;
+    }
+    if (early) {
+        pack_fix_kernel<<<64, 256, 0, s_k>>>(static_cast<const int*>(list.p), n_marked, p.iter, p.status, p.u0, f.nu, static_cast<int*>(d.fix.p));
+        RT(cudaGetLastError());
+        s->launches += 1;
+    }
+    RT(cudaEventRecord(d.k1[0], s_k));
+    if (early) {
+        RT(cudaMemcpyAsync(d.hfix, d.fix.p, sizeof(int) * (4 + fix_entry * (size_t)std::min(n, fix_first)), cudaMemcpyDeviceToHost, s_k));
+    } else {
+        if (out.x) RT(cudaMemcpyAsync(out.x + sx * lo, d.x.p, sizeof(float) * sx * n, cudaMemcpyDeviceToHost, s_k));
+        if (out.u) RT(cudaMemcpyAsync(out.u + su * lo, d.u.p, sizeof(float) * su * n, cudaMemcpyDeviceToHost, s_k));
+        if (out.u0) RT(cudaMemcpyAsync(out.u0 + (size_t)f.nu * lo, d.u0.p, sizeof(float) * f.nu * n, cudaMemcpyDeviceToHost, s_k));
+        RT(cudaMemcpyAsync(out.iter + lo, d.iter.p, sizeof(int) * n, cudaMemcpyDeviceToHost, s_k));
+        RT(cudaMemcpyAsync(out.status + lo, d.status.p, sizeof(int) * n, cudaMemcpyDeviceToHost, s_k));
+        if (out.residuals) RT(cudaMemcpyAsync(out.residuals + 4 * (size_t)lo, d.res.p, sizeof(float) * 4 * n, cudaMemcpyDeviceToHost, s_k));
+        if (out.rho) RT(cudaMemcpyAsync(out.rho + lo, d.rho.p, sizeof(float) * n, cudaMemcpyDeviceToHost, s_k));
+    }
+#undef RT
+    for (int k = 0; k < kStreams; ++k) CU(s, cudaStreamSynchronize(d.streams[k]));
+    float ms = 0;
+    CU(s, cudaEventElapsedTime(&ms, d.k0[0], d.k1[0]));
+    *kernel_ms = ms;
+    *nchunks_out = nch;
+    if (early) {
+        const int cnt = d.hfix[0];
+        if (cnt < 0 || cnt > n) return fail(s, TINYMPC_CUDA_ECUDA, "internal: corrupt result list of the fp64 pass");
+        if (cnt > fix_first)   // a wide band: fetch the rest of the list
+            CU(s, cudaMemcpy(d.hfix + 4 + fix_entry * (size_t)fix_first, static_cast<const int*>(d.fix.p) + 4 + fix_entry * (size_t)fix_first,
+                             sizeof(int) * fix_entry * (size_t)(cnt - fix_first), cudaMemcpyDeviceToHost));
+        for (int k = 0; k < cnt; ++k) {
+            const int* e = d.hfix + 4 + fix_entry * (size_t)k;
+            const size_t g = (size_t)lo + (size_t)e[0];
+            out.iter[g] = e[1];
+            out.status[g] = e[2];
+            std::memcpy(out.u0 + (size_t)f.nu * g, e + 3, sizeof(float) * f.nu);
+        }
+        *marked_out = cnt;
+    } else if (mixed) {
+        int q = 0;
+        CU(s, cudaMemcpy(&q, n_marked, sizeof(int), cudaMemcpyDeviceToHost));
+        *marked_out = q;
+    }
+    return TINYMPC_CUDA_OK;
+}
+
 // One device's share of a host batch: chunked H2D -> kernel -> D2H pipeline over kStreams streams.
 int run_shard(tinympc_cuda_solver* s, DeviceCtx& d, const tinympc_cuda_batch_in& in, const tinympc_cuda_batch_out& out, int lo, int hi,
               double* kernel_ms, int* nchunks_out, long long* marked_out) {
@@ -643,6 +889,18 @@ int run_shard(tinympc_cuda_solver* s, DeviceCtx& d, const tinympc_cuda_batch_in&
         int nst = s->chunks > 0 ? std::min(s->chunks, kMaxGranules) : (n >= (1 << 16) ? 0 : n / 16384);
         if (ke && ke->streaming && (!mixed || (ke64 && ke64->streaming)) && (nst == 0 || nst >= 2) && (ppb || f.shared_bounds_ok))
             return run_shard_streamed(s, d, ke, ke64, in, out, lo, hi, nst, kernel_ms, nchunks_out, marked_out);
+    }
+    // compact I/O: one launch chain behind an arrival watermark, when the kernels of the batch wait for the watermark and read
+    // the compact reference in place (chunks = 1 keeps the single chunked launch, fixer_sms >= 0 the concurrent exact-count pair)
+    if (compact && s->compact_streamed && !s->force_wpp && stream_memops().ok && !(mixed && s->fixer_sms >= 0) &&
+        (s->chunks >= 2 || (s->chunks <= 0 && n >= (1 << 16))) && (ppb || f.shared_bounds_ok)) {
+        const KernelEntry *ke = nullptr, *ke64 = nullptr;
+        const bool refs = in.xref_const || in.Xref || in.Uref;
+        // a compact reference must be read in place: an expansion kernel could not run next to the persistent launch that waits for it
+        const bool ck = compact_in_kernel(s, d, ppb, refs, n, &ke, &ke64);
+        const bool ok = in.xref_const ? ck : (ke && (!mixed || ke64));
+        if (ok && ke->streaming && ke->family == KF_TPP)
+            return run_shard_compact_streamed(s, d, ke, mixed ? ke64 : nullptr, in, out, lo, hi, kernel_ms, nchunks_out, marked_out);
     }
     // chunking: enough chunks to overlap copies with compute, each still many waves of the GPU.  Compact I/O moves ~120 bytes per
     // problem, so there is next to nothing to overlap and every extra chunk costs a partial last wave of the persistent kernel plus
@@ -773,6 +1031,7 @@ int tinympc_cuda_create(tinympc_cuda_solver** out, const int* devices, int n_dev
             cudaEventCreateWithFlags(&d.ev_join[k], cudaEventDisableTiming);
         }
         cudaEventCreateWithFlags(&d.ev_ctl, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&d.ev_pass, cudaEventDisableTiming);
         cudaEventCreate(&d.ev_p0); cudaEventCreate(&d.ev_p1); cudaEventCreate(&d.ev_p2);
         for (int k = 0; k < kStreams; ++k) cudaStreamCreateWithFlags(&d.streams[k], cudaStreamNonBlocking);
         for (int c = 0; c < kMaxChunks; ++c) { cudaEventCreate(&d.k0[c]); cudaEventCreate(&d.k1[c]); }
@@ -811,6 +1070,9 @@ int tinympc_cuda_destroy(tinympc_cuda_solver* s) {
             if (d.ev_join[k]) cudaEventDestroy(d.ev_join[k]);
         }
         if (d.ev_ctl) cudaEventDestroy(d.ev_ctl);
+        if (d.ev_pass) cudaEventDestroy(d.ev_pass);
+        if (d.hfix) cudaFreeHost(d.hfix);
+        d.fix.release();
         for (DevBuf* b : {&d.x0, &d.Xref, &d.Uref, &d.xmin, &d.xmax, &d.umin, &d.umax, &d.x, &d.u, &d.iter, &d.status, &d.res, &d.rho, &d.xrc, &d.u0}) b->release();
         for (auto& b : d.exp_xref) b.release();
         for (auto& b : d.exp_x) b.release();
@@ -1320,6 +1582,12 @@ int tinympc_cuda_set_option(tinympc_cuda_solver* s, const char* name, double val
         s->force_wpp = (int)value;
     } else if (n == "streamed") {
         s->streamed = value != 0;
+    } else if (n == "compact_streamed") {
+        s->compact_streamed = value != 0;
+    } else if (n == "compact_early_d2h") {
+        s->compact_early_d2h = value != 0;
+    } else if (n == "compact_in_kernel") {
+        s->compact_in_kernel = value != 0;
     } else if (n == "refill_min") {
         s->refill_min = (int)value;
     } else {

@@ -132,6 +132,14 @@ struct SolveParams {
     // none is busy).  Claim + input loads + tensor-memory parking are warp-wide code executed for however few lanes need it,
     // so sharing one pass between several lanes trades a little idle lane time for fewer passes.  1: refill at once; 0: adaptive.
     int refill_min;
+    // Compact I/O in the kernel, honoured by the kernels whose KernelEntry::compact_ok is set (for the others the library expands /
+    // gathers on the device around the launch and leaves these 0 / NULL):
+    //   xref_const  1: Xref holds ONE state per problem (batch*nx), which stands for every column of the horizon
+    //               (tinympc_cuda_batch_in::xref_const)
+    //   u0          not NULL: the only solution output is the first control, batch*nu (tinympc_cuda_batch_out::u0); x and u are
+    //               then not written (and may be NULL)
+    int xref_const;
+    float* u0;
 };
 
 constexpr int kAmbiguousBit = 0x100;

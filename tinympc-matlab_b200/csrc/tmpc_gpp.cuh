@@ -353,9 +353,15 @@ gpp_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ GppT
                 if (is_x) {
                     x0r = static_cast<T>(__ldg(prm.x0 + (size_t)prob * NX + row));
                     if (prm.Xref) {
-                        const float* src = prm.Xref + (size_t)prob * SXL + row;
+                        if (prm.xref_const) {   // compact reference input: one state per problem for every column of the horizon
+                            const float v = __ldg(prm.Xref + (size_t)prob * NX + row);
 #pragma unroll
-                        for (int s = 0; s < NH - 1; ++s) RF[s] = __ldg(src + (s + 1) * NX);
+                            for (int s = 0; s < NH - 1; ++s) RF[s] = v;
+                        } else {
+                            const float* src = prm.Xref + (size_t)prob * SXL + row;
+#pragma unroll
+                            for (int s = 0; s < NH - 1; ++s) RF[s] = __ldg(src + (s + 1) * NX);
+                        }
                     }
                 } else if (is_u) {
                     if (prm.Uref) {
@@ -647,7 +653,9 @@ gpp_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ GppT
         if (k >= max_iter) finish = true;
         if (active && finish) {
             // solution = (vnew, znew) (admm.cpp:364-376, 384-388)
-            if (!SESSION || prm.x != nullptr) {
+            if (!SESSION && prm.u0 != nullptr) {   // compact output: the first control is all the caller reads
+                if (is_u) prm.u0[(size_t)prob * NU + row] = static_cast<float>(V[0]);
+            } else if (!SESSION || prm.x != nullptr) {
             if (is_x) {
                 float* dst = prm.x + (size_t)prob * SXL + row;
                 dst[0] = static_cast<float>(V[NH - 1]);

@@ -40,6 +40,10 @@ struct KernelEntry {
     // instance has no session form (the warp-per-problem kernel serves the session)
     cudaError_t (*session_launch)(const SolveParams& p, int grid, size_t smem, cudaStream_t st, const double* master_pack, const PackLayout& L,
                                   double* ws, const WppLayout& W, int full);
+    // 1: honours SolveParams::xref_const (Xref = one state per problem, read in place of every column of the horizon) and
+    // SolveParams::u0 (first control as the only solution output); 0: the library expands a compact reference on the device
+    // before the launch and gathers u0 from the full trajectories after it
+    int compact_ok;
 };
 
 const KernelEntry* const* kernel_table(int* count);   // defined in gen/tmpc_table.cu
@@ -88,7 +92,8 @@ const KernelEntry* const* kernel_table(int* count);   // defined in gen/tmpc_tab
     }                                                                                                               \
     extern const KernelEntry SYM = {#SYM, KF_TPP, CFG::NX, CFG::NU, CFG::NH, FEATV, BITS, CFG::REFMODE,             \
                                     CFG::PPB ? 1 : 0, CFG::FB ? 1 : 0, CFG::AFF ? 1 : 0, CFG::BLOCK, VAR, 1, SYM##_smem, SYM##_prepare, \
-                                    SYM##_occ, SYM##_launch, CFG::CONSTR ? 1 : 0, CFG::SCS, CFG::SCD, CFG::UCS, CFG::UCD, CFG::NSL, CFG::NIL};                                 \
+                                    SYM##_occ, SYM##_launch, CFG::CONSTR ? 1 : 0, CFG::SCS, CFG::SCD, CFG::UCS, CFG::UCD, CFG::NSL, CFG::NIL, \
+                                    0, nullptr, 1};                                                                 \
     }
 
 // mixed-precision rocket-family kernel (tmpc_tpp4.cuh)
@@ -146,5 +151,5 @@ const KernelEntry* const* kernel_table(int* count);   // defined in gen/tmpc_tab
     extern const KernelEntry SYM = {#SYM, KF_TPP, CFG::NX, CFG::NU, CFG::NH, CFG::CONSTR ? 1 : (CFG::ADAPT ? 2 : 0) /* FEAT_CONSTR : FEAT_ADAPT : FEAT_BOX */, 64, 1 /* serves batches with and without references */, \
                                     0, 0, 1, CFG::BLOCK, VAR, 1, SYM##_smem, SYM##_prepare,                        \
                                     SYM##_occ, SYM##_launch, CFG::CONSTR ? 1 : 0, CFG::SCS, CFG::SCD, CFG::UCS, CFG::UCD, CFG::NSL, CFG::NIL, CFG::GS,     \
-                                    (CFG::ADAPT || CFG::CONSTR) ? nullptr : SYM##_session};                         \
+                                    (CFG::ADAPT || CFG::CONSTR) ? nullptr : SYM##_session, 1};                      \
     }

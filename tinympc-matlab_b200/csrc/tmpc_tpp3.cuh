@@ -383,8 +383,10 @@ tpp3_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ typ
                     res_px = res_dx = res_pu = res_du = 0;
                 }
                 const bool have_xref = C::REFS && prm.Xref != nullptr, have_uref = C::REFS && prm.Uref != nullptr;
+                // compact reference input (SolveParams::xref_const): one state per problem stands for every column of the horizon
+                const bool xconst = have_xref && prm.xref_const != 0;
                 if (mine) {
-                    if (have_xref) {   // pull the whole problem towards L2 first: the blocks below then cost one DRAM round trip
+                    if (have_xref && !xconst) {   // pull the whole problem towards L2 first: the blocks below then cost one DRAM round trip
                         const char* s = reinterpret_cast<const char*>(prm.Xref + (size_t)prob * SXL);
 #pragma unroll
                         for (int b = 0; b <= (SXL * 4 + 127) / 128; ++b) prefetch_l2(s + (b * 128 < SXL * 4 ? b * 128 : SXL * 4 - 4));
@@ -400,7 +402,7 @@ tpp3_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ typ
                 // (tcgen05.st has no lane mask: read - select - write, warp-wide)
                 if (have_xref) {
                     constexpr int GX = steps_per_block(NH, NX, 64);
-                    const float* src = prm.Xref + (size_t)prob * SXL;
+                    const float* src = prm.Xref + (size_t)prob * (xconst ? NX : SXL);
                     T xr_last[NX];
 #pragma unroll
                     for (int r = 0; r < NX; ++r) xr_last[r] = 0;
@@ -409,7 +411,16 @@ tpp3_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ typ
                         float buf[GX * NX];
 #pragma unroll
                         for (int e = 0; e < GX * NX; ++e) buf[e] = 0.f;
-                        if (mine) load_span<GX * NX, vec_width(SXL, GX * NX)>(src + b * GX * NX, [&](int e, float v) { buf[e] = v; });
+                        if (mine) {
+                            if (xconst) {
+                                load_span<NX, vec_width(NX, NX)>(src, [&](int e, float v) {
+#pragma unroll
+                                    for (int g = 0; g < GX; ++g) buf[g * NX + e] = v;
+                                });
+                            } else {
+                                load_span<GX * NX, vec_width(SXL, GX * NX)>(src + b * GX * NX, [&](int e, float v) { buf[e] = v; });
+                            }
+                        }
 #pragma unroll
                         for (int r = 0; r < NX; ++r) xr_last[r] = buf[(GX - 1) * NX + r];   // after the last block: xref_N
 #pragma unroll
@@ -858,7 +869,8 @@ tpp3_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ typ
             queue_push(prm, amb, prob, lane);
             if (amb) { fin = false; active = false; last_k = k; }
         }
-        if (__any_sync(FULL, fin)) {
+        const bool u0_only = prm.u0 != nullptr;   // compact output (SolveParams::u0): x and u are not written
+        if (!u0_only && __any_sync(FULL, fin)) {
             // solution = (vnew, znew) = clamp of the stored pre-clamp values (the T read is warp-collective)
 #pragma unroll 1
             for (int i = 0; i < NH; ++i) {
@@ -878,12 +890,13 @@ tpp3_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ typ
         }
         if (fin) {
 #pragma unroll 1
-            for (int i = 0; i < NH - 1; ++i) {
+            for (int i = 0; i < (u0_only ? 1 : NH - 1); ++i) {
                 VU z;
 #pragma unroll
                 for (int j = 0; j < NU / 2; ++j) { P lo, hi; ub_pair(i, j, pbu, lo, hi); z.p[j] = clampv(TZ.getp(i, j), lo, hi); }
                 if constexpr (NU & 1) { T lo, hi; ub_tail(i, pbu, lo, hi); z.t = clampv(TZ.gett(i), lo, hi); }
-                store_span<NU, vec_width(SUL, NU)>(prm.u + pbu + i * NU, [&](int a) { return z.get(a); });
+                if (u0_only) store_span<NU, vec_width(NU, NU)>(prm.u0 + (size_t)prob * NU, [&](int a) { return z.get(a); });
+                else store_span<NU, vec_width(SUL, NU)>(prm.u + pbu + i * NU, [&](int a) { return z.get(a); });
             }
             prm.iter[prob] = k;
             prm.status[prob] = st;
