@@ -374,18 +374,14 @@ def test_compact_io_matches_full_trajectories(B, mixed, pipeline, capi, oracle_m
     s.set_family(cases.family_from_spec(p, oracle_mod.get_cache(p, "port")))
     full = s.solve_batch(b.x0, b.Xref, None)
     xc = np.ascontiguousarray(b.Xref[:, 0, :])
-    for early in (1, 0, 1):   # (the control words are reused from call to call)
-        # exact-count mode of the streamed form: result copies under the fp64 pass + its packed result list, or all copies at the end
-        s.set_option("compact_early_d2h", early)
+    for _ in range(2):   # twice: the control words are reused
         c = s.solve_batch(b.x0, xref_const=xc, compact_out=True)
         assert (s.last_timing()["chunks"] >= 2) == (pipeline == "streamed" and B >= 65536), s.last_timing()
         if mixed > 0:
             assert s.last_marked > 0 and "+" in s.last_kernel, (s.last_marked, s.last_kernel)
         assert set(c) == {"u0", "iter", "status"}
-        assert np.array_equal(c["iter"], full["iter"]) and np.array_equal(c["status"], full["status"]), f"early={early}"
-        assert np.array_equal(c["u0"], full["u"][:, 0, :]), f"early={early}"
-    assert np.array_equal(c["iter"], full["iter"]) and np.array_equal(c["status"], full["status"])
-    assert np.array_equal(c["u0"], full["u"][:, 0, :])
+        assert np.array_equal(c["iter"], full["iter"]) and np.array_equal(c["status"], full["status"])
+        assert np.array_equal(c["u0"], full["u"][:, 0, :])
     # mixed forms: compact input with full output, full input with compact output
     a = s.solve_batch(b.x0, xref_const=xc)
     assert np.array_equal(a["x"], full["x"]) and np.array_equal(a["u"], full["u"])
@@ -403,27 +399,6 @@ def test_compact_io_matches_full_trajectories(B, mixed, pipeline, capi, oracle_m
     with pytest.raises(capi.TinympcCudaError):
         s.solve_batch(b.x0, b.Xref, None, xref_const=xc)
     s.close()
-
-
-def test_compact_streamed_wide_band(capi, oracle_mod, problems):
-    """A band so wide that the fp64 pass re-solves more problems than the first fetch of its packed result list holds
-    (run_shard_compact_streamed: the rest of the list is fetched separately)."""
-    p = problems.quadrotor()
-    B = 70001
-    b = problems.make_batch(p, B, 1.0, seed=23)
-    xc = np.ascontiguousarray(b.Xref[:, 0, :])
-    s = capi.CudaSolver()
-    s.set_option("mixed", 0.25)
-    s.set_family(cases.family_from_spec(p, oracle_mod.get_cache(p, "port")))
-    s.set_option("chunks", 1)
-    s.set_option("fixer_sms", -1)
-    full = s.solve_batch(b.x0, b.Xref, None)
-    s.set_option("chunks", 0)
-    c = s.solve_batch(b.x0, xref_const=xc, compact_out=True)
-    assert s.last_timing()["chunks"] >= 2 and s.last_marked > max(1024, B // 16), (s.last_timing(), s.last_marked)
-    s.close()
-    assert np.array_equal(c["iter"], full["iter"]) and np.array_equal(c["status"], full["status"])
-    assert np.array_equal(c["u0"], full["u"][:, 0, :])
 
 
 @pytest.mark.parametrize("family,precision,B", [("cartpole", 32, 3000), ("cartpole", 64, 3000), ("quadrotor", 64, 3000), ("quadrotor", 32, 60000),

@@ -68,10 +68,6 @@ struct DeviceCtx {
     DevBuf wpp_scratch[kStreams + 1];   // warp-per-problem workspaces (one per pipeline stream + the device/workspace entry)
     DevBuf ref_scratch64[kStreams + 1]; // mixed mode: reference terms of the fp64 re-solve pass
     DevBuf marked[kStreams + 1];        // mixed mode: indices of the problems the fp32 pass marked ambiguous (two-pass form) / the queue
-    DevBuf fix;                         // compact streamed pipeline: results of the fp64 pass as a packed list (run_shard_compact_streamed)
-    int* hfix = nullptr;                // ... and its pinned host copy
-    size_t hfix_cap = 0;
-    cudaEvent_t ev_pass = nullptr;      // ... end of the first pass: the early result copies wait for it
     // exact-count mode, concurrent form: per slot {q_tail, producer CTAs done, consumer ticket counter, pad}
     int* qctl = nullptr;                // 4 * kMaxChunks ints, indexed like the work counters (chunk index; the last one = device entry)
     cudaStream_t fix_stream[kStreams + 1] = {nullptr, nullptr, nullptr, nullptr};   // the fp64 consumer launches
@@ -107,8 +103,6 @@ struct tinympc_cuda_solver {
     int streamed = 1;                  // option "streamed": 1 = single-launch streamed host pipeline where it applies, 0 = chunked launches
     int compact_streamed = 1;          // option "compact_streamed": compact host I/O through one launch chain behind an arrival watermark
                                        // (run_shard_compact_streamed); 0 = the chunked pipeline
-    int compact_early_d2h = 1;         // option "compact_early_d2h": exact-count mode of that pipeline -- the results of the first pass go
-                                       // back while the fp64 pass runs, which returns a packed list the host scatters over them
     int compact_in_kernel = 1;         // option "compact_in_kernel": kernels read tinympc_cuda_batch_in::xref_const in place where they can;
                                        // 0 = always replicate it over the horizon on the device first
     double mixed_band = 0;             // option "mixed": > 0 = fp32 pass + fp64 re-solve of the problems whose termination decision
@@ -228,20 +222,6 @@ __global__ void gather_u0_kernel(const float* __restrict__ u, float* __restrict_
     if (i >= total) return;
     const size_t b = i / nu;
     u0[i] = u[b * su + (i - b * nu)];
-}
-
-// compact streamed pipeline: what the fp64 pass produced, as a packed list the host scatters over the early result copies.
-// fix[0] = number of entries; entry k at fix + 4 + k * (3 + nu): problem index, iter, status, u0[nu].
-__global__ void pack_fix_kernel(const int* __restrict__ list, const int* __restrict__ count, const int* __restrict__ iter,
-                                const int* __restrict__ status, const float* __restrict__ u0, int nu, int* __restrict__ fix) {
-    const int n = *count;
-    if (blockIdx.x == 0 && threadIdx.x == 0) fix[0] = n;
-    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
-        const int i = list[k];
-        int* e = fix + 4 + (size_t)k * (3 + nu);
-        e[0] = i; e[1] = iter[i]; e[2] = status[i];
-        for (int a = 0; a < nu; ++a) e[3 + a] = __float_as_int(u0[(size_t)i * nu + a]);
-    }
 }
 
 int upload_family(tinympc_cuda_solver* s) {
@@ -673,11 +653,16 @@ int run_shard_streamed(tinympc_cuda_solver* s, DeviceCtx& d, const KernelEntry* 
 // The chunked pipeline pays for every chunk a partial last wave of the persistent kernel and the latency-bound end of its fp64
 // pass, and its first launch waits for the first chunk's upload; here stream 0 uploads the inputs in a few chunks of doubling
 // size, each followed by a write of the arrival watermark, and stream 1 runs the solve over the WHOLE shard -- first kernel
-// (lanes start a claimed problem once the watermark covers it; the kernels read the compact reference in place, so no
-// expansion kernel has to find room next to a persistent launch), then, in the exact-count mode, compaction + fp64 pass,
-// then the u0 gather and the result copies.  The link delivers ~50 GB/s, the kernel consumes ~7: after the first chunk
-// (1/64 of the shard) the upload is entirely hidden.  Enqueue order as in run_shard_streamed: every copy the kernel waits
-// for is enqueued before its launch.
+// (lanes start a claimed problem once the watermark covers it), then, in the exact-count mode, compaction + fp64 pass, then the
+// result copies.  Kernels with KernelEntry::compact_ok read the compact reference in place and write the first control alone,
+// so no expansion kernel has to find room next to a persistent launch that waits for it, and there is no trajectory scratch and
+// no gather.  The link delivers ~55 GB/s, the kernel consumes ~7: after the first chunk (1/64 of the shard) the upload is
+// hidden, and what is left of the bus is the 24 bytes per problem that come back (0.45 ms per 2^20 problems).  Enqueue order as
+// in run_shard_streamed: every copy the kernel waits for is enqueued before its launch.
+// Measured (quadrotor, 2^20 problems, exact-count mode, profiles/r02/e2e_compact_sweep.jsonl): 15.06 ms end to end against 14.52 ms
+// of kernels (chunked pipeline with expansion / gather kernels: 17.1 ms).  Tried, not kept: result copies started right after the
+// first pass, under the fp64 pass, which then returns a packed list {index, iter, status, u0} for the host to scatter over
+// them -- the scatter of ~14 000 entries over three 4-25 MB host arrays costs more (15.34 ms) than the 0.45 ms of copies it hides.
 int run_shard_compact_streamed(tinympc_cuda_solver* s, DeviceCtx& d, const KernelEntry* ke, const KernelEntry* ke64, const tinympc_cuda_batch_in& in,
                                const tinympc_cuda_batch_out& out, int lo, int hi, double* kernel_ms, int* nchunks_out, long long* marked_out) {
     const Family& f = s->fam;
@@ -716,23 +701,6 @@ int run_shard_compact_streamed(tinympc_cuda_solver* s, DeviceCtx& d, const Kerne
     }
     DevBuf& list = d.marked[0];
     if (mixed) CU(s, list.reserve(sizeof(int) * (size_t)n));
-    // Exact-count mode with compact output: everything but the ~1 % of marked problems is final after the first pass, so the
-    // result copies (u0, iter, status: the whole D2H volume) start then, on the third stream, under the fp64 pass.  That pass
-    // returns its results as a packed list {index, iter, status, u0} which the host scatters over the copied arrays.  (The copies
-    // may see a marked problem's entries before or after the fp64 pass rewrites them; either way the list overrides them.)
-    const bool early = mixed && u0_direct && s->compact_early_d2h && !out.residuals && !out.rho;
-    const size_t fix_entry = 3 + (size_t)f.nu, fix_words = 4 + fix_entry * (size_t)n;
-    const int fix_first = std::max(1024, n / 16);          // entries fetched with the header; more only if the band is wide
-    if (early) {
-        CU(s, d.fix.reserve(sizeof(int) * fix_words));
-        if (d.hfix_cap < fix_words) {
-            if (d.hfix) cudaFreeHost(d.hfix);
-            d.hfix = nullptr; d.hfix_cap = 0;
-            CU(s, cudaMallocHost(reinterpret_cast<void**>(&d.hfix), sizeof(int) * fix_words));
-            d.hfix_cap = fix_words;
-        }
-    }
-
     const int bits = ke->dtype_bits;
     SolveParams p = f.base;
     p.pack = bits == 64 ? (const void*)((const double*)d.pack64 + f.L.cold) : (const void*)((const float*)d.pack32 + f.L.cold);
@@ -780,14 +748,6 @@ int run_shard_compact_streamed(tinympc_cuda_solver* s, DeviceCtx& d, const Kerne
         p.amb_band = static_cast<float>(s->mixed_band);
         int rc = launch_tpp(s, d, ke, p, d.ref_scratch[0], 32, ctl, s_k);
         if (rc) return sync_fail(rc);
-        if (early) {
-            cudaStream_t s_out = d.streams[2];
-            RT(cudaEventRecord(d.ev_pass, s_k));
-            RT(cudaStreamWaitEvent(s_out, d.ev_pass, 0));
-            RT(cudaMemcpyAsync(out.u0 + (size_t)f.nu * lo, d.u0.p, sizeof(float) * f.nu * n, cudaMemcpyDeviceToHost, s_out));
-            RT(cudaMemcpyAsync(out.iter + lo, d.iter.p, sizeof(int) * n, cudaMemcpyDeviceToHost, s_out));
-            RT(cudaMemcpyAsync(out.status + lo, d.status.p, sizeof(int) * n, cudaMemcpyDeviceToHost, s_out));
-        }
         RT(cudaMemsetAsync(n_marked, 0, sizeof(int), s_k));
         collect_marked_kernel<<<(n + 255) / 256, 256, 0, s_k>>>(p.status, n, static_cast<int*>(list.p), n_marked);
         RT(cudaGetLastError());
@@ -808,44 +768,21 @@ int run_shard_compact_streamed(tinympc_cuda_solver* s, DeviceCtx& d, const Kerne
         RT(cudaGetLastError());
         s->launches += 1;
     }
-    if (early) {
-        pack_fix_kernel<<<64, 256, 0, s_k>>>(static_cast<const int*>(list.p), n_marked, p.iter, p.status, p.u0, f.nu, static_cast<int*>(d.fix.p));
-        RT(cudaGetLastError());
-        s->launches += 1;
-    }
     RT(cudaEventRecord(d.k1[0], s_k));
-    if (early) {
-        RT(cudaMemcpyAsync(d.hfix, d.fix.p, sizeof(int) * (4 + fix_entry * (size_t)std::min(n, fix_first)), cudaMemcpyDeviceToHost, s_k));
-    } else {
-        if (out.x) RT(cudaMemcpyAsync(out.x + sx * lo, d.x.p, sizeof(float) * sx * n, cudaMemcpyDeviceToHost, s_k));
-        if (out.u) RT(cudaMemcpyAsync(out.u + su * lo, d.u.p, sizeof(float) * su * n, cudaMemcpyDeviceToHost, s_k));
-        if (out.u0) RT(cudaMemcpyAsync(out.u0 + (size_t)f.nu * lo, d.u0.p, sizeof(float) * f.nu * n, cudaMemcpyDeviceToHost, s_k));
-        RT(cudaMemcpyAsync(out.iter + lo, d.iter.p, sizeof(int) * n, cudaMemcpyDeviceToHost, s_k));
-        RT(cudaMemcpyAsync(out.status + lo, d.status.p, sizeof(int) * n, cudaMemcpyDeviceToHost, s_k));
-        if (out.residuals) RT(cudaMemcpyAsync(out.residuals + 4 * (size_t)lo, d.res.p, sizeof(float) * 4 * n, cudaMemcpyDeviceToHost, s_k));
-        if (out.rho) RT(cudaMemcpyAsync(out.rho + lo, d.rho.p, sizeof(float) * n, cudaMemcpyDeviceToHost, s_k));
-    }
+    if (out.x) RT(cudaMemcpyAsync(out.x + sx * lo, d.x.p, sizeof(float) * sx * n, cudaMemcpyDeviceToHost, s_k));
+    if (out.u) RT(cudaMemcpyAsync(out.u + su * lo, d.u.p, sizeof(float) * su * n, cudaMemcpyDeviceToHost, s_k));
+    if (out.u0) RT(cudaMemcpyAsync(out.u0 + (size_t)f.nu * lo, d.u0.p, sizeof(float) * f.nu * n, cudaMemcpyDeviceToHost, s_k));
+    RT(cudaMemcpyAsync(out.iter + lo, d.iter.p, sizeof(int) * n, cudaMemcpyDeviceToHost, s_k));
+    RT(cudaMemcpyAsync(out.status + lo, d.status.p, sizeof(int) * n, cudaMemcpyDeviceToHost, s_k));
+    if (out.residuals) RT(cudaMemcpyAsync(out.residuals + 4 * (size_t)lo, d.res.p, sizeof(float) * 4 * n, cudaMemcpyDeviceToHost, s_k));
+    if (out.rho) RT(cudaMemcpyAsync(out.rho + lo, d.rho.p, sizeof(float) * n, cudaMemcpyDeviceToHost, s_k));
 #undef RT
     for (int k = 0; k < kStreams; ++k) CU(s, cudaStreamSynchronize(d.streams[k]));
     float ms = 0;
     CU(s, cudaEventElapsedTime(&ms, d.k0[0], d.k1[0]));
     *kernel_ms = ms;
     *nchunks_out = nch;
-    if (early) {
-        const int cnt = d.hfix[0];
-        if (cnt < 0 || cnt > n) return fail(s, TINYMPC_CUDA_ECUDA, "internal: corrupt result list of the fp64 pass");
-        if (cnt > fix_first)   // a wide band: fetch the rest of the list
-            CU(s, cudaMemcpy(d.hfix + 4 + fix_entry * (size_t)fix_first, static_cast<const int*>(d.fix.p) + 4 + fix_entry * (size_t)fix_first,
-                             sizeof(int) * fix_entry * (size_t)(cnt - fix_first), cudaMemcpyDeviceToHost));
-        for (int k = 0; k < cnt; ++k) {
-            const int* e = d.hfix + 4 + fix_entry * (size_t)k;
-            const size_t g = (size_t)lo + (size_t)e[0];
-            out.iter[g] = e[1];
-            out.status[g] = e[2];
-            std::memcpy(out.u0 + (size_t)f.nu * g, e + 3, sizeof(float) * f.nu);
-        }
-        *marked_out = cnt;
-    } else if (mixed) {
+    if (mixed) {
         int q = 0;
         CU(s, cudaMemcpy(&q, n_marked, sizeof(int), cudaMemcpyDeviceToHost));
         *marked_out = q;
@@ -1031,7 +968,6 @@ int tinympc_cuda_create(tinympc_cuda_solver** out, const int* devices, int n_dev
             cudaEventCreateWithFlags(&d.ev_join[k], cudaEventDisableTiming);
         }
         cudaEventCreateWithFlags(&d.ev_ctl, cudaEventDisableTiming);
-        cudaEventCreateWithFlags(&d.ev_pass, cudaEventDisableTiming);
         cudaEventCreate(&d.ev_p0); cudaEventCreate(&d.ev_p1); cudaEventCreate(&d.ev_p2);
         for (int k = 0; k < kStreams; ++k) cudaStreamCreateWithFlags(&d.streams[k], cudaStreamNonBlocking);
         for (int c = 0; c < kMaxChunks; ++c) { cudaEventCreate(&d.k0[c]); cudaEventCreate(&d.k1[c]); }
@@ -1070,9 +1006,6 @@ int tinympc_cuda_destroy(tinympc_cuda_solver* s) {
             if (d.ev_join[k]) cudaEventDestroy(d.ev_join[k]);
         }
         if (d.ev_ctl) cudaEventDestroy(d.ev_ctl);
-        if (d.ev_pass) cudaEventDestroy(d.ev_pass);
-        if (d.hfix) cudaFreeHost(d.hfix);
-        d.fix.release();
         for (DevBuf* b : {&d.x0, &d.Xref, &d.Uref, &d.xmin, &d.xmax, &d.umin, &d.umax, &d.x, &d.u, &d.iter, &d.status, &d.res, &d.rho, &d.xrc, &d.u0}) b->release();
         for (auto& b : d.exp_xref) b.release();
         for (auto& b : d.exp_x) b.release();
@@ -1584,8 +1517,6 @@ int tinympc_cuda_set_option(tinympc_cuda_solver* s, const char* name, double val
         s->streamed = value != 0;
     } else if (n == "compact_streamed") {
         s->compact_streamed = value != 0;
-    } else if (n == "compact_early_d2h") {
-        s->compact_early_d2h = value != 0;
     } else if (n == "compact_in_kernel") {
         s->compact_in_kernel = value != 0;
     } else if (n == "refill_min") {
