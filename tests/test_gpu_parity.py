@@ -382,6 +382,17 @@ def test_compact_io_matches_full_trajectories(B, mixed, pipeline, capi, oracle_m
         assert set(c) == {"u0", "iter", "status"}
         assert np.array_equal(c["iter"], full["iter"]) and np.array_equal(c["status"], full["status"])
         assert np.array_equal(c["u0"], full["u"][:, 0, :])
+    # pinned result arrays: in the exact-count mode of the streamed form the results of the first pass are copied back under the
+    # fp64 pass, whose results a kernel then writes over them through the device alias of the host arrays (compact_early_d2h)
+    pinned = dict(u0=torch.empty((B, p.nu)).pin_memory().numpy(), iter=torch.empty(B, dtype=torch.int32).pin_memory().numpy(),
+                  status=torch.empty(B, dtype=torch.int32).pin_memory().numpy())
+    for early in (1, 0, 1):
+        s.set_option("compact_early_d2h", early)
+        for a in pinned.values():
+            a.fill(-7)
+        s.solve_batch(b.x0, xref_const=xc, out=pinned, compact_out=True)
+        assert np.array_equal(pinned["iter"], full["iter"]) and np.array_equal(pinned["status"], full["status"]), f"early={early}"
+        assert np.array_equal(pinned["u0"], full["u"][:, 0, :]), f"early={early}"
     # mixed forms: compact input with full output, full input with compact output
     a = s.solve_batch(b.x0, xref_const=xc)
     assert np.array_equal(a["x"], full["x"]) and np.array_equal(a["u"], full["u"])

@@ -68,6 +68,7 @@ struct DeviceCtx {
     DevBuf wpp_scratch[kStreams + 1];   // warp-per-problem workspaces (one per pipeline stream + the device/workspace entry)
     DevBuf ref_scratch64[kStreams + 1]; // mixed mode: reference terms of the fp64 re-solve pass
     DevBuf marked[kStreams + 1];        // mixed mode: indices of the problems the fp32 pass marked ambiguous (two-pass form) / the queue
+    cudaEvent_t ev_pass = nullptr, ev_copied = nullptr;   // compact streamed pipeline: end of the first pass / of the early result copies
     // exact-count mode, concurrent form: per slot {q_tail, producer CTAs done, consumer ticket counter, pad}
     int* qctl = nullptr;                // 4 * kMaxChunks ints, indexed like the work counters (chunk index; the last one = device entry)
     cudaStream_t fix_stream[kStreams + 1] = {nullptr, nullptr, nullptr, nullptr};   // the fp64 consumer launches
@@ -103,6 +104,8 @@ struct tinympc_cuda_solver {
     int streamed = 1;                  // option "streamed": 1 = single-launch streamed host pipeline where it applies, 0 = chunked launches
     int compact_streamed = 1;          // option "compact_streamed": compact host I/O through one launch chain behind an arrival watermark
                                        // (run_shard_compact_streamed); 0 = the chunked pipeline
+    int compact_early_d2h = 1;         // option "compact_early_d2h": exact-count mode of that pipeline with pinned result arrays -- the results
+                                       // of the first pass are copied back under the fp64 pass, whose results a kernel then writes over them
     int compact_in_kernel = 1;         // option "compact_in_kernel": kernels read tinympc_cuda_batch_in::xref_const in place where they can;
                                        // 0 = always replicate it over the horizon on the device first
     double mixed_band = 0;             // option "mixed": > 0 = fp32 pass + fp64 re-solve of the problems whose termination decision
@@ -222,6 +225,30 @@ __global__ void gather_u0_kernel(const float* __restrict__ u, float* __restrict_
     if (i >= total) return;
     const size_t b = i / nu;
     u0[i] = u[b * su + (i - b * nu)];
+}
+
+// compact streamed pipeline, exact-count mode: the results of the fp64 pass (the marked problems) written straight into the caller's
+// pinned host arrays, over the copies of the first pass's results that are already there (hu0 / hiter / hstatus: device aliases of
+// those host arrays).  ~1 % of the batch, one thread per marked problem.
+__global__ void scatter_marked_to_host_kernel(const int* __restrict__ list, const int* __restrict__ count, const int* __restrict__ iter,
+                                              const int* __restrict__ status, const float* __restrict__ u0, int nu,
+                                              int* __restrict__ hiter, int* __restrict__ hstatus, float* __restrict__ hu0) {
+    const int n = *count;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const int i = list[k];
+        hiter[i] = iter[i];
+        hstatus[i] = status[i];
+        for (int a = 0; a < nu; ++a) hu0[(size_t)i * nu + a] = u0[(size_t)i * nu + a];
+    }
+}
+
+// device alias of a pinned (page-locked, mapped) host pointer; false for pageable memory
+bool host_alias(const void* p, void** alias) {
+    cudaPointerAttributes a{};
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    if (a.type != cudaMemoryTypeHost || a.devicePointer == nullptr) return false;
+    *alias = a.devicePointer;
+    return true;
 }
 
 int upload_family(tinympc_cuda_solver* s) {
@@ -701,6 +728,13 @@ int run_shard_compact_streamed(tinympc_cuda_solver* s, DeviceCtx& d, const Kerne
     }
     DevBuf& list = d.marked[0];
     if (mixed) CU(s, list.reserve(sizeof(int) * (size_t)n));
+    // Exact-count mode with compact output into PINNED host arrays: all but the ~1 % of marked problems is final after the first
+    // pass, so the result copies (the whole D2H volume) start then, on the third stream, under the fp64 pass; once both are done a
+    // small kernel writes the fp64 pass's results over them through the device alias of the host arrays.  (Scattering a packed
+    // result list on the host instead was tried: ~14 000 entries over three 4-17 MB arrays cost more than the copies hide.)
+    void *hu0 = nullptr, *hiter = nullptr, *hstatus = nullptr;
+    const bool early = mixed && u0_direct && s->compact_early_d2h && !out.residuals && !out.rho &&
+                       host_alias(out.u0, &hu0) && host_alias(out.iter, &hiter) && host_alias(out.status, &hstatus);
     const int bits = ke->dtype_bits;
     SolveParams p = f.base;
     p.pack = bits == 64 ? (const void*)((const double*)d.pack64 + f.L.cold) : (const void*)((const float*)d.pack32 + f.L.cold);
@@ -748,6 +782,15 @@ int run_shard_compact_streamed(tinympc_cuda_solver* s, DeviceCtx& d, const Kerne
         p.amb_band = static_cast<float>(s->mixed_band);
         int rc = launch_tpp(s, d, ke, p, d.ref_scratch[0], 32, ctl, s_k);
         if (rc) return sync_fail(rc);
+        if (early) {
+            cudaStream_t s_out = d.streams[2];
+            RT(cudaEventRecord(d.ev_pass, s_k));
+            RT(cudaStreamWaitEvent(s_out, d.ev_pass, 0));
+            RT(cudaMemcpyAsync(out.u0 + (size_t)f.nu * lo, d.u0.p, sizeof(float) * f.nu * n, cudaMemcpyDeviceToHost, s_out));
+            RT(cudaMemcpyAsync(out.iter + lo, d.iter.p, sizeof(int) * n, cudaMemcpyDeviceToHost, s_out));
+            RT(cudaMemcpyAsync(out.status + lo, d.status.p, sizeof(int) * n, cudaMemcpyDeviceToHost, s_out));
+            RT(cudaEventRecord(d.ev_copied, s_out));
+        }
         RT(cudaMemsetAsync(n_marked, 0, sizeof(int), s_k));
         collect_marked_kernel<<<(n + 255) / 256, 256, 0, s_k>>>(p.status, n, static_cast<int*>(list.p), n_marked);
         RT(cudaGetLastError());
@@ -769,13 +812,22 @@ int run_shard_compact_streamed(tinympc_cuda_solver* s, DeviceCtx& d, const Kerne
         s->launches += 1;
     }
     RT(cudaEventRecord(d.k1[0], s_k));
-    if (out.x) RT(cudaMemcpyAsync(out.x + sx * lo, d.x.p, sizeof(float) * sx * n, cudaMemcpyDeviceToHost, s_k));
-    if (out.u) RT(cudaMemcpyAsync(out.u + su * lo, d.u.p, sizeof(float) * su * n, cudaMemcpyDeviceToHost, s_k));
-    if (out.u0) RT(cudaMemcpyAsync(out.u0 + (size_t)f.nu * lo, d.u0.p, sizeof(float) * f.nu * n, cudaMemcpyDeviceToHost, s_k));
-    RT(cudaMemcpyAsync(out.iter + lo, d.iter.p, sizeof(int) * n, cudaMemcpyDeviceToHost, s_k));
-    RT(cudaMemcpyAsync(out.status + lo, d.status.p, sizeof(int) * n, cudaMemcpyDeviceToHost, s_k));
-    if (out.residuals) RT(cudaMemcpyAsync(out.residuals + 4 * (size_t)lo, d.res.p, sizeof(float) * 4 * n, cudaMemcpyDeviceToHost, s_k));
-    if (out.rho) RT(cudaMemcpyAsync(out.rho + lo, d.rho.p, sizeof(float) * n, cudaMemcpyDeviceToHost, s_k));
+    if (early) {
+        RT(cudaStreamWaitEvent(s_k, d.ev_copied, 0));
+        scatter_marked_to_host_kernel<<<32, 256, 0, s_k>>>(static_cast<const int*>(list.p), n_marked, p.iter, p.status, p.u0, f.nu,
+                                                           static_cast<int*>(hiter) + lo, static_cast<int*>(hstatus) + lo,
+                                                           static_cast<float*>(hu0) + (size_t)f.nu * lo);
+        RT(cudaGetLastError());
+        s->launches += 1;
+    } else {
+        if (out.x) RT(cudaMemcpyAsync(out.x + sx * lo, d.x.p, sizeof(float) * sx * n, cudaMemcpyDeviceToHost, s_k));
+        if (out.u) RT(cudaMemcpyAsync(out.u + su * lo, d.u.p, sizeof(float) * su * n, cudaMemcpyDeviceToHost, s_k));
+        if (out.u0) RT(cudaMemcpyAsync(out.u0 + (size_t)f.nu * lo, d.u0.p, sizeof(float) * f.nu * n, cudaMemcpyDeviceToHost, s_k));
+        RT(cudaMemcpyAsync(out.iter + lo, d.iter.p, sizeof(int) * n, cudaMemcpyDeviceToHost, s_k));
+        RT(cudaMemcpyAsync(out.status + lo, d.status.p, sizeof(int) * n, cudaMemcpyDeviceToHost, s_k));
+        if (out.residuals) RT(cudaMemcpyAsync(out.residuals + 4 * (size_t)lo, d.res.p, sizeof(float) * 4 * n, cudaMemcpyDeviceToHost, s_k));
+        if (out.rho) RT(cudaMemcpyAsync(out.rho + lo, d.rho.p, sizeof(float) * n, cudaMemcpyDeviceToHost, s_k));
+    }
 #undef RT
     for (int k = 0; k < kStreams; ++k) CU(s, cudaStreamSynchronize(d.streams[k]));
     float ms = 0;
@@ -968,6 +1020,8 @@ int tinympc_cuda_create(tinympc_cuda_solver** out, const int* devices, int n_dev
             cudaEventCreateWithFlags(&d.ev_join[k], cudaEventDisableTiming);
         }
         cudaEventCreateWithFlags(&d.ev_ctl, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&d.ev_pass, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&d.ev_copied, cudaEventDisableTiming);
         cudaEventCreate(&d.ev_p0); cudaEventCreate(&d.ev_p1); cudaEventCreate(&d.ev_p2);
         for (int k = 0; k < kStreams; ++k) cudaStreamCreateWithFlags(&d.streams[k], cudaStreamNonBlocking);
         for (int c = 0; c < kMaxChunks; ++c) { cudaEventCreate(&d.k0[c]); cudaEventCreate(&d.k1[c]); }
@@ -1006,6 +1060,8 @@ int tinympc_cuda_destroy(tinympc_cuda_solver* s) {
             if (d.ev_join[k]) cudaEventDestroy(d.ev_join[k]);
         }
         if (d.ev_ctl) cudaEventDestroy(d.ev_ctl);
+        if (d.ev_pass) cudaEventDestroy(d.ev_pass);
+        if (d.ev_copied) cudaEventDestroy(d.ev_copied);
         for (DevBuf* b : {&d.x0, &d.Xref, &d.Uref, &d.xmin, &d.xmax, &d.umin, &d.umax, &d.x, &d.u, &d.iter, &d.status, &d.res, &d.rho, &d.xrc, &d.u0}) b->release();
         for (auto& b : d.exp_xref) b.release();
         for (auto& b : d.exp_x) b.release();
@@ -1517,6 +1573,8 @@ int tinympc_cuda_set_option(tinympc_cuda_solver* s, const char* name, double val
         s->streamed = value != 0;
     } else if (n == "compact_streamed") {
         s->compact_streamed = value != 0;
+    } else if (n == "compact_early_d2h") {
+        s->compact_early_d2h = value != 0;
     } else if (n == "compact_in_kernel") {
         s->compact_in_kernel = value != 0;
     } else if (n == "refill_min") {
