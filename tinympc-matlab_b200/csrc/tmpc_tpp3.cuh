@@ -604,10 +604,8 @@ tpp3_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ typ
             }
             if (!__any_sync(FULL, active)) {
                 publish_done(prm, unpub);
-                if (__all_sync(FULL, exhausted)) break;
-                // every lane that is not done waits for the copy engine / for the list of deferred problems to be complete -- or
-                // (easy problems last) has just handed its third claim in a row to that list and claims again at once
-                if (!__any_sync(FULL, !exhausted && !pending)) __nanosleep(256);
+                if (!__any_sync(FULL, pending)) break;
+                __nanosleep(256);   // the whole warp is waiting for the copy engine
                 continue;
             }
         }
