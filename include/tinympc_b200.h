@@ -202,12 +202,6 @@ int  tinympc_cuda_session_read(tinympc_cuda_session *ss, const char *field, doub
    device runs as one launch chain over the whole shard while its inputs are still arriving in a few chunks of doubling size
    behind an arrival watermark; 0: the chunked pipeline), "compact_in_kernel" (1 [default]: kernels read xref_const in place
    where they can; 0: always replicate it on the device first),
-   "compact_early_d2h" (1 [default]: in the exact-count mode of that chain, with PINNED result arrays, the results of the fp32 pass are
-   copied back under the fp64 pass and a kernel writes the fp64 results over them through the device alias of the host arrays),
-   "defer_thr" (easy problems last, 0.6 [default], 0 = off: in a device-resident or compact-streamed batch of a family with shared
-   time-invariant box bounds, a problem whose unconstrained feedback |Kinf (x0 - xref_0)| stays below this fraction of the input
-   bounds -- it converges within the first termination checks -- is solved after all the others, so that the persistent
-   kernel's tail consists of short problems; scheduling only, results do not depend on it),
    "ctas_per_sm" (0 = occupancy API), "chunks" (host pipeline depth, 0 = auto),
    "fixer_sms" (how the exact-count mode schedules its fp64 pass: -2 [default] the sequential two-pass form for device-resident and
    chunked batches, the concurrent producer / consumer pair inside the streamed host pipeline; -1 always sequential; 0 always the
@@ -229,9 +223,6 @@ int  tinympc_cuda_last_timing(const tinympc_cuda_solver *s, double ms[3]);
 int  tinympc_cuda_last_pass_ms(tinympc_cuda_solver *s, double ms[2]);
 /* number of problems the last "mixed" solve re-solved in fp64 (after a device-resident solve this synchronises the device) */
 long long tinympc_cuda_last_marked(tinympc_cuda_solver *s);
-/* number of problems the last solve on device `dev_index` scheduled after all others (option "defer_thr"; 0 if it did not apply;
-   synchronises the device) */
-long long tinympc_cuda_last_deferred(tinympc_cuda_solver *s, int dev_index);
 const char *tinympc_cuda_last_error(const tinympc_cuda_solver *s);
 const char *tinympc_cuda_version(void);
 

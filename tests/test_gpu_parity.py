@@ -412,51 +412,6 @@ def test_compact_io_matches_full_trajectories(B, mixed, pipeline, capi, oracle_m
     s.close()
 
 
-@pytest.mark.parametrize("family,mixed", [("quadrotor", 0.0), ("quadrotor", 0.002), ("cartpole", 0.003), ("quadrotor_noref", 0.0)])
-def test_easy_problems_last_is_scheduling_only(family, mixed, capi, oracle_mod, problems):
-    """Option "defer_thr" (SolveParams::defer_ctl): lanes push the problems whose unconstrained feedback stays well inside the input
-    bounds onto a device list and solve them after all others, so that the persistent kernel ends on short problems.  Pure
-    scheduling -- off, default, and "everything deferred" return the same bits, through the device entry and through the compact
-    streamed host pipeline -- and the default threshold does send a fair share of the batch to the list."""
-    import torch
-    p = problems.cartpole() if family == "cartpole" else problems.quadrotor()
-    B = 300007
-    b = problems.make_batch(p, B, 1.0, seed=61)
-    if family == "quadrotor_noref":
-        b = problems.Batch(b.x0, None, None)
-    s = capi.CudaSolver()
-    s.set_option("mixed", mixed)
-    s.set_family(cases.family_from_spec(p, oracle_mod.get_cache(p, "port")))
-    dev = torch.device("cuda", 0)
-    tdev = lambda a: None if a is None else torch.from_numpy(a).to(dev)
-    ptr = lambda t: None if t is None else t.data_ptr()
-    x0, Xref, Uref = tdev(b.x0), tdev(b.Xref), tdev(b.Uref)
-    res = {}
-    for thr in (0.0, 0.6, 1e9, 0.6):
-        s.set_option("defer_thr", thr)
-        x = torch.full((B, p.N, p.nx), -3.0, device=dev); u = torch.full((B, p.N - 1, p.nu), -3.0, device=dev)
-        it = torch.full((B,), -3, dtype=torch.int32, device=dev); st = torch.full((B,), -3, dtype=torch.int32, device=dev)
-        s.solve_batch_device(B, ptr(x0), ptr(Xref), ptr(Uref), ptr(x), ptr(u), ptr(it), ptr(st), stream=torch.cuda.current_stream().cuda_stream)
-        torch.cuda.synchronize()
-        nd = s.last_deferred()
-        assert (nd == 0) if thr == 0.0 else (nd == B if thr > 1 else 0.05 * B < nd < 0.8 * B), (thr, nd)
-        assert s.last_kernel.startswith("tpp3_"), s.last_kernel
-        r = dict(x=x.cpu().numpy(), u=u.cpu().numpy(), iter=it.cpu().numpy(), status=st.cpu().numpy())
-        if not res:
-            res = r
-            assert (r["iter"] >= 1).all() and np.isin(r["status"], (1, 11)).all()
-        for k in res:
-            assert np.array_equal(res[k], r[k]), f"{family}: defer_thr={thr} changes {k}"
-    # the compact streamed host pipeline defers too (its lanes also wait for the arrival watermark)
-    xc = None if b.Xref is None else np.ascontiguousarray(b.Xref[:, 0, :])
-    if b.Xref is None or (b.Xref == b.Xref[:, :1]).all():
-        c = s.solve_batch(b.x0, xref_const=xc, compact_out=True)
-        assert s.last_timing()["chunks"] >= 2 and 0.05 * B < s.last_deferred() < 0.8 * B, (s.last_timing(), s.last_deferred())
-        assert np.array_equal(c["iter"], res["iter"]) and np.array_equal(c["status"], res["status"])
-        assert np.array_equal(c["u0"], res["u"][:, 0, :])
-    s.close()
-
-
 @pytest.mark.parametrize("family,precision,B", [("cartpole", 32, 3000), ("cartpole", 64, 3000), ("quadrotor", 64, 3000), ("quadrotor", 32, 60000),
                                                 ("rocket", 32, 3000), ("quadrotor_adaptive", 64, 3000), ("cartpole", 32, 140000)])
 def test_compact_reference_read_in_place(family, precision, B, capi, oracle_mod, problems):

@@ -68,8 +68,6 @@ struct DeviceCtx {
     DevBuf wpp_scratch[kStreams + 1];   // warp-per-problem workspaces (one per pipeline stream + the device/workspace entry)
     DevBuf ref_scratch64[kStreams + 1]; // mixed mode: reference terms of the fp64 re-solve pass
     DevBuf marked[kStreams + 1];        // mixed mode: indices of the problems the fp32 pass marked ambiguous (two-pass form) / the queue
-    const DevBuf* defer_last = nullptr; // the buffer the last first-pass launch on this device deferred into (NULL: it did not defer)
-    DevBuf defer_buf[2];                // easy problems last (SolveParams::defer_ctl): 4 control words + the list; [0] device-resident entry, [1] compact streamed pipeline
     cudaEvent_t ev_pass = nullptr, ev_copied = nullptr;   // compact streamed pipeline: end of the first pass / of the early result copies
     // exact-count mode, concurrent form: per slot {q_tail, producer CTAs done, consumer ticket counter, pad}
     int* qctl = nullptr;                // 4 * kMaxChunks ints, indexed like the work counters (chunk index; the last one = device entry)
@@ -108,8 +106,6 @@ struct tinympc_cuda_solver {
                                        // (run_shard_compact_streamed); 0 = the chunked pipeline
     int compact_early_d2h = 1;         // option "compact_early_d2h": exact-count mode of that pipeline with pinned result arrays -- the results
                                        // of the first pass are copied back under the fp64 pass, whose results a kernel then writes over them
-    double defer_thr = 0.6;            // option "defer_thr": easy problems last (SolveParams::defer_ctl) -- a problem whose unconstrained feedback
-                                       // stays below this fraction of the input bounds is solved after all others; 0 = claim order
     int compact_in_kernel = 1;         // option "compact_in_kernel": kernels read tinympc_cuda_batch_in::xref_const in place where they can;
                                        // 0 = always replicate it over the horizon on the device first
     double mixed_band = 0;             // option "mixed": > 0 = fp32 pass + fp64 re-solve of the problems whose termination decision
@@ -285,7 +281,7 @@ const KernelEntry* pick_kernel(const tinympc_cuda_solver* s, const DeviceCtx& d,
 }
 
 int launch_tpp(tinympc_cuda_solver* s, DeviceCtx& d, const KernelEntry* ke, SolveParams& p, DevBuf& rb, int bits, int* counter, cudaStream_t st,
-               int reserve_sms = 0, int* grid_out = nullptr, int max_sms = 0, DevBuf* defer = nullptr) {
+               int reserve_sms = 0, int* grid_out = nullptr, int max_sms = 0) {
     const Family& f = s->fam;
     const size_t smem = ke->smem_bytes(f.L.cold_size);
     if (smem > 227u * 1024u) return fail(s, TINYMPC_CUDA_EUNSUPPORTED, std::string("kernel ") + ke->name + " needs more shared memory than an SM has");
@@ -307,18 +303,6 @@ int launch_tpp(tinympc_cuda_solver* s, DeviceCtx& d, const KernelEntry* ke, Solv
     }
     p.work_counter = counter;
     p.refill_min = s->refill_min;
-    // easy problems last (SolveParams::defer_ctl): worth it from a few waves of the persistent grid on
-    p.defer_ctl = nullptr; p.defer_list = nullptr; p.defer_thr = 0.f;
-    if (defer) d.defer_last = nullptr;
-    if (defer && ke->defer_ok && s->defer_thr > 0 && !p.index_list && !p.batch_ptr && !p.q_tail && p.en_input_bound && !p.x_min &&
-        (long long)p.batch >= 2LL * grid * per_cta) {
-        CU(s, defer->reserve(sizeof(int) * (4 + (size_t)p.batch)));
-        int* base = static_cast<int*>(defer->p);
-        CU(s, cudaMemsetAsync(base, 0, sizeof(int) * 4, st));
-        CU(s, cudaMemsetAsync(base + 4, 0xFF, sizeof(int) * (size_t)p.batch, st));      // every entry -1 = "not written yet"
-        p.defer_ctl = base; p.defer_list = base + 4; p.defer_thr = static_cast<float>(s->defer_thr);
-        d.defer_last = defer;
-    }
     CU(s, cudaMemsetAsync(counter, 0, sizeof(int), st));
     CU(s, ke->launch(p, grid, smem, st, f.pack.data(), f.L));
     s->launches += 1;
@@ -479,9 +463,8 @@ int enqueue(tinympc_cuda_solver* s, DeviceCtx& d, const tinympc_cuda_batch_in& i
         return TINYMPC_CUDA_OK;
     }
     int* const counter = d.counters + counter_slot;
-    DevBuf* const defer = scratch_slot == kStreams ? &d.defer_buf[0] : nullptr;   // the device-resident entry point
     if (!mixed) {
-        int rc = launch_tpp(s, d, ke, p, d.ref_scratch[scratch_slot], bits, counter, st, 0, nullptr, 0, defer);
+        int rc = launch_tpp(s, d, ke, p, d.ref_scratch[scratch_slot], bits, counter, st);
         if (rc) return rc;
         note_kernel(s, ke->name);
         return TINYMPC_CUDA_OK;
@@ -495,7 +478,7 @@ int enqueue(tinympc_cuda_solver* s, DeviceCtx& d, const tinympc_cuda_batch_in& i
     p.amb_band = static_cast<float>(s->mixed_band);
     const bool timed = s->pass_timing != 0 && scratch_slot == kStreams;     // the device-resident entry point only
     if (timed) CU(s, cudaEventRecord(d.ev_p0, st));
-    int rc = launch_tpp(s, d, ke, p, d.ref_scratch[scratch_slot], 32, counter, st, 0, nullptr, 0, defer);
+    int rc = launch_tpp(s, d, ke, p, d.ref_scratch[scratch_slot], 32, counter, st);
     if (rc) return rc;
     if (timed) CU(s, cudaEventRecord(d.ev_p1, st));
     CU(s, cudaMemsetAsync(n_marked, 0, sizeof(int), st));
@@ -792,12 +775,12 @@ int run_shard_compact_streamed(tinympc_cuda_solver* s, DeviceCtx& d, const Kerne
     RT(cudaEventRecord(d.k0[0], s_k));
     int* const n_marked = d.counters + 2 * kMaxChunks;
     if (!mixed) {
-        int rc = launch_tpp(s, d, ke, p, d.ref_scratch[0], bits, ctl, s_k, 0, nullptr, 0, &d.defer_buf[1]);
+        int rc = launch_tpp(s, d, ke, p, d.ref_scratch[0], bits, ctl, s_k);
         if (rc) return sync_fail(rc);
         note_kernel(s, ke->name);
     } else {   // sequential exact-count form (enqueue()): fp32 pass that marks, compaction, fp64 re-solve of the marked problems
         p.amb_band = static_cast<float>(s->mixed_band);
-        int rc = launch_tpp(s, d, ke, p, d.ref_scratch[0], 32, ctl, s_k, 0, nullptr, 0, &d.defer_buf[1]);
+        int rc = launch_tpp(s, d, ke, p, d.ref_scratch[0], 32, ctl, s_k);
         if (rc) return sync_fail(rc);
         if (early) {
             cudaStream_t s_out = d.streams[2];
@@ -1087,7 +1070,6 @@ int tinympc_cuda_destroy(tinympc_cuda_solver* s) {
         for (auto& b : d.ref_scratch) b.release();
         for (auto& b : d.ref_scratch64) b.release();
         for (auto& b : d.marked) b.release();
-        for (auto& b : d.defer_buf) b.release();
     }
     cudaSetDevice(prev);
     delete s;
@@ -1593,9 +1575,6 @@ int tinympc_cuda_set_option(tinympc_cuda_solver* s, const char* name, double val
         s->compact_streamed = value != 0;
     } else if (n == "compact_early_d2h") {
         s->compact_early_d2h = value != 0;
-    } else if (n == "defer_thr") {
-        if (!(value >= 0)) return fail(s, TINYMPC_CUDA_EINVAL, "defer_thr must be >= 0");
-        s->defer_thr = value;
     } else if (n == "compact_in_kernel") {
         s->compact_in_kernel = value != 0;
     } else if (n == "refill_min") {
@@ -1645,18 +1624,6 @@ long long tinympc_cuda_last_marked(tinympc_cuda_solver* s) {
         s->mixed_pending_dev = -1;
     }
     return s->mixed_marked;
-}
-long long tinympc_cuda_last_deferred(tinympc_cuda_solver* s, int dev_index) {
-    if (!s || dev_index < 0 || dev_index >= (int)s->devs.size()) return -1;
-    DeviceCtx& d = s->devs[dev_index];
-    if (!d.defer_last || !d.defer_last->p) return 0;
-    int prev = 0, n = 0;
-    cudaGetDevice(&prev);
-    cudaSetDevice(d.device);
-    cudaDeviceSynchronize();
-    cudaMemcpy(&n, d.defer_last->p, sizeof(int), cudaMemcpyDeviceToHost);
-    cudaSetDevice(prev);
-    return n;
 }
 const char* tinympc_cuda_last_error(const tinympc_cuda_solver* s) { return s ? s->err.c_str() : "null solver"; }
 

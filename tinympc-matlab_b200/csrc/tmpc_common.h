@@ -140,18 +140,6 @@ struct SolveParams {
     //               then not written (and may be NULL)
     int xref_const;
     float* u0;
-    // Easy problems last (tmpc_tpp3.cuh, refill): the persistent kernel ends with a tail in which every lane finishes the problem
-    // it holds; with problems of 10 .. max_iter iterations in claim order that tail is ~max_iter iterations long at falling lane
-    // occupancy (7-9 % of the launch).  A lane that claims a problem first looks at how far the unconstrained feedback
-    // -Kinf (x0 - xref_0) stays inside the input bounds; a problem well inside (it converges within the first checks) is pushed
-    // onto a device list instead of being started, and the lanes turn to that list once the main queue is empty -- the tail then
-    // consists of short problems.  Pure scheduling: every problem is solved by the same code whatever its position.
-    //   defer_ctl   NULL = off; [0] list entries reserved, [1] main-queue problems looked at, [2] list tickets handed out (zeroed before launch)
-    //   defer_list  batch ints preset to -1
-    //   defer_thr   easy: |Kinf (x0 - xref_0)|_a < defer_thr * min(-u_min_a, u_max_a) for every input a
-    int* defer_ctl;
-    int* defer_list;
-    float defer_thr;
 };
 
 constexpr int kAmbiguousBit = 0x100;

@@ -127,18 +127,6 @@ __device__ __forceinline__ bool queue_take(const SolveParams& prm, int t, int& p
     if (ld_acquire_gpu(prm.q_prod_done) >= prm.q_prod_total) none = t >= ld_relaxed_gpu(prm.q_tail);
     return false;
 }
-// The same protocol on the list of deferred problems (SolveParams::defer_ctl / defer_list): ticket t of the list, which is
-// complete once all `total` problems of the main queue have been looked at.
-__device__ __forceinline__ bool defer_take(const int* ctl, const int* list, int total, int t, int& prob, bool& none) {
-    none = false;
-    if (t < ld_relaxed_gpu(ctl)) {
-        const int e = ld_acquire_gpu(list + t);
-        if (e >= 0) { prob = e; return true; }
-        return false;
-    }
-    if (ld_acquire_gpu(ctl + 1) >= total) none = t >= ld_relaxed_gpu(ctl);
-    return false;
-}
 // Producer CTA exit (after its last push): call from one thread behind a __syncthreads().
 __device__ __forceinline__ void queue_producer_exit(const SolveParams& prm) {
     __threadfence();

@@ -137,8 +137,6 @@ struct Tpp3Cfg {
     // (measured on the N = 20 cartpole batch: rolled 119.9, x4 137.6, x10 148.5, fully unrolled 145.0 M solves/s; the rocket
     // instance with its ~600-instruction column loses 4 % when unrolled x3 and stays rolled).
     static constexpr int TUNROLL = (NX_ <= 4 && FEAT_ == FEAT_BOX) ? TMPC_TUNROLL_SMALL : 1;
-    // easy problems last (SolveParams::defer_ctl): instances with shared, time-invariant box bounds
-    static constexpr bool DEFER = FB_ && !PPB_ && FEAT_ == FEAT_BOX;
     static constexpr int TTM = HYB ? TTM_ : NH_;
     static_assert(!HYB || (FEAT_ == FEAT_BOX && NH_ >= 3 && TTM_ <= NH_ - 1), "hybrid layout: box instances only");
     // shared memory: u, u + y_prev, -dd (+ the pre-projection input slacks of the cone and half-space families; + the T columns
@@ -264,8 +262,6 @@ tpp3_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ typ
     int prob = 0;
     bool active = false, exhausted = false;
     bool pending = false;   // holds a claimed problem (claim) whose inputs have not landed yet (streamed host pipeline)
-    bool phase2 = false;    // easy problems last: the main queue is empty, this lane takes tickets of the deferred list
-    const bool deferring = C::DEFER && prm.defer_ctl != nullptr;
     int last_k = 32;        // iterations of the last problem this lane finished (batched refill)
     int claim = 0, seen = 0, unpub = -1;   // seen: cached arrival watermark; unpub: finished problem not yet counted for its chunk
     int k = 0;
@@ -342,129 +338,45 @@ tpp3_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ typ
     for (;;) {
         // ------------------------------------------------------------------ refill idle lanes
         {
-            const bool have_xref0 = C::REFS && prm.Xref != nullptr;
-            bool mine = false;   // lanes that start a problem in this pass
-            // One round unless easy problems are deferred: a lane whose claim went to the list claims again at once (three rounds
-            // leave < 2 % of such lanes waiting for the warp's next pass).
-#pragma unroll 1
-            for (int round = 0; round < 3; ++round) {
-                const bool want = !active && !mine && !exhausted && !pending;
-                unsigned mw = __ballot_sync(FULL, want);
-                // Batched refill: wait until a few lanes are free, unless nothing else keeps the warp busy.  One refill pass costs the
-                // warp R ~ 0.23 iterations whatever the number of lanes it serves; with I iterations per problem 32 / I lanes finish
-                // per iteration, so a threshold m costs 32 R / (I m) in passes and (m - 1) / 64 in idle lanes: m* = sqrt(2048 R / I)
-                // (3 for the hard quadrotor batch, 7 for the easy one; measured optimum 3-4 and >= 8).  I is the warp's mean over
-                // the last problem of each lane.  refill_min > 0 fixes the threshold instead.
-                if (round == 0 && mw && __any_sync(FULL, active)) {
-                    int m = prm.refill_min;
-                    if (m <= 0) {
-                        const int sum_k = __reduce_add_sync(FULL, last_k);
-                        m = __float2int_rn(sqrtf(__fdividef(471.f * 32.f, (float)max(sum_k, 32))));
-                        m = min(max(m, 1), 12);
-                    }
-                    if (__popc(mw) < m) mw = 0;
+            const bool want = !active && !exhausted && !pending;
+            unsigned mw = __ballot_sync(FULL, want);
+            // Batched refill: wait until a few lanes are free, unless nothing else keeps the warp busy.  One refill pass costs the
+            // warp R ~ 0.23 iterations whatever the number of lanes it serves; with I iterations per problem 32 / I lanes finish
+            // per iteration, so a threshold m costs 32 R / (I m) in passes and (m - 1) / 64 in idle lanes: m* = sqrt(2048 R / I)
+            // (3 for the hard quadrotor batch, 7 for the easy one; measured optimum 3-4 and >= 8).  I is the warp's mean over
+            // the last problem of each lane.  refill_min > 0 fixes the threshold instead.
+            if (mw && __any_sync(FULL, active)) {
+                int m = prm.refill_min;
+                if (m <= 0) {
+                    const int sum_k = __reduce_add_sync(FULL, last_k);
+                    m = __float2int_rn(sqrtf(__fdividef(471.f * 32.f, (float)max(sum_k, 32))));
+                    m = min(max(m, 1), 12);
                 }
-                const bool go = want && mw != 0;
-                if (mw) {   // claim the next problem indices (one atomic per warp)
-                    const unsigned m1 = __ballot_sync(FULL, go && !phase2);
-                    if (m1) {
-                        const int leader = __ffs(m1) - 1;
-                        int base = 0;
-                        if (lane == leader) base = atomicAdd(prm.work_counter, __popc(m1));
-                        base = __shfl_sync(FULL, base, leader);
-                        if (go && !phase2) {
-                            claim = base + __popc(m1 & ((1u << lane) - 1u));
-                            if (claim >= n_items) {
-                                if (deferring) { phase2 = true; } else { exhausted = true; prob = 0; }
-                            } else {
-                                if (prm.index_list) claim = __ldg(prm.index_list + claim);
-                                pending = true;
-                            }
-                        }
-                    }
-                    if (deferring) {   // the main queue is empty: a ticket of the deferred list
-                        const bool t2 = go && phase2 && !pending;
-                        const unsigned m2 = __ballot_sync(FULL, t2);
-                        if (m2) {
-                            const int leader = __ffs(m2) - 1;
-                            int base = 0;
-                            if (lane == leader) base = atomicAdd(prm.defer_ctl + 2, __popc(m2));
-                            base = __shfl_sync(FULL, base, leader);
-                            if (t2) { claim = base + __popc(m2 & ((1u << lane) - 1u)); pending = true; }
-                        }
-                    }
-                }
-                // a claimed problem starts once its inputs have landed (always, unless the host streams the batch in); a ticket
-                // once its list entry is written
-                bool got = false;
-                if (pending) {
-                    if (!phase2) {
-                        got = problem_ready(prm, claim, seen);
-                    } else {
-                        bool none;
-                        int e = 0;
-                        if (defer_take(prm.defer_ctl, prm.defer_list, n_items, claim, e, none)) { got = true; claim = e; }
-                        else if (none) { pending = false; exhausted = true; prob = 0; }
-                    }
-                }
-                bool again = false;   // a lane's claim went to the list: one more round
-                if constexpr (C::DEFER) {
-                    const bool look = deferring && got && !phase2;
-                    const unsigned ml = __ballot_sync(FULL, look);
-                    if (ml) {
-                        bool easy = false;
-                        if (look) {   // how far inside the input bounds does the unconstrained feedback stay?
-                            // (the lane holds no problem, so its x0 registers are free: no second vector is live here)
-                            load_span<NX, vec_width(NX, NX)>(prm.x0 + (size_t)claim * NX, [&](int i, float v) { x0v.set(i, v); });
-                            const int zc = opaque_zero4();                  // keeps the coefficient loads here instead of hoisted out of the solve loop
-                            const T* __restrict__ NKc = cp.NK + zc;
-                            VU kd;
-                            kd.fill(T(0));
-                            mv_acc<NU, NX>(cp.NK, zc, x0v, kd);             // -Kinf x0
-                            if (have_xref0) {                               // + Kinf xref_0, a few columns at a time
-                                constexpr int W = vec_width(SXL, NX);
-                                const float* xr = prm.Xref + (size_t)claim * (prm.xref_const ? NX : SXL);
-#pragma unroll
-                                for (int c0 = 0; c0 < NX; c0 += W) {
-                                    float rv[W];
-                                    load_span<W, W>(xr + c0, [&](int i, float v) { rv[i] = v; });
-#pragma unroll
-                                    for (int c = 0; c < W; ++c) {
-#pragma unroll
-                                        for (int j = 0; j < NU / 2; ++j)
-                                            kd.p[j] = fmas(mk2(NKc[(c0 + c) * NUP + 2 * j], NKc[(c0 + c) * NUP + 2 * j + 1]), -rv[c], kd.p[j]);
-                                        if constexpr (NU & 1) kd.t = fmas(NKc[(c0 + c) * NUP + NU - 1], -rv[c], kd.t);
-                                    }
-                                }
-                            }
-                            easy = true;
-#pragma unroll
-                            for (int a = 0; a < NU; ++a)
-                                easy = easy && fabsf(kd.get(a)) < prm.defer_thr * fminf(-cp.umin[zc + a], cp.umax[zc + a]);
-                        }
-                        const unsigned md = __ballot_sync(FULL, easy);
-                        again = md != 0;
-                        if (md) {
-                            const int leader = __ffs(md) - 1;
-                            int base = 0;
-                            if (lane == leader) base = atomicAdd(prm.defer_ctl, __popc(md));
-                            base = __shfl_sync(FULL, base, leader);
-                            if (easy) {
-                                st_release_gpu(prm.defer_list + base + __popc(md & ((1u << lane) - 1u)), claim);
-                                pending = false;   // the lane is free again
-                                got = false;
-                            }
-                        }
-                        __syncwarp();
-                        if (lane == __ffs(ml) - 1) { __threadfence(); atomicAdd(prm.defer_ctl + 1, __popc(ml)); }
-                    }
-                }
-                if (got) { mine = true; pending = false; prob = claim; }
-                if (!again) break;
+                if (__popc(mw) < m) mw = 0;
             }
+            if (mw) {   // claim the next problem indices (one atomic per warp)
+                const int leader = __ffs(mw) - 1;
+                int base = 0;
+                if (lane == leader) base = atomicAdd(prm.work_counter, __popc(mw));
+                base = __shfl_sync(FULL, base, leader);
+                if (want) {
+                    claim = base + __popc(mw & ((1u << lane) - 1u));
+                    if (claim >= n_items) {
+                        exhausted = true;
+                        prob = 0;
+                    } else {
+                        if (prm.index_list) claim = __ldg(prm.index_list + claim);
+                        pending = true;
+                    }
+                }
+            }
+            // a claimed problem starts once its inputs have landed (always, unless the host streams the batch in)
+            const bool mine = pending && problem_ready(prm, claim, seen);
             const unsigned m = __ballot_sync(FULL, mine);
             if (m) {
                 if (mine) {
+                    prob = claim;
+                    pending = false;
                     active = true;
                     k = 0;
                     next_check = check_every;
