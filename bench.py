@@ -353,6 +353,33 @@ def main():
     value = world * B * args.steps / (ms_all * 1e-3)
     ns_iter = ms_all * 1e6 / (iters_all * args.steps)
 
+    # ---- the same resident step with compact I/O (device pointers: one reference state per problem in, first control out): what
+    # the kernels cost when they neither read a replicated reference nor write trajectories -- the floor of the compact e2e mode
+    resident_compact = None
+    const_ref = batch_np.Xref is None or bool((batch_np.Xref == batch_np.Xref[:, :1]).all())
+    if const_ref and (batch_np.Uref is None or not batch_np.Uref.any()):
+        xc_dev = None if Xref is None else Xref[:, 0, :].contiguous()
+        u0_dev = torch.empty((B, m), device=dev)
+        it_c = torch.empty_like(it); st_c = torch.empty_like(st)
+
+        def step_c():
+            solver.cuda.solve_batch_device(B, ptr(x0), None, None, None, None, ptr(it_c), ptr(st_c), xref_const=ptr(xc_dev), u0=ptr(u0_dev),
+                                           stream=stream.cuda_stream)
+        for _ in range(2):
+            step_c()
+        barrier()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        kc = max(1, args.steps // 2)
+        c0.record(stream)
+        for _ in range(kc):
+            step_c()
+        c1.record(stream)
+        barrier()
+        ms_c = S.reduce_report(c0.elapsed_time(c1), [0], dist, dev)[0]
+        assert torch.equal(it_c, it) and torch.equal(u0_dev, u[:, 0, :]), "compact device path and full device path disagree"
+        resident_compact = {"value": world * B * kc / (ms_c * 1e-3), "unit": "solves/s", "ms_per_step": ms_c / kc, "kernel": solver.cuda.last_kernel,
+                            "io": "device-resident, x0" + ("" if xc_dev is None else " + one reference state per problem") + " in, u0 + iter + status out"}
+
     # ---- end to end through the host-buffer C-ABI call (pinned host memory, copies inside the timed region), two I/O modes:
     #   full    : what the reference-shaped interface moves -- x0, full Xref (nx x N), full Uref in; full x, u, iter, status out
     #   compact : x0 + ONE reference state per problem (xref_const: config 3 replicates its set point over the horizon) in;
@@ -473,7 +500,7 @@ def main():
             "dtype": "f32" if args.precision == 32 else "f64", "data": "synthetic", "config": config,
             "ns_per_admm_iter": ns_iter, "mean_iters": iters_all / (world * B), "unsolved_frac": unsolved,
             "clocks": clk.summary(), "e2e": e2e, "fp64_resolved": int(marked), "gpu_launches": launches_all, "roofline": roof,
-            "e2e_other": e2e_other, "parity": parity, "run": run}
+            "e2e_other": e2e_other, "resident_compact": resident_compact, "parity": parity, "run": run}
     if not args.no_cpu_baseline:
         os.sched_setaffinity(0, prev_affinity)
         try:

@@ -202,6 +202,8 @@ int  tinympc_cuda_session_read(tinympc_cuda_session *ss, const char *field, doub
    device runs as one launch chain over the whole shard while its inputs are still arriving in a few chunks of doubling size
    behind an arrival watermark; 0: the chunked pipeline), "compact_in_kernel" (1 [default]: kernels read xref_const in place
    where they can; 0: always replicate it on the device first),
+   "compact_early_d2h" (1 [default]: in the exact-count mode of that chain, with PINNED result arrays, the results of the fp32 pass are
+   copied back under the fp64 pass and a kernel writes the fp64 results over them through the device alias of the host arrays),
    "ctas_per_sm" (0 = occupancy API), "chunks" (host pipeline depth, 0 = auto),
    "fixer_sms" (how the exact-count mode schedules its fp64 pass: -2 [default] the sequential two-pass form for device-resident and
    chunked batches, the concurrent producer / consumer pair inside the streamed host pipeline; -1 always sequential; 0 always the
