@@ -224,6 +224,7 @@ def main():
     ap.add_argument("--steps-cpu", dest="steps_cpu", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--order", type=int, default=-1, help="option order of the library (claim the hardest problems first); -1 = library default (1), 0 = index order")
     ap.add_argument("--e2e-mode", dest="e2e_mode", default="compact", choices=["compact", "full"],
                     help="I/O mode of the headline end-to-end number (the other one is reported as e2e_other)")
     args = ap.parse_args()
@@ -308,6 +309,9 @@ def main():
         band = 0.0
     solver.cuda.set_option("mixed", band)
     solver.cuda.set_option("fixer_sms", args.fixer_sms)
+    if args.order >= 0:
+        solver.cuda.set_option("order", args.order)
+    run["order"] = "library default (hardest first)" if args.order < 0 else ("hardest first" if args.order else "index order")
     run["fixer_sms"] = args.fixer_sms
     run["mixed_band"] = band
     run["e2e_mode"] = args.e2e_mode

@@ -204,6 +204,10 @@ int  tinympc_cuda_session_read(tinympc_cuda_session *ss, const char *field, doub
    where they can; 0: always replicate it on the device first),
    "compact_early_d2h" (1 [default]: in the exact-count mode of that chain, with PINNED result arrays, the results of the fp32 pass are
    copied back under the fp64 pass and a kernel writes the fp64 results over them through the device alias of the host arrays),
+   "order" (1 [default]: a device-resident batch of a box-constrained family, from a few waves of the persistent grid on, is
+   bucketed on the device by its expected difficulty |Kinf (x0 - xref_0)| / u_bound and the fp32 kernel claims the hardest
+   problems first -- lanes of a warp then hold problems of similar length and the launch ends on the shortest ones, ~9 % on the
+   2^20 quadrotor batch; scheduling only, the results do not depend on it; 0: index order),
    "ctas_per_sm" (0 = occupancy API), "chunks" (host pipeline depth, 0 = auto),
    "fixer_sms" (how the exact-count mode schedules its fp64 pass: -2 [default] the sequential two-pass form for device-resident and
    chunked batches, the concurrent producer / consumer pair inside the streamed host pipeline; -1 always sequential; 0 always the

@@ -412,6 +412,53 @@ def test_compact_io_matches_full_trajectories(B, mixed, pipeline, capi, oracle_m
     s.close()
 
 
+@pytest.mark.parametrize("family,mixed,fixer_sms", [("quadrotor", 0.0, -2), ("quadrotor", 0.002, -2), ("quadrotor", 0.002, 0), ("cartpole", 0.003, -2),
+                                                    ("quadrotor_noref", 0.0, -2), ("quadrotor_compact", 0.002, -2)])
+def test_claim_order_is_scheduling_only(family, mixed, fixer_sms, capi, oracle_mod, problems):
+    """Option "order" (default on): a device-resident batch of a box family is bucketed by its expected difficulty
+    |Kinf (x0 - xref_0)| / u_bound on the device (counting sort, tmpc_capi.cu order_*_kernel) and the thread-per-problem kernel
+    claims the hardest problems first.  Pure scheduling: the results are, bit for bit, those of the index-order run -- in plain fp32,
+    in both forms of the exact-count mode, without references, and with compact I/O."""
+    import torch
+    p = problems.cartpole() if family == "cartpole" else problems.quadrotor()
+    B = 300007
+    b = problems.make_batch(p, B, 1.0, seed=61)
+    if family == "quadrotor_noref":
+        b = problems.Batch(b.x0, None, None)
+    s = capi.CudaSolver()
+    s.set_option("mixed", mixed)
+    s.set_option("fixer_sms", fixer_sms)
+    s.set_family(cases.family_from_spec(p, oracle_mod.get_cache(p, "port")))
+    dev = torch.device("cuda", 0)
+    tdev = lambda a: None if a is None else torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    ptr = lambda t: None if t is None else t.data_ptr()
+    x0, Xref, Uref = tdev(b.x0), tdev(b.Xref), tdev(b.Uref)
+    compact = family == "quadrotor_compact"
+    xc = tdev(b.Xref[:, 0, :]) if compact else None
+    res, launches = {}, {}
+    for order in (0, 1, 1, 0):
+        s.set_option("order", order)
+        x = torch.full((B, p.N, p.nx), -3.0, device=dev); u = torch.full((B, p.N - 1, p.nu), -3.0, device=dev)
+        u0 = torch.full((B, p.nu), -3.0, device=dev)
+        it = torch.full((B,), -3, dtype=torch.int32, device=dev); st = torch.full((B,), -3, dtype=torch.int32, device=dev)
+        n0 = s.launch_count
+        if compact:
+            s.solve_batch_device(B, ptr(x0), None, None, None, None, ptr(it), ptr(st), xref_const=ptr(xc), u0=ptr(u0), stream=torch.cuda.current_stream().cuda_stream)
+        else:
+            s.solve_batch_device(B, ptr(x0), ptr(Xref), ptr(Uref), ptr(x), ptr(u), ptr(it), ptr(st), stream=torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        launches[order] = s.launch_count - n0
+        assert s.last_kernel.startswith("tpp3_"), s.last_kernel
+        r = dict(iter=it.cpu().numpy(), status=st.cpu().numpy(), **(dict(u0=u0.cpu().numpy()) if compact else dict(x=x.cpu().numpy(), u=u.cpu().numpy())))
+        if not res:
+            res = r
+            assert (r["iter"] >= 1).all() and np.isin(r["status"], (1, 11)).all()
+        for k in res:
+            assert np.array_equal(res[k], r[k]), f"{family}: order={order} changes {k}"
+    assert launches[1] == launches[0] + 3, launches      # count, scan, scatter
+    s.close()
+
+
 @pytest.mark.parametrize("family,precision,B", [("cartpole", 32, 3000), ("cartpole", 64, 3000), ("quadrotor", 64, 3000), ("quadrotor", 32, 60000),
                                                 ("rocket", 32, 3000), ("quadrotor_adaptive", 64, 3000), ("cartpole", 32, 140000)])
 def test_compact_reference_read_in_place(family, precision, B, capi, oracle_mod, problems):

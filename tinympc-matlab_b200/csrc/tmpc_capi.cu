@@ -68,6 +68,7 @@ struct DeviceCtx {
     DevBuf wpp_scratch[kStreams + 1];   // warp-per-problem workspaces (one per pipeline stream + the device/workspace entry)
     DevBuf ref_scratch64[kStreams + 1]; // mixed mode: reference terms of the fp64 re-solve pass
     DevBuf marked[kStreams + 1];        // mixed mode: indices of the problems the fp32 pass marked ambiguous (two-pass form) / the queue
+    DevBuf order_buf;                   // claim order of the device-resident entry: 256 histogram words, n list words, n bucket bytes
     cudaEvent_t ev_pass = nullptr, ev_copied = nullptr;   // compact streamed pipeline: end of the first pass / of the early result copies
     // exact-count mode, concurrent form: per slot {q_tail, producer CTAs done, consumer ticket counter, pad}
     int* qctl = nullptr;                // 4 * kMaxChunks ints, indexed like the work counters (chunk index; the last one = device entry)
@@ -106,6 +107,8 @@ struct tinympc_cuda_solver {
                                        // (run_shard_compact_streamed); 0 = the chunked pipeline
     int compact_early_d2h = 1;         // option "compact_early_d2h": exact-count mode of that pipeline with pinned result arrays -- the results
                                        // of the first pass are copied back under the fp64 pass, whose results a kernel then writes over them
+    int order = 1;                     // option "order": 1 = device-resident batches of box families are claimed hardest-first (counting sort by
+                                       // the expected difficulty, see order_count_kernel), 0 = in index order
     int compact_in_kernel = 1;         // option "compact_in_kernel": kernels read tinympc_cuda_batch_in::xref_const in place where they can;
                                        // 0 = always replicate it over the horizon on the device first
     double mixed_band = 0;             // option "mixed": > 0 = fp32 pass + fp64 re-solve of the problems whose termination decision
@@ -242,6 +245,87 @@ __global__ void scatter_marked_to_host_kernel(const int* __restrict__ list, cons
     }
 }
 
+// ---- claim order: hardest problems first -----------------------------------------------------------------------------------
+// The thread-per-problem kernels hold one problem per lane until it converges, and problems take anything from one check
+// interval to max_iter iterations.  In claim order = index order a warp's lanes hold problems of all lengths (its refill passes
+// serve one or two lanes at a time) and the launch ends with a tail in which every lane finishes whatever it happened to hold.
+// How far the unconstrained feedback -Kinf (x0 - xref_0) leaves the input bounds predicts the iteration count well (rank
+// correlation 0.9 on the quadrotor batch): key = max_a |Kinf (x0 - xref_0)|_a / min(-u_min_a, u_max_a).  The three kernels below
+// bucket the batch by that key (256 buckets, hardest first; counting sort: count, scan, scatter) into an index list the solve
+// kernel claims from.  Lanes of a warp then hold problems of similar length and the tail consists of the shortest ones:
+// 15.2 -> 13.9 ms on the 2^20 quadrotor batch (profiles/r02/order_study.jsonl) for ~0.05 ms of pre-pass.  Scheduling only:
+// every problem is solved by the same code whatever its position (the permutation test holds the results to bit identity).
+constexpr int kOrderBuckets = 256, kOrderBlock = 256, kOrderItems = 4;
+struct OrderParams {
+    float K[8 * 16];      // Kinf, row-major nu x nx
+    float inv_ub[8];      // 1 / min(-u_min_a, u_max_a)
+    int nx, nu, xref_stride;   // xref_stride: floats between the reference states of consecutive problems (nx: compact, nx*N: full, 0: none)
+};
+__device__ __forceinline__ int order_bucket(const OrderParams& op, const float* __restrict__ x0, const float* __restrict__ xref, int i) {
+    float key = 0.f;
+    for (int a = 0; a < op.nu; ++a) {
+        float acc = 0.f;
+        for (int c = 0; c < op.nx; ++c) {
+            float dv = __ldg(x0 + (size_t)i * op.nx + c);
+            if (xref) dv -= __ldg(xref + (size_t)i * op.xref_stride + c);
+            acc = fmaf(op.K[a * op.nx + c], dv, acc);
+        }
+        key = fmaxf(key, fabsf(acc) * op.inv_ub[a]);
+    }
+    // 64 buckets per unit of key: everything beyond 4x the bound is "hardest"; bucket 0 of the LIST is the hardest
+    const int b = min(kOrderBuckets - 1, __float2int_rd(key * 64.f));
+    return kOrderBuckets - 1 - (b < 0 ? kOrderBuckets - 1 : b);      // NaN / negative: treat as hardest
+}
+__global__ void __launch_bounds__(kOrderBlock) order_count_kernel(const __grid_constant__ OrderParams op, const float* __restrict__ x0,
+                                                                  const float* __restrict__ xref, int n, unsigned char* __restrict__ bucket,
+                                                                  int* __restrict__ hist) {
+    __shared__ int sh[kOrderBuckets];
+    for (int b = threadIdx.x; b < kOrderBuckets; b += kOrderBlock) sh[b] = 0;
+    __syncthreads();
+    for (int k = 0; k < kOrderItems; ++k) {
+        const int i = (blockIdx.x * kOrderItems + k) * kOrderBlock + threadIdx.x;
+        if (i < n) {
+            const int b = order_bucket(op, x0, xref, i);
+            bucket[i] = (unsigned char)b;
+            atomicAdd(&sh[b], 1);
+        }
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < kOrderBuckets; b += kOrderBlock) if (sh[b]) atomicAdd(&hist[b], sh[b]);
+}
+__global__ void order_scan_kernel(int* __restrict__ hist) {   // one block of kOrderBuckets threads: exclusive prefix sum in place
+    __shared__ int sh[kOrderBuckets];
+    const int t = threadIdx.x;
+    sh[t] = hist[t];
+    __syncthreads();
+    for (int o = 1; o < kOrderBuckets; o <<= 1) {
+        const int v = t >= o ? sh[t - o] : 0;
+        __syncthreads();
+        sh[t] += v;
+        __syncthreads();
+    }
+    hist[t] = sh[t] - hist[t];
+}
+__global__ void __launch_bounds__(kOrderBlock) order_scatter_kernel(const unsigned char* __restrict__ bucket, int n, int* __restrict__ offset,
+                                                                    int* __restrict__ list) {
+    __shared__ int cnt[kOrderBuckets], base[kOrderBuckets];
+    for (int b = threadIdx.x; b < kOrderBuckets; b += kOrderBlock) cnt[b] = 0;
+    __syncthreads();
+    int bk[kOrderItems], rk[kOrderItems];
+    for (int k = 0; k < kOrderItems; ++k) {
+        const int i = (blockIdx.x * kOrderItems + k) * kOrderBlock + threadIdx.x;
+        bk[k] = i < n ? bucket[i] : -1;
+        rk[k] = bk[k] >= 0 ? atomicAdd(&cnt[bk[k]], 1) : 0;          // rank inside the block's share of the bucket
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < kOrderBuckets; b += kOrderBlock) base[b] = cnt[b] ? atomicAdd(&offset[b], cnt[b]) : 0;
+    __syncthreads();
+    for (int k = 0; k < kOrderItems; ++k) {
+        const int i = (blockIdx.x * kOrderItems + k) * kOrderBlock + threadIdx.x;
+        if (bk[k] >= 0) list[base[bk[k]] + rk[k]] = i;
+    }
+}
+
 // device alias of a pinned (page-locked, mapped) host pointer; false for pageable memory
 bool host_alias(const void* p, void** alias) {
     cudaPointerAttributes a{};
@@ -369,6 +453,32 @@ bool compact_in_kernel(const tinympc_cuda_solver* s, const DeviceCtx& d, bool pp
 
 constexpr int kDirectXref = 1, kDirectU0 = 2;   // enqueue(): compact I/O handed to the kernels as it is
 
+// Claim order of a device-resident batch (order_count_kernel): the index list, hardest problems first, built on `st`.
+int build_order(tinympc_cuda_solver* s, DeviceCtx& d, const SolveParams& p, int n, cudaStream_t st, const int** list_out) {
+    const Family& f = s->fam;
+    OrderParams op{};
+    op.nx = f.nx; op.nu = f.nu;
+    op.xref_stride = p.Xref ? (p.xref_const ? f.nx : f.nx * f.N) : 0;
+    for (int a = 0; a < f.nu; ++a) {
+        for (int c = 0; c < f.nx; ++c) op.K[a * f.nx + c] = static_cast<float>(f.pack[f.L.Kinf + a * f.nx + c]);
+        const double ub = std::min(-f.pack[f.L.umin + a], f.pack[f.L.umax + a]);     // the bounds of the first step
+        op.inv_ub[a] = (ub > 0 && std::isfinite(ub)) ? static_cast<float>(1.0 / ub) : 0.f;
+    }
+    CU(s, d.order_buf.reserve(sizeof(int) * (kOrderBuckets + (size_t)n) + (size_t)n));
+    int* hist = static_cast<int*>(d.order_buf.p);
+    int* list = hist + kOrderBuckets;
+    unsigned char* bucket = reinterpret_cast<unsigned char*>(list + n);
+    const int blocks = (n + kOrderBlock * kOrderItems - 1) / (kOrderBlock * kOrderItems);
+    CU(s, cudaMemsetAsync(hist, 0, sizeof(int) * kOrderBuckets, st));
+    order_count_kernel<<<blocks, kOrderBlock, 0, st>>>(op, p.x0, p.Xref, n, bucket, hist);
+    order_scan_kernel<<<1, kOrderBuckets, 0, st>>>(hist);
+    order_scatter_kernel<<<blocks, kOrderBlock, 0, st>>>(bucket, n, hist, list);
+    CU(s, cudaGetLastError());
+    s->launches += 3;
+    *list_out = list;
+    return TINYMPC_CUDA_OK;
+}
+
 // Enqueue the solve of `in`/`out` (device pointers) on `st`.  slot selects the work counters and scratch buffers
 // (one set per pipeline stream + one for the device-resident entry point).
 int enqueue(tinympc_cuda_solver* s, DeviceCtx& d, const tinympc_cuda_batch_in& in, const tinympc_cuda_batch_out& out, int counter_slot,
@@ -463,13 +573,23 @@ int enqueue(tinympc_cuda_solver* s, DeviceCtx& d, const tinympc_cuda_batch_in& i
         return TINYMPC_CUDA_OK;
     }
     int* const counter = d.counters + counter_slot;
+    // device-resident batches of a few waves: the fp32 thread-per-problem kernels claim the hardest problems first (build_order)
+    if (s->order && scratch_slot == kStreams && bits == 32 && f.feat == kFeatBox && !ppb && f.shared_bounds_ok && p.en_input_bound &&
+        ke->lanes_per_problem <= 1 && f.nx <= 16 && f.nu <= 8 && (long long)in.batch >= 2LL * d.sm_count * ke->block) {
+        int rc = build_order(s, d, p, in.batch, st, &p.index_list);
+        if (rc) return rc;
+    }
     if (!mixed) {
         int rc = launch_tpp(s, d, ke, p, d.ref_scratch[scratch_slot], bits, counter, st);
         if (rc) return rc;
         note_kernel(s, ke->name);
         return TINYMPC_CUDA_OK;
     }
-    if (s->fixer_sms >= 0) return launch_exact_pair(s, d, ke, ke64, p, p, in.batch, counter_slot, scratch_slot, counter, st);
+    if (s->fixer_sms >= 0) {
+        SolveParams p64 = p;
+        p64.index_list = nullptr;          // the consumer takes its problems from the queue
+        return launch_exact_pair(s, d, ke, ke64, p, p64, in.batch, counter_slot, scratch_slot, counter, st);
+    }
     // ---- mixed mode, sequential form: fp32 pass that marks the ambiguous problems, compaction, fp64 re-solve of the marked ones ----
     int* const counter2 = d.counters + kMaxChunks + counter_slot;
     int* const n_marked = d.counters + 2 * kMaxChunks + counter_slot;
@@ -1070,6 +1190,7 @@ int tinympc_cuda_destroy(tinympc_cuda_solver* s) {
         for (auto& b : d.ref_scratch) b.release();
         for (auto& b : d.ref_scratch64) b.release();
         for (auto& b : d.marked) b.release();
+        d.order_buf.release();
     }
     cudaSetDevice(prev);
     delete s;
@@ -1575,6 +1696,8 @@ int tinympc_cuda_set_option(tinympc_cuda_solver* s, const char* name, double val
         s->compact_streamed = value != 0;
     } else if (n == "compact_early_d2h") {
         s->compact_early_d2h = value != 0;
+    } else if (n == "order") {
+        s->order = value != 0;
     } else if (n == "compact_in_kernel") {
         s->compact_in_kernel = value != 0;
     } else if (n == "refill_min") {
