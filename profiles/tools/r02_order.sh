@@ -14,15 +14,11 @@ for f in sys.argv[1:]:
     except Exception as ex: print(f, "failed", ex)
 PY
 }
+timeout 200 python profiles/tools/e2e_compact_sweep.py > $O/e2e_compact_sweep.jsonl 2> $O/e2e_compact_sweep.err; cut -c1-250 $O/e2e_compact_sweep.jsonl; tail -3 $O/e2e_compact_sweep.err
 timeout 300 python bench.py --no-cpu-baseline > $O/bench_quadrotor_order.json 2> $O/bench.err
 timeout 300 python bench.py --no-cpu-baseline --order 0 > $O/bench_quadrotor_indexorder.json 2>> $O/bench.err
 timeout 300 python bench.py --config cartpole --no-cpu-baseline > $O/bench_cartpole_order.json 2>> $O/bench.err
 timeout 300 python bench.py --config cartpole --no-cpu-baseline --order 0 > $O/bench_cartpole_indexorder.json 2>> $O/bench.err
-timeout 300 python bench.py --scale 0.3 --no-cpu-baseline --parity-n 0 > $O/bench_quadrotor_easy_order.json 2>> $O/bench.err
-timeout 300 python bench.py --scale 0.3 --no-cpu-baseline --parity-n 0 --order 0 > $O/bench_quadrotor_easy_indexorder.json 2>> $O/bench.err
-timeout 300 python bench.py --mixed 0 --no-cpu-baseline --no-e2e > $O/bench_quadrotor_plainfp32_order.json 2>> $O/bench.err
-timeout 300 python bench.py --batch 131072 --no-cpu-baseline --no-e2e --parity-n 0 > $O/bench_quadrotor_b131072_order.json 2>> $O/bench.err
-timeout 300 python bench.py --batch 131072 --no-cpu-baseline --no-e2e --parity-n 0 --order 0 > $O/bench_quadrotor_b131072_indexorder.json 2>> $O/bench.err
 tail -3 $O/bench.err
 show $O/bench_*.json
 (time timeout 600 python -m pytest tests -m gpu -q) > $O/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> $O/pytest_gpu.log; tail -6 $O/pytest_gpu.log

@@ -456,6 +456,19 @@ def test_claim_order_is_scheduling_only(family, mixed, fixer_sms, capi, oracle_m
         for k in res:
             assert np.array_equal(res[k], r[k]), f"{family}: order={order} changes {k}"
     assert launches[1] == launches[0] + 3, launches      # count, scan, scatter
+    # the compact streamed host pipeline orders too: the first quarter of the shard in index order while the rest is still
+    # arriving, the rest hardest-first through a list built meanwhile on the SMs the persistent launch leaves free
+    if fixer_sms < 0 and (b.Xref is None or (b.Xref == b.Xref[:, :1]).all()):
+        xcn = None if b.Xref is None else np.ascontiguousarray(b.Xref[:, 0, :])
+        for order in (1, 0, 1):
+            s.set_option("order", order)
+            n0 = s.launch_count
+            c = s.solve_batch(b.x0, xref_const=xcn, compact_out=True)
+            launches[order] = s.launch_count - n0
+            assert s.last_timing()["chunks"] >= 3, s.last_timing()
+            assert np.array_equal(c["iter"], res["iter"]) and np.array_equal(c["status"], res["status"]), f"{family}: streamed, order={order}"
+            assert np.array_equal(c["u0"], res["u0"] if compact else res["u"][:, 0, :]), f"{family}: streamed, order={order}"
+        assert launches[1] == launches[0] + 3, launches
     s.close()
 
 

@@ -276,16 +276,17 @@ __device__ __forceinline__ int order_bucket(const OrderParams& op, const float* 
     const int b = min(kOrderBuckets - 1, __float2int_rd(key * 64.f));
     return kOrderBuckets - 1 - (b < 0 ? kOrderBuckets - 1 : b);      // NaN / negative: treat as hardest
 }
+// problems first .. first + n - 1 of the arrays; bucket[] and the list positions are relative to `first`, the list ENTRIES are problem indices
 __global__ void __launch_bounds__(kOrderBlock) order_count_kernel(const __grid_constant__ OrderParams op, const float* __restrict__ x0,
-                                                                  const float* __restrict__ xref, int n, unsigned char* __restrict__ bucket,
-                                                                  int* __restrict__ hist) {
+                                                                  const float* __restrict__ xref, int first, int n,
+                                                                  unsigned char* __restrict__ bucket, int* __restrict__ hist) {
     __shared__ int sh[kOrderBuckets];
     for (int b = threadIdx.x; b < kOrderBuckets; b += kOrderBlock) sh[b] = 0;
     __syncthreads();
     for (int k = 0; k < kOrderItems; ++k) {
         const int i = (blockIdx.x * kOrderItems + k) * kOrderBlock + threadIdx.x;
         if (i < n) {
-            const int b = order_bucket(op, x0, xref, i);
+            const int b = order_bucket(op, x0, xref, first + i);
             bucket[i] = (unsigned char)b;
             atomicAdd(&sh[b], 1);
         }
@@ -306,8 +307,8 @@ __global__ void order_scan_kernel(int* __restrict__ hist) {   // one block of kO
     }
     hist[t] = sh[t] - hist[t];
 }
-__global__ void __launch_bounds__(kOrderBlock) order_scatter_kernel(const unsigned char* __restrict__ bucket, int n, int* __restrict__ offset,
-                                                                    int* __restrict__ list) {
+__global__ void __launch_bounds__(kOrderBlock) order_scatter_kernel(const unsigned char* __restrict__ bucket, int first, int n,
+                                                                    int* __restrict__ offset, int* __restrict__ list) {
     __shared__ int cnt[kOrderBuckets], base[kOrderBuckets];
     for (int b = threadIdx.x; b < kOrderBuckets; b += kOrderBlock) cnt[b] = 0;
     __syncthreads();
@@ -322,7 +323,7 @@ __global__ void __launch_bounds__(kOrderBlock) order_scatter_kernel(const unsign
     __syncthreads();
     for (int k = 0; k < kOrderItems; ++k) {
         const int i = (blockIdx.x * kOrderItems + k) * kOrderBlock + threadIdx.x;
-        if (bk[k] >= 0) list[base[bk[k]] + rk[k]] = i;
+        if (bk[k] >= 0) list[base[bk[k]] + rk[k]] = first + i;
     }
 }
 
@@ -454,7 +455,7 @@ bool compact_in_kernel(const tinympc_cuda_solver* s, const DeviceCtx& d, bool pp
 constexpr int kDirectXref = 1, kDirectU0 = 2;   // enqueue(): compact I/O handed to the kernels as it is
 
 // Claim order of a device-resident batch (order_count_kernel): the index list, hardest problems first, built on `st`.
-int build_order(tinympc_cuda_solver* s, DeviceCtx& d, const SolveParams& p, int n, cudaStream_t st, const int** list_out) {
+int build_order(tinympc_cuda_solver* s, DeviceCtx& d, const SolveParams& p, int first, int n, cudaStream_t st, const int** list_out) {
     const Family& f = s->fam;
     OrderParams op{};
     op.nx = f.nx; op.nu = f.nu;
@@ -470,9 +471,9 @@ int build_order(tinympc_cuda_solver* s, DeviceCtx& d, const SolveParams& p, int 
     unsigned char* bucket = reinterpret_cast<unsigned char*>(list + n);
     const int blocks = (n + kOrderBlock * kOrderItems - 1) / (kOrderBlock * kOrderItems);
     CU(s, cudaMemsetAsync(hist, 0, sizeof(int) * kOrderBuckets, st));
-    order_count_kernel<<<blocks, kOrderBlock, 0, st>>>(op, p.x0, p.Xref, n, bucket, hist);
+    order_count_kernel<<<blocks, kOrderBlock, 0, st>>>(op, p.x0, p.Xref, first, n, bucket, hist);
     order_scan_kernel<<<1, kOrderBuckets, 0, st>>>(hist);
-    order_scatter_kernel<<<blocks, kOrderBlock, 0, st>>>(bucket, n, hist, list);
+    order_scatter_kernel<<<blocks, kOrderBlock, 0, st>>>(bucket, first, n, hist, list);
     CU(s, cudaGetLastError());
     s->launches += 3;
     *list_out = list;
@@ -576,7 +577,7 @@ int enqueue(tinympc_cuda_solver* s, DeviceCtx& d, const tinympc_cuda_batch_in& i
     // device-resident batches of a few waves: the fp32 thread-per-problem kernels claim the hardest problems first (build_order)
     if (s->order && scratch_slot == kStreams && bits == 32 && f.feat == kFeatBox && !ppb && f.shared_bounds_ok && p.en_input_bound &&
         ke->lanes_per_problem <= 1 && f.nx <= 16 && f.nu <= 8 && (long long)in.batch >= 2LL * d.sm_count * ke->block) {
-        int rc = build_order(s, d, p, in.batch, st, &p.index_list);
+        int rc = build_order(s, d, p, 0, in.batch, st, &p.index_list);
         if (rc) return rc;
     }
     if (!mixed) {
@@ -892,15 +893,31 @@ int run_shard_compact_streamed(tinympc_cuda_solver* s, DeviceCtx& d, const Kerne
         CUresult r = ops.write(reinterpret_cast<CUstream>(s_in), reinterpret_cast<CUdeviceptr>(ctl + 1), (cuuint32_t)c1, 0);
         if (r != CUDA_SUCCESS) return sync_fail(fail(s, TINYMPC_CUDA_ECUDA, "cuStreamWriteValue32 failed with CUresult " + std::to_string((int)r)));
     }
+    // Claim order (option "order", build_order): the first quarter of the shard is claimed in index order behind the watermark,
+    // as it arrives; the rest is bucketed by expected difficulty once it has all landed -- on the input stream, on the two SMs
+    // the persistent launch leaves free for it -- and claimed hardest-first through the list (SolveParams::order_from), whose
+    // completion the host signals by moving the watermark past the shard size.
+    int reserve = 0;
+    if (s->order && ke->order_from_ok && bits == 32 && f.feat == kFeatBox && !ppb && f.shared_bounds_ok && p.en_input_bound &&
+        f.nx <= 16 && f.nu <= 8 && n >= (1 << 18) && nch >= 3) {
+        int first = bounds[1];
+        for (int c = 1; c <= nch && bounds[c] <= n / 4; ++c) first = bounds[c];     // a chunk boundary: whole 128-byte lines on either side
+        int rc = build_order(s, d, p, first, n - first, s_in, &p.index_list);
+        if (rc) return sync_fail(rc);
+        p.order_from = first;
+        CUresult r = ops.write(reinterpret_cast<CUstream>(s_in), reinterpret_cast<CUdeviceptr>(ctl + 1), (cuuint32_t)(n + 1), 0);
+        if (r != CUDA_SUCCESS) return sync_fail(fail(s, TINYMPC_CUDA_ECUDA, "cuStreamWriteValue32 failed with CUresult " + std::to_string((int)r)));
+        reserve = 2;
+    }
     RT(cudaEventRecord(d.k0[0], s_k));
     int* const n_marked = d.counters + 2 * kMaxChunks;
     if (!mixed) {
-        int rc = launch_tpp(s, d, ke, p, d.ref_scratch[0], bits, ctl, s_k);
+        int rc = launch_tpp(s, d, ke, p, d.ref_scratch[0], bits, ctl, s_k, reserve);
         if (rc) return sync_fail(rc);
         note_kernel(s, ke->name);
     } else {   // sequential exact-count form (enqueue()): fp32 pass that marks, compaction, fp64 re-solve of the marked problems
         p.amb_band = static_cast<float>(s->mixed_band);
-        int rc = launch_tpp(s, d, ke, p, d.ref_scratch[0], 32, ctl, s_k);
+        int rc = launch_tpp(s, d, ke, p, d.ref_scratch[0], 32, ctl, s_k, reserve);
         if (rc) return sync_fail(rc);
         if (early) {
             cudaStream_t s_out = d.streams[2];
@@ -919,6 +936,7 @@ int run_shard_compact_streamed(tinympc_cuda_solver* s, DeviceCtx& d, const Kerne
         p2.pack = (const void*)((const double*)d.pack64 + f.L.cold);
         p2.amb_band = 0.f;
         p2.avail_ptr = nullptr;            // the first pass has seen every problem
+        p2.order_from = 0;
         p2.index_list = static_cast<const int*>(list.p);
         p2.batch_ptr = n_marked;
         rc = launch_tpp(s, d, ke64, p2, d.ref_scratch64[0], 64, d.counters + kMaxChunks, s_k);

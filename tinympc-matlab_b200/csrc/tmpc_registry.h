@@ -44,6 +44,8 @@ struct KernelEntry {
     // SolveParams::u0 (first control as the only solution output); 0: the library expands a compact reference on the device
     // before the launch and gathers u0 from the full trajectories after it
     int compact_ok;
+    // 1: honours SolveParams::order_from (a streamed batch whose later part is claimed through a list built meanwhile)
+    int order_from_ok;
 };
 
 const KernelEntry* const* kernel_table(int* count);   // defined in gen/tmpc_table.cu
@@ -93,7 +95,7 @@ const KernelEntry* const* kernel_table(int* count);   // defined in gen/tmpc_tab
     extern const KernelEntry SYM = {#SYM, KF_TPP, CFG::NX, CFG::NU, CFG::NH, FEATV, BITS, CFG::REFMODE,             \
                                     CFG::PPB ? 1 : 0, CFG::FB ? 1 : 0, CFG::AFF ? 1 : 0, CFG::BLOCK, VAR, 1, SYM##_smem, SYM##_prepare, \
                                     SYM##_occ, SYM##_launch, CFG::CONSTR ? 1 : 0, CFG::SCS, CFG::SCD, CFG::UCS, CFG::UCD, CFG::NSL, CFG::NIL, \
-                                    0, nullptr, 1};                                                                 \
+                                    0, nullptr, 1, 1};                                                              \
     }
 
 // mixed-precision rocket-family kernel (tmpc_tpp4.cuh)

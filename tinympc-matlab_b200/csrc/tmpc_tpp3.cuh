@@ -365,17 +365,19 @@ tpp3_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ typ
                         exhausted = true;
                         prob = 0;
                     } else {
-                        if (prm.index_list) claim = __ldg(prm.index_list + claim);
+                        if (prm.index_list && prm.order_from == 0) claim = __ldg(prm.index_list + claim);
                         pending = true;
                     }
                 }
             }
-            // a claimed problem starts once its inputs have landed (always, unless the host streams the batch in)
-            const bool mine = pending && problem_ready(prm, claim, seen);
+            // a claimed problem starts once its inputs have landed (always, unless the host streams the batch in); a work item of the
+            // ordered part of a streamed batch (SolveParams::order_from) once its list is complete, i.e. the watermark has passed `batch`
+            const bool listed = prm.order_from > 0 && claim >= prm.order_from;
+            const bool mine = pending && problem_ready(prm, listed ? prm.batch : claim, seen);
             const unsigned m = __ballot_sync(FULL, mine);
             if (m) {
                 if (mine) {
-                    prob = claim;
+                    prob = listed ? ld_relaxed_gpu(prm.index_list + (claim - prm.order_from)) : claim;
                     pending = false;
                     active = true;
                     k = 0;
