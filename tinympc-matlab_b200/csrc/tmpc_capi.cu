@@ -454,8 +454,9 @@ bool compact_in_kernel(const tinympc_cuda_solver* s, const DeviceCtx& d, bool pp
 
 constexpr int kDirectXref = 1, kDirectU0 = 2;   // enqueue(): compact I/O handed to the kernels as it is
 
-// Claim order of a device-resident batch (order_count_kernel): the index list, hardest problems first, built on `st`.
-int build_order(tinympc_cuda_solver* s, DeviceCtx& d, const SolveParams& p, int first, int n, cudaStream_t st, const int** list_out) {
+// Claim order (order_count_kernel): problems first .. first + n - 1 bucketed hardest-first into list[0 .. n) (entries = problem
+// indices), on `st`.  hist: kOrderBuckets ints, bucket: n bytes of scratch.
+int build_order_range(tinympc_cuda_solver* s, const SolveParams& p, int first, int n, int* hist, int* list, unsigned char* bucket, cudaStream_t st) {
     const Family& f = s->fam;
     OrderParams op{};
     op.nx = f.nx; op.nu = f.nu;
@@ -465,10 +466,6 @@ int build_order(tinympc_cuda_solver* s, DeviceCtx& d, const SolveParams& p, int 
         const double ub = std::min(-f.pack[f.L.umin + a], f.pack[f.L.umax + a]);     // the bounds of the first step
         op.inv_ub[a] = (ub > 0 && std::isfinite(ub)) ? static_cast<float>(1.0 / ub) : 0.f;
     }
-    CU(s, d.order_buf.reserve(sizeof(int) * (kOrderBuckets + (size_t)n) + (size_t)n));
-    int* hist = static_cast<int*>(d.order_buf.p);
-    int* list = hist + kOrderBuckets;
-    unsigned char* bucket = reinterpret_cast<unsigned char*>(list + n);
     const int blocks = (n + kOrderBlock * kOrderItems - 1) / (kOrderBlock * kOrderItems);
     CU(s, cudaMemsetAsync(hist, 0, sizeof(int) * kOrderBuckets, st));
     order_count_kernel<<<blocks, kOrderBlock, 0, st>>>(op, p.x0, p.Xref, first, n, bucket, hist);
@@ -476,8 +473,24 @@ int build_order(tinympc_cuda_solver* s, DeviceCtx& d, const SolveParams& p, int 
     order_scatter_kernel<<<blocks, kOrderBlock, 0, st>>>(bucket, first, n, hist, list);
     CU(s, cudaGetLastError());
     s->launches += 3;
-    *list_out = list;
     return TINYMPC_CUDA_OK;
+}
+// ... of a whole device-resident batch; order_buf: hist per range (kMaxGranules of them) | list | bucket bytes
+int reserve_order(tinympc_cuda_solver* s, DeviceCtx& d, int n, int** hist, int** list, unsigned char** bucket) {
+    CU(s, d.order_buf.reserve(sizeof(int) * ((size_t)kOrderBuckets * kMaxGranules + (size_t)n) + (size_t)n));
+    *hist = static_cast<int*>(d.order_buf.p);
+    *list = *hist + kOrderBuckets * kMaxGranules;
+    *bucket = reinterpret_cast<unsigned char*>(*list + n);
+    return TINYMPC_CUDA_OK;
+}
+int build_order(tinympc_cuda_solver* s, DeviceCtx& d, const SolveParams& p, int n, cudaStream_t st, const int** list_out) {
+    int *hist, *list;
+    unsigned char* bucket;
+    int rc = reserve_order(s, d, n, &hist, &list, &bucket);
+    if (rc) return rc;
+    rc = build_order_range(s, p, 0, n, hist, list, bucket, st);
+    *list_out = list;
+    return rc;
 }
 
 // Enqueue the solve of `in`/`out` (device pointers) on `st`.  slot selects the work counters and scratch buffers
@@ -577,7 +590,7 @@ int enqueue(tinympc_cuda_solver* s, DeviceCtx& d, const tinympc_cuda_batch_in& i
     // device-resident batches of a few waves: the fp32 thread-per-problem kernels claim the hardest problems first (build_order)
     if (s->order && scratch_slot == kStreams && bits == 32 && f.feat == kFeatBox && !ppb && f.shared_bounds_ok && p.en_input_bound &&
         ke->lanes_per_problem <= 1 && f.nx <= 16 && f.nu <= 8 && (long long)in.batch >= 2LL * d.sm_count * ke->block) {
-        int rc = build_order(s, d, p, 0, in.batch, st, &p.index_list);
+        int rc = build_order(s, d, p, in.batch, st, &p.index_list);
         if (rc) return rc;
     }
     if (!mixed) {
@@ -879,6 +892,25 @@ int run_shard_compact_streamed(tinympc_cuda_solver* s, DeviceCtx& d, const Kerne
 
     auto sync_fail = [&](int rc) -> int { cudaDeviceSynchronize(); return rc; };
 #define RT(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return sync_fail(cuda_fail(s, e__, #call)); } while (0)
+    // Claim order (option "order", order_count_kernel): the chunks of the first quarter of the shard are claimed in index order as they
+    // arrive; every later chunk is bucketed by expected difficulty as soon as it has landed -- on the third stream, on the two SMs the
+    // persistent launch leaves free for it -- and claimed hardest-first through its part of the list (SolveParams::order_from); the
+    // watermark moves past such a chunk when its list is written.  The last chunk (half the shard) is ordered ~0.5 ms after it
+    // landed, long before the lanes get there, and it ends on its easiest problems: the tail of the launch.
+    int reserve = 0, first_ordered = nch;
+    int *ohist = nullptr, *olist = nullptr;
+    unsigned char* obucket = nullptr;
+    if (s->order && ke->order_from_ok && bits == 32 && f.feat == kFeatBox && !ppb && f.shared_bounds_ok && p.en_input_bound &&
+        f.nx <= 16 && f.nu <= 8 && n >= (1 << 18) && nch >= 3 && nch <= kMaxGranules) {
+        first_ordered = 1;
+        while (first_ordered < nch - 1 && bounds[first_ordered + 1] <= n / 4) ++first_ordered;
+        int rc = reserve_order(s, d, n, &ohist, &olist, &obucket);
+        if (rc) return sync_fail(rc);
+        p.index_list = olist;                       // entry (c - order_from) for work item c
+        p.order_from = bounds[first_ordered];
+        reserve = 2;                                // SMs for the ordering kernels: the 1/4 .. 1/2 chunk must be listed before the first quarter is used up
+    }
+    cudaStream_t s_ord = d.streams[2];
     for (int c = 0; c < nch; ++c) {
         const int c0 = bounds[c], c1 = bounds[c + 1], cn = c1 - c0;
         const size_t g0 = (size_t)lo + c0;
@@ -890,24 +922,18 @@ int run_shard_compact_streamed(tinympc_cuda_solver* s, DeviceCtx& d, const Kerne
         if (in.Xref) RT(h2d(d.Xref, in.Xref, sx));
         if (in.Uref) RT(h2d(d.Uref, in.Uref, su));
         if (ppb) { RT(h2d(d.xmin, in.x_min, sx)); RT(h2d(d.xmax, in.x_max, sx)); RT(h2d(d.umin, in.u_min, su)); RT(h2d(d.umax, in.u_max, su)); }
-        CUresult r = ops.write(reinterpret_cast<CUstream>(s_in), reinterpret_cast<CUdeviceptr>(ctl + 1), (cuuint32_t)c1, 0);
+        cudaStream_t s_w = s_in;                    // the stream that publishes the chunk
+        if (c >= first_ordered) {
+            // (the events of the chunked pipeline are idle here; the watermark writes of the ordered chunks follow those of the
+            // chunks before them: s_ord waits for an event recorded behind them)
+            RT(cudaEventRecord(d.k1[c], s_in));
+            RT(cudaStreamWaitEvent(s_ord, d.k1[c], 0));
+            int rc = build_order_range(s, p, c0, cn, ohist + (size_t)kOrderBuckets * c, olist + (c0 - p.order_from), obucket + c0, s_ord);
+            if (rc) return sync_fail(rc);
+            s_w = s_ord;
+        }
+        CUresult r = ops.write(reinterpret_cast<CUstream>(s_w), reinterpret_cast<CUdeviceptr>(ctl + 1), (cuuint32_t)c1, 0);
         if (r != CUDA_SUCCESS) return sync_fail(fail(s, TINYMPC_CUDA_ECUDA, "cuStreamWriteValue32 failed with CUresult " + std::to_string((int)r)));
-    }
-    // Claim order (option "order", build_order): the first quarter of the shard is claimed in index order behind the watermark,
-    // as it arrives; the rest is bucketed by expected difficulty once it has all landed -- on the input stream, on the two SMs
-    // the persistent launch leaves free for it -- and claimed hardest-first through the list (SolveParams::order_from), whose
-    // completion the host signals by moving the watermark past the shard size.
-    int reserve = 0;
-    if (s->order && ke->order_from_ok && bits == 32 && f.feat == kFeatBox && !ppb && f.shared_bounds_ok && p.en_input_bound &&
-        f.nx <= 16 && f.nu <= 8 && n >= (1 << 18) && nch >= 3) {
-        int first = bounds[1];
-        for (int c = 1; c <= nch && bounds[c] <= n / 4; ++c) first = bounds[c];     // a chunk boundary: whole 128-byte lines on either side
-        int rc = build_order(s, d, p, first, n - first, s_in, &p.index_list);
-        if (rc) return sync_fail(rc);
-        p.order_from = first;
-        CUresult r = ops.write(reinterpret_cast<CUstream>(s_in), reinterpret_cast<CUdeviceptr>(ctl + 1), (cuuint32_t)(n + 1), 0);
-        if (r != CUDA_SUCCESS) return sync_fail(fail(s, TINYMPC_CUDA_ECUDA, "cuStreamWriteValue32 failed with CUresult " + std::to_string((int)r)));
-        reserve = 2;
     }
     RT(cudaEventRecord(d.k0[0], s_k));
     int* const n_marked = d.counters + 2 * kMaxChunks;

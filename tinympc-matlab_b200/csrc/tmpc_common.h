@@ -141,10 +141,10 @@ struct SolveParams {
     int xref_const;
     float* u0;
     // Streamed batch with an ordered part (tmpc_capi.cu run_shard_compact_streamed): work items below order_from are problem
-    // indices, claimed in index order behind the arrival watermark; item c >= order_from is problem index_list[c - order_from]
-    // of a list that is built on the device while the first part is being solved and is complete once the watermark has passed
-    // `batch` (the host writes batch + 1 behind the kernels that build it).  0 = index_list, if any, covers every work item.
-    // Honoured by the incremental fp32 kernel (tmpc_tpp3.cuh).
+    // indices; item c >= order_from is problem index_list[c - order_from].  The list is built on the device chunk by chunk, as
+    // the chunks arrive and while earlier items are being solved; the arrival watermark moves past a chunk only when its part of
+    // the list is written too, so a lane waits for item c exactly as it waits for problem c.  0 = index_list, if any, covers every
+    // work item.  Honoured by the incremental fp32 kernel (tmpc_tpp3.cuh).
     int order_from;
 };
 

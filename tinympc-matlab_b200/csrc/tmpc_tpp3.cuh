@@ -370,10 +370,10 @@ tpp3_kernel(const __grid_constant__ SolveParams prm, const __grid_constant__ typ
                     }
                 }
             }
-            // a claimed problem starts once its inputs have landed (always, unless the host streams the batch in); a work item of the
-            // ordered part of a streamed batch (SolveParams::order_from) once its list is complete, i.e. the watermark has passed `batch`
+            // a claimed work item starts once the watermark covers it (always, unless the host streams the batch in): its inputs have
+            // landed and, in the ordered part of a streamed batch (SolveParams::order_from), its list entry is written
             const bool listed = prm.order_from > 0 && claim >= prm.order_from;
-            const bool mine = pending && problem_ready(prm, listed ? prm.batch : claim, seen);
+            const bool mine = pending && problem_ready(prm, claim, seen);
             const unsigned m = __ballot_sync(FULL, mine);
             if (m) {
                 if (mine) {
