@@ -468,7 +468,7 @@ def test_claim_order_is_scheduling_only(family, mixed, fixer_sms, capi, oracle_m
             assert s.last_timing()["chunks"] >= 3, s.last_timing()
             assert np.array_equal(c["iter"], res["iter"]) and np.array_equal(c["status"], res["status"]), f"{family}: streamed, order={order}"
             assert np.array_equal(c["u0"], res["u0"] if compact else res["u"][:, 0, :]), f"{family}: streamed, order={order}"
-        assert launches[1] == launches[0] + 3, launches
+        assert launches[1] > launches[0] and (launches[1] - launches[0]) % 3 == 0, launches     # count, scan, scatter per ordered chunk
     s.close()
 
 

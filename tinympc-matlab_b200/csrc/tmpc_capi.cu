@@ -109,6 +109,8 @@ struct tinympc_cuda_solver {
                                        // of the first pass are copied back under the fp64 pass, whose results a kernel then writes over them
     int order = 1;                     // option "order": 1 = device-resident batches of box families are claimed hardest-first (counting sort by
                                        // the expected difficulty, see order_count_kernel), 0 = in index order
+    int order_sms = 2, order_from_div = 4;   // options "order_sms", "order_from_div": the compact streamed pipeline leaves that many SMs to the
+                                       // ordering kernels and claims the first 1 / order_from_div of a shard in index order
     int compact_in_kernel = 1;         // option "compact_in_kernel": kernels read tinympc_cuda_batch_in::xref_const in place where they can;
                                        // 0 = always replicate it over the horizon on the device first
     double mixed_band = 0;             // option "mixed": > 0 = fp32 pass + fp64 re-solve of the problems whose termination decision
@@ -902,13 +904,14 @@ int run_shard_compact_streamed(tinympc_cuda_solver* s, DeviceCtx& d, const Kerne
     unsigned char* obucket = nullptr;
     if (s->order && ke->order_from_ok && bits == 32 && f.feat == kFeatBox && !ppb && f.shared_bounds_ok && p.en_input_bound &&
         f.nx <= 16 && f.nu <= 8 && n >= (1 << 18) && nch >= 3 && nch <= kMaxGranules) {
+        const int div = std::max(2, s->order_from_div);
         first_ordered = 1;
-        while (first_ordered < nch - 1 && bounds[first_ordered + 1] <= n / 4) ++first_ordered;
+        while (first_ordered < nch - 1 && bounds[first_ordered + 1] <= n / div) ++first_ordered;
         int rc = reserve_order(s, d, n, &ohist, &olist, &obucket);
         if (rc) return sync_fail(rc);
         p.index_list = olist;                       // entry (c - order_from) for work item c
         p.order_from = bounds[first_ordered];
-        reserve = 2;                                // SMs for the ordering kernels: the 1/4 .. 1/2 chunk must be listed before the first quarter is used up
+        reserve = std::max(1, s->order_sms);        // SMs for the ordering kernels: the 1/4 .. 1/2 chunk must be listed before the first quarter is used up
     }
     cudaStream_t s_ord = d.streams[2];
     for (int c = 0; c < nch; ++c) {
@@ -1742,6 +1745,10 @@ int tinympc_cuda_set_option(tinympc_cuda_solver* s, const char* name, double val
         s->compact_early_d2h = value != 0;
     } else if (n == "order") {
         s->order = value != 0;
+    } else if (n == "order_sms") {
+        s->order_sms = (int)value;
+    } else if (n == "order_from_div") {
+        s->order_from_div = (int)value;
     } else if (n == "compact_in_kernel") {
         s->compact_in_kernel = value != 0;
     } else if (n == "refill_min") {
