@@ -468,12 +468,14 @@ def test_claim_order_is_scheduling_only(family, mixed, fixer_sms, capi, oracle_m
             assert s.last_timing()["chunks"] >= 3, s.last_timing()
             assert np.array_equal(c["iter"], res["iter"]) and np.array_equal(c["status"], res["status"]), f"{family}: streamed, order={order}"
             assert np.array_equal(c["u0"], res["u0"] if compact else res["u"][:, 0, :]), f"{family}: streamed, order={order}"
-        assert launches[1] > launches[0] and (launches[1] - launches[0]) % 3 == 0, launches     # count, scan, scatter per ordered chunk
+        if p.nx >= 8:    # (the streamed form orders only shards of problems with >= 8 states)
+            assert launches[1] > launches[0] and (launches[1] - launches[0]) % 3 == 0, launches     # count, scan, scatter per ordered chunk
     s.close()
 
 
 @pytest.mark.parametrize("family,precision,B", [("cartpole", 32, 3000), ("cartpole", 64, 3000), ("quadrotor", 64, 3000), ("quadrotor", 32, 60000),
-                                                ("rocket", 32, 3000), ("quadrotor_adaptive", 64, 3000), ("cartpole", 32, 140000)])
+                                                ("rocket", 32, 3000), ("quadrotor_adaptive", 64, 3000), ("cartpole", 32, 140000), ("quadrotor", 64, 70000),
+                                                ("quadrotor_adaptive", 64, 66000), ("rocket", 32, 70000)])
 def test_compact_reference_read_in_place(family, precision, B, capi, oracle_mod, problems):
     """SolveParams::xref_const: the incremental fp32 kernel and the lane-group fp64 kernel read ONE reference state per problem in
     place of every column of the horizon; every other kernel (here: the rocket's mixed-precision kernel) gets the reference

@@ -109,8 +109,9 @@ struct tinympc_cuda_solver {
                                        // of the first pass are copied back under the fp64 pass, whose results a kernel then writes over them
     int order = 1;                     // option "order": 1 = device-resident batches of box families are claimed hardest-first (counting sort by
                                        // the expected difficulty, see order_count_kernel), 0 = in index order
-    int order_sms = 2, order_from_div = 4;   // options "order_sms", "order_from_div": the compact streamed pipeline leaves that many SMs to the
-                                       // ordering kernels and claims the first 1 / order_from_div of a shard in index order
+    int order_sms = 1, order_from_div = 2;   // options "order_sms", "order_from_div": the compact streamed pipeline leaves that many SMs to the
+                                       // ordering kernels and claims the first 1 / order_from_div of a shard in index order (measured,
+                                       // profiles/r02/order_streamed_*.jsonl: 1 SM and the second half ordered is the best pair)
     int compact_in_kernel = 1;         // option "compact_in_kernel": kernels read tinympc_cuda_batch_in::xref_const in place where they can;
                                        // 0 = always replicate it over the horizon on the device first
     double mixed_band = 0;             // option "mixed": > 0 = fp32 pass + fp64 re-solve of the problems whose termination decision
@@ -894,16 +895,19 @@ int run_shard_compact_streamed(tinympc_cuda_solver* s, DeviceCtx& d, const Kerne
 
     auto sync_fail = [&](int rc) -> int { cudaDeviceSynchronize(); return rc; };
 #define RT(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return sync_fail(cuda_fail(s, e__, #call)); } while (0)
-    // Claim order (option "order", order_count_kernel): the chunks of the first quarter of the shard are claimed in index order as they
-    // arrive; every later chunk is bucketed by expected difficulty as soon as it has landed -- on the third stream, on the two SMs the
+    // Claim order (option "order", order_count_kernel): the chunks of the first half of the shard are claimed in index order as they
+    // arrive; a later chunk is bucketed by expected difficulty as soon as it has landed -- on the third stream, on the SM the
     // persistent launch leaves free for it -- and claimed hardest-first through its part of the list (SolveParams::order_from); the
-    // watermark moves past such a chunk when its list is written.  The last chunk (half the shard) is ordered ~0.5 ms after it
-    // landed, long before the lanes get there, and it ends on its easiest problems: the tail of the launch.
+    // watermark moves past such a chunk when its list is written.  With the default chunks that is the last chunk, half the shard:
+    // listed ~1.5 ms after it landed, long before the lanes get there, and ending on its easiest problems, the tail of the launch.
+    // Measured on 2^20 problems (profiles/r02/order_streamed_*.jsonl): quadrotor 14.80 -> 14.35 ms end to end; the 4-state cartpole
+    // loses 1 % (its solve is too short for the ordered half to pay for the SM), hence nx >= 8.  The device-resident entry orders
+    // the whole batch before the launch and gains 7-9 % on both.
     int reserve = 0, first_ordered = nch;
     int *ohist = nullptr, *olist = nullptr;
     unsigned char* obucket = nullptr;
     if (s->order && ke->order_from_ok && bits == 32 && f.feat == kFeatBox && !ppb && f.shared_bounds_ok && p.en_input_bound &&
-        f.nx <= 16 && f.nu <= 8 && n >= (1 << 18) && nch >= 3 && nch <= kMaxGranules) {
+        f.nx >= 8 && f.nx <= 16 && f.nu <= 8 && n >= (1 << 18) && nch >= 3 && nch <= kMaxGranules) {
         const int div = std::max(2, s->order_from_div);
         first_ordered = 1;
         while (first_ordered < nch - 1 && bounds[first_ordered + 1] <= n / div) ++first_ordered;
@@ -911,7 +915,7 @@ int run_shard_compact_streamed(tinympc_cuda_solver* s, DeviceCtx& d, const Kerne
         if (rc) return sync_fail(rc);
         p.index_list = olist;                       // entry (c - order_from) for work item c
         p.order_from = bounds[first_ordered];
-        reserve = std::max(1, s->order_sms);        // SMs for the ordering kernels: the 1/4 .. 1/2 chunk must be listed before the first quarter is used up
+        reserve = std::max(1, s->order_sms);        // SMs for the ordering kernels
     }
     cudaStream_t s_ord = d.streams[2];
     for (int c = 0; c < nch; ++c) {
