@@ -209,7 +209,9 @@ int  tinympc_cuda_session_read(tinympc_cuda_session *ss, const char *field, doub
    problems first -- lanes of a warp then hold problems of similar length and the launch ends on the shortest ones, ~9 % on the
    2^20 quadrotor batch; the compact streamed host pipeline orders the later half of a shard of >= 2^18 problems with >= 8 states
    the same way, on "order_sms" [1] SMs the persistent launch leaves free, while the first 1 / "order_from_div" [2] of the shard is
-   being solved; scheduling only, the results do not depend on it; 0: index order),
+   being solved; scheduling only, the results do not depend on it; 0: index order.  Host batch calls are serialised per device
+   within the process, so that SM stays free; a device-resident call or another process that runs a persistent launch on the same
+   device at the same time can take it and delay the ordered half -- set "order" 0 for such use),
    "ctas_per_sm" (0 = occupancy API), "chunks" (host pipeline depth, 0 = auto),
    "fixer_sms" (how the exact-count mode schedules its fp64 pass: -2 [default] the sequential two-pass form for device-resident and
    chunked batches, the concurrent producer / consumer pair inside the streamed host pipeline; -1 always sequential; 0 always the

@@ -473,6 +473,28 @@ def test_claim_order_is_scheduling_only(family, mixed, fixer_sms, capi, oracle_m
     s.close()
 
 
+@pytest.mark.timeout(180)
+def test_ordered_streamed_shards_of_two_contexts_on_one_device(capi, oracle_mod, problems):
+    """Two device contexts on the SAME GPU, each with a compact shard large enough for the ordered streamed form: its ordering kernels
+    run on the SM the persistent launch leaves free, which a second persistent launch would take (both would then wait for ordering
+    kernels that can never be scheduled) -- host batch calls are therefore serialised per device.  Same bits as one context."""
+    p = problems.quadrotor()
+    B = 600014
+    b = problems.make_batch(p, B, 1.0, seed=71)
+    xc = np.ascontiguousarray(b.Xref[:, 0, :])
+    fam = cases.family_from_spec(p, oracle_mod.get_cache(p, "port"))
+    res = []
+    for devices in ([0], [0, 0]):
+        s = capi.CudaSolver(devices=devices)
+        s.set_option("mixed", problems.exact_band(p))
+        s.set_family(fam)
+        res.append(s.solve_batch(b.x0, xref_const=xc, compact_out=True))
+        assert s.last_timing()["chunks"] >= 3
+        s.close()
+    for k in ("iter", "status", "u0"):
+        assert np.array_equal(res[0][k], res[1][k]), k
+
+
 @pytest.mark.parametrize("family,precision,B", [("cartpole", 32, 3000), ("cartpole", 64, 3000), ("quadrotor", 64, 3000), ("quadrotor", 32, 60000),
                                                 ("rocket", 32, 3000), ("quadrotor_adaptive", 64, 3000), ("cartpole", 32, 140000), ("quadrotor", 64, 70000),
                                                 ("quadrotor_adaptive", 64, 66000), ("rocket", 32, 70000)])

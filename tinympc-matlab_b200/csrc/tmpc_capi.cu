@@ -1013,6 +1013,16 @@ int run_shard_compact_streamed(tinympc_cuda_solver* s, DeviceCtx& d, const Kerne
     return TINYMPC_CUDA_OK;
 }
 
+// Host batch calls are serialised per device within the process.  Every pipeline below ends in a persistent launch that wants the
+// whole GPU, so two of them on one device (two solver handles, or one handle created with the same device twice) gain nothing from
+// running together -- and the compact streamed pipeline with claim order relies on the SM its launch leaves free staying free
+// for its ordering kernels: another persistent launch of ours would take it and both would wait for ordering kernels that can
+// never be scheduled.
+std::mutex& device_call_mutex(int device) {
+    static std::mutex mu[64];
+    return mu[device & 63];
+}
+
 // One device's share of a host batch: chunked H2D -> kernel -> D2H pipeline over kStreams streams.
 int run_shard(tinympc_cuda_solver* s, DeviceCtx& d, const tinympc_cuda_batch_in& in, const tinympc_cuda_batch_out& out, int lo, int hi,
               double* kernel_ms, int* nchunks_out, long long* marked_out) {
@@ -1020,6 +1030,7 @@ int run_shard(tinympc_cuda_solver* s, DeviceCtx& d, const tinympc_cuda_batch_in&
     const int n = hi - lo;
     *kernel_ms = 0; *nchunks_out = 0; *marked_out = 0;
     if (n <= 0) return TINYMPC_CUDA_OK;
+    std::lock_guard<std::mutex> one_call_per_device(device_call_mutex(d.device));
     CU(s, cudaSetDevice(d.device));
     const size_t sx = (size_t)f.nx * f.N, su = (size_t)f.nu * (f.N - 1);
     const bool ppb = in.x_min != nullptr;
