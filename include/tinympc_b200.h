@@ -233,6 +233,10 @@ int  tinympc_cuda_last_timing(const tinympc_cuda_solver *s, double ms[3]);
 int  tinympc_cuda_last_pass_ms(tinympc_cuda_solver *s, double ms[2]);
 /* number of problems the last "mixed" solve re-solved in fp64 (after a device-resident solve this synchronises the device) */
 long long tinympc_cuda_last_marked(tinympc_cuda_solver *s);
+/* upload plan of the compact streamed host pipeline for a shard of n problems (no device needed): chunk c = problems
+   [bounds[c], bounds[c+1]); *first_ordered = the first chunk claimed hardest-first when option "order" applies.  Returns the
+   number of chunks, -1 if `bounds` (max_bounds ints) is too small. */
+int  tinympc_cuda_plan_compact_chunks(int n, int chunks, int order_from_div, int *bounds, int max_bounds, int *first_ordered);
 const char *tinympc_cuda_last_error(const tinympc_cuda_solver *s);
 const char *tinympc_cuda_version(void);
 

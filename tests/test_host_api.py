@@ -184,3 +184,34 @@ def test_instance_list_covers_the_dispatch_rules():
     q = [i for i in inst if i["gen"] == 3 and (i["nx"], i["nu"]) == (12, 4) and i["feat"] == b.BOX]
     assert all(i["conv"] == -1 for i in q if i["variant"] in (0, 9)) and any(i["conv"] == 0 and i["variant"] == 7 for i in q)
     assert len(names) == len(set(names))
+
+
+def test_compact_pipeline_upload_plan():
+    """tinympc_cuda_plan_compact_chunks (tmpc_capi.cu plan_compact_chunks): the upload plan of the compact streamed host pipeline.
+    Chunks tile the shard, every inner boundary falls on a multiple of 32 problems (no 128-byte line holds inputs of two chunks), the
+    auto plan starts with 1/64 of the shard and doubles, and the chunks before the first ordered one cover at most n / div problems."""
+    import ctypes as C
+    tm = importlib.import_module("tinympc-matlab_b200")
+    L = tm.capi.load()
+    buf = (C.c_int * 80)()
+    fo = C.c_int()
+    for n in (65536, 70001, 300007, 1 << 20, (1 << 20) + 17, 1 << 24):
+        for chunks in (0, 2, 3, 7, 16, 64, 1000):
+            for div in (2, 4, 8):
+                nch = L.tinympc_cuda_plan_compact_chunks(n, chunks, div, buf, 80, C.byref(fo))
+                b = list(buf[:nch + 1])
+                assert nch >= 1 and b[0] == 0 and b[-1] == n and all(x < y for x, y in zip(b, b[1:])), (n, chunks, b)
+                assert all(x % 32 == 0 for x in b[:-1]), (n, chunks, b)
+                assert 1 <= fo.value <= max(1, nch - 1) and (fo.value == 1 or b[fo.value] <= n // div), (n, chunks, div, fo.value, b)
+                if fo.value + 1 < nch:
+                    assert b[fo.value + 1] > n // div          # the next boundary would exceed the unordered share
+                if chunks == 0:
+                    sizes = [y - x for x, y in zip(b, b[1:])]
+                    assert nch == 7 and sizes[0] == sizes[1] and sizes[0] <= -(-n // 64) + 31, (n, sizes)
+                    assert all(abs(s2 - 2 * s1) <= 0 for s1, s2 in zip(sizes[1:-2], sizes[2:-1])), (n, sizes)   # doubling (the last takes the rest)
+                elif chunks >= 2:
+                    assert nch <= min(chunks, 64)
+    assert L.tinympc_cuda_plan_compact_chunks(1 << 20, 0, 2, buf, 4, C.byref(fo)) == -1      # buffer too small
+    n = 1 << 20
+    assert L.tinympc_cuda_plan_compact_chunks(n, 0, 2, buf, 80, C.byref(fo)) == 7 and buf[fo.value] == n // 2     # the second half is ordered
+    assert L.tinympc_cuda_plan_compact_chunks(n, 0, 4, buf, 80, C.byref(fo)) == 7 and buf[fo.value] == n // 4

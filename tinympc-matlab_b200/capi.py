@@ -36,7 +36,7 @@ HOST_EXPORTS = [
 EXPORTS = [
     "tinympc_cuda_create", "tinympc_cuda_destroy", "tinympc_cuda_set_family", "tinympc_cuda_solve_batch",
     "tinympc_cuda_solve_batch_device", "tinympc_cuda_solve_workspace", "tinympc_cuda_set_option", "tinympc_cuda_device_count", "tinympc_cuda_num_devices",
-    "tinympc_cuda_last_kernel", "tinympc_cuda_launch_count", "tinympc_cuda_last_timing", "tinympc_cuda_last_pass_ms", "tinympc_cuda_last_marked", "tinympc_cuda_last_error",
+    "tinympc_cuda_last_kernel", "tinympc_cuda_launch_count", "tinympc_cuda_last_timing", "tinympc_cuda_last_pass_ms", "tinympc_cuda_last_marked", "tinympc_cuda_plan_compact_chunks", "tinympc_cuda_last_error",
     "tinympc_cuda_version", "tinympc_cuda_host_alloc", "tinympc_cuda_host_free",
     "tinympc_cuda_session_create", "tinympc_cuda_session_destroy", "tinympc_cuda_session_set_x0", "tinympc_cuda_session_set_x_ref",
     "tinympc_cuda_session_set_u_ref", "tinympc_cuda_session_solve", "tinympc_cuda_session_step", "tinympc_cuda_session_read",
@@ -146,6 +146,8 @@ def load():
         L.tinympc_cuda_last_pass_ms.restype = C.c_int
         L.tinympc_cuda_last_marked.argtypes = [C.c_void_p]
         L.tinympc_cuda_last_marked.restype = C.c_longlong
+        L.tinympc_cuda_plan_compact_chunks.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_int)]
+        L.tinympc_cuda_plan_compact_chunks.restype = C.c_int
         L.tinympc_cuda_last_error.argtypes = [C.c_void_p]
         L.tinympc_cuda_last_error.restype = C.c_char_p
         L.tinympc_cuda_version.restype = C.c_char_p

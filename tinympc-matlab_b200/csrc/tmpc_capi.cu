@@ -265,15 +265,37 @@ struct OrderParams {
     int nx, nu, xref_stride;   // xref_stride: floats between the reference states of consecutive problems (nx: compact, nx*N: full, 0: none)
 };
 __device__ __forceinline__ int order_bucket(const OrderParams& op, const float* __restrict__ x0, const float* __restrict__ xref, int i) {
-    float key = 0.f;
-    for (int a = 0; a < op.nu; ++a) {
-        float acc = 0.f;
-        for (int c = 0; c < op.nx; ++c) {
-            float dv = __ldg(x0 + (size_t)i * op.nx + c);
-            if (xref) dv -= __ldg(xref + (size_t)i * op.xref_stride + c);
-            acc = fmaf(op.K[a * op.nx + c], dv, acc);
+    // d = x0 - xref_0 in registers (nx <= 16): 128-bit loads when the rows are 16-byte multiples (every compiled shape but nx = 6)
+    float d[16];
+    const int nx = op.nx;
+    const float* px = x0 + (size_t)i * nx;
+    const float* pr = xref ? xref + (size_t)i * op.xref_stride : nullptr;
+    if (((nx | op.xref_stride) & 3) == 0) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (4 * q < nx) {
+                v = __ldg(reinterpret_cast<const float4*>(px) + q);
+                if (pr) {
+                    const float4 r = __ldg(reinterpret_cast<const float4*>(pr) + q);
+                    v.x -= r.x; v.y -= r.y; v.z -= r.z; v.w -= r.w;
+                }
+            }
+            d[4 * q] = v.x; d[4 * q + 1] = v.y; d[4 * q + 2] = v.z; d[4 * q + 3] = v.w;
         }
-        key = fmaxf(key, fabsf(acc) * op.inv_ub[a]);
+    } else {
+#pragma unroll
+        for (int c = 0; c < 16; ++c) d[c] = c < nx ? __ldg(px + c) - (pr ? __ldg(pr + c) : 0.f) : 0.f;
+    }
+    float key = 0.f;
+#pragma unroll
+    for (int a = 0; a < 8; ++a) {
+        if (a < op.nu) {
+            float acc = 0.f;
+#pragma unroll
+            for (int c = 0; c < 16; ++c) if (c < nx) acc = fmaf(op.K[a * nx + c], d[c], acc);
+            key = fmaxf(key, fabsf(acc) * op.inv_ub[a]);
+        }
     }
     // 64 buckets per unit of key: everything beyond 4x the bound is "hardest"; bucket 0 of the LIST is the hardest
     const int b = min(kOrderBuckets - 1, __float2int_rd(key * 64.f));
@@ -286,6 +308,7 @@ __global__ void __launch_bounds__(kOrderBlock) order_count_kernel(const __grid_c
     __shared__ int sh[kOrderBuckets];
     for (int b = threadIdx.x; b < kOrderBuckets; b += kOrderBlock) sh[b] = 0;
     __syncthreads();
+#pragma unroll 2
     for (int k = 0; k < kOrderItems; ++k) {
         const int i = (blockIdx.x * kOrderItems + k) * kOrderBlock + threadIdx.x;
         if (i < n) {
@@ -813,6 +836,30 @@ int run_shard_streamed(tinympc_cuda_solver* s, DeviceCtx& d, const KernelEntry* 
     return TINYMPC_CUDA_OK;
 }
 
+// Upload plan of the compact streamed pipeline for a shard of n problems.  bounds: chunk c = problems [bounds[c], bounds[c + 1]),
+// runs of granules of a multiple of 32 problems (no 128-byte line holds inputs of two chunks, see run_shard_streamed); chunks <= 0
+// (auto): 1, 1, 2, 4, 8, ... sixty-fourths of the shard, so that the kernel starts after 1/64 of the upload; chunks = k > 1: k equal
+// chunks.  Returns the first chunk that is claimed through an ordered list when claim order applies: the chunks before it cover
+// at most n / div problems (but always the first chunk).
+int plan_compact_chunks(int n, int chunks, int div, std::vector<int>& bounds) {
+    const bool ramp = chunks <= 0;
+    const int ng_target = ramp ? kMaxGranules : std::min(chunks, kMaxGranules);
+    const int gran = (((n + ng_target - 1) / ng_target) + 31) & ~31;
+    const int ng = (n + gran - 1) / gran;
+    bounds.clear();
+    bounds.push_back(0);
+    int g = 0, run = 1;
+    while (g < ng) {
+        g = std::min(ng, g + run);
+        bounds.push_back(std::min(n, g * gran));
+        if (ramp && bounds.size() > 2) run *= 2;
+    }
+    const int nch = (int)bounds.size() - 1;
+    int first_ordered = 1;
+    while (first_ordered < nch - 1 && bounds[first_ordered + 1] <= n / std::max(2, div)) ++first_ordered;
+    return first_ordered;
+}
+
 // Compact host I/O (x0 + one reference state per problem in, u0 + iter + status out: ~120 bytes per problem) as ONE launch chain.
 // The chunked pipeline pays for every chunk a partial last wave of the persistent kernel and the latency-bound end of its fp64
 // pass, and its first launch waits for the first chunk's upload; here stream 0 uploads the inputs in a few chunks of doubling
@@ -835,22 +882,8 @@ int run_shard_compact_streamed(tinympc_cuda_solver* s, DeviceCtx& d, const Kerne
     const size_t sx = (size_t)f.nx * f.N, su = (size_t)f.nu * (f.N - 1);
     const bool ppb = in.x_min != nullptr;
     const bool mixed = ke64 != nullptr;
-    // chunks = runs of granules of a multiple of 32 problems (no 128-byte line holds inputs of two chunks, see run_shard_streamed);
-    // auto: 1, 1, 2, 4, 8, ... sixty-fourths of the shard; chunks = k > 1: k equal chunks
     std::vector<int> bounds;
-    {
-        const bool ramp = s->chunks <= 0;
-        const int ng_target = ramp ? kMaxGranules : std::min(s->chunks, kMaxGranules);
-        const int gran = (((n + ng_target - 1) / ng_target) + 31) & ~31;
-        const int ng = (n + gran - 1) / gran;
-        bounds.push_back(0);
-        int g = 0, run = 1;
-        while (g < ng) {
-            g = std::min(ng, g + run);
-            bounds.push_back(std::min(n, g * gran));
-            if (ramp && bounds.size() > 2) run *= 2;
-        }
-    }
+    const int plan_first_ordered = plan_compact_chunks(n, s->chunks, s->order_from_div, bounds);
     const int nch = (int)bounds.size() - 1;
     cudaStream_t s_in = d.streams[0], s_k = d.streams[1];
     int* ctl = d.stream_ctl;   // [0] work counter of the first kernel, [1] arrival watermark
@@ -908,9 +941,7 @@ int run_shard_compact_streamed(tinympc_cuda_solver* s, DeviceCtx& d, const Kerne
     unsigned char* obucket = nullptr;
     if (s->order && ke->order_from_ok && bits == 32 && f.feat == kFeatBox && !ppb && f.shared_bounds_ok && p.en_input_bound &&
         f.nx >= 8 && f.nx <= 16 && f.nu <= 8 && n >= (1 << 18) && nch >= 3 && nch <= kMaxGranules) {
-        const int div = std::max(2, s->order_from_div);
-        first_ordered = 1;
-        while (first_ordered < nch - 1 && bounds[first_ordered + 1] <= n / div) ++first_ordered;
+        first_ordered = plan_first_ordered;
         int rc = reserve_order(s, d, n, &ohist, &olist, &obucket);
         if (rc) return sync_fail(rc);
         p.index_list = olist;                       // entry (c - order_from) for work item c
@@ -1813,6 +1844,15 @@ long long tinympc_cuda_last_marked(tinympc_cuda_solver* s) {
         s->mixed_pending_dev = -1;
     }
     return s->mixed_marked;
+}
+int tinympc_cuda_plan_compact_chunks(int n, int chunks, int order_from_div, int* bounds, int max_bounds, int* first_ordered) {
+    if (n <= 0 || !bounds || max_bounds < 2) return -1;
+    std::vector<int> b;
+    const int fo = plan_compact_chunks(n, chunks, order_from_div, b);
+    if ((int)b.size() > max_bounds) return -1;
+    for (size_t k = 0; k < b.size(); ++k) bounds[k] = b[k];
+    if (first_ordered) *first_ordered = fo;
+    return (int)b.size() - 1;
 }
 const char* tinympc_cuda_last_error(const tinympc_cuda_solver* s) { return s ? s->err.c_str() : "null solver"; }
 
