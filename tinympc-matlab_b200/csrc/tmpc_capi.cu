@@ -870,10 +870,9 @@ int plan_compact_chunks(int n, int chunks, int div, std::vector<int>& bounds) {
 // no gather.  The link delivers ~55 GB/s, the kernel consumes ~7: after the first chunk (1/64 of the shard) the upload is
 // hidden, and what is left of the bus is the 24 bytes per problem that come back (0.45 ms per 2^20 problems).  Enqueue order as
 // in run_shard_streamed: every copy the kernel waits for is enqueued before its launch.
-// Measured (quadrotor, 2^20 problems, exact-count mode, profiles/r02/e2e_compact_sweep.jsonl): 15.06 ms end to end against 14.52 ms
-// of kernels (chunked pipeline with expansion / gather kernels: 17.1 ms).  Tried, not kept: result copies started right after the
-// first pass, under the fp64 pass, which then returns a packed list {index, iter, status, u0} for the host to scatter over
-// them -- the scatter of ~14 000 entries over three 4-25 MB host arrays costs more (15.34 ms) than the 0.45 ms of copies it hides.
+// Measured (quadrotor, 2^20 problems, exact-count mode, profiles/r02/e2e_compact_sweep*.jsonl): chunked pipeline with expansion /
+// gather kernels 17.1 ms end to end -> 15.1 ms as one launch chain -> 14.8 ms with the result copies under the fp64 pass (below)
+// -> 14.4 ms with the second half of the shard claimed hardest-first (below), against 14.1 ms of kernels.
 int run_shard_compact_streamed(tinympc_cuda_solver* s, DeviceCtx& d, const KernelEntry* ke, const KernelEntry* ke64, const tinympc_cuda_batch_in& in,
                                const tinympc_cuda_batch_out& out, int lo, int hi, double* kernel_ms, int* nchunks_out, long long* marked_out) {
     const Family& f = s->fam;
