@@ -13,6 +13,7 @@ sys.path.insert(0, str(ROOT / "tests"))
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    config.addinivalue_line("markers", "timeout: per-test limit in seconds (pytest-timeout; ignored if the plugin is absent)")
 
 
 @pytest.fixture(scope="session")
